@@ -1,0 +1,155 @@
+/*
+ * kc_api.h -- C ABI of the B200-native k-mer counting path (libkc_b200.so).
+ *
+ * This is the drop-in boundary for the counting path of jsdjayanga/kmer-counter.
+ * Plain pointers and sizes only; every call returns an int status (0 = KC_OK,
+ * negative = error, message from kc_last_error) and never exits or throws.
+ * Citations are file:line into the reference tree.
+ *
+ * Data contracts
+ *   reads    "packed lines": n_bytes of reads back to back at stride read_len,
+ *            no separators -- exactly FASTQData::getData() as handed to
+ *            processKMers (FASTQFileReader.cpp:63-64, GPUHandler.h:63).  A partial
+ *            trailing read is ignored (GPUHandler.cu:13,134).
+ *   records  packed, no padding: W = ceil(k/32) little-endian uint64 words (word 0
+ *            = most significant bases) + uint32 count; 12/20/28/36 bytes
+ *            (KMerSizes.h:10-28 under GPUHandler.h:15's pack(1)).  This is the
+ *            run-file / output-file / KMerPrinter format (SortedKMerFile.cpp:22-27).
+ *   run      a sorted, key-unique sequence of records, resident on the device.
+ *
+ * Threading: one kc_ctx may be driven from several host threads as long as each
+ * thread uses its own slot (the reference calls processKMers from up to 8
+ * threads, one GPUStream each, KMerCounter.cpp:136-138).  Calls that take no slot
+ * are serialised internally.
+ */
+#ifndef KC_API_H
+#define KC_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_OK               0
+#define KC_ERR_ARG         -1   /* bad argument / unsupported (k, read_len)            */
+#define KC_ERR_CUDA        -2   /* a CUDA call failed                                  */
+#define KC_ERR_NOMEM       -3   /* device or pinned allocation failed                  */
+#define KC_ERR_CAPACITY    -4   /* destination buffer / slot too small                 */
+#define KC_ERR_IO          -5   /* file open / write failed                            */
+#define KC_ERR_STATE       -6   /* call out of order (e.g. wait on an idle slot)       */
+
+/* kc_config.flags */
+#define KC_COMPAT_REF       0x0u  /* bit-exact with the reference, quirks included (default):
+                                     unmasked tail window at k%32 in {29,30,31} and the
+                                     zero-count key-0 record           */
+#define KC_COMPAT_STRICT    0x1u  /* true k-mers: tail always masked to k bases, no phantom */
+
+/* kc_config.method: how occurrences are counted inside one chunk */
+#define KC_COUNT_AUTO       0u
+#define KC_COUNT_SORT       1u    /* radix sort + run-length (replaces sortKmers+reduceKMers,
+                                     GPUHandler.cu:300-360)                                */
+#define KC_COUNT_HASH       2u    /* open-addressing table (replaces the TBB accumulate,
+                                     KMerCounter.cpp:61-82), then sort of the distinct set */
+
+typedef struct kc_ctx kc_ctx;
+typedef struct kc_run kc_run;
+
+typedef struct kc_config {
+    uint32_t struct_size;      /* sizeof(kc_config), for ABI growth                        */
+    uint32_t k;                /* kmerLength= (main.cpp:33), 1..128                        */
+    uint32_t read_len;         /* lineLength (FASTQFileReader.cpp:30-35), k..4096          */
+    int32_t  device;           /* CUDA device ordinal                                      */
+    uint32_t flags;            /* KC_COMPAT_*                                              */
+    uint32_t method;           /* KC_COUNT_*                                               */
+    uint32_t n_slots;          /* pinned input slots (the reference's 8 GPUStreams,
+                                  KMerCounter.cpp:117); 0 -> 2                             */
+    uint32_t reserved0;
+    uint64_t max_chunk_bytes;  /* capacity of each slot = largest chunk submitted;
+                                  replaces PrepareGPU's inputSize (GPUHandler.cu:479)      */
+    uint64_t table_slots;      /* hash capacity hint, 0 = derive from the chunk            */
+    void    *stream;           /* cudaStream_t to run on, NULL = a stream owned by the ctx */
+} kc_config;
+
+typedef struct kc_stats {
+    uint64_t chunks;           /* chunks counted                                           */
+    uint64_t reads;            /* reads consumed                                           */
+    uint64_t kmer_slots;       /* reads * (L-k+1): the reference's output slots            */
+    uint64_t kmers_valid;      /* occurrences actually counted                             */
+    uint64_t distinct_last;    /* records in the most recent run                           */
+    uint64_t launches;         /* kernels launched by this library so far                  */
+    uint64_t h2d_bytes, d2h_bytes;
+    /* device time of the most recent chunk, by stage, CUDA events on the ctx stream */
+    float ms_extract, ms_count, ms_emit, ms_total;
+    /* dominant kernel of the most recent chunk (radix scatter pass or hash insert) */
+    float ms_dominant;         /* summed over its launches                                 */
+    uint32_t dominant_launches;
+    uint32_t method_used;      /* KC_COUNT_SORT or KC_COUNT_HASH                           */
+    uint64_t dominant_bytes;   /* algorithmic bytes moved by those launches                */
+} kc_stats;
+
+/* ---- library ---- */
+const char *kc_version(void);
+uint32_t kc_key_words(uint32_t k);             /* ceil(k/32)                               */
+uint32_t kc_record_size(uint32_t k);           /* 8*W+4 (GPUHandler.cu:235-245)            */
+/* R*(L-k+1)*S: the reference's raw output size for a chunk (calculateOutputSize) */
+uint64_t kc_output_size(uint64_t n_bytes, uint32_t read_len, uint32_t k);
+
+/* ---- context: replaces PrepareGPU / FreeGPU (GPUHandler.h:61-62, GPUHandler.cu:479-519) ---- */
+int  kc_create(const kc_config *cfg, kc_ctx **out);
+void kc_destroy(kc_ctx *ctx);
+const char *kc_last_error(const kc_ctx *ctx);   /* ctx may be NULL: last create error      */
+int  kc_sync(kc_ctx *ctx);                      /* wait for everything queued on the ctx   */
+int  kc_stats_get(kc_ctx *ctx, kc_stats *out);
+
+/* pinned host memory for callers that want zero-copy staging (e2e path) */
+int  kc_host_alloc(kc_ctx *ctx, uint64_t bytes, void **out);
+int  kc_host_free(kc_ctx *ctx, void *p);
+
+/* ---- counting one chunk: replaces processKMers (GPUHandler.h:63, GPUHandler.cu:397-477) ---- */
+
+/* Synchronous, host in / host out: H2D, extract, count, D2H.  On return
+ * records[0..*n_bytes) is the chunk's sorted key-unique run and `reads` may be
+ * freed (KMerCounter.cpp:88).  records may be NULL to only learn *n_bytes. */
+int  kc_process_chunk(kc_ctx *ctx, uint32_t slot, const char *reads, uint64_t n_bytes,
+                      void *records, uint64_t records_cap, uint64_t *out_bytes);
+
+/* Asynchronous, pinned double-buffered: fill the slot's pinned buffer, submit,
+ * fill the next slot while this one is copied and counted, then wait. */
+int  kc_slot_buffer(kc_ctx *ctx, uint32_t slot, void **ptr, uint64_t *cap);
+int  kc_submit(kc_ctx *ctx, uint32_t slot, uint64_t n_bytes);
+int  kc_wait(kc_ctx *ctx, uint32_t slot, kc_run **run);   /* caller owns *run (may be NULL
+                                                             for an empty chunk)           */
+
+/* Device-resident input (d_reads: device pointer, 16-byte aligned). */
+int  kc_count_device(kc_ctx *ctx, const void *d_reads, uint64_t n_bytes, kc_run **run);
+
+/* ---- runs: the sorted-run dump (FileDump.cpp:51-58) and its consumers ---- */
+uint64_t kc_run_records(const kc_run *run);
+int  kc_run_free(kc_ctx *ctx, kc_run *run);
+/* packed records out (D2H), into pageable or pinned memory */
+int  kc_run_copy_records(kc_ctx *ctx, const kc_run *run, void *dst, uint64_t cap, uint64_t *out_bytes);
+/* packed records in: a run file's bytes (must be sorted; adjacent equal keys are
+ * folded like SortedKMerFile::ReadKmer does, SortedKMerFile.cpp:57-82) */
+int  kc_run_upload(kc_ctx *ctx, const void *records, uint64_t n_bytes, kc_run **run);
+/* device views for the multi-GPU exchange: keys = n*W uint64 (key-major), counts = n uint32 */
+int  kc_run_device(const kc_run *run, void **d_keys, void **d_counts, uint64_t *n);
+/* build a run from device arrays holding sorted unique keys (copied) */
+int  kc_run_from_device(kc_ctx *ctx, const void *d_keys, const void *d_counts, uint64_t n, kc_run **run);
+/* write dumpKmersToFile-style: truncates unless append != 0 */
+int  kc_run_write(kc_ctx *ctx, const kc_run *run, const char *path, int append);
+/* lower-bound positions of n_splitters keys (each W words, ascending) inside the
+ * run: offsets[0]=0, offsets[i+1]=first record >= splitter i, offsets[n_splitters+1]=n */
+int  kc_run_split(kc_ctx *ctx, const kc_run *run, const uint64_t *splitters, uint32_t n_splitters,
+                  uint64_t *offsets);
+
+/* ---- merge: replaces KMerFileMerger::Merge (KMerFileMerger.cpp:49-96) ---- */
+/* Merge n sorted runs into one, adding the counts of equal keys (uint32 wrap).
+ * Inputs stay valid and owned by the caller. n may be 0 (empty run) or 1 (copy). */
+int  kc_merge_runs(kc_ctx *ctx, kc_run *const *runs, uint32_t n, kc_run **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KC_API_H */

@@ -1,0 +1,771 @@
+// kc_api.cu -- the C ABI (include/kc_api.h) over the kernels of this directory.
+//
+// Host-side orchestration only: buffer lifetime, stream ordering, stage timing.
+// There is no CPU compute path here; if the device cannot run a kernel the call
+// fails with KC_ERR_CUDA.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kc_api.h"
+#include "kc_internal.h"
+
+using namespace kc;
+
+struct kc_run {
+    int W = 1;
+    uint64_t n = 0;          // records
+    uint64_t skip = 0;       // leading records hidden (strict mode drops an empty key-0 record)
+    uint64_t *d_keys = nullptr;
+    uint32_t *d_counts = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum { SC_INVALID = 0, SC_UNIQUE = 1, SC_MERGE = 2, SC_HASHNUM = 3, SC_SIDE = 4 /* 4..7 */, SC_COUNT = 16 };
+
+struct Pending {                 // a chunk whose kernels are queued but whose run is not built yet
+    bool active = false;
+    uint32_t method = 0;
+    uint64_t n_reads = 0, n_slots = 0;
+    uint64_t *keys_a = nullptr, *keys_b = nullptr, *sorted = nullptr, *uniq = nullptr;
+    uint32_t *starts = nullptr;
+    void *ws_sort = nullptr, *ws_rle = nullptr;
+    HashTable table{nullptr, 0, nullptr};
+    unsigned long long *d_scal = nullptr;   // SC_COUNT device scalars
+    unsigned long long *h_scal = nullptr;   // pinned mirror
+    cudaEvent_t ev[6] = {};                  // start, extracted, pass0, passN, counted, end
+    int n_passes = 0;
+};
+
+struct Slot {
+    void *h_in = nullptr;        // pinned
+    void *d_in = nullptr;
+    uint64_t cap = 0;
+    cudaStream_t stream = nullptr;
+    Pending pend;
+    uint64_t n_bytes = 0;
+};
+
+}  // namespace
+
+struct kc_ctx {
+    kc_config cfg{};
+    int W = 1, S = 12;
+    bool strict = false;
+    int n_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<Slot> slots;
+    Pending direct;              // kc_count_device / kc_process_chunk without slots use this
+    std::mutex mu;
+    kc_stats stats{};
+    int last_code = 0;
+    char err[512] = {0};
+
+    int set_error(int code, const char *fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, sizeof err, fmt, ap);
+        va_end(ap);
+        last_code = code;
+        return code;
+    }
+};
+
+namespace {
+
+#define KC_TRY(expr)                         \
+    do {                                     \
+        int _rc = (expr);                    \
+        if (_rc != KC_OK) return _rc;        \
+    } while (0)
+
+int dev_alloc(kc_ctx *c, cudaStream_t s, uint64_t bytes, void **out) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(out, bytes, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes failed: %s", (unsigned long long)bytes,
+                            cudaGetErrorString(e));
+    }
+    return KC_OK;
+}
+void dev_free(cudaStream_t s, void *p) {
+    if (p) cudaFreeAsync(p, s);
+}
+
+int pending_init(kc_ctx *c, Pending &p) {
+    if (p.d_scal) return KC_OK;
+    KC_CUDA_TRY(c, cudaMalloc((void **)&p.d_scal, SC_COUNT * 8));
+    KC_CUDA_TRY(c, cudaMallocHost((void **)&p.h_scal, SC_COUNT * 8));
+    for (auto &e : p.ev) KC_CUDA_TRY(c, cudaEventCreate(&e));
+    return KC_OK;
+}
+void pending_destroy(Pending &p) {
+    if (p.d_scal) cudaFree(p.d_scal);
+    if (p.h_scal) cudaFreeHost(p.h_scal);
+    for (auto &e : p.ev)
+        if (e) cudaEventDestroy(e);
+    p = Pending();
+}
+
+void pending_release(cudaStream_t s, Pending &p) {
+    dev_free(s, p.keys_a); dev_free(s, p.keys_b); dev_free(s, p.starts);
+    dev_free(s, p.ws_sort); dev_free(s, p.ws_rle); dev_free(s, p.table.slots);
+    p.keys_a = p.keys_b = p.sorted = p.uniq = nullptr;
+    p.starts = nullptr;
+    p.ws_sort = p.ws_rle = nullptr;
+    p.table = HashTable{nullptr, 0, nullptr};
+    p.active = false;
+}
+
+uint64_t pow2_ceil(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// low bits of the last key word that are zero for every key (masked tail): the
+// radix sort skips the passes that would only see zeros
+int static_zero_bits(const kc_ctx *c) {
+    uint32_t m = c->cfg.k % 32;
+    bool masked = c->strict ? (m != 0) : (m >= 1 && m <= 28);
+    return masked ? (int)(64 - 2 * m) : 0;
+}
+
+constexpr uint64_t kMaxSortKeys = (1ull << 30) - 1;
+
+uint32_t pick_method(const kc_ctx *c) {
+    uint32_t m = c->cfg.method;
+    if (c->W != 1) return KC_COUNT_SORT;           // 128-bit+ keys: sort + run-length (config 3)
+    if (m == KC_COUNT_AUTO) return KC_COUNT_SORT;  // see DESIGN.md "method selection"
+    return m;
+}
+
+// Queue extraction + counting of one chunk on stream s. Nothing is synchronised.
+int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, uint32_t method) {
+    KC_TRY(pending_init(c, p));
+    const uint32_t L = c->cfg.read_len, k = c->cfg.k;
+    const int W = c->W;
+    p.n_reads = n_bytes / L;
+    p.n_slots = p.n_reads * (uint64_t)(L - k + 1);
+    p.method = method;
+    p.active = true;
+    p.n_passes = 0;
+    int launches = 0;
+    KC_CUDA_TRY(c, cudaMemsetAsync(p.d_scal, 0, SC_COUNT * 8, s));
+    KC_CUDA_TRY(c, cudaEventRecord(p.ev[0], s));
+    if (p.n_slots == 0) {
+        for (int i = 1; i < 6; i++) KC_CUDA_TRY(c, cudaEventRecord(p.ev[i], s));
+        return KC_OK;
+    }
+    if (p.n_slots > kMaxSortKeys) return c->set_error(KC_ERR_ARG, "chunk too large: %llu k-mer slots (max %llu)",
+                                                      (unsigned long long)p.n_slots, (unsigned long long)kMaxSortKeys);
+    ExtractParams ep;
+    if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep))
+        return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
+
+    if (method == KC_COUNT_HASH) {
+        uint64_t cap = c->cfg.table_slots ? pow2_ceil(c->cfg.table_slots) : pow2_ceil(p.n_slots / 2 + 1);
+        if (cap < (1u << 16)) cap = 1u << 16;
+        void *mem = nullptr;
+        KC_TRY(dev_alloc(c, s, hash_table_bytes(cap), &mem));
+        p.table.slots = static_cast<uint64_t *>(mem);
+        p.table.capacity = cap;
+        p.table.side = &p.d_scal[SC_SIDE];
+        KC_CUDA_TRY(c, hash_clear(p.table, s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));     // "extract" stage is empty: it is fused into the insert
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[2], s));
+        KC_CUDA_TRY(c, launch_extract_hash(ep, p.table, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[3], s));
+        KC_CUDA_TRY(c, hash_touch_zero(p.table, c->strict ? &p.d_scal[SC_COUNT - 1] : &p.d_scal[SC_INVALID], s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[4], s));
+        launches += 3;
+        p.n_passes = 1;
+    } else {
+        void *mem = nullptr;
+        KC_TRY(dev_alloc(c, s, p.n_slots * W * 8, &mem)); p.keys_a = static_cast<uint64_t *>(mem);
+        KC_TRY(dev_alloc(c, s, p.n_slots * W * 8, &mem)); p.keys_b = static_cast<uint64_t *>(mem);
+        KC_TRY(dev_alloc(c, s, (p.n_slots + 1) * 4, &mem)); p.starts = static_cast<uint32_t *>(mem);
+        const uint64_t ws_bytes = sort_workspace_bytes(p.n_slots, W);
+        KC_TRY(dev_alloc(c, s, ws_bytes, &p.ws_sort));
+        KC_TRY(dev_alloc(c, s, rle_workspace_bytes(p.n_slots), &p.ws_rle));
+        KC_CUDA_TRY(c, launch_extract_store(ep, W, p.keys_a, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));
+        const int lo_bit = static_zero_bits(c);
+        p.n_passes = (64 * W - (lo_bit & ~7)) / 8;
+        int sort_launches = 0;
+        KC_CUDA_TRY(c, radix_sort(p.keys_a, p.keys_b, nullptr, nullptr, p.n_slots, W, lo_bit,
+                                  SortWorkspace{p.ws_sort, ws_bytes}, s, &p.sorted, nullptr, &sort_launches,
+                                  p.ev[2], p.ev[3]));
+        p.uniq = (p.sorted == p.keys_a) ? p.keys_b : p.keys_a;
+        KC_CUDA_TRY(c, rle_unique(p.sorted, p.n_slots, W, p.uniq, p.starts, &p.d_scal[SC_UNIQUE], p.ws_rle, s,
+                                  &sort_launches));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[4], s));
+        launches += 1 + sort_launches;
+    }
+    KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += launches;
+    }
+    return KC_OK;
+}
+
+int make_run(kc_ctx *c, cudaStream_t s, uint64_t n, kc_run **out) {
+    kc_run *r = new kc_run();
+    r->W = c->W;
+    r->n = n;
+    void *mem = nullptr;
+    int rc = dev_alloc(c, s, n * c->W * 8, &mem);
+    if (rc != KC_OK) { delete r; return rc; }
+    r->d_keys = static_cast<uint64_t *>(mem);
+    rc = dev_alloc(c, s, n * 4, &mem);
+    if (rc != KC_OK) { dev_free(s, r->d_keys); delete r; return rc; }
+    r->d_counts = static_cast<uint32_t *>(mem);
+    *out = r;
+    return KC_OK;
+}
+
+int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
+int count_finish_hash(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, kc_run **out);
+
+// Wait for the queued kernels, build the run, record stage timings.
+int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, kc_run **out) {
+    *out = nullptr;
+    if (!p.active) return c->set_error(KC_ERR_STATE, "no chunk queued");
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    int rc;
+    uint32_t used = p.method;
+    if (p.n_slots == 0) {
+        rc = make_run(c, s, 0, out);
+    } else if (p.method == KC_COUNT_HASH) {
+        if (p.h_scal[SC_SIDE + 1]) {             // table overflow: redo this chunk with sort + run-length
+            pending_release(s, p);
+            KC_TRY(count_enqueue(c, p, d_reads, n_bytes, s, KC_COUNT_SORT));
+            KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+            used = KC_COUNT_SORT;
+            rc = count_finish_sort(c, p, s, out);
+        } else {
+            rc = count_finish_hash(c, p, d_reads, n_bytes, s, out);
+        }
+    } else {
+        rc = count_finish_sort(c, p, s, out);
+    }
+    if (rc != KC_OK) { pending_release(s, p); return rc; }
+    KC_CUDA_TRY(c, cudaEventRecord(p.ev[5], s));
+    KC_CUDA_TRY(c, cudaEventSynchronize(p.ev[5]));
+    float t01 = 0, t14 = 0, t23 = 0, t45 = 0, t05 = 0;
+    cudaEventElapsedTime(&t01, p.ev[0], p.ev[1]);
+    cudaEventElapsedTime(&t14, p.ev[1], p.ev[4]);
+    cudaEventElapsedTime(&t23, p.ev[2], p.ev[3]);
+    cudaEventElapsedTime(&t45, p.ev[4], p.ev[5]);
+    cudaEventElapsedTime(&t05, p.ev[0], p.ev[5]);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        kc_stats &st = c->stats;
+        st.chunks++;
+        st.reads += p.n_reads;
+        st.kmer_slots += p.n_slots;
+        const uint64_t invalid = p.h_scal[SC_INVALID];
+        st.kmers_valid += p.n_slots - invalid;
+        st.distinct_last = (*out)->n - (*out)->skip;
+        st.ms_extract = t01; st.ms_count = t14; st.ms_emit = t45; st.ms_total = t05;
+        st.ms_dominant = t23;
+        st.dominant_launches = (uint32_t)p.n_passes;
+        st.method_used = used;
+        if (used == KC_COUNT_SORT)
+            st.dominant_bytes = (uint64_t)p.n_passes * p.n_slots * 2ull * 8ull * c->W;   // read + write each key per pass
+        else
+            st.dominant_bytes = p.n_reads * c->cfg.read_len + (p.n_slots - invalid) * 16ull;   // SURVEY 8(d) per-occurrence terms
+    }
+    pending_release(s, p);
+    return KC_OK;
+}
+
+int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
+    const uint64_t U = p.h_scal[SC_UNIQUE];
+    kc_run *r = nullptr;
+    KC_TRY(make_run(c, s, U, &r));
+    if (U) {
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_keys, p.uniq, U * c->W * 8, cudaMemcpyDeviceToDevice, s));
+        KC_CUDA_TRY(c, starts_to_counts(p.starts, r->d_keys, c->W, U, &p.d_scal[SC_INVALID], r->d_counts, s));
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += 1;
+    }
+    // strict mode: empty slots were sorted in as key 0; if nothing real is left there, hide that record
+    if (c->strict && U && p.h_scal[SC_INVALID]) {
+        uint64_t k0[kMaxWords] = {0};
+        uint32_t c0 = 0;
+        KC_CUDA_TRY(c, cudaMemcpyAsync(k0, r->d_keys, c->W * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(&c0, r->d_counts, 4, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        bool zero = true;
+        for (int w = 0; w < c->W; w++) zero = zero && k0[w] == 0;
+        if (zero && c0 == 0) r->skip = 1;
+    }
+    *out = r;
+    return KC_OK;
+}
+
+int count_finish_hash(kc_ctx *c, Pending &p, const void *, uint64_t, cudaStream_t s, kc_run **out) {
+    const uint64_t U = p.h_scal[SC_SIDE + 3] + (p.h_scal[SC_SIDE + 0] ? 1 : 0);
+    kc_run *ra = nullptr, *rb = nullptr;
+    KC_TRY(make_run(c, s, U, &ra));
+    int rc = make_run(c, s, U, &rb);
+    if (rc != KC_OK) { kc_run_free(c, ra); return rc; }
+    int launches = 0;
+    KC_CUDA_TRY(c, hash_compact(p.table, ra->d_keys, ra->d_counts, &p.d_scal[SC_HASHNUM], s, &launches));
+    const uint64_t ws_bytes = sort_workspace_bytes(U, 1);
+    void *ws = nullptr;
+    KC_TRY(dev_alloc(c, s, ws_bytes, &ws));
+    uint64_t *sk = nullptr;
+    uint32_t *sv = nullptr;
+    KC_CUDA_TRY(c, radix_sort(ra->d_keys, rb->d_keys, ra->d_counts, rb->d_counts, U, 1, static_zero_bits(c),
+                              SortWorkspace{ws, ws_bytes}, s, &sk, &sv, &launches, nullptr, nullptr));
+    dev_free(s, ws);
+    kc_run *keep = (sk == ra->d_keys) ? ra : rb, *drop = (keep == ra) ? rb : ra;
+    kc_run_free(c, drop);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += launches;
+    }
+    *out = keep;
+    return KC_OK;
+}
+
+int check_ctx(const kc_ctx *c) { return c ? KC_OK : KC_ERR_ARG; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------- library
+extern "C" {
+
+const char *kc_version(void) { return "kc_b200 0.1 (sm_100a)"; }
+uint32_t kc_key_words(uint32_t k) { return (k + 31) / 32; }
+uint32_t kc_record_size(uint32_t k) { return 8 * kc_key_words(k) + 4; }
+uint64_t kc_output_size(uint64_t n_bytes, uint32_t read_len, uint32_t k) {
+    if (read_len == 0 || k == 0 || k > read_len) return 0;
+    return (n_bytes / read_len) * (uint64_t)(read_len - k + 1) * kc_record_size(k);
+}
+
+int kc_create(const kc_config *cfg, kc_ctx **out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out) { g_create_error = "kc_create: null argument"; return KC_ERR_ARG; }
+    kc_config c0{};
+    memcpy(&c0, cfg, cfg->struct_size && cfg->struct_size < sizeof(kc_config) ? cfg->struct_size : sizeof(kc_config));
+    if (c0.k < 1 || c0.k > 128) { g_create_error = "kc_create: k must be in 1..128 (KMerSizes.h holds 4 words)"; return KC_ERR_ARG; }
+    if (c0.read_len < c0.k || c0.read_len > 4096) { g_create_error = "kc_create: read_len must be in k..4096"; return KC_ERR_ARG; }
+    if (c0.method > KC_COUNT_HASH) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
+    if (c0.method == KC_COUNT_HASH && c0.k > 32) { g_create_error = "kc_create: hash counting needs k <= 32"; return KC_ERR_ARG; }
+    cudaError_t e = cudaSetDevice(c0.device);
+    if (e != cudaSuccess) { g_create_error = std::string("kc_create: cudaSetDevice failed: ") + cudaGetErrorString(e); return KC_ERR_CUDA; }
+    kc_ctx *c = new kc_ctx();
+    c->cfg = c0;
+    c->W = (int)kc_key_words(c0.k);
+    c->S = (int)kc_record_size(c0.k);
+    c->strict = (c0.flags & KC_COMPAT_STRICT) != 0;
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c0.device);
+    if (c->n_sms <= 0) c->n_sms = 148;
+    // keep freed blocks in the stream-ordered pool: chunk after chunk reuses the same arena
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c0.device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (c0.stream) {
+        c->stream = static_cast<cudaStream_t>(c0.stream);
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_create_error = std::string("kc_create: stream: ") + cudaGetErrorString(e); delete c; return KC_ERR_CUDA; }
+        c->own_stream = true;
+    }
+    uint32_t ns = c0.n_slots ? c0.n_slots : 2;
+    if (ns > 64) ns = 64;
+    c->slots.resize(ns);
+    if (c0.max_chunk_bytes) {
+        for (auto &sl : c->slots) {
+            sl.cap = (c0.max_chunk_bytes + 255) & ~255ull;
+            if (cudaMallocHost(&sl.h_in, sl.cap) != cudaSuccess || cudaMalloc(&sl.d_in, sl.cap + 256) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) {
+                g_create_error = "kc_create: slot buffers: out of memory";
+                kc_destroy(c);
+                return KC_ERR_NOMEM;
+            }
+        }
+    }
+    *out = c;
+    return KC_OK;
+}
+
+void kc_destroy(kc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto &sl : c->slots) {
+        pending_release(sl.stream ? sl.stream : c->stream, sl.pend);
+        pending_destroy(sl.pend);
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    pending_release(c->stream, c->direct);
+    pending_destroy(c->direct);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *kc_last_error(const kc_ctx *c) { return c ? c->err : g_create_error.c_str(); }
+
+int kc_sync(kc_ctx *c) {
+    KC_TRY(check_ctx(c));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto &sl : c->slots)
+        if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+    return KC_OK;
+}
+
+int kc_stats_get(kc_ctx *c, kc_stats *out) {
+    KC_TRY(check_ctx(c));
+    if (!out) return c->set_error(KC_ERR_ARG, "null stats");
+    std::lock_guard<std::mutex> g(c->mu);
+    *out = c->stats;
+    return KC_OK;
+}
+
+int kc_host_alloc(kc_ctx *c, uint64_t bytes, void **out) {
+    KC_TRY(check_ctx(c));
+    if (!out) return c->set_error(KC_ERR_ARG, "null out");
+    if (cudaMallocHost(out, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return c->set_error(KC_ERR_NOMEM, "pinned allocation of %llu bytes failed", (unsigned long long)bytes);
+    }
+    return KC_OK;
+}
+int kc_host_free(kc_ctx *c, void *p) {
+    KC_TRY(check_ctx(c));
+    if (p) KC_CUDA_TRY(c, cudaFreeHost(p));
+    return KC_OK;
+}
+
+// ------------------------------------------------------------------------ chunks
+int kc_count_device(kc_ctx *c, const void *d_reads, uint64_t n_bytes, kc_run **run) {
+    KC_TRY(check_ctx(c));
+    if (!run) return c->set_error(KC_ERR_ARG, "null run");
+    if (n_bytes && (!d_reads || (reinterpret_cast<uintptr_t>(d_reads) & 15)))
+        return c->set_error(KC_ERR_ARG, "d_reads must be a 16-byte aligned device pointer");
+    cudaSetDevice(c->cfg.device);
+    // chunks beyond the sorter's per-call limit are cut into pieces whose runs are merged
+    const uint32_t L = c->cfg.read_len;
+    const uint64_t nk = L - c->cfg.k + 1;
+    uint64_t n_reads = n_bytes / L;
+    uint64_t max_reads = kMaxSortKeys / nk;
+    max_reads -= max_reads % 16;                      // keep every piece 16-byte aligned
+    if (n_reads <= max_reads) {
+        KC_TRY(count_enqueue(c, c->direct, d_reads, n_bytes, c->stream, pick_method(c)));
+        return count_finish(c, c->direct, d_reads, n_bytes, c->stream, run);
+    }
+    std::vector<kc_run *> parts;
+    int rc = KC_OK;
+    for (uint64_t r0 = 0; r0 < n_reads && rc == KC_OK; r0 += max_reads) {
+        uint64_t nr = n_reads - r0 < max_reads ? n_reads - r0 : max_reads;
+        const uint8_t *ptr = static_cast<const uint8_t *>(d_reads) + r0 * L;
+        kc_run *part = nullptr;
+        rc = count_enqueue(c, c->direct, ptr, nr * L, c->stream, pick_method(c));
+        if (rc == KC_OK) rc = count_finish(c, c->direct, ptr, nr * L, c->stream, &part);
+        if (rc == KC_OK) parts.push_back(part);
+    }
+    if (rc == KC_OK) rc = kc_merge_runs(c, parts.data(), (uint32_t)parts.size(), run);
+    for (auto *p : parts) kc_run_free(c, p);
+    return rc;
+}
+
+int kc_slot_buffer(kc_ctx *c, uint32_t slot, void **ptr, uint64_t *cap) {
+    KC_TRY(check_ctx(c));
+    if (slot >= c->slots.size() || !c->slots[slot].h_in)
+        return c->set_error(KC_ERR_ARG, "slot %u not available (n_slots=%zu, max_chunk_bytes=%llu)", slot,
+                            c->slots.size(), (unsigned long long)c->cfg.max_chunk_bytes);
+    if (ptr) *ptr = c->slots[slot].h_in;
+    if (cap) *cap = c->cfg.max_chunk_bytes;
+    return KC_OK;
+}
+
+static int submit_from(kc_ctx *c, uint32_t slot, const void *host_src, uint64_t n_bytes) {
+    Slot &sl = c->slots[slot];
+    if (sl.pend.active) return c->set_error(KC_ERR_STATE, "slot %u already has a chunk in flight", slot);
+    if (n_bytes > c->cfg.max_chunk_bytes) return c->set_error(KC_ERR_CAPACITY, "chunk of %llu bytes exceeds max_chunk_bytes=%llu",
+                                                              (unsigned long long)n_bytes, (unsigned long long)c->cfg.max_chunk_bytes);
+    const uint64_t nk = c->cfg.read_len - c->cfg.k + 1;
+    if ((n_bytes / c->cfg.read_len) * nk > kMaxSortKeys)
+        return c->set_error(KC_ERR_CAPACITY, "chunk holds more than %llu k-mer slots; submit smaller chunks", (unsigned long long)kMaxSortKeys);
+    cudaSetDevice(c->cfg.device);
+    sl.n_bytes = n_bytes;
+    if (n_bytes) KC_CUDA_TRY(c, cudaMemcpyAsync(sl.d_in, host_src, n_bytes, cudaMemcpyHostToDevice, sl.stream));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.h2d_bytes += n_bytes;
+    }
+    return count_enqueue(c, sl.pend, sl.d_in, n_bytes, sl.stream, pick_method(c));
+}
+
+int kc_submit(kc_ctx *c, uint32_t slot, uint64_t n_bytes) {
+    KC_TRY(check_ctx(c));
+    if (slot >= c->slots.size() || !c->slots[slot].h_in) return c->set_error(KC_ERR_ARG, "slot %u not available", slot);
+    return submit_from(c, slot, c->slots[slot].h_in, n_bytes);
+}
+
+int kc_wait(kc_ctx *c, uint32_t slot, kc_run **run) {
+    KC_TRY(check_ctx(c));
+    if (slot >= c->slots.size() || !run) return c->set_error(KC_ERR_ARG, "bad slot or null run");
+    Slot &sl = c->slots[slot];
+    cudaSetDevice(c->cfg.device);
+    return count_finish(c, sl.pend, sl.d_in, sl.n_bytes, sl.stream, run);
+}
+
+int kc_process_chunk(kc_ctx *c, uint32_t slot, const char *reads, uint64_t n_bytes, void *records,
+                     uint64_t records_cap, uint64_t *out_bytes) {
+    KC_TRY(check_ctx(c));
+    if (out_bytes) *out_bytes = 0;
+    if (slot >= c->slots.size() || !c->slots[slot].d_in) return c->set_error(KC_ERR_ARG, "slot %u not available", slot);
+    if (n_bytes && !reads) return c->set_error(KC_ERR_ARG, "null reads");
+    KC_TRY(submit_from(c, slot, reads, n_bytes));
+    kc_run *run = nullptr;
+    KC_TRY(kc_wait(c, slot, &run));
+    int rc = KC_OK;
+    uint64_t nb = (run->n - run->skip) * (uint64_t)c->S;
+    if (out_bytes) *out_bytes = nb;
+    if (records) {
+        if (nb > records_cap) rc = c->set_error(KC_ERR_CAPACITY, "run needs %llu bytes, buffer holds %llu", (unsigned long long)nb, (unsigned long long)records_cap);
+        else rc = kc_run_copy_records(c, run, records, records_cap, out_bytes);
+    }
+    kc_run_free(c, run);
+    return rc;
+}
+
+// -------------------------------------------------------------------------- runs
+uint64_t kc_run_records(const kc_run *r) { return r ? r->n - r->skip : 0; }
+
+int kc_run_free(kc_ctx *c, kc_run *r) {
+    KC_TRY(check_ctx(c));
+    if (!r) return KC_OK;
+    dev_free(c->stream, r->d_keys);
+    dev_free(c->stream, r->d_counts);
+    delete r;
+    return KC_OK;
+}
+
+int kc_run_device(const kc_run *r, void **d_keys, void **d_counts, uint64_t *n) {
+    if (!r) return KC_ERR_ARG;
+    if (d_keys) *d_keys = r->d_keys + r->skip * r->W;
+    if (d_counts) *d_counts = r->d_counts + r->skip;
+    if (n) *n = r->n - r->skip;
+    return KC_OK;
+}
+
+int kc_run_copy_records(kc_ctx *c, const kc_run *r, void *dst, uint64_t cap, uint64_t *out_bytes) {
+    KC_TRY(check_ctx(c));
+    if (!r) return c->set_error(KC_ERR_ARG, "null run");
+    const uint64_t n = r->n - r->skip, nb = n * (uint64_t)c->S;
+    if (out_bytes) *out_bytes = nb;
+    if (nb > cap || (nb && !dst)) return c->set_error(KC_ERR_CAPACITY, "run needs %llu bytes, buffer holds %llu", (unsigned long long)nb, (unsigned long long)cap);
+    if (n == 0) return KC_OK;
+    cudaSetDevice(c->cfg.device);
+    void *d_rec = nullptr;
+    KC_TRY(dev_alloc(c, c->stream, nb, &d_rec));
+    KC_CUDA_TRY(c, pack_records(r->d_keys + r->skip * r->W, r->d_counts + r->skip, n, r->W, d_rec, c->stream));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(dst, d_rec, nb, cudaMemcpyDeviceToHost, c->stream));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    dev_free(c->stream, d_rec);
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stats.d2h_bytes += nb;
+    c->stats.launches += 1;
+    return KC_OK;
+}
+
+int kc_run_from_device(kc_ctx *c, const void *d_keys, const void *d_counts, uint64_t n, kc_run **out) {
+    KC_TRY(check_ctx(c));
+    if (!out || (n && (!d_keys || !d_counts))) return c->set_error(KC_ERR_ARG, "null argument");
+    cudaSetDevice(c->cfg.device);
+    kc_run *r = nullptr;
+    KC_TRY(make_run(c, c->stream, n, &r));
+    if (n) {
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_keys, d_keys, n * c->W * 8, cudaMemcpyDeviceToDevice, c->stream));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_counts, d_counts, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    *out = r;
+    return KC_OK;
+}
+
+int kc_run_upload(kc_ctx *c, const void *records, uint64_t n_bytes, kc_run **out) {
+    KC_TRY(check_ctx(c));
+    if (!out || (n_bytes && !records)) return c->set_error(KC_ERR_ARG, "null argument");
+    const uint64_t n = n_bytes / c->S;
+    if (n >= (1ull << 32)) return c->set_error(KC_ERR_CAPACITY, "run too long for one upload");
+    cudaSetDevice(c->cfg.device);
+    cudaStream_t s = c->stream;
+    if (n == 0) return make_run(c, s, 0, out);
+    void *d_rec = nullptr, *ws = nullptr;
+    kc_run *raw = nullptr, *folded = nullptr;
+    KC_TRY(dev_alloc(c, s, n * c->S, &d_rec));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(d_rec, records, n * c->S, cudaMemcpyHostToDevice, s));
+    KC_TRY(make_run(c, s, n, &raw));
+    KC_TRY(make_run(c, s, n, &folded));
+    KC_CUDA_TRY(c, unpack_records(d_rec, n, c->W, raw->d_keys, raw->d_counts, s));
+    const uint64_t ws_bytes = ((rle_workspace_bytes(n) + 255) & ~255ull) + (n + 1) * 4 + 256;
+    KC_TRY(dev_alloc(c, s, ws_bytes, &ws));
+    unsigned long long *d_num = nullptr;
+    KC_TRY(dev_alloc(c, s, 8, (void **)&d_num));
+    int launches = 1;
+    KC_CUDA_TRY(c, fold_sorted_pairs(raw->d_keys, raw->d_counts, n, c->W, folded->d_keys, folded->d_counts, d_num,
+                                     ws, s, &launches));
+    unsigned long long U = 0;
+    KC_CUDA_TRY(c, cudaMemcpyAsync(&U, d_num, 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    folded->n = U;
+    dev_free(s, d_rec); dev_free(s, ws); dev_free(s, d_num);
+    kc_run_free(c, raw);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.h2d_bytes += n * c->S;
+        c->stats.launches += launches;
+    }
+    *out = folded;
+    return KC_OK;
+}
+
+int kc_run_write(kc_ctx *c, const kc_run *r, const char *path, int append) {
+    KC_TRY(check_ctx(c));
+    if (!r || !path) return c->set_error(KC_ERR_ARG, "null argument");
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) return c->set_error(KC_ERR_IO, "cannot open %s", path);
+    const uint64_t n = r->n - r->skip;
+    const uint64_t piece = (64ull << 20) / c->S;      // 64 MiB staging
+    void *h = nullptr;
+    int rc = KC_OK;
+    if (n) rc = kc_host_alloc(c, (n < piece ? n : piece) * c->S, &h);
+    for (uint64_t i = 0; i < n && rc == KC_OK; i += piece) {
+        kc_run view = *r;
+        view.skip = r->skip + i;
+        view.n = r->skip + (i + piece < n ? i + piece : n);
+        uint64_t nb = 0;
+        rc = kc_run_copy_records(c, &view, h, piece * c->S, &nb);
+        if (rc == KC_OK && fwrite(h, 1, nb, f) != nb) rc = c->set_error(KC_ERR_IO, "short write to %s", path);
+    }
+    if (h) kc_host_free(c, h);
+    if (fclose(f) != 0 && rc == KC_OK) rc = c->set_error(KC_ERR_IO, "close failed on %s", path);
+    return rc;
+}
+
+int kc_run_split(kc_ctx *c, const kc_run *r, const uint64_t *splitters, uint32_t n_splitters, uint64_t *offsets) {
+    KC_TRY(check_ctx(c));
+    if (!r || !offsets || (n_splitters && !splitters)) return c->set_error(KC_ERR_ARG, "null argument");
+    const uint64_t n = r->n - r->skip;
+    offsets[0] = 0;
+    offsets[n_splitters + 1] = n;
+    if (n_splitters == 0) return KC_OK;
+    cudaSetDevice(c->cfg.device);
+    cudaStream_t s = c->stream;
+    void *dq = nullptr, *dout = nullptr;
+    KC_TRY(dev_alloc(c, s, (uint64_t)n_splitters * c->W * 8, &dq));
+    KC_TRY(dev_alloc(c, s, (uint64_t)n_splitters * 8, &dout));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(dq, splitters, (uint64_t)n_splitters * c->W * 8, cudaMemcpyHostToDevice, s));
+    KC_CUDA_TRY(c, lower_bounds(r->d_keys + r->skip * r->W, n, r->W, static_cast<uint64_t *>(dq), n_splitters,
+                                static_cast<unsigned long long *>(dout), s));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(offsets + 1, dout, (uint64_t)n_splitters * 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    dev_free(s, dq); dev_free(s, dout);
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stats.launches += 1;
+    return KC_OK;
+}
+
+// ------------------------------------------------------------------------- merge
+int kc_merge_runs(kc_ctx *c, kc_run *const *runs, uint32_t n, kc_run **out) {
+    KC_TRY(check_ctx(c));
+    if (!out || (n && !runs)) return c->set_error(KC_ERR_ARG, "null argument");
+    cudaSetDevice(c->cfg.device);
+    cudaStream_t s = c->stream;
+    // other streams (slots) may have produced the inputs
+    for (auto &sl : c->slots)
+        if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+    if (n == 0) return make_run(c, s, 0, out);
+    std::vector<kc_run *> level;
+    std::vector<bool> owned;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!runs[i]) return c->set_error(KC_ERR_ARG, "null run in merge list");
+        level.push_back(runs[i]);
+        owned.push_back(false);
+    }
+    if (n == 1) {
+        const kc_run *r = runs[0];
+        return kc_run_from_device(c, r->d_keys + r->skip * r->W, r->d_counts + r->skip, r->n - r->skip, out);
+    }
+    unsigned long long *d_num = nullptr;
+    KC_TRY(dev_alloc(c, s, 8, (void **)&d_num));
+    int rc = KC_OK;
+    int launches = 0;
+    while (level.size() > 1 && rc == KC_OK) {
+        std::vector<kc_run *> next;
+        std::vector<bool> next_owned;
+        for (size_t i = 0; i + 1 < level.size() && rc == KC_OK; i += 2) {
+            kc_run *a = level[i], *b = level[i + 1];
+            const uint64_t na = a->n - a->skip, nb = b->n - b->skip;
+            kc_run *m = nullptr;
+            rc = make_run(c, s, na + nb, &m);
+            if (rc != KC_OK) break;
+            void *ws = nullptr;
+            rc = dev_alloc(c, s, merge_workspace_bytes(na, nb), &ws);
+            if (rc != KC_OK) { kc_run_free(c, m); break; }
+            cudaError_t e = merge_pair(a->d_keys + a->skip * a->W, a->d_counts + a->skip, na,
+                                       b->d_keys + b->skip * b->W, b->d_counts + b->skip, nb, c->W, m->d_keys,
+                                       m->d_counts, d_num, ws, s, &launches);
+            unsigned long long U = 0;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&U, d_num, 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            dev_free(s, ws);
+            if (e != cudaSuccess) {
+                kc_run_free(c, m);
+                rc = c->set_error(KC_ERR_CUDA, "merge failed: %s", cudaGetErrorString(e));
+                break;
+            }
+            m->n = U;
+            if (owned[i]) kc_run_free(c, a);
+            if (owned[i + 1]) kc_run_free(c, b);
+            owned[i] = owned[i + 1] = false;
+            next.push_back(m);
+            next_owned.push_back(true);
+        }
+        if (rc == KC_OK && (level.size() & 1)) {
+            next.push_back(level.back());
+            next_owned.push_back(owned.back());
+            owned.back() = false;
+        }
+        if (rc != KC_OK) {
+            for (size_t i = 0; i < next.size(); i++)
+                if (next_owned[i]) kc_run_free(c, next[i]);
+            for (size_t i = 0; i < level.size(); i++)
+                if (owned[i]) kc_run_free(c, level[i]);
+            break;
+        }
+        level.swap(next);
+        owned.swap(next_owned);
+    }
+    dev_free(s, d_num);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += launches;
+    }
+    if (rc != KC_OK) return rc;
+    *out = level[0];
+    return KC_OK;
+}
+
+}  // extern "C"

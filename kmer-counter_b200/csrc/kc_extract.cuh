@@ -1,0 +1,190 @@
+// kc_extract.cuh -- fused 2-bit encode + k-mer window extraction (sm_100a).
+//
+// Replaces bitEncode (GPUHandler.cu:10-111) and extractKMers (:129-233): the
+// encoded reads never travel through HBM.  A persistent CTA streams tiles of
+// whole reads into shared memory with TMA bulk copies (double-buffered behind
+// mbarriers), encodes each read once into 2-bit words, and then every thread
+// assembles one key per output slot with a 64-bit funnel shift and hands it to a
+// Sink (store to the slot array, hash-table insert, ...).
+//
+// Key semantics (verified against the reference's own
+// kernels by tests/): the key for position p is the 2-bit codes of the bases
+// s[p .. p+span), MSB first, where span = 32*W when k%32 is 0/29/30/31 (the
+// reference's missing tail mask, F4) and k otherwise; positions past the read end
+// contribute 0; non-ACGT letters contribute 3 and invalidate every k-mer [p,p+k)
+// that contains them.  The span is carried by Params::last_mask.
+#pragma once
+
+#include "kc_common.cuh"
+
+namespace kc {
+
+struct ExtractParams {
+    const uint8_t *reads;    // packed lines, stride L, 16-byte aligned
+    uint64_t n_reads;
+    uint32_t L, k;
+    uint32_t nk;             // L - k + 1 slots per read
+    uint32_t nw;             // ceil(L/32) encoded words per read (+1 zero pad word in smem)
+    uint32_t nb4;            // ceil(L/4) bytes of bad-nibbles per read
+    uint32_t tile_reads;     // reads per tile, multiple of 16 -> tile bytes % 16 == 0
+    uint32_t n_tiles;
+    uint32_t nk_magic;       // floor(2^32 / nk) + 1
+    uint64_t last_mask;      // applied to key word W-1
+    unsigned long long *n_invalid;  // += slots that hold no k-mer (the phantom of SURVEY F7)
+    uint32_t stage_bytes, enc_off, bad_off, flag_off, bar_off, smem_total;  // shared-memory layout
+};
+
+inline void extract_smem_layout(ExtractParams &p) {
+    p.stage_bytes = (p.tile_reads * p.L + 127u) & ~127u;
+    p.enc_off = 2 * p.stage_bytes;
+    p.bad_off = p.enc_off + p.tile_reads * (p.nw + 1) * 8;
+    p.flag_off = p.bad_off + ((p.tile_reads * p.nb4 + 15u) & ~15u);
+    p.bar_off = (p.flag_off + p.tile_reads + 15u) & ~15u;
+    p.smem_total = p.bar_off + 16;
+}
+
+constexpr int kExtractThreads = 256;
+
+// code: A0 C1 G2 T3, anything else 3 + bad (GPUHandler.cu:42-88)
+__device__ __forceinline__ uint32_t base_code(uint32_t c, uint32_t &bad) {
+    uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
+    bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+    bad = ok ? 0u : 1u;
+    return ok ? code : 3u;
+}
+
+template <int W, class Sink>
+__global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams p, Sink sink) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t stage_bytes = p.stage_bytes;
+    uint8_t *stage0 = smem;
+    uint64_t *enc = reinterpret_cast<uint64_t *>(smem + p.enc_off);
+    uint8_t *enc_b = reinterpret_cast<uint8_t *>(enc);
+    const uint32_t enc_row = p.nw + 1;
+    uint8_t *bad4 = smem + p.bad_off;
+    uint8_t *flag = smem + p.flag_off;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.bar_off);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t kWarps = kExtractThreads / 32;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto tile_reads_of = [&](uint32_t t) -> uint32_t {
+        uint64_t first = (uint64_t)t * p.tile_reads;
+        uint64_t left = p.n_reads - first;
+        return left < p.tile_reads ? (uint32_t)left : p.tile_reads;
+    };
+    // Full tiles go through the TMA unit; a ragged last tile whose byte count is
+    // not a multiple of 16 is copied with plain loads by the whole CTA.
+    auto issue_load = [&](uint32_t t, uint32_t s) {
+        uint32_t bytes = tile_reads_of(t) * p.L;
+        const uint8_t *src = p.reads + (uint64_t)t * p.tile_reads * p.L;
+        uint8_t *dst = stage0 + s * stage_bytes;
+        if ((bytes & 15u) == 0) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[s], bytes);
+                tma_load_1d(dst, src, bytes, &bars[s]);
+            }
+        } else {
+            for (uint32_t i = tid; i < bytes; i += kExtractThreads) dst[i] = src[i];
+        }
+    };
+
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+    uint32_t stage = 0;
+    unsigned long long invalid_local = 0;
+
+    uint32_t tile = blockIdx.x;
+    if (tile < p.n_tiles) issue_load(tile, 0);
+
+    for (; tile < p.n_tiles; tile += gridDim.x) {
+        const uint32_t next = tile + gridDim.x;
+        if (next < p.n_tiles) issue_load(next, stage ^ 1);
+
+        const uint32_t nreads = tile_reads_of(tile);
+        if (((nreads * p.L) & 15u) == 0) {
+            mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
+            phase_bits ^= 1u << stage;
+        } else {
+            __syncthreads();
+        }
+        const uint8_t *src_tile = stage0 + stage * stage_bytes;
+
+        // ---- phase A: one warp per read, 4 bases per lane per step ----
+        for (uint32_t r = warp; r < nreads; r += kWarps) {
+            const uint8_t *src = src_tile + r * p.L;
+            uint32_t any_bad = 0;
+            const uint32_t span_bases = enc_row * 32;
+            for (uint32_t j0 = lane * 4; j0 < span_bases; j0 += 128) {
+                uint32_t codes = 0, badn = 0;
+#pragma unroll
+                for (uint32_t b = 0; b < 4; b++) {
+                    uint32_t j = j0 + b;
+                    uint32_t code = 0, bad = 0;
+                    if (j < p.L) code = base_code(src[j], bad);
+                    codes = (codes << 2) | code;
+                    badn |= bad << b;
+                }
+                // byte (j0/4) of the big-endian bit string -> little-endian byte inside its word
+                uint32_t q = j0 >> 2;
+                enc_b[(r * enc_row + (q >> 3)) * 8 + (7 - (q & 7))] = (uint8_t)codes;
+                if (j0 < p.L) bad4[r * p.nb4 + q] = (uint8_t)badn;
+                any_bad |= badn;
+            }
+            any_bad = __any_sync(0xffffffffu, any_bad != 0);
+            if (lane == 0) flag[r] = (uint8_t)any_bad;
+        }
+        __syncthreads();
+
+        // ---- phase B: one key per thread per step, slots are contiguous in the output ----
+        const uint32_t total = nreads * p.nk;
+        const uint64_t slot0 = (uint64_t)tile * p.tile_reads * p.nk;
+        for (uint32_t s = tid; s < total; s += kExtractThreads) {
+            uint32_t r = p.nk == 1 ? s : __umulhi(s, p.nk_magic);
+            if (r * p.nk > s) r--;
+            const uint32_t pos = s - r * p.nk;
+            const uint64_t *e = enc + r * enc_row + (pos >> 5);
+            const uint32_t sh = (pos & 31u) * 2u;
+            Key<W> key;
+            uint64_t a = e[0];
+#pragma unroll
+            for (int q = 0; q < W; q++) {
+                uint64_t b = e[q + 1];
+                key.w[q] = sh ? ((a << sh) | (b >> (64 - sh))) : a;
+                a = b;
+            }
+            key.w[W - 1] &= p.last_mask;
+            bool valid = true;
+            if (flag[r]) {
+                // rare path: any bad base inside [pos, pos+k) kills the k-mer
+                const uint8_t *bn = bad4 + r * p.nb4;
+                uint32_t lo = pos, hi = pos + p.k;  // [lo, hi)
+                for (uint32_t q = lo >> 2; q <= (hi - 1) >> 2; q++) {
+                    uint32_t m = bn[q];
+                    uint32_t b0 = q * 4;
+                    if (b0 < lo) m &= 0xFu << (lo - b0);
+                    if (b0 + 4 > hi) m &= 0xFu >> (b0 + 4 - hi);
+                    if (m & 0xFu) { valid = false; break; }
+                }
+            }
+            if (!valid) invalid_local++;
+            sink(slot0 + s, key, valid);
+        }
+        __syncthreads();
+        stage ^= 1;
+    }
+
+    // one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) invalid_local += __shfl_xor_sync(0xffffffffu, invalid_local, o);
+    if (lane == 0 && invalid_local) atomicAdd(p.n_invalid, invalid_local);
+    sink.finish();
+}
+
+}  // namespace kc

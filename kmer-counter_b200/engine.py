@@ -1,0 +1,223 @@
+"""Object wrappers over the C ABI. No compute happens in Python."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KcConfig, KcStats, METHODS, METHOD_NAMES, KC_COMPAT_REF, KC_COMPAT_STRICT
+
+
+class KcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("kc error %d: %s" % (code, msg))
+        self.code = code
+
+
+def key_words(k):
+    return _lib.load().kc_key_words(k)
+
+
+def record_size(k):
+    return _lib.load().kc_record_size(k)
+
+
+class Run:
+    """A sorted key-unique run resident on the device (the reference's run file, in HBM)."""
+
+    def __init__(self, counter, handle):
+        self._c = counter
+        self._h = handle
+
+    def __len__(self):
+        return int(self._c._lib.kc_run_records(self._h)) if self._h else 0
+
+    @property
+    def nbytes(self):
+        return len(self) * self._c.record_size
+
+    def to_bytes(self) -> bytes:
+        """Packed records (the SortedKMerFile format)."""
+        buf = np.empty(max(self.nbytes, 1), dtype=np.uint8)
+        n = C.c_uint64()
+        self._c._check(self._c._lib.kc_run_copy_records(self._c._ctx, self._h, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def copy_into(self, host_ptr, cap) -> int:
+        n = C.c_uint64()
+        self._c._check(self._c._lib.kc_run_copy_records(self._c._ctx, self._h, host_ptr, cap, C.byref(n)))
+        return n.value
+
+    def write(self, path, append=False):
+        self._c._check(self._c._lib.kc_run_write(self._c._ctx, self._h, path.encode(), 1 if append else 0))
+
+    def device_arrays(self):
+        """(keys_ptr, counts_ptr, n): device pointers to n*W uint64 and n uint32."""
+        k, c, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._c._check(self._c._lib.kc_run_device(self._h, C.byref(k), C.byref(c), C.byref(n)))
+        return k.value or 0, c.value or 0, n.value
+
+    def split(self, splitters):
+        """Lower-bound offsets of the splitter keys ([n_split, W] uint64) -> n_split+2 offsets."""
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64).reshape(-1, self._c.words)
+        off = np.zeros(sp.shape[0] + 2, dtype=np.uint64)
+        self._c._check(self._c._lib.kc_run_split(
+            self._c._ctx, self._h, sp.ctypes.data_as(C.POINTER(C.c_uint64)), sp.shape[0],
+            off.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return off
+
+    def free(self):
+        if self._h and self._c._ctx:
+            self._c._lib.kc_run_free(self._c._ctx, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Counter:
+    """One kc_ctx: the replacement for PrepareGPU's GPUStream array (GPUHandler.cu:479-509)."""
+
+    def __init__(self, k, read_len, device=0, method="auto", compat="ref", n_slots=2, max_chunk_bytes=0,
+                 table_slots=0, stream=None):
+        self._lib = _lib.load()
+        cfg = KcConfig()
+        cfg.struct_size = C.sizeof(KcConfig)
+        cfg.k, cfg.read_len, cfg.device = k, read_len, device
+        cfg.flags = KC_COMPAT_STRICT if compat == "strict" else KC_COMPAT_REF
+        cfg.method = METHODS[method] if isinstance(method, str) else int(method)
+        cfg.n_slots, cfg.max_chunk_bytes, cfg.table_slots = n_slots, max_chunk_bytes, table_slots
+        cfg.stream = stream
+        ctx = C.c_void_p()
+        rc = self._lib.kc_create(C.byref(cfg), C.byref(ctx))
+        if rc != 0:
+            raise KcError(rc, (self._lib.kc_last_error(None) or b"").decode())
+        self._ctx = ctx
+        self.k, self.read_len, self.device = k, read_len, device
+        self.words = self._lib.kc_key_words(k)
+        self.record_size = self._lib.kc_record_size(k)
+        self.max_chunk_bytes = max_chunk_bytes
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise KcError(rc, (self._lib.kc_last_error(self._ctx) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.kc_destroy(self._ctx)
+            self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self._lib.kc_sync(self._ctx))
+
+    def stats(self) -> dict:
+        st = KcStats()
+        self._check(self._lib.kc_stats_get(self._ctx, C.byref(st)))
+        d = {name: getattr(st, name) for name, _ in KcStats._fields_}
+        d["method_used"] = METHOD_NAMES.get(d["method_used"], "none")
+        return d
+
+    def host_alloc(self, nbytes) -> np.ndarray:
+        """Pinned host buffer as a uint8 array (freed with host_free)."""
+        p = C.c_void_p()
+        self._check(self._lib.kc_host_alloc(self._ctx, nbytes, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(max(nbytes, 1),))
+
+    def host_free(self, arr):
+        self._check(self._lib.kc_host_free(self._ctx, arr.ctypes.data))
+
+    # -- one chunk
+    def process_chunk(self, reads, slot=0) -> bytes:
+        """processKMers (GPUHandler.cu:397-477) with the sort step on: host reads in, the
+        chunk's sorted unique records out."""
+        a = np.frombuffer(reads, dtype=np.uint8) if isinstance(reads, (bytes, bytearray)) else \
+            np.ascontiguousarray(reads, dtype=np.uint8)
+        n = C.c_uint64()
+        cap = self._lib.kc_output_size(a.size, self.read_len, self.k) + self.record_size
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        self._check(self._lib.kc_process_chunk(self._ctx, slot, a.ctypes.data, a.size, out.ctypes.data, out.size,
+                                               C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def slot_buffer(self, slot) -> np.ndarray:
+        p, cap = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.kc_slot_buffer(self._ctx, slot, C.byref(p), C.byref(cap)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(cap.value,))
+
+    def submit(self, slot, n_bytes):
+        self._check(self._lib.kc_submit(self._ctx, slot, n_bytes))
+
+    def wait(self, slot) -> Run:
+        h = C.c_void_p()
+        self._check(self._lib.kc_wait(self._ctx, slot, C.byref(h)))
+        return Run(self, h)
+
+    def count_device(self, d_ptr, n_bytes) -> Run:
+        h = C.c_void_p()
+        self._check(self._lib.kc_count_device(self._ctx, d_ptr, n_bytes, C.byref(h)))
+        return Run(self, h)
+
+    # -- runs
+    def upload_run(self, records) -> Run:
+        a = np.frombuffer(records, dtype=np.uint8) if isinstance(records, (bytes, bytearray)) else \
+            np.ascontiguousarray(records, dtype=np.uint8)
+        h = C.c_void_p()
+        self._check(self._lib.kc_run_upload(self._ctx, a.ctypes.data, a.size, C.byref(h)))
+        return Run(self, h)
+
+    def run_from_device(self, keys_ptr, counts_ptr, n) -> Run:
+        h = C.c_void_p()
+        self._check(self._lib.kc_run_from_device(self._ctx, keys_ptr, counts_ptr, n, C.byref(h)))
+        return Run(self, h)
+
+    def merge(self, runs) -> Run:
+        n = len(runs)
+        arr = (C.c_void_p * max(n, 1))(*[r._h for r in runs])
+        h = C.c_void_p()
+        self._check(self._lib.kc_merge_runs(self._ctx, arr, n, C.byref(h)))
+        return Run(self, h)
+
+    # -- whole input held in host memory: chunk, count, merge (the path KMerCounter::Start drives)
+    def count_reads(self, reads, chunk_reads=0) -> Run:
+        a = np.frombuffer(reads, dtype=np.uint8) if isinstance(reads, (bytes, bytearray)) else \
+            np.ascontiguousarray(reads, dtype=np.uint8)
+        L = self.read_len
+        n_reads = a.size // L
+        if chunk_reads <= 0:
+            chunk_reads = max(1, self.max_chunk_bytes // L) if self.max_chunk_bytes else max(n_reads, 1)
+        if self.max_chunk_bytes == 0:
+            raise KcError(-1, "Counter was created without slots (max_chunk_bytes=0)")
+        chunk_reads = min(chunk_reads, self.max_chunk_bytes // L)
+        n_slots = 2
+        runs, inflight = [], []
+        pos, slot = 0, 0
+        while pos < n_reads or inflight:
+            if pos < n_reads and len(inflight) < n_slots:
+                nr = min(chunk_reads, n_reads - pos)
+                buf = self.slot_buffer(slot)
+                buf[: nr * L] = a[pos * L:(pos + nr) * L]
+                self.submit(slot, nr * L)
+                inflight.append(slot)
+                pos += nr
+                slot = (slot + 1) % n_slots
+            else:
+                runs.append(self.wait(inflight.pop(0)))
+        out = self.merge(runs)
+        for r in runs:
+            r.free()
+        return out

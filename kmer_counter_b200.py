@@ -1,0 +1,12 @@
+"""Import alias: ``import kmer_counter_b200`` loads the package kept in ``kmer-counter_b200/``
+(the project's hyphenated name is not a legal Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kmer-counter_b200")
+_spec = importlib.util.spec_from_file_location(
+    "kmer_counter_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["kmer_counter_b200"] = _mod
+_spec.loader.exec_module(_mod)

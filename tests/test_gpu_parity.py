@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Every comparison is on packed record bytes -- the parity artefact of SURVEY.md 0.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kc():
+    import kmer_counter_b200 as kc
+    return kc
+
+
+def _counter(kc, k, L, method="sort", compat="ref", cap=1 << 24, **kw):
+    return kc.Counter(k, L, method=method, compat=compat, n_slots=2, max_chunk_bytes=cap, **kw)
+
+
+CASES = [
+    # (reads, L, k, genome, sub, n_rate)
+    (2000, 100, 31, 30000, 0.01, 0.002),     # headline k, with N (phantom record)
+    (2000, 100, 31, 30000, 0.0, 0.0),        # no N: no phantom
+    (1500, 100, 32, 20000, 0.01, 0.001),     # k % 32 == 0
+    (1500, 100, 28, 20000, 0.0, 0.001),      # masked tail (k % 32 in 1..28)
+    (1500, 100, 29, 20000, 0.0, 0.001),      # first unmasked k
+    (700, 70, 63, 5000, 0.001, 0.001),       # 128-bit keys, unmasked
+    (700, 70, 60, 5000, 0.001, 0.001),       # 128-bit keys, masked
+    (500, 41, 33, 0, 0.0, 0.01),             # iid reads, 1 base in the second word
+    (300, 150, 96, 2000, 0.01, 0.01),        # 3 words
+    (300, 150, 128, 2000, 0.01, 0.01),       # 4 words, k % 32 == 0
+    (300, 150, 100, 2000, 0.01, 0.0),        # 4 words masked
+    (300, 45, 5, 0, 0.0, 0.02),              # tiny k: few distinct keys, heavy duplication
+    (257, 33, 33, 0, 0.0, 0.0),              # one k-mer per read
+    (1000, 133, 31, 8000, 0.002, 0.0),       # L % 4 != 0
+    (64, 10, 1, 0, 0.0, 0.1),                # k = 1, shortest read the reference handles
+]
+
+
+@pytest.mark.parametrize("R,L,k,G,e,n", CASES)
+def test_chunk_matches_oracle_sort(kc, R, L, k, G, e, n):
+    reads = oracle.gen_reads(R, L, G, e, n, seed=R + k)
+    want = oracle.process_chunk(reads, L, k)
+    with _counter(kc, k, L) as c:
+        got = c.process_chunk(reads)
+    assert got == want
+
+
+@pytest.mark.parametrize("R,L,k,G,e,n", [c for c in CASES if c[2] <= 32])
+def test_chunk_matches_oracle_hash(kc, R, L, k, G, e, n):
+    reads = oracle.gen_reads(R, L, G, e, n, seed=R + k)
+    want = oracle.process_chunk(reads, L, k)
+    with _counter(kc, k, L, method="hash") as c:
+        got = c.process_chunk(reads)
+        assert c.stats()["method_used"] == "hash"
+    assert got == want
+
+
+def test_empty_and_ragged_inputs(kc):
+    L, k = 100, 31
+    with _counter(kc, k, L) as c:
+        assert c.process_chunk(b"") == b""
+        assert c.process_chunk(b"ACGT" * 10) == b""              # shorter than one read: ignored
+        reads = oracle.gen_reads(10, L, 0, 0, 0, seed=3)
+        ragged = np.concatenate([reads, np.frombuffer(b"ACGTACGTAC", dtype=np.uint8)])
+        assert c.process_chunk(ragged) == oracle.process_chunk(reads, L, k)   # partial tail ignored
+        one = oracle.gen_reads(1, L, 0, 0, 0, seed=4)
+        assert c.process_chunk(one) == oracle.process_chunk(one, L, k)
+
+
+def test_all_invalid_reads_give_only_the_phantom(kc):
+    L, k = 50, 31
+    reads = np.frombuffer(b"N" * (L * 40), dtype=np.uint8)
+    want = oracle.process_chunk(reads, L, k)
+    assert want == bytes(12)                                      # key 0, count 0
+    for method in ("sort", "hash"):
+        with _counter(kc, k, L, method=method) as c:
+            assert c.process_chunk(reads) == want
+
+
+def test_poly_a_and_poly_t(kc):
+    L, k = 64 + 5, 31
+    reads = np.frombuffer((b"A" * L) * 30 + (b"T" * L) * 20 + (b"A" * 40 + b"N" + b"A" * (L - 41)) * 3, dtype=np.uint8)
+    want = oracle.process_chunk(reads, L, k)
+    for method in ("sort", "hash"):
+        with _counter(kc, k, L, method=method) as c:
+            assert c.process_chunk(reads) == want
+
+
+def test_lowercase_is_invalid(kc):
+    L, k = 40, 9
+    reads = np.frombuffer((b"ACGTacgtACGTACGTNNACGTACGTACGTACGTACGTAC") * 7, dtype=np.uint8)
+    want = oracle.process_chunk(reads, L, k)
+    with _counter(kc, k, L) as c:
+        assert c.process_chunk(reads) == want
+
+
+def test_strict_mode_matches_naive_model(kc):
+    for (R, L, k) in [(800, 100, 31), (500, 80, 63), (500, 60, 28)]:
+        reads = oracle.gen_reads(R, L, 9000, 0.005, 0.003, seed=k)
+        want = oracle.naive_count(reads, L, k, strict=True)
+        with _counter(kc, k, L, compat="strict") as c:
+            assert c.process_chunk(reads) == want
+
+
+def test_chunking_invariance_and_merge(kc):
+    R, L, k = 5000, 100, 31
+    reads = oracle.gen_reads(R, L, 40000, 0.01, 0.002, seed=11)
+    want = oracle.count(reads, L, k, chunk_reads=777)
+    assert want == oracle.process_chunk(reads, L, k)              # the artefact ignores chunking
+    with _counter(kc, k, L) as c:
+        for chunk in (R, 1000, 777, 64):
+            run = c.count_reads(reads, chunk_reads=chunk)
+            assert run.to_bytes() == want
+            run.free()
+
+
+def test_merge_runs_against_oracle_merger(kc):
+    L, k = 100, 63
+    parts = [oracle.gen_reads(400 + 37 * i, L, 6000, 0.01, 0.003, seed=100 + i) for i in range(5)]
+    runs_bytes = [oracle.process_chunk(p, L, k) for p in parts]
+    want = oracle.merge_runs(runs_bytes, k)
+    with _counter(kc, k, L) as c:
+        runs = [c.upload_run(b) for b in runs_bytes]
+        for n in (0, 1, 2, 3, 5):
+            m = c.merge(runs[:n])
+            assert m.to_bytes() == oracle.merge_runs(runs_bytes[:n], k)
+            m.free()
+        m = c.merge(runs)
+        assert m.to_bytes() == want
+
+
+def test_upload_folds_adjacent_duplicates(kc):
+    # a run file may repeat a key; SortedKMerFile::ReadKmer folds them (SortedKMerFile.cpp:57-82)
+    k = 31
+    rec = np.zeros(6, dtype=[("key", "<u8"), ("cnt", "<u4")])
+    rec["key"] = [5, 5, 9, 9, 9, 12]
+    rec["cnt"] = [1, 2, 0xFFFFFFFF, 2, 1, 7]
+    raw = rec.tobytes()
+    assert len(raw) == 72
+    want = oracle.merge_runs([raw], k)
+    with _counter(kc, k, 100) as c:
+        assert c.upload_run(raw).to_bytes() == want
+
+
+def test_count_wraps_at_32_bits(kc):
+    # uint32 counts wrap: merge two runs whose counts overflow
+    k = 31
+    a = np.zeros(2, dtype=[("key", "<u8"), ("cnt", "<u4")]); a["key"] = [3, 8]; a["cnt"] = [0xFFFFFFF0, 5]
+    b = np.zeros(2, dtype=[("key", "<u8"), ("cnt", "<u4")]); b["key"] = [3, 9]; b["cnt"] = [0x20, 6]
+    want = oracle.merge_runs([a.tobytes(), b.tobytes()], k)
+    with _counter(kc, k, 100) as c:
+        m = c.merge([c.upload_run(a.tobytes()), c.upload_run(b.tobytes())])
+        assert m.to_bytes() == want
+
+
+def test_config1_full_size(kc):
+    """BASELINE config 1: 100k reads x 100 bp, k=31, against the oracle."""
+    R, L, k = 100_000, 100, 31
+    reads = oracle.gen_reads(R, L, 1_000_000, 0.0, 1e-3, seed=1)
+    want = oracle.count(reads, L, k, chunk_reads=89364, threads=4)
+    for method in ("sort", "hash"):
+        with _counter(kc, k, L, method=method) as c:
+            got = c.process_chunk(reads)
+        assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+
+
+def test_device_resident_input(kc):
+    import torch
+    R, L, k = 3000, 100, 31
+    reads = oracle.gen_reads(R, L, 20000, 0.01, 0.001, seed=5)
+    d = torch.from_numpy(reads).cuda()
+    want = oracle.process_chunk(reads, L, k)
+    with kc.Counter(k, L, method="sort") as c:
+        run = c.count_device(d.data_ptr(), d.numel())
+        assert run.to_bytes() == want
+        st = c.stats()
+        assert st["reads"] == R and st["kmer_slots"] == R * (L - k + 1)
+        assert st["launches"] > 0 and st["dominant_launches"] == 8
+
+
+def test_run_split_and_file_write(kc, tmp_path):
+    R, L, k = 2000, 100, 31
+    reads = oracle.gen_reads(R, L, 20000, 0.0, 0.0, seed=6)
+    want = oracle.process_chunk(reads, L, k)
+    keys, _ = oracle.records_to_arrays(want, k)
+    with _counter(kc, k, L) as c:
+        run = c.count_reads(reads)
+        sp = np.array([[1 << 62], [2 << 62], [3 << 62]], dtype=np.uint64)
+        off = run.split(sp)
+        exp = [0] + [int(np.searchsorted(keys[:, 0], s[0], side="left")) for s in sp] + [len(keys)]
+        assert list(map(int, off)) == exp
+        p = str(tmp_path / "out.bin")
+        run.write(p)
+        assert open(p, "rb").read() == want
+        run.write(p)                                   # truncates, unlike KMerFileMerger.cpp:129
+        assert os.path.getsize(p) == len(want)
