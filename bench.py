@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers counted per second at k=31 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...   (the reference's CPU path)
+
+A step is one pass of the whole counting path over one batch of synthetic reads of
+BASELINE.json configs[1]'s shape (10M x 100 bp, k=31; per GPU when N > 1 -- weak
+scaling): extract -> count -> sorted key-unique run [-> exchange -> merge].
+  value : whole-job k-mers/s with the reads already resident in HBM
+  e2e   : the same through the host-buffer API: pinned host reads -> H2D -> count ->
+          packed records D2H into pinned host memory, every step
+  roofline      : dominant kernel (radix scatter pass / hash insert), algorithmic bytes per
+                  launch over its device time (CUDA events inside libkc_b200 on the stream
+                  the kernels run on), against MEASURED_PEAKS.json's HBM copy bandwidth
+  path_roofline : SURVEY.md 8(d)'s whole-path figure B_alg = B_in + N*(Kb+8) + U*S over step time
+  cpu_baseline  : oracle/_ref (the reference's own sources) on a bounded sample, host cores
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "k-mers counted/s at k=31"
+UNIT = "kmers/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (configs[1]: 10M)")
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--k", type=int, default=31)
+    ap.add_argument("--genome", type=int, default=100_000_000)
+    ap.add_argument("--sub-rate", type=float, default=1e-3)
+    ap.add_argument("--n-rate", type=float, default=0.0)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--zipf-loci", type=int, default=0)
+    ap.add_argument("--method", default="auto", choices=["auto", "sort", "hash"])
+    ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--check", action="store_true", help="verify a prefix against the oracle before timing")
+    return ap.parse_args()
+
+
+def workload(a):
+    return {"workload": "configs[1]: synthetic 10M x 100 bp reads, k=31, one B200" if a.gpus == 1 and a.reads == 10_000_000
+            else "configs[1] shape per GPU (weak scaling)" if a.reads == 10_000_000 else "custom",
+            "reads_per_gpu": a.reads, "read_len": a.read_len, "k": a.k, "genome_len": a.genome,
+            "sub_rate": a.sub_rate, "n_rate": a.n_rate, "seed": a.seed, "zipf_loci": a.zipf_loci,
+            "kmers_per_step_per_gpu": a.reads * (a.read_len - a.k + 1),
+            "l2_policy": "inputs larger than L2 (1 GB of reads, 5.6 GB of keys per step vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------- reference arm
+def run_reference(a, rank):
+    """The reference's own CPU implementation of the path (oracle/_ref: its sources compiled in
+    place) on the host cores, on a bounded sample of this arm's workload."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle
+    cores = os.cpu_count() or 1
+    L, k = a.read_len, a.k
+    sample = min(a.reads, a.cpu_sample_reads)
+    kind = "reference" if oracle.ref_available() else "port"
+    reads = oracle.gen_reads(sample, L, a.genome, a.sub_rate, a.n_rate, seed=a.seed, zipf_loci=a.zipf_loci)
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+
+    def one_step():
+        t0 = time.perf_counter()
+        if kind == "reference":
+            with tempfile.TemporaryDirectory(dir=tmp_root) as d:
+                oracle.ref_count_packed(reads, L, k, 89364, cores, d, os.path.join(d, "out.bin"))
+        else:
+            oracle.count(reads, L, k, 89364, threads=cores)
+        return time.perf_counter() - t0
+
+    for _ in range(min(a.warmup, 1)):
+        one_step()
+    times = [one_step() for _ in range(max(a.steps, 1))]
+    dt = sum(times) / len(times)
+    kmers = sample * (L - k + 1)
+    val = kmers / dt
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "impl": "reference", "config": workload(a),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d reads (%d k-mers) of the workload per step; runs through FileDump files in %s, "
+                                       "8-thread chunk workers like KMerCounter.cpp:117, single KMerFileMerger" %
+                                       (sample, kmers, tmp_root or "tmp")},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(a):
+    import oracle
+    cores = os.cpu_count() or 1
+    L, k = a.read_len, a.k
+    sample = min(a.reads, a.cpu_sample_reads)
+    kind = "reference" if oracle.ref_available() else "port"
+    reads = oracle.gen_reads(sample, L, a.genome, a.sub_rate, a.n_rate, seed=a.seed, zipf_loci=a.zipf_loci)
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    t0 = time.perf_counter()
+    if kind == "reference":
+        with tempfile.TemporaryDirectory(dir=tmp_root) as d:
+            oracle.ref_count_packed(reads, L, k, 89364, cores, d, os.path.join(d, "out.bin"))
+    else:
+        oracle.count(reads, L, k, 89364, threads=cores)
+    dt = time.perf_counter() - t0
+    kmers = sample * (L - k + 1)
+    return {"value": kmers / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
+            "sample": "first %d reads (%d k-mers) of the workload, chunks of 89,364 reads (the reference's default), "
+                      "%d chunk-worker threads, one serial KMerFileMerger" % (sample, kmers, cores)}
+
+
+# ------------------------------------------------------------------- our arm
+def run_ours(a, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import kmer_counter_b200 as kc
+    from kmer_counter_b200 import multigpu, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L, k, R = a.read_len, a.k, a.reads
+    nk = L - k + 1
+    n_bytes = R * L
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    counter = kc.Counter(k, L, device=local_rank, method=a.method, n_slots=1, max_chunk_bytes=0 if a.no_e2e else n_bytes,
+                         stream=stream.cuda_stream)
+    d_reads = torch.empty(n_bytes + 256, dtype=torch.uint8, device=dev)
+    synth.synth_reads_device(d_reads.data_ptr(), R, L, a.genome, a.sub_rate, a.n_rate, a.seed,
+                             first_read=rank * R, zipf_loci=a.zipf_loci, stream=stream.cuda_stream)
+    stream.synchronize()
+
+    if a.check and rank == 0:
+        import oracle
+        pre = min(R, 200_000)
+        host = d_reads[: pre * L].cpu().numpy()
+        assert bytes(host) == bytes(oracle.gen_reads(pre, L, a.genome, a.sub_rate, a.n_rate, seed=a.seed,
+                                                     zipf_loci=a.zipf_loci)), "device generator != host generator"
+        want = oracle.count(host, L, k, threads=os.cpu_count() or 1)
+        r = counter.count_device(d_reads.data_ptr(), pre * L)
+        assert r.to_bytes() == want, "prefix parity failed"
+        r.free()
+        sys.stderr.write("check: %d-read prefix bit-exact against the oracle\n" % pre)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            run = multigpu.count_shard(counter, d_reads.data_ptr(), n_bytes, dev)
+        else:
+            run = counter.count_device(d_reads.data_ptr(), n_bytes)
+        n = len(run)
+        run.free()
+        return n
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    st0 = counter.stats()
+    dom_ms, dom_bytes, dom_launch, tot_ms = 0.0, 0, 0, 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        distinct = 0
+        for _ in range(a.steps):
+            distinct = step()
+            s = counter.stats()
+            dom_ms += s["ms_dominant"]; dom_bytes += s["dominant_bytes"]; dom_launch += s["dominant_launches"]
+            tot_ms += s["ms_total"]
+        ev1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    st1 = counter.stats()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / a.steps
+    kmers_step = R * nk * world
+    value = kmers_step / (ms_per_step * 1e-3)
+    method_used = st1["method_used"]
+    launches = st1["launches"] - st0["launches"]
+
+    # ---- end to end through the host-buffer API (pinned in, pinned out)
+    e2e = None
+    if not a.no_e2e:
+        buf = counter.slot_buffer(0)
+        buf[:n_bytes] = d_reads[:n_bytes].cpu().numpy()
+        out_cap = (distinct + 1024) * counter.record_size if world == 1 else (R * nk // 2) * counter.record_size
+        pinned_out = counter.host_alloc(out_cap)
+        d2h = 0
+
+        def e2e_step():
+            counter.submit(0, n_bytes)
+            run = counter.wait(0)
+            if world > 1:
+                off = run.split(multigpu.range_splitters(world, counter.words))
+                keys_t, counts_t = multigpu.run_as_tensors(run, dev)
+                rk, rc, sizes = multigpu.exchange_slices(keys_t, counts_t, off)
+                torch.cuda.current_stream().synchronize()
+                parts, pos = [], 0
+                for sz in sizes:
+                    parts.append(counter.run_from_device(rk.data_ptr() + pos * counter.words * 8, rc.data_ptr() + pos * 4, sz))
+                    pos += sz
+                run.free()
+                run = counter.merge(parts)
+                for p in parts:
+                    p.free()
+            nb = run.copy_into(pinned_out.ctypes.data, out_cap)
+            run.free()
+            return nb
+
+        for _ in range(min(a.warmup, 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            d2h = e2e_step()
+        barrier()
+        e2e_dt = (time.perf_counter() - t0) / a.steps
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+        e2e = {"value": kmers_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_dt * 1e3, "timing": "wall clock around K steps, sync on both sides, max over ranks"}
+        counter.host_free(pinned_out)
+
+    clocks = clk.summary()
+    peak, peak_src = measured_peak_gbs()
+    if rank == 0:
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        Kb, S = 8 * counter.words, counter.record_size
+        b_alg = R * L + R * nk * (Kb + 8) + distinct * S
+        path_ach = b_alg / (tot_ms / a.steps * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": dict(workload(a), method=method_used),
+            "bases_per_s": R * L * world / (ms_per_step * 1e-3),
+            "distinct_per_gpu": distinct,
+            "roofline": {"bound": "hbm", "kernel": "onesweep radix scatter pass" if method_used == "sort" else "fused extract + hash insert",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "peak_source": peak_src + " HBM copy bandwidth (MEASURED_PEAKS.json)",
+                         "bytes_per_launch": dom_bytes / max(dom_launch, 1), "launches_per_step": dom_launch / a.steps,
+                         "ms_per_launch": dom_ms / max(dom_launch, 1),
+                         "share_of_step": dom_ms / tot_ms if tot_ms else None, "traffic": None},
+            "path_roofline": {"bound": "hbm", "b_alg_bytes": b_alg, "achieved": path_ach, "peak": peak, "unit": "GB/s",
+                              "frac": path_ach / peak if peak else None,
+                              "definition": "SURVEY 8(d): B_in + N*(Kb+8) + U*S over the local counting time"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "wall_ms_per_step": wall / a.steps * 1e3,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(a)
+        print(json.dumps(line), flush=True)
+    counter.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    if world != a.gpus and world == 1 and a.gpus > 1:
+        sys.stderr.write("bench.py: --gpus %d needs torchrun (WORLD_SIZE=%d)\n" % (a.gpus, world))
+        sys.exit(2)
+    run_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,8 +50,11 @@ extern "C" {
 #define KC_COUNT_AUTO       0u
 #define KC_COUNT_SORT       1u    /* radix sort + run-length (replaces sortKmers+reduceKMers,
                                      GPUHandler.cu:300-360)                                */
-#define KC_COUNT_HASH       2u    /* open-addressing table (replaces the TBB accumulate,
-                                     KMerCounter.cpp:61-82), then sort of the distinct set */
+#define KC_COUNT_HASH       2u    /* open-addressing hash tables in shared memory over key-range
+                                     partitions (replaces the TBB accumulate, KMerCounter.cpp:61-82);
+                                     k <= 32                                                 */
+#define KC_COUNT_HASH_GLOBAL 3u   /* one open-addressing table in HBM, then a sort of the distinct
+                                     set; kept as the measured baseline for KC_COUNT_HASH      */
 
 typedef struct kc_ctx kc_ctx;
 typedef struct kc_run kc_run;
@@ -82,11 +85,21 @@ typedef struct kc_stats {
     uint64_t h2d_bytes, d2h_bytes;
     /* device time of the most recent chunk, by stage, CUDA events on the ctx stream */
     float ms_extract, ms_count, ms_emit, ms_total;
-    /* dominant kernel of the most recent chunk (radix scatter pass or hash insert) */
+    /* dominant stage of the most recent chunk = the slowest entry of ms_stage */
     float ms_dominant;         /* summed over its launches                                 */
     uint32_t dominant_launches;
-    uint32_t method_used;      /* KC_COUNT_SORT or KC_COUNT_HASH                           */
+    uint32_t method_used;      /* KC_COUNT_* actually run (a full hash table falls back to sort) */
     uint64_t dominant_bytes;   /* algorithmic bytes moved by those launches                */
+    /* per-stage device time and algorithmic bytes of the most recent chunk.
+     *   KC_COUNT_SORT : 0 extract, 1 digit histogram, 2 radix scatter passes, 3 run-length, 4 emit
+     *   KC_COUNT_HASH : 0 level-1 histogram, 1 extract+scatter1, 2 level-2 histogram, 3 scatter2,
+     *                   4 shared-memory count+sort+write, 5 emit
+     *   KC_COUNT_HASH_GLOBAL : 0 table clear, 1 extract+insert, 2 compact+sort, 3 emit          */
+    uint32_t n_stages;
+    uint32_t dominant_stage;
+    float    ms_stage[8];
+    uint64_t stage_bytes[8];
+    uint32_t stage_launches[8];
 } kc_stats;
 
 /* ---- library ---- */
@@ -148,6 +161,14 @@ int  kc_run_split(kc_ctx *ctx, const kc_run *run, const uint64_t *splitters, uin
 /* Merge n sorted runs into one, adding the counts of equal keys (uint32 wrap).
  * Inputs stay valid and owned by the caller. n may be 0 (empty run) or 1 (copy). */
 int  kc_merge_runs(kc_ctx *ctx, kc_run *const *runs, uint32_t n, kc_run **out);
+
+/* ---- measurement support (not a reference interface): deterministic synthetic reads
+ * written straight into device memory as packed lines; bit-identical to the host
+ * generator used by the tests.  genome_len == 0 -> iid bases; zipf_loci > 0 -> half of
+ * the reads start at one of zipf_loci hot loci with P(rank) ~ 1/rank. ---- */
+int  kc_synth_reads(void *d_out, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
+                    uint64_t genome_len, double sub_rate, double n_rate, uint64_t seed,
+                    uint64_t zipf_loci, void *stream);
 
 #ifdef __cplusplus
 }

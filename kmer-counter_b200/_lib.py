@@ -13,8 +13,8 @@ CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 KC_OK = 0
 KC_COMPAT_REF, KC_COMPAT_STRICT = 0, 1
-KC_COUNT_AUTO, KC_COUNT_SORT, KC_COUNT_HASH = 0, 1, 2
-METHODS = {"auto": KC_COUNT_AUTO, "sort": KC_COUNT_SORT, "hash": KC_COUNT_HASH}
+KC_COUNT_AUTO, KC_COUNT_SORT, KC_COUNT_HASH, KC_COUNT_HASH_GLOBAL = 0, 1, 2, 3
+METHODS = {"auto": KC_COUNT_AUTO, "sort": KC_COUNT_SORT, "hash": KC_COUNT_HASH, "hash_global": KC_COUNT_HASH_GLOBAL}
 METHOD_NAMES = {v: k for k, v in METHODS.items()}
 
 
@@ -33,6 +33,8 @@ class KcStats(C.Structure):
         ("ms_extract", C.c_float), ("ms_count", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
         ("ms_dominant", C.c_float), ("dominant_launches", C.c_uint32), ("method_used", C.c_uint32),
         ("dominant_bytes", C.c_uint64),
+        ("n_stages", C.c_uint32), ("dominant_stage", C.c_uint32),
+        ("ms_stage", C.c_float * 8), ("stage_bytes", C.c_uint64 * 8), ("stage_launches", C.c_uint32 * 8),
     ]
 
 
@@ -66,6 +68,7 @@ SYMBOLS = {
     "kc_run_write": (_i, [_vp, _vp, C.c_char_p, _i]),
     "kc_run_split": (_i, [_vp, _vp, _pu64, _u32, _pu64]),
     "kc_merge_runs": (_i, [_vp, _pp, _u32, _pp]),
+    "kc_synth_reads": (_i, [_vp, _u64, _u64, _u32, _u64, C.c_double, C.c_double, _u64, _u64, _vp]),
 }
 
 

@@ -40,8 +40,11 @@ struct Pending {                 // a chunk whose kernels are queued but whose r
     HashTable table{nullptr, 0, nullptr};
     unsigned long long *d_scal = nullptr;   // SC_COUNT device scalars
     unsigned long long *h_scal = nullptr;   // pinned mirror
-    cudaEvent_t ev[6] = {};                  // start, extracted, pass0, passN, counted, end
+    cudaEvent_t ev[8] = {};                  // stage k runs from ev[k] to ev[k+1]
+    int n_ev = 0;                            // events recorded by count_enqueue (the emit stage adds one)
     int n_passes = 0;
+    uint32_t *counts = nullptr;              // partition path: counts next to the unique keys
+    void *ws_part = nullptr;
 };
 
 struct Slot {
@@ -120,9 +123,11 @@ void pending_destroy(Pending &p) {
 void pending_release(cudaStream_t s, Pending &p) {
     dev_free(s, p.keys_a); dev_free(s, p.keys_b); dev_free(s, p.starts);
     dev_free(s, p.ws_sort); dev_free(s, p.ws_rle); dev_free(s, p.table.slots);
+    dev_free(s, p.counts); dev_free(s, p.ws_part);
     p.keys_a = p.keys_b = p.sorted = p.uniq = nullptr;
     p.starts = nullptr;
-    p.ws_sort = p.ws_rle = nullptr;
+    p.counts = nullptr;
+    p.ws_sort = p.ws_rle = p.ws_part = nullptr;
     p.table = HashTable{nullptr, 0, nullptr};
     p.active = false;
 }
@@ -146,7 +151,9 @@ constexpr uint64_t kMaxSortKeys = (1ull << 30) - 1;
 uint32_t pick_method(const kc_ctx *c) {
     uint32_t m = c->cfg.method;
     if (c->W != 1) return KC_COUNT_SORT;           // 128-bit+ keys: sort + run-length (config 3)
-    if (m == KC_COUNT_AUTO) return KC_COUNT_SORT;  // see DESIGN.md "method selection"
+    // 64-bit keys: partitioned shared-memory hashing unless the key has too few significant
+    // bits to partition on (tiny k); see DESIGN.md "method selection"
+    if (m == KC_COUNT_AUTO) return (64 - static_zero_bits(c)) >= 24 ? KC_COUNT_HASH : KC_COUNT_SORT;
     return m;
 }
 
@@ -163,10 +170,8 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
     int launches = 0;
     KC_CUDA_TRY(c, cudaMemsetAsync(p.d_scal, 0, SC_COUNT * 8, s));
     KC_CUDA_TRY(c, cudaEventRecord(p.ev[0], s));
-    if (p.n_slots == 0) {
-        for (int i = 1; i < 6; i++) KC_CUDA_TRY(c, cudaEventRecord(p.ev[i], s));
-        return KC_OK;
-    }
+    p.n_ev = 1;
+    if (p.n_slots == 0) return KC_OK;
     if (p.n_slots > kMaxSortKeys) return c->set_error(KC_ERR_ARG, "chunk too large: %llu k-mer slots (max %llu)",
                                                       (unsigned long long)p.n_slots, (unsigned long long)kMaxSortKeys);
     ExtractParams ep;
@@ -174,6 +179,24 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
         return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
 
     if (method == KC_COUNT_HASH) {
+        // partitioned shared-memory hash counting (kc_partition.cu)
+        ExtractParams ep64;
+        if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep64, 6400))
+            return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
+        void *mem = nullptr;
+        KC_TRY(dev_alloc(c, s, p.n_slots * 8 + 64, &mem)); p.keys_a = static_cast<uint64_t *>(mem);
+        KC_TRY(dev_alloc(c, s, p.n_slots * 8 + 64, &mem)); p.keys_b = static_cast<uint64_t *>(mem);
+        KC_TRY(dev_alloc(c, s, (p.n_slots + 2) * 4, &mem)); p.counts = static_cast<uint32_t *>(mem);
+        KC_TRY(dev_alloc(c, s, partition_workspace_bytes(p.n_slots), &p.ws_part));
+        const int sig = 64 - static_zero_bits(c);
+        const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;   // keys per sub-bucket (0 = default)
+        p.uniq = partition_two_levels(p.n_slots, sig, target) ? p.keys_a : p.keys_b;
+        KC_CUDA_TRY(c, partition_count(ep64, p.n_slots, sig, !c->strict, p.keys_a, p.keys_b, p.uniq, p.counts,
+                                       &p.d_scal[SC_UNIQUE], &p.d_scal[SC_SIDE + 1], &p.d_scal[SC_COUNT - 2],
+                                       p.ws_part, c->n_sms, target, s, &launches, &p.ev[1]));
+        p.n_ev = 6;
+        p.n_passes = 1;
+    } else if (method == KC_COUNT_HASH_GLOBAL) {
         uint64_t cap = c->cfg.table_slots ? pow2_ceil(c->cfg.table_slots) : pow2_ceil(p.n_slots / 2 + 1);
         if (cap < (1u << 16)) cap = 1u << 16;
         void *mem = nullptr;
@@ -182,12 +205,11 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
         p.table.capacity = cap;
         p.table.side = &p.d_scal[SC_SIDE];
         KC_CUDA_TRY(c, hash_clear(p.table, s));
-        KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));     // "extract" stage is empty: it is fused into the insert
-        KC_CUDA_TRY(c, cudaEventRecord(p.ev[2], s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));
         KC_CUDA_TRY(c, launch_extract_hash(ep, p.table, c->n_sms, s));
-        KC_CUDA_TRY(c, cudaEventRecord(p.ev[3], s));
         KC_CUDA_TRY(c, hash_touch_zero(p.table, c->strict ? &p.d_scal[SC_COUNT - 1] : &p.d_scal[SC_INVALID], s));
-        KC_CUDA_TRY(c, cudaEventRecord(p.ev[4], s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[2], s));
+        p.n_ev = 3;
         launches += 3;
         p.n_passes = 1;
     } else {
@@ -210,6 +232,7 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
         KC_CUDA_TRY(c, rle_unique(p.sorted, p.n_slots, W, p.uniq, p.starts, &p.d_scal[SC_UNIQUE], p.ws_rle, s,
                                   &sort_launches));
         KC_CUDA_TRY(c, cudaEventRecord(p.ev[4], s));
+        p.n_ev = 5;
         launches += 1 + sort_launches;
     }
     KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
@@ -236,7 +259,8 @@ int make_run(kc_ctx *c, cudaStream_t s, uint64_t n, kc_run **out) {
 }
 
 int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
-int count_finish_hash(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, kc_run **out);
+int count_finish_hash_global(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
+int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 
 // Wait for the queued kernels, build the run, record stage timings.
 int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, kc_run **out) {
@@ -245,30 +269,22 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
     KC_CUDA_TRY(c, cudaStreamSynchronize(s));
     int rc;
     uint32_t used = p.method;
-    if (p.n_slots == 0) {
-        rc = make_run(c, s, 0, out);
-    } else if (p.method == KC_COUNT_HASH) {
-        if (p.h_scal[SC_SIDE + 1]) {             // table overflow: redo this chunk with sort + run-length
-            pending_release(s, p);
-            KC_TRY(count_enqueue(c, p, d_reads, n_bytes, s, KC_COUNT_SORT));
-            KC_CUDA_TRY(c, cudaStreamSynchronize(s));
-            used = KC_COUNT_SORT;
-            rc = count_finish_sort(c, p, s, out);
-        } else {
-            rc = count_finish_hash(c, p, d_reads, n_bytes, s, out);
-        }
-    } else {
-        rc = count_finish_sort(c, p, s, out);
+    const bool overflow = p.n_slots && (p.method == KC_COUNT_HASH || p.method == KC_COUNT_HASH_GLOBAL) &&
+                          p.h_scal[SC_SIDE + 1];
+    if (overflow) {                               // table(s) full: redo this chunk with sort + run-length
+        pending_release(s, p);
+        KC_TRY(count_enqueue(c, p, d_reads, n_bytes, s, KC_COUNT_SORT));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        used = KC_COUNT_SORT;
     }
+    if (p.n_slots == 0) rc = make_run(c, s, 0, out);
+    else if (used == KC_COUNT_HASH) rc = count_finish_partition(c, p, s, out);
+    else if (used == KC_COUNT_HASH_GLOBAL) rc = count_finish_hash_global(c, p, s, out);
+    else rc = count_finish_sort(c, p, s, out);
     if (rc != KC_OK) { pending_release(s, p); return rc; }
-    KC_CUDA_TRY(c, cudaEventRecord(p.ev[5], s));
-    KC_CUDA_TRY(c, cudaEventSynchronize(p.ev[5]));
-    float t01 = 0, t14 = 0, t23 = 0, t45 = 0, t05 = 0;
-    cudaEventElapsedTime(&t01, p.ev[0], p.ev[1]);
-    cudaEventElapsedTime(&t14, p.ev[1], p.ev[4]);
-    cudaEventElapsedTime(&t23, p.ev[2], p.ev[3]);
-    cudaEventElapsedTime(&t45, p.ev[4], p.ev[5]);
-    cudaEventElapsedTime(&t05, p.ev[0], p.ev[5]);
+    const int n_stages = p.n_ev;                  // the last stage (emit) ends at the event recorded now
+    KC_CUDA_TRY(c, cudaEventRecord(p.ev[p.n_ev], s));
+    KC_CUDA_TRY(c, cudaEventSynchronize(p.ev[p.n_ev]));
     {
         std::lock_guard<std::mutex> g(c->mu);
         kc_stats &st = c->stats;
@@ -276,18 +292,59 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
         st.reads += p.n_reads;
         st.kmer_slots += p.n_slots;
         const uint64_t invalid = p.h_scal[SC_INVALID];
-        st.kmers_valid += p.n_slots - invalid;
+        const uint64_t nv = p.n_slots - invalid, U = (*out)->n;
+        const uint64_t in_bytes = p.n_reads * c->cfg.read_len, Kb = 8ull * c->W;
+        st.kmers_valid += nv;
         st.distinct_last = (*out)->n - (*out)->skip;
-        st.ms_extract = t01; st.ms_count = t14; st.ms_emit = t45; st.ms_total = t05;
-        st.ms_dominant = t23;
-        st.dominant_launches = (uint32_t)p.n_passes;
         st.method_used = used;
-        if (used == KC_COUNT_SORT)
-            st.dominant_bytes = (uint64_t)p.n_passes * p.n_slots * 2ull * 8ull * c->W;   // read + write each key per pass
-        else
-            st.dominant_bytes = p.n_reads * c->cfg.read_len + (p.n_slots - invalid) * 16ull;   // SURVEY 8(d) per-occurrence terms
+        st.n_stages = (uint32_t)n_stages;
+        for (int i = 0; i < 8; i++) { st.ms_stage[i] = 0; st.stage_bytes[i] = 0; st.stage_launches[i] = 0; }
+        for (int i = 0; i < n_stages; i++) cudaEventElapsedTime(&st.ms_stage[i], p.ev[i], p.ev[i + 1]);
+        cudaEventElapsedTime(&st.ms_total, p.ev[0], p.ev[n_stages]);
+        // algorithmic bytes per stage: what the stage must read and write once
+        if (used == KC_COUNT_SORT && p.n_slots) {
+            const uint64_t N = p.n_slots;
+            st.stage_bytes[0] = in_bytes + Kb * N;                         st.stage_launches[0] = 1;
+            st.stage_bytes[1] = Kb * N;                                    st.stage_launches[1] = 2;
+            st.stage_bytes[2] = (uint64_t)p.n_passes * 2 * Kb * N;         st.stage_launches[2] = (uint32_t)p.n_passes;
+            st.stage_bytes[3] = Kb * N + U * (Kb + 4);                     st.stage_launches[3] = 1;
+            st.stage_bytes[4] = U * (2 * Kb + 8);                          st.stage_launches[4] = 1;
+        } else if (used == KC_COUNT_HASH && p.n_slots) {
+            st.stage_bytes[0] = in_bytes;                                  st.stage_launches[0] = 2;
+            st.stage_bytes[1] = in_bytes + 8 * nv;                         st.stage_launches[1] = 1;
+            st.stage_bytes[2] = 8 * nv;                                    st.stage_launches[2] = 2;
+            st.stage_bytes[3] = 16 * nv;                                   st.stage_launches[3] = 1;
+            st.stage_bytes[4] = 8 * nv + 12 * U;                           st.stage_launches[4] = 1;
+            st.stage_bytes[5] = 24 * U;                                    st.stage_launches[5] = 0;
+        } else if (used == KC_COUNT_HASH_GLOBAL && p.n_slots) {
+            st.stage_bytes[0] = p.table.capacity * 16;                     st.stage_launches[0] = 1;
+            st.stage_bytes[1] = in_bytes + nv * 16;                        st.stage_launches[1] = 1;   // SURVEY 8(d) terms
+            st.stage_bytes[2] = p.table.capacity * 16 + U * 12 * 17;       st.stage_launches[2] = 10;
+        }
+        int dom = 0;
+        for (int i = 1; i + 1 < n_stages; i++)
+            if (st.ms_stage[i] > st.ms_stage[dom]) dom = i;
+        st.dominant_stage = (uint32_t)dom;
+        st.ms_dominant = st.ms_stage[dom];
+        st.dominant_bytes = st.stage_bytes[dom];
+        st.dominant_launches = st.stage_launches[dom] ? st.stage_launches[dom] : 1;
+        st.ms_extract = st.ms_stage[0];
+        st.ms_emit = n_stages ? st.ms_stage[n_stages - 1] : 0;
+        st.ms_count = st.ms_total - st.ms_extract - st.ms_emit;
     }
     pending_release(s, p);
+    return KC_OK;
+}
+
+int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
+    const uint64_t U = p.h_scal[SC_UNIQUE];
+    kc_run *r = nullptr;
+    KC_TRY(make_run(c, s, U, &r));
+    if (U) {
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_keys, p.uniq, U * 8, cudaMemcpyDeviceToDevice, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_counts, p.counts, U * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    *out = r;
     return KC_OK;
 }
 
@@ -316,7 +373,7 @@ int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
     return KC_OK;
 }
 
-int count_finish_hash(kc_ctx *c, Pending &p, const void *, uint64_t, cudaStream_t s, kc_run **out) {
+int count_finish_hash_global(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
     const uint64_t U = p.h_scal[SC_SIDE + 3] + (p.h_scal[SC_SIDE + 0] ? 1 : 0);
     kc_run *ra = nullptr, *rb = nullptr;
     KC_TRY(make_run(c, s, U, &ra));
@@ -364,8 +421,8 @@ int kc_create(const kc_config *cfg, kc_ctx **out) {
     memcpy(&c0, cfg, cfg->struct_size && cfg->struct_size < sizeof(kc_config) ? cfg->struct_size : sizeof(kc_config));
     if (c0.k < 1 || c0.k > 128) { g_create_error = "kc_create: k must be in 1..128 (KMerSizes.h holds 4 words)"; return KC_ERR_ARG; }
     if (c0.read_len < c0.k || c0.read_len > 4096) { g_create_error = "kc_create: read_len must be in k..4096"; return KC_ERR_ARG; }
-    if (c0.method > KC_COUNT_HASH) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
-    if (c0.method == KC_COUNT_HASH && c0.k > 32) { g_create_error = "kc_create: hash counting needs k <= 32"; return KC_ERR_ARG; }
+    if (c0.method > KC_COUNT_HASH_GLOBAL) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
+    if ((c0.method == KC_COUNT_HASH || c0.method == KC_COUNT_HASH_GLOBAL) && c0.k > 32) { g_create_error = "kc_create: hash counting needs k <= 32"; return KC_ERR_ARG; }
     cudaError_t e = cudaSetDevice(c0.device);
     if (e != cudaSuccess) { g_create_error = std::string("kc_create: cudaSetDevice failed: ") + cudaGetErrorString(e); return KC_ERR_CUDA; }
     kc_ctx *c = new kc_ctx();

@@ -45,6 +45,23 @@ inline void extract_smem_layout(ExtractParams &p) {
 
 constexpr int kExtractThreads = 256;
 
+// Sink protocol (all members __device__; every thread of the CTA calls every hook):
+//   static constexpr int kSweeps      phase-B sweeps over a tile's slots (1, or 2 for rank-then-place)
+//   void begin(uint8_t *extra_smem)   once per CTA; the kernel syncs afterwards
+//   void sweep_begin(int sw, uint32_t n_slots) / void sweep_end(int sw)
+//                                     around each sweep; may __syncthreads(); the kernel syncs
+//                                     between the slot loop and sweep_end
+//   void operator()(int sw, uint64_t slot, const Key<W>&, bool valid)
+//   void finish()                     once per CTA after the last tile
+// extra_smem starts at ExtractParams::smem_total (16-byte aligned); launch with that many more bytes.
+struct SinkBase {
+    static constexpr int kSweeps = 1;
+    __device__ __forceinline__ void begin(uint8_t *) {}
+    __device__ __forceinline__ void sweep_begin(int, uint32_t) {}
+    __device__ __forceinline__ void sweep_end(int) {}
+    __device__ __forceinline__ void finish() {}
+};
+
 // code: A0 C1 G2 T3, anything else 3 + bad (GPUHandler.cu:42-88)
 __device__ __forceinline__ uint32_t base_code(uint32_t c, uint32_t &bad) {
     uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
@@ -72,6 +89,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
+    sink.begin(smem + p.smem_total);
     __syncthreads();
 
     auto tile_reads_of = [&](uint32_t t) -> uint32_t {
@@ -145,36 +163,42 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         // ---- phase B: one key per thread per step, slots are contiguous in the output ----
         const uint32_t total = nreads * p.nk;
         const uint64_t slot0 = (uint64_t)tile * p.tile_reads * p.nk;
-        for (uint32_t s = tid; s < total; s += kExtractThreads) {
-            uint32_t r = p.nk == 1 ? s : __umulhi(s, p.nk_magic);
-            if (r * p.nk > s) r--;
-            const uint32_t pos = s - r * p.nk;
-            const uint64_t *e = enc + r * enc_row + (pos >> 5);
-            const uint32_t sh = (pos & 31u) * 2u;
-            Key<W> key;
-            uint64_t a = e[0];
 #pragma unroll
-            for (int q = 0; q < W; q++) {
-                uint64_t b = e[q + 1];
-                key.w[q] = sh ? ((a << sh) | (b >> (64 - sh))) : a;
-                a = b;
-            }
-            key.w[W - 1] &= p.last_mask;
-            bool valid = true;
-            if (flag[r]) {
-                // rare path: any bad base inside [pos, pos+k) kills the k-mer
-                const uint8_t *bn = bad4 + r * p.nb4;
-                uint32_t lo = pos, hi = pos + p.k;  // [lo, hi)
-                for (uint32_t q = lo >> 2; q <= (hi - 1) >> 2; q++) {
-                    uint32_t m = bn[q];
-                    uint32_t b0 = q * 4;
-                    if (b0 < lo) m &= 0xFu << (lo - b0);
-                    if (b0 + 4 > hi) m &= 0xFu >> (b0 + 4 - hi);
-                    if (m & 0xFu) { valid = false; break; }
+        for (int sw = 0; sw < Sink::kSweeps; sw++) {
+            sink.sweep_begin(sw, total);
+            for (uint32_t s = tid; s < total; s += kExtractThreads) {
+                uint32_t r = p.nk == 1 ? s : __umulhi(s, p.nk_magic);
+                if (r * p.nk > s) r--;
+                const uint32_t pos = s - r * p.nk;
+                const uint64_t *e = enc + r * enc_row + (pos >> 5);
+                const uint32_t sh = (pos & 31u) * 2u;
+                Key<W> key;
+                uint64_t a = e[0];
+#pragma unroll
+                for (int q = 0; q < W; q++) {
+                    uint64_t b = e[q + 1];
+                    key.w[q] = sh ? ((a << sh) | (b >> (64 - sh))) : a;
+                    a = b;
                 }
+                key.w[W - 1] &= p.last_mask;
+                bool valid = true;
+                if (flag[r]) {
+                    // rare path: any bad base inside [pos, pos+k) kills the k-mer
+                    const uint8_t *bn = bad4 + r * p.nb4;
+                    uint32_t lo = pos, hi = pos + p.k;  // [lo, hi)
+                    for (uint32_t q = lo >> 2; q <= (hi - 1) >> 2; q++) {
+                        uint32_t m = bn[q];
+                        uint32_t b0 = q * 4;
+                        if (b0 < lo) m &= 0xFu << (lo - b0);
+                        if (b0 + 4 > hi) m &= 0xFu >> (b0 + 4 - hi);
+                        if (m & 0xFu) { valid = false; break; }
+                    }
+                }
+                if (sw == 0 && !valid) invalid_local++;
+                sink(sw, slot0 + s, key, valid);
             }
-            if (!valid) invalid_local++;
-            sink(slot0 + s, key, valid);
+            __syncthreads();
+            sink.sweep_end(sw);
         }
         __syncthreads();
         stage ^= 1;

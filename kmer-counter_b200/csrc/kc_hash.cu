@@ -44,10 +44,10 @@ __device__ __forceinline__ uint32_t table_add(const HashTable &t, uint64_t k, ui
     return 0;
 }
 
-struct HashSink {
+struct HashSink : SinkBase {
     HashTable t;
     uint32_t claimed;   // slots this thread claimed (= new distinct keys)
-    __device__ __forceinline__ void operator()(uint64_t, const Key<1> &key, bool valid) {
+    __device__ __forceinline__ void operator()(int, uint64_t, const Key<1> &key, bool valid) {
         if (valid) claimed += table_add(t, key.w[0], 1u);
     }
     // one atomic per warp: side[3] accumulates the number of distinct keys in the table
@@ -126,7 +126,7 @@ cudaError_t launch_extract_hash(const ExtractParams &p, HashTable t, int n_sms, 
     if (per_sm > 6) per_sm = 6;            // random-access bound: more resident warps hide more latency
     uint32_t grid = (uint32_t)n_sms * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    kern<<<grid, kExtractThreads, p.smem_total, s>>>(p, HashSink{t, 0u});
+    kern<<<grid, kExtractThreads, p.smem_total, s>>>(p, HashSink{{}, t, 0u});
     return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@ namespace kc {
 // Fills every field of ExtractParams for (reads, n_reads, L, k); strict selects
 // KC_COMPAT_STRICT masking. Returns false for unsupported shapes.
 bool extract_plan(const void *d_reads, uint64_t n_reads, uint32_t L, uint32_t k, bool strict,
-                  unsigned long long *d_n_invalid, ExtractParams *out);
+                  unsigned long long *d_n_invalid, ExtractParams *out, uint32_t stage_bytes_target = 12800);
 // keys[slot] for every slot r*(L-k+1)+p; slots without a k-mer get key 0
 cudaError_t launch_extract_store(const ExtractParams &p, int W, uint64_t *d_keys, int n_sms, cudaStream_t s);
 
@@ -73,5 +73,15 @@ cudaError_t hash_touch_zero(HashTable t, const unsigned long long *d_n_invalid, 
 // occupied slots (+ the all-ones key if seen) -> (keys, counts), unordered; *d_num = records
 cudaError_t hash_compact(HashTable t, uint64_t *out_keys, uint32_t *out_counts, unsigned long long *d_num,
                          cudaStream_t s, int *n_launches);
+
+// ---- partitioned shared-memory hash counting (kc_partition.cu), W == 1 only
+uint64_t partition_workspace_bytes(uint64_t n_slots);
+// true when out_keys must be keys_a (two partition levels) rather than keys_b
+bool partition_two_levels(uint64_t n_slots, int sig_bits, int target_sub);
+cudaError_t partition_count(const ExtractParams &ep, uint64_t n_slots, int sig_bits, bool add_phantom,
+                            uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
+                            unsigned long long *d_num_out, unsigned long long *d_overflow,
+                            unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,
+                            cudaStream_t s, int *n_launches, cudaEvent_t *evs);
 
 }  // namespace kc

@@ -1,0 +1,643 @@
+// kc_partition.cu -- partitioned hash counting for 64-bit keys (k <= 32), sm_100a.
+//
+// This is the B200 replacement for the reference's counting step (one TBB hash
+// insert per k-mer occurrence on the host, KMerCounter.cpp:61-82) AND for its
+// sort + reduce (GPUHandler.cu:300-360) in one design: keys are partitioned by
+// their leading bits (= leading bases, so partitions are key ranges and their
+// concatenation is already sorted), then every partition is counted in an
+// open-addressing hash table that lives in SHARED MEMORY, its distinct keys are
+// sorted there, and the records are written once, in final order.
+//
+// Why: measured on B200 (tools/ubench), shared-memory atomics run at ~2.8 T ops/s
+// and 64-bit shared CAS at ~0.75 T ops/s chip-wide, against ~15 G inserts/s for a
+// table in HBM and ~380 G keys/s for ballot-based stable ranking.  A most-
+// significant-digit partition needs no stable ranking -- a key's position inside
+// its bucket is irrelevant -- so ranking is one shared atomicAdd per key.
+//
+//   P0  hist1     extract (fused encode) -> level-1 digit histogram      reads R*L
+//   PA  scatter1  extract -> keys grouped by level-1 digit (2^b1 buckets) writes 8N
+//   H2  hist2     level-2 digit histogram inside each bucket             reads 8N
+//   PB  scatter2  keys grouped by the b1+b2 leading bits                 reads 8N, writes 8N
+//   PC  finish    per sub-bucket: shared-memory hash count, sort of the distinct keys,
+//                 ordered write via decoupled look-back                  reads 8N, writes 12U
+#include "kc_internal.h"
+
+namespace kc {
+
+namespace {
+
+constexpr int kMaxBins = 1024;          // bins per level
+constexpr uint64_t kEmptyKey = ~0ull;   // the all-ones key (poly-T window) is the empty marker; counted aside
+constexpr int kPbThreads = 256, kPbItems = 16, kPbTile = kPbThreads * kPbItems;
+constexpr int kPcThreads = 256;
+constexpr int kHcap = 4096;             // hash slots per sub-bucket table
+constexpr int kLcap = 2048;             // distinct keys per round (load <= 0.5)
+
+// exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_t *start, int nb, uint32_t *s_warp) {
+    constexpr int PER = kMaxBins / THREADS > 0 ? kMaxBins / THREADS : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int b = tid * PER + i;
+        v[i] = b < nb ? cnt[b] : 0;
+        sum += v[i];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        const uint32_t t = s_warp[w];
+        if (w < warp) off += t;
+        total += t;
+    }
+    uint32_t run = off + incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int b = tid * PER + i;
+        if (b < nb) start[b] = run;
+        run += v[i];
+    }
+    __syncthreads();
+    return total;
+}
+
+// ------------------------------------------------------------------- P0: hist1
+struct Hist1Sink : SinkBase {
+    uint32_t *g_hist1;
+    int shift1, nb1;
+    uint32_t *sh;
+    __device__ __forceinline__ void begin(uint8_t *extra) {
+        sh = reinterpret_cast<uint32_t *>(extra);
+        for (int i = threadIdx.x; i < nb1; i += kExtractThreads) sh[i] = 0;
+    }
+    __device__ __forceinline__ void operator()(int, uint64_t, const Key<1> &key, bool valid) {
+        if (valid) atomicAdd(&sh[key.w[0] >> shift1], 1u);
+    }
+    __device__ __forceinline__ void finish() {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb1; i += kExtractThreads) {
+            const uint32_t c = sh[i];
+            if (c) atomicAdd(&g_hist1[i], c);
+        }
+    }
+};
+
+// one block: bucket bases, the mutable cursors, and the tile map for H2 / PB
+__global__ void __launch_bounds__(1024) scan1_kernel(const uint32_t *__restrict__ hist1, int nb1,
+                                                     uint32_t *__restrict__ base1, uint32_t *__restrict__ cursor1,
+                                                     uint32_t *__restrict__ tile_prefix) {
+    __shared__ uint32_t s_a[32], s_b[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = tid < nb1 ? hist1[tid] : 0;
+    const uint32_t t = (c + kPbTile - 1) / kPbTile;
+    uint32_t ia = c, ib = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += xa; ib += xb; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+    __syncthreads();
+    uint32_t oa = 0, ob = 0;
+    for (int w = 0; w < warp; w++) { oa += s_a[w]; ob += s_b[w]; }
+    if (tid < nb1) {
+        base1[tid] = oa + ia - c;
+        cursor1[tid] = oa + ia - c;
+        tile_prefix[tid] = ob + ib - t;
+        if (tid == nb1 - 1) { base1[nb1] = oa + ia; tile_prefix[nb1] = ob + ib; }
+    }
+}
+
+// ---------------------------------------------------------------- PA: scatter1
+struct Scatter1Sink : SinkBase {
+    static constexpr int kSweeps = 2;
+    uint32_t *g_cursor1;
+    uint64_t *out;
+    int shift1, nb1;
+    // shared
+    uint32_t *cnt, *start, *gbase, *s_warp;
+    uint64_t *staging;
+    uint32_t total;
+
+    static __host__ __device__ uint32_t smem_bytes(uint32_t max_tile_keys) {
+        return 3 * kMaxBins * 4 + 64 + max_tile_keys * 8;
+    }
+    __device__ __forceinline__ void begin(uint8_t *extra) {
+        cnt = reinterpret_cast<uint32_t *>(extra);
+        start = cnt + kMaxBins;
+        gbase = start + kMaxBins;
+        s_warp = gbase + kMaxBins;
+        staging = reinterpret_cast<uint64_t *>(s_warp + 16);
+        for (int i = threadIdx.x; i < nb1; i += kExtractThreads) cnt[i] = 0;
+        total = 0;
+    }
+    __device__ __forceinline__ void operator()(int sw, uint64_t, const Key<1> &key, bool valid) {
+        if (!valid) return;
+        const uint32_t d = (uint32_t)(key.w[0] >> shift1);
+        if (sw == 0) {
+            atomicAdd(&cnt[d], 1u);
+        } else {
+            const uint32_t pos = start[d] + atomicAdd(&cnt[d], 1u);
+            staging[pos] = key.w[0];
+        }
+    }
+    __device__ __forceinline__ void sweep_end(int sw) {
+        if (sw == 0) {
+            total = block_scan_bins<kExtractThreads>(cnt, start, nb1, s_warp);
+            for (int b = threadIdx.x; b < nb1; b += kExtractThreads) {
+                const uint32_t c = cnt[b];
+                if (c) gbase[b] = atomicAdd(&g_cursor1[b], c) - start[b];   // dst = gbase[d] + staging index
+                cnt[b] = 0;
+            }
+            __syncthreads();
+        } else {
+            for (uint32_t i = threadIdx.x; i < total; i += kExtractThreads) {
+                const uint64_t k = staging[i];
+                out[gbase[k >> shift1] + i] = k;
+            }
+            for (int b = threadIdx.x; b < nb1; b += kExtractThreads) cnt[b] = 0;
+            __syncthreads();
+        }
+    }
+};
+
+// -------------------------------------------------------------- tile map (H2 / PB)
+__device__ __forceinline__ bool map_tile(const uint32_t *__restrict__ tile_prefix, const uint32_t *__restrict__ base1,
+                                         int nb1, uint32_t tile, uint32_t *s_map, uint32_t &bucket, uint32_t &begin,
+                                         uint32_t &end) {
+    if (threadIdx.x == 0) {
+        uint32_t b = 0xffffffffu, lo_i = 0, hi_i = 0;
+        if (tile < tile_prefix[nb1]) {
+            int lo = 0, hi = nb1 - 1;                 // last b with tile_prefix[b] <= tile
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+            }
+            b = lo;
+            const uint32_t t = tile - tile_prefix[b];
+            lo_i = base1[b] + t * kPbTile;
+            hi_i = base1[b + 1];
+            if (hi_i - lo_i > (uint32_t)kPbTile) hi_i = lo_i + kPbTile;
+        }
+        s_map[0] = b; s_map[1] = lo_i; s_map[2] = hi_i;
+    }
+    __syncthreads();
+    bucket = s_map[0]; begin = s_map[1]; end = s_map[2];
+    return bucket != 0xffffffffu;
+}
+
+// ------------------------------------------------------------------- H2: hist2
+__global__ void __launch_bounds__(kPbThreads) hist2_kernel(const uint64_t *__restrict__ keys,
+                                                           const uint32_t *__restrict__ tile_prefix,
+                                                           const uint32_t *__restrict__ base1, int nb1, int shift2,
+                                                           int nb2, uint32_t *__restrict__ g_hist2) {
+    __shared__ uint32_t sh[kMaxBins];
+    __shared__ uint32_t s_map[4];
+    uint32_t bucket, begin, end;
+    for (int i = threadIdx.x; i < nb2; i += kPbThreads) sh[i] = 0;
+    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, s_map, bucket, begin, end)) return;
+    const uint32_t m2 = (uint32_t)nb2 - 1;
+#pragma unroll 4
+    for (int i = 0; i < kPbItems; i++) {
+        const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
+        if (idx < end) atomicAdd(&sh[(uint32_t)(keys[idx] >> shift2) & m2], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb2; i += kPbThreads) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&g_hist2[(size_t)bucket * nb2 + i], c);
+    }
+}
+
+// one block: exclusive scan over all sub-buckets -> base2 (n+1) and the mutable cursors
+__global__ void __launch_bounds__(1024) scan2_kernel(const uint32_t *__restrict__ hist2, uint32_t n,
+                                                     uint32_t *__restrict__ base2, uint32_t *__restrict__ cursor2) {
+    __shared__ uint32_t s_w[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b0 = tid * per, b1 = b0 + per < n ? b0 + per : n;
+    uint32_t sum = 0;
+    for (uint32_t i = b0; i < b1; i++) sum += hist2[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t w = 0; w < warp; w++) off += s_w[w];
+    uint32_t run = off + incl - sum;
+    for (uint32_t i = b0; i < b1; i++) {
+        base2[i] = run;
+        cursor2[i] = run;
+        run += hist2[i];
+    }
+    if (tid == 1023) base2[n] = off + incl;
+}
+
+// ---------------------------------------------------------------- PB: scatter2
+__global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__restrict__ keys,
+                                                              uint64_t *__restrict__ out,
+                                                              const uint32_t *__restrict__ tile_prefix,
+                                                              const uint32_t *__restrict__ base1, int nb1, int shift2,
+                                                              int nb2, uint32_t *__restrict__ g_cursor2) {
+    __shared__ uint32_t cnt[kMaxBins], start[kMaxBins], gbase[kMaxBins];
+    __shared__ uint32_t s_warp[kPbThreads / 32], s_map[4];
+    __shared__ uint64_t staging[kPbTile];
+    uint32_t bucket, begin, end;
+    for (int i = threadIdx.x; i < nb2; i += kPbThreads) cnt[i] = 0;
+    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, s_map, bucket, begin, end)) return;
+    const uint32_t m2 = (uint32_t)nb2 - 1;
+    uint64_t key[kPbItems];
+    uint16_t rank[kPbItems];
+#pragma unroll
+    for (int i = 0; i < kPbItems; i++) {
+        const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
+        key[i] = idx < end ? keys[idx] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < kPbItems; i++) {
+        const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
+        if (idx < end) rank[i] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key[i] >> shift2) & m2], 1u);
+    }
+    __syncthreads();
+    const uint32_t total = block_scan_bins<kPbThreads>(cnt, start, nb2, s_warp);
+    for (int b = threadIdx.x; b < nb2; b += kPbThreads) {
+        const uint32_t c = cnt[b];
+        if (c) gbase[b] = atomicAdd(&g_cursor2[(size_t)bucket * nb2 + b], c) - start[b];
+    }
+#pragma unroll
+    for (int i = 0; i < kPbItems; i++) {
+        const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
+        if (idx < end) staging[start[(uint32_t)(key[i] >> shift2) & m2] + rank[i]] = key[i];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += kPbThreads) {
+        const uint64_t k = staging[i];
+        out[gbase[(uint32_t)(k >> shift2) & m2] + i] = k;
+    }
+}
+
+// ------------------------------------------------------------------ PC: finish
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 31; x *= 0x7fb5d329728ea185ull;
+    x ^= x >> 27; x *= 0x81dadef4bc2dd44dull;
+    x ^= x >> 33;
+    return (uint32_t)x;
+}
+
+struct FinishParams {
+    const uint64_t *keys;          // grouped by sub-bucket
+    const uint32_t *base2;         // [n_sub + 1]
+    uint32_t n_sub;
+    int prefix_bits;               // b1 + b2
+    uint64_t *out_keys;
+    uint32_t *out_counts;
+    uint64_t *status;              // [n_sub], zeroed
+    unsigned long long *d_num_out; // total records
+    unsigned long long *d_overflow;
+    const unsigned long long *d_n_invalid;
+    int add_phantom;               // KC_COMPAT_REF: key 0 exists whenever a slot was empty
+};
+
+// warp-parallel decoupled look-back, called by warp 0 of the CTA. Sub-buckets are
+// assigned round-robin to a grid that is fully resident, so every predecessor is
+// either finished or being processed right now.
+__device__ __forceinline__ uint64_t lookback_warp(uint64_t *status, uint32_t j, uint64_t aggregate) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (j == 0) {
+        if (lane == 0) st_release_u64(&status[0], kLbInclusive | aggregate);
+        return 0;
+    }
+    if (lane == 0) st_release_u64(&status[j], kLbAggregate | aggregate);
+    uint64_t excl = 0;
+    int64_t pos = (int64_t)j - 1;
+    while (true) {
+        const int64_t idx = pos - lane;
+        const uint64_t s = idx >= 0 ? ld_acquire_u64(&status[idx]) : kLbInclusive;
+        const uint64_t st = s & ~kLbValueMask;
+        const uint32_t m_incl = __ballot_sync(0xffffffffu, st == kLbInclusive);
+        const uint32_t m_empty = __ballot_sync(0xffffffffu, st == kLbEmpty);
+        uint32_t take;                        // lanes whose value is consumed this round
+        bool done = false;
+        if (m_incl) {
+            const uint32_t first = __ffs(m_incl) - 1;
+            take = first == 31 ? 0xffffffffu : ((2u << first) - 1);
+            if (m_empty & take) { __nanosleep(40); continue; }
+            done = true;
+        } else {
+            if (m_empty) { __nanosleep(40); continue; }
+            take = 0xffffffffu;
+        }
+        uint64_t v = ((take >> lane) & 1u) ? (s & kLbValueMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (done) break;
+        pos -= 32;
+    }
+    if (lane == 0) st_release_u64(&status[j], kLbInclusive | (excl + aggregate));
+    return excl;
+}
+
+constexpr uint32_t kPcSmemBytes = kHcap * 12 + kLcap * 12;
+
+__global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
+    extern __shared__ __align__(16) uint8_t pc_smem[];
+    uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]
+    uint64_t *lk = tk + kHcap;                                       // list keys    [kLcap]
+    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);         // table counts [kHcap]
+    uint32_t *lc = tc + kHcap;                                       // list counts  [kLcap]
+    __shared__ uint32_t s_m, s_ones, s_over;
+    __shared__ uint64_t s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (uint32_t j = blockIdx.x; j < p.n_sub; j += gridDim.x) {
+        const uint32_t begin = p.base2[j], end = p.base2[j + 1];
+        const bool phantom = (j == 0) && p.add_phantom && (*p.d_n_invalid != 0);
+        const bool last = j + 1 == p.n_sub;
+        if (begin == end && !phantom) {           // empty sub-bucket: only keeps the chain alive
+            if (warp == 0) {
+                const uint64_t e = lookback_warp(p.status, j, 0);
+                if (last && lane == 0) *p.d_num_out = e;
+            }
+            continue;
+        }
+
+        // Hash-count the keys of round r (of 2^round_bits) and compact the distinct ones into
+        // lk/lc. Returns false if they do not fit. All threads call it.
+        auto build = [&](uint32_t r, uint32_t round_bits, uint32_t &m, uint32_t &ones) -> bool {
+            for (uint32_t i = tid; i < kHcap; i += kPcThreads) { tk[i] = kEmptyKey; tc[i] = 0; }
+            if (tid == 0) { s_m = 0; s_ones = 0; s_over = 0; }
+            __syncthreads();
+            const int rshift = 64 - p.prefix_bits - (int)round_bits;
+            const uint32_t rmask = (1u << round_bits) - 1;
+            for (uint32_t i = begin + tid; i < end; i += kPcThreads) {
+                const uint64_t k = p.keys[i];
+                if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
+                if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
+                uint32_t h = mix32(k) & (kHcap - 1);
+                uint32_t probes = 0;
+                while (true) {
+                    unsigned long long cur = tk[h];
+                    if (cur == kEmptyKey) cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
+                    if (cur == kEmptyKey || cur == k) { atomicAdd(&tc[h], 1u); break; }
+                    h = (h + 1) & (kHcap - 1);
+                    if (++probes >= kHcap) { s_over = 1; break; }
+                }
+            }
+            if (phantom && r == 0 && tid == 0) {           // key 0 joins with count += 0
+                uint32_t h = mix32(0ull) & (kHcap - 1);
+                for (uint32_t probes = 0; probes < kHcap; probes++) {
+                    const unsigned long long cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, 0ull);
+                    if (cur == kEmptyKey || cur == 0ull) break;
+                    h = (h + 1) & (kHcap - 1);
+                }
+            }
+            __syncthreads();
+            for (uint32_t i0 = 0; i0 < kHcap; i0 += kPcThreads) {
+                const uint32_t i = i0 + tid;
+                const uint64_t k = tk[i];
+                const bool live = k != kEmptyKey;
+                const uint32_t bal = __ballot_sync(0xffffffffu, live);
+                if (bal) {
+                    uint32_t b = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if ((int)lane == leader) b = atomicAdd(&s_m, (uint32_t)__popc(bal));
+                    b = __shfl_sync(0xffffffffu, b, leader);
+                    const uint32_t o = b + __popc(bal & lanemask_lt());
+                    if (live && o < kLcap) { lk[o] = k; lc[o] = tc[i]; }
+                }
+            }
+            __syncthreads();
+            m = s_m;
+            ones = s_ones;
+            const bool ok = !s_over && m <= (uint32_t)kLcap;
+            __syncthreads();
+            return ok;
+        };
+        // bitonic network over the next power of two (pads = all ones), then write at ob
+        auto sort_and_write = [&](uint32_t m, uint32_t ones, uint64_t ob) {
+            uint32_t p2 = 1;
+            while (p2 < m) p2 <<= 1;
+            for (uint32_t i = m + tid; i < p2; i += kPcThreads) { lk[i] = kEmptyKey; lc[i] = 0; }
+            __syncthreads();
+            for (uint32_t size = 2; size <= p2; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t t = tid; t < (p2 >> 1); t += kPcThreads) {
+                        const uint32_t lo = 2 * t - (t & (stride - 1));
+                        const uint32_t hi = lo + stride;
+                        const bool up = (lo & size) == 0;
+                        const uint64_t a = lk[lo], b = lk[hi];
+                        if ((a > b) == up) {
+                            lk[lo] = b; lk[hi] = a;
+                            const uint32_t ca = lc[lo]; lc[lo] = lc[hi]; lc[hi] = ca;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (uint32_t i = tid; i < m; i += kPcThreads) {
+                p.out_keys[ob + i] = lk[i];
+                p.out_counts[ob + i] = lc[i];
+            }
+            if (ones && tid == 0) {                        // the all-ones key is the largest key there is
+                p.out_keys[ob + m] = kEmptyKey;
+                p.out_counts[ob + m] = ones;
+            }
+            __syncthreads();
+        };
+        auto publish = [&](uint32_t total) -> uint64_t {
+            if (warp == 0) {
+                const uint64_t e = lookback_warp(p.status, j, total);
+                if (lane == 0) {
+                    s_base = e;
+                    if (last) *p.d_num_out = e + total;
+                }
+            }
+            __syncthreads();
+            return s_base;
+        };
+
+        uint32_t round_bits = 0;
+        while (true) {
+            uint32_t m = 0, ones = 0;
+            if (round_bits == 0) {
+                if (build(0, 0, m, ones)) {                // the common case: one table, built once
+                    const uint64_t ob = publish(m + (ones ? 1 : 0));
+                    sort_and_write(m, ones, ob);
+                    break;
+                }
+            } else {
+                // A sub-bucket with more distinct keys than one table holds is counted in
+                // 2^round_bits passes over its keys (pass r takes the keys whose next bits are r):
+                // first to learn the total, then again to write.
+                const uint32_t n_rounds = 1u << round_bits;
+                uint32_t total = 0;
+                bool ok = true;
+                for (uint32_t r = 0; r < n_rounds && ok; r++) {
+                    ok = build(r, round_bits, m, ones);
+                    total += m + (ones ? 1 : 0);
+                }
+                if (ok) {
+                    const uint64_t ob = publish(total);
+                    uint32_t running = 0;
+                    for (uint32_t r = 0; r < n_rounds; r++) {
+                        build(r, round_bits, m, ones);
+                        sort_and_write(m, ones, ob + running);
+                        running += m + (ones ? 1 : 0);
+                    }
+                    break;
+                }
+            }
+            round_bits += 4;
+            if (p.prefix_bits + (int)round_bits > 60 || round_bits > 16) {   // give up: caller re-counts by sorting
+                if (tid == 0) atomicExch(p.d_overflow, 1ull);
+                publish(0);
+                break;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------ host
+struct PartitionPlan {
+    int b1, b2;
+    uint32_t nb1, nb2, n_sub;
+};
+
+static PartitionPlan make_plan(uint64_t n_slots, int sig_bits, int target) {
+    int B = 2;
+    while (B < 20 && (n_slots >> B) > (uint64_t)target) B++;
+    if (B > sig_bits) B = sig_bits;        // never partition on bits that are always zero (masked tail)
+    if (B < 2) B = 2;
+    PartitionPlan pl;
+    pl.b1 = (B + 1) / 2;
+    pl.b2 = B - pl.b1;
+    pl.nb1 = 1u << pl.b1;
+    pl.nb2 = 1u << pl.b2;
+    pl.n_sub = pl.nb1 * pl.nb2;
+    return pl;
+}
+
+bool partition_two_levels(uint64_t n_slots, int sig_bits, int target_sub) {
+    return make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : 1536).b2 > 0;
+}
+
+uint64_t partition_workspace_bytes(uint64_t n_slots) {
+    (void)n_slots;
+    const uint64_t nsub = 1u << 20;
+    // hist1, base1, cursor1, tile_prefix | hist2, base2, cursor2 | status | flags
+    return 4 * (kMaxBins + 8) * 4 + 3 * (nsub + 8) * 4 + nsub * 8 + 256;
+}
+
+// Counts the k-mers of `ep` (W == 1) into sorted unique (out_keys, out_counts).
+// keys_a / keys_b: scratch of n_slots keys each. *d_num_out = records; *d_overflow != 0
+// means a sub-bucket could not be counted (caller falls back to sort + run-length).
+cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int sig_bits, bool add_phantom,
+                            uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
+                            unsigned long long *d_num_out, unsigned long long *d_overflow,
+                            unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,
+                            cudaStream_t s, int *n_launches, cudaEvent_t *evs /* 5: after P0, PA, H2, PB, PC */) {
+    const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : 1536);
+    uint8_t *w = static_cast<uint8_t *>(ws);
+    uint32_t *hist1 = reinterpret_cast<uint32_t *>(w);
+    uint32_t *base1 = hist1 + kMaxBins + 8;
+    uint32_t *cursor1 = base1 + kMaxBins + 8;
+    uint32_t *tile_prefix = cursor1 + kMaxBins + 8;
+    uint32_t *hist2 = tile_prefix + kMaxBins + 8;
+    uint32_t *base2 = hist2 + pl.n_sub + 8;
+    uint32_t *cursor2 = base2 + pl.n_sub + 8;
+    uint64_t *status = reinterpret_cast<uint64_t *>(cursor2 + pl.n_sub + 8);
+    cudaError_t e;
+    const size_t zero_bytes = reinterpret_cast<uint8_t *>(status + pl.n_sub) - w;
+    if ((e = cudaMemsetAsync(ws, 0, zero_bytes, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(d_num_out, 0, 8, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(d_overflow, 0, 8, s)) != cudaSuccess) return e;
+
+    const int shift1 = 64 - pl.b1, shift2 = 64 - pl.b1 - pl.b2;
+    // P0: level-1 histogram (invalid-slot count goes to a scratch counter: PA counts it for real)
+    {
+        ExtractParams ep = ep_in;
+        ep.n_invalid = d_scratch_invalid;
+        auto kern = extract_kernel<1, Hist1Sink>;
+        const uint32_t smem = ep.smem_total + kMaxBins * 4;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kExtractThreads, smem);
+        per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+        uint32_t grid = (uint32_t)n_sms * per_sm;
+        if (grid > ep.n_tiles) grid = ep.n_tiles;
+        Hist1Sink sink{{}, hist1, shift1, (int)pl.nb1, nullptr};
+        kern<<<grid, kExtractThreads, smem, s>>>(ep, sink);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    scan1_kernel<<<1, 1024, 0, s>>>(hist1, (int)pl.nb1, base1, cursor1, tile_prefix);
+    if (evs) cudaEventRecord(evs[0], s);
+    // PA: keys grouped by level-1 digit
+    {
+        auto kern = extract_kernel<1, Scatter1Sink>;
+        const uint32_t max_tile_keys = ep_in.tile_reads * ep_in.nk;
+        const uint32_t smem = ep_in.smem_total + Scatter1Sink::smem_bytes(max_tile_keys);
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kExtractThreads, smem);
+        per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+        uint32_t grid = (uint32_t)n_sms * per_sm;
+        if (grid > ep_in.n_tiles) grid = ep_in.n_tiles;
+        Scatter1Sink sink{};
+        sink.g_cursor1 = cursor1; sink.out = keys_a; sink.shift1 = shift1; sink.nb1 = (int)pl.nb1;
+        kern<<<grid, kExtractThreads, smem, s>>>(ep_in, sink);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (evs) cudaEventRecord(evs[1], s);
+    // H2 + PB over the level-1 buckets
+    const uint32_t max_tiles = (uint32_t)(n_slots / kPbTile) + pl.nb1 + 1;
+    if (pl.b2 > 0) {
+        hist2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, tile_prefix, base1, (int)pl.nb1, shift2, (int)pl.nb2, hist2);
+        scan2_kernel<<<1, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
+        if (evs) cudaEventRecord(evs[2], s);
+        scatter2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,
+                                                         (int)pl.nb2, cursor2);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    } else {
+        if ((e = cudaMemcpyAsync(base2, base1, (pl.nb1 + 1) * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+        if (evs) cudaEventRecord(evs[2], s);
+    }
+    const uint64_t *grouped = pl.b2 > 0 ? keys_b : keys_a;
+    if (evs) cudaEventRecord(evs[3], s);
+    // PC: count + sort + ordered write
+    {
+        if (out_keys == grouped) return cudaErrorInvalidValue;
+        FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, status, d_num_out, d_overflow,
+                        ep_in.n_invalid, add_phantom ? 1 : 0};
+        if ((e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPcSmemBytes)) != cudaSuccess) return e;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_kernel, kPcThreads, kPcSmemBytes);
+        if (per_sm < 1) per_sm = 1;
+        uint32_t grid = (uint32_t)n_sms * per_sm;           // every CTA resident: the look-back relies on it
+        if (grid > pl.n_sub) grid = pl.n_sub;
+        finish_kernel<<<grid, kPcThreads, kPcSmemBytes, s>>>(fp);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (evs) cudaEventRecord(evs[4], s);
+    if (n_launches) *n_launches += pl.b2 > 0 ? 7 : 4;
+    return cudaSuccess;
+}
+
+}  // namespace kc

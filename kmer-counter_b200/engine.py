@@ -7,6 +7,13 @@ from . import _lib
 from ._lib import KcConfig, KcStats, METHODS, METHOD_NAMES, KC_COMPAT_REF, KC_COMPAT_STRICT
 
 
+STAGE_NAMES = {
+    "sort": ["extract", "digit_histogram", "radix_scatter_passes", "run_length", "emit"],
+    "hash": ["level1_histogram", "extract_scatter1", "level2_histogram", "scatter2", "smem_count_sort_write", "emit"],
+    "hash_global": ["table_clear", "extract_insert", "compact_sort", "emit"],
+}
+
+
 class KcError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("kc error %d: %s" % (code, msg))
@@ -130,6 +137,12 @@ class Counter:
         self._check(self._lib.kc_stats_get(self._ctx, C.byref(st)))
         d = {name: getattr(st, name) for name, _ in KcStats._fields_}
         d["method_used"] = METHOD_NAMES.get(d["method_used"], "none")
+        n = d["n_stages"]
+        names = STAGE_NAMES.get(d["method_used"], [])
+        d["ms_stage"] = [float(x) for x in st.ms_stage][:n]
+        d["stage_bytes"] = [int(x) for x in st.stage_bytes][:n]
+        d["stage_launches"] = [int(x) for x in st.stage_launches][:n]
+        d["stage_names"] = (names + ["stage%d" % i for i in range(len(names), n)])[:n]
         return d
 
     def host_alloc(self, nbytes) -> np.ndarray:

@@ -506,19 +506,21 @@ static inline unsigned genome_code(uint64_t seed, uint64_t g) {
     return (unsigned)(w >> (2 * (g & 31))) & 3u;
 }
 
-static uint64_t zipf_rank(double u, uint64_t M, double s) {
-    double r;
-    if (fabs(s - 1.0) < 1e-9) r = pow((double)M, u);
-    else r = pow(u * (pow((double)M, 1.0 - s) - 1.0) + 1.0, 1.0 / (1.0 - s));
-    uint64_t k = (uint64_t)r;
-    if (k < 1) k = 1;
-    if (k > M) k = M;
-    return k - 1;
+/* Zipf-like rank in [0, M) using integers only (so a device twin can be bit-identical):
+ * pick an octave uniformly, then a rank uniformly inside it => P(rank) ~ 1/rank (s = 1). */
+static uint64_t zipf_rank(uint64_t h, uint64_t M) {
+    uint32_t levels = 0;
+    while ((1ull << levels) < M + 1 && levels < 63) levels++;       /* octaves covering [0, M) */
+    if (levels == 0) return 0;
+    uint32_t j = (uint32_t)((h >> 40) % levels);
+    uint64_t r = ((1ull << j) - 1) + ((h & 0xFFFFFFFFFFull) & ((1ull << j) - 1));
+    return r < M ? r : r % M;
 }
 
 void kco_gen_reads_zipf(char *out, uint64_t first_read, uint64_t n_reads, uint32_t L,
                         uint64_t genome_len, double sub_rate, double n_rate, uint64_t seed,
                         uint64_t zipf_loci, double zipf_s) {
+    (void)zipf_s;   /* the octave sampler realises s = 1; kept in the signature for config files */
     static const char letters[4] = { 'A', 'C', 'G', 'T' };
     const double inv53 = 1.0 / 9007199254740992.0;
     int noisy = (sub_rate > 0.0) || (n_rate > 0.0);
@@ -531,9 +533,8 @@ void kco_gen_reads_zipf(char *out, uint64_t first_read, uint64_t n_reads, uint32
             start = kco_splitmix64(seed ^ SEED_START ^ (i * 0x9E3779B97F4A7C15ull)) % span;
             if (zipf_loci) {
                 uint64_t h = kco_splitmix64(seed ^ SEED_PICK ^ i);
-                if (h & 1) {
-                    double u = (double)(h >> 11) * inv53;
-                    uint64_t rank = zipf_rank(u, zipf_loci, zipf_s);
+                if (h >> 63) {
+                    uint64_t rank = zipf_rank(h, zipf_loci);
                     start = kco_splitmix64(seed ^ SEED_LOCUS ^ rank) % span;
                 }
             }

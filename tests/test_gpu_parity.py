@@ -52,14 +52,39 @@ def test_chunk_matches_oracle_sort(kc, R, L, k, G, e, n):
     assert got == want
 
 
+@pytest.mark.parametrize("method", ["hash", "hash_global"])
 @pytest.mark.parametrize("R,L,k,G,e,n", [c for c in CASES if c[2] <= 32])
-def test_chunk_matches_oracle_hash(kc, R, L, k, G, e, n):
+def test_chunk_matches_oracle_hash(kc, R, L, k, G, e, n, method):
     reads = oracle.gen_reads(R, L, G, e, n, seed=R + k)
     want = oracle.process_chunk(reads, L, k)
-    with _counter(kc, k, L, method="hash") as c:
+    with _counter(kc, k, L, method=method) as c:
+        got = c.process_chunk(reads)
+        assert c.stats()["method_used"] == method
+    assert got == want
+
+
+@pytest.mark.parametrize("target", [16, 64, 300, 4000])
+def test_partitioned_hash_bucket_sizes_and_rounds(kc, target):
+    """table_slots doubles as the keys-per-sub-bucket target of the partitioned hash: small
+    targets give many tiny sub-buckets, large ones overflow one shared-memory table and go
+    through the multi-round path.  The artefact must not depend on it."""
+    R, L, k = 6000, 100, 31
+    reads = oracle.gen_reads(R, L, 0, 0.0, 0.001, seed=77)          # iid reads: almost every k-mer distinct
+    want = oracle.process_chunk(reads, L, k)
+    with _counter(kc, k, L, method="hash", table_slots=target) as c:
         got = c.process_chunk(reads)
         assert c.stats()["method_used"] == "hash"
     assert got == want
+
+
+def test_partitioned_hash_heavy_hitters(kc):
+    """A few keys with huge counts (skew): they stream through one table without overflowing it."""
+    L, k = 100, 31
+    hot = oracle.gen_reads(3, L, 0, 0, 0, seed=5)
+    reads = np.concatenate([np.tile(hot, 4000), oracle.gen_reads(2000, L, 50000, 0.01, 0.001, seed=6)])
+    want = oracle.process_chunk(reads, L, k)
+    with _counter(kc, k, L, method="hash", cap=1 << 26) as c:
+        assert c.process_chunk(reads) == want
 
 
 def test_empty_and_ragged_inputs(kc):
@@ -79,7 +104,7 @@ def test_all_invalid_reads_give_only_the_phantom(kc):
     reads = np.frombuffer(b"N" * (L * 40), dtype=np.uint8)
     want = oracle.process_chunk(reads, L, k)
     assert want == bytes(12)                                      # key 0, count 0
-    for method in ("sort", "hash"):
+    for method in ("sort", "hash", "hash_global"):
         with _counter(kc, k, L, method=method) as c:
             assert c.process_chunk(reads) == want
 
@@ -88,7 +113,7 @@ def test_poly_a_and_poly_t(kc):
     L, k = 64 + 5, 31
     reads = np.frombuffer((b"A" * L) * 30 + (b"T" * L) * 20 + (b"A" * 40 + b"N" + b"A" * (L - 41)) * 3, dtype=np.uint8)
     want = oracle.process_chunk(reads, L, k)
-    for method in ("sort", "hash"):
+    for method in ("sort", "hash", "hash_global"):
         with _counter(kc, k, L, method=method) as c:
             assert c.process_chunk(reads) == want
 
@@ -105,8 +130,9 @@ def test_strict_mode_matches_naive_model(kc):
     for (R, L, k) in [(800, 100, 31), (500, 80, 63), (500, 60, 28)]:
         reads = oracle.gen_reads(R, L, 9000, 0.005, 0.003, seed=k)
         want = oracle.naive_count(reads, L, k, strict=True)
-        with _counter(kc, k, L, compat="strict") as c:
-            assert c.process_chunk(reads) == want
+        for method in (("sort", "hash", "hash_global") if k <= 32 else ("sort",)):
+            with _counter(kc, k, L, compat="strict", method=method) as c:
+                assert c.process_chunk(reads) == want, (k, method)
 
 
 def test_chunking_invariance_and_merge(kc):
@@ -165,10 +191,10 @@ def test_config1_full_size(kc):
     R, L, k = 100_000, 100, 31
     reads = oracle.gen_reads(R, L, 1_000_000, 0.0, 1e-3, seed=1)
     want = oracle.count(reads, L, k, chunk_reads=89364, threads=4)
-    for method in ("sort", "hash"):
+    for method in ("sort", "hash", "hash_global"):
         with _counter(kc, k, L, method=method) as c:
             got = c.process_chunk(reads)
-        assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+        assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest(), method
 
 
 def test_device_resident_input(kc):

@@ -12,21 +12,22 @@ ap.add_argument("--genome", type=int, default=100_000_000)
 ap.add_argument("--method", default="sort")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--check", type=int, default=0)
+ap.add_argument("--target", type=int, default=0)
 a = ap.parse_args()
 t = time.time()
 reads = oracle.gen_reads(a.reads, a.L, a.genome, 1e-3, 0.0, seed=2)
 print("gen %.1fs" % (time.time() - t), flush=True)
 d = torch.from_numpy(reads).cuda()
-with kc.Counter(a.k, a.L, method=a.method) as c:
+with kc.Counter(a.k, a.L, method=a.method, table_slots=a.target) as c:
     for it in range(a.iters):
         torch.cuda.synchronize(); t = time.time()
         run = c.count_device(d.data_ptr(), d.numel())
         torch.cuda.synchronize(); dt = time.time() - t
         st = c.stats()
         n = a.reads * (a.L - a.k + 1)
-        print("iter %d wall %.2f ms  total %.2f extract %.2f count %.2f emit %.2f dominant %.2f (%d launches) U=%d  -> %.1f Gkmer/s  dominant %.0f GB/s"
-              % (it, dt * 1e3, st["ms_total"], st["ms_extract"], st["ms_count"], st["ms_emit"], st["ms_dominant"],
-                 st["dominant_launches"], len(run), n / dt / 1e9, st["dominant_bytes"] / st["ms_dominant"] / 1e6), flush=True)
+        print("iter %d wall %.2f ms total %.2f U=%d -> %.1f Gkmer/s | " % (it, dt * 1e3, st["ms_total"], len(run), n / dt / 1e9)
+              + "  ".join("%s %.2fms %.0fGB/s" % (nm, ms, b / ms / 1e6 if ms > 0 else 0)
+                          for nm, ms, b in zip(st["stage_names"], st["ms_stage"], st["stage_bytes"])), flush=True)
         if it == 0 and a.check:
             sub = reads[: a.check * a.L]
             want = oracle.count(sub, a.L, a.k, threads=8)
