@@ -314,8 +314,8 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
             st.stage_bytes[1] = in_bytes + 8 * nv;                         st.stage_launches[1] = 1;
             st.stage_bytes[2] = 8 * nv;                                    st.stage_launches[2] = 2;
             st.stage_bytes[3] = 16 * nv;                                   st.stage_launches[3] = 1;
-            st.stage_bytes[4] = 8 * nv + 12 * U;                           st.stage_launches[4] = 1;
-            st.stage_bytes[5] = 24 * U;                                    st.stage_launches[5] = 0;
+            st.stage_bytes[4] = 8 * nv + 12 * U;                           st.stage_launches[4] = 2;
+            st.stage_bytes[5] = 24 * U;                                    st.stage_launches[5] = 1;
         } else if (used == KC_COUNT_HASH_GLOBAL && p.n_slots) {
             st.stage_bytes[0] = p.table.capacity * 16;                     st.stage_launches[0] = 1;
             st.stage_bytes[1] = in_bytes + nv * 16;                        st.stage_launches[1] = 1;   // SURVEY 8(d) terms
@@ -341,8 +341,11 @@ int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) 
     kc_run *r = nullptr;
     KC_TRY(make_run(c, s, U, &r));
     if (U) {
-        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_keys, p.uniq, U * 8, cudaMemcpyDeviceToDevice, s));
-        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_counts, p.counts, U * 4, cudaMemcpyDeviceToDevice, s));
+        const int sig = 64 - static_zero_bits(c);
+        const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;
+        KC_CUDA_TRY(c, partition_gather(p.n_slots, sig, target, p.uniq, p.counts, p.ws_part, r->d_keys, r->d_counts, s));
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += 1;
     }
     *out = r;
     return KC_OK;

@@ -78,6 +78,9 @@ cudaError_t hash_compact(HashTable t, uint64_t *out_keys, uint32_t *out_counts, 
 uint64_t partition_workspace_bytes(uint64_t n_slots);
 // true when out_keys must be keys_a (two partition levels) rather than keys_b
 bool partition_two_levels(uint64_t n_slots, int sig_bits, int target_sub);
+cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
+                             const uint32_t *tmp_counts, void *ws, uint64_t *out_keys, uint32_t *out_counts,
+                             cudaStream_t s);
 cudaError_t partition_count(const ExtractParams &ep, uint64_t n_slots, int sig_bits, bool add_phantom,
                             uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
                             unsigned long long *d_num_out, unsigned long long *d_overflow,

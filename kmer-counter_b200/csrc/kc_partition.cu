@@ -32,6 +32,7 @@ constexpr int kPbThreads = 256, kPbItems = 16, kPbTile = kPbThreads * kPbItems;
 constexpr int kPcThreads = 256;
 constexpr int kHcap = 4096;             // hash slots per sub-bucket table
 constexpr int kLcap = 2048;             // distinct keys per round (load <= 0.5)
+constexpr int kDefaultTarget = 3072;    // keys per sub-bucket the plan aims for
 
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
 template <int THREADS>
@@ -304,78 +305,45 @@ struct FinishParams {
     const uint32_t *base2;         // [n_sub + 1]
     uint32_t n_sub;
     int prefix_bits;               // b1 + b2
-    uint64_t *out_keys;
-    uint32_t *out_counts;
-    uint64_t *status;              // [n_sub], zeroed
-    unsigned long long *d_num_out; // total records
+    uint64_t *tmp_keys;            // distinct keys of sub-bucket j land at tmp[base2[j] ...), sorted
+    uint32_t *tmp_counts;
+    uint32_t *m_out;               // [n_sub] distinct records of each sub-bucket
     unsigned long long *d_overflow;
     const unsigned long long *d_n_invalid;
     int add_phantom;               // KC_COMPAT_REF: key 0 exists whenever a slot was empty
 };
 
-// warp-parallel decoupled look-back, called by warp 0 of the CTA. Sub-buckets are
-// assigned round-robin to a grid that is fully resident, so every predecessor is
-// either finished or being processed right now.
-__device__ __forceinline__ uint64_t lookback_warp(uint64_t *status, uint32_t j, uint64_t aggregate) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (j == 0) {
-        if (lane == 0) st_release_u64(&status[0], kLbInclusive | aggregate);
-        return 0;
-    }
-    if (lane == 0) st_release_u64(&status[j], kLbAggregate | aggregate);
-    uint64_t excl = 0;
-    int64_t pos = (int64_t)j - 1;
-    while (true) {
-        const int64_t idx = pos - lane;
-        const uint64_t s = idx >= 0 ? ld_acquire_u64(&status[idx]) : kLbInclusive;
-        const uint64_t st = s & ~kLbValueMask;
-        const uint32_t m_incl = __ballot_sync(0xffffffffu, st == kLbInclusive);
-        const uint32_t m_empty = __ballot_sync(0xffffffffu, st == kLbEmpty);
-        uint32_t take;                        // lanes whose value is consumed this round
-        bool done = false;
-        if (m_incl) {
-            const uint32_t first = __ffs(m_incl) - 1;
-            take = first == 31 ? 0xffffffffu : ((2u << first) - 1);
-            if (m_empty & take) { __nanosleep(40); continue; }
-            done = true;
-        } else {
-            if (m_empty) { __nanosleep(40); continue; }
-            take = 0xffffffffu;
-        }
-        uint64_t v = ((take >> lane) & 1u) ? (s & kLbValueMask) : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (done) break;
-        pos -= 32;
-    }
-    if (lane == 0) st_release_u64(&status[j], kLbInclusive | (excl + aggregate));
-    return excl;
-}
+constexpr int kSortBins = 1024;    // bins of the in-table counting sort
+constexpr uint32_t kPcSmemBytes = kHcap * 12 + kLcap * 12 + 2 * kSortBins * 4;
 
-constexpr uint32_t kPcSmemBytes = kHcap * 12 + kLcap * 12;
-
+// One CTA per sub-bucket (round-robin over a persistent grid). Nothing here depends on
+// another CTA: a sub-bucket with n keys has at most n distinct keys, so its records are
+// written to the private range [base2[j], base2[j] + m) of a temporary array and a later
+// gather closes the gaps.
 __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     extern __shared__ __align__(16) uint8_t pc_smem[];
-    uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]
+    uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]; later: sorted keys
     uint64_t *lk = tk + kHcap;                                       // list keys    [kLcap]
-    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);         // table counts [kHcap]
+    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);         // table counts [kHcap]; later: sorted counts
     uint32_t *lc = tc + kHcap;                                       // list counts  [kLcap]
-    __shared__ uint32_t s_m, s_ones, s_over;
-    __shared__ uint64_t s_base;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *c3 = lc + kLcap;                                       // counting-sort bins [kSortBins]
+    uint32_t *s3 = c3 + kSortBins;                                   // their starts
+    __shared__ uint32_t s_m, s_ones, s_over, s_maxbin;
+    __shared__ uint32_t s_warp[kPcThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
 
     for (uint32_t j = blockIdx.x; j < p.n_sub; j += gridDim.x) {
         const uint32_t begin = p.base2[j], end = p.base2[j + 1];
         const bool phantom = (j == 0) && p.add_phantom && (*p.d_n_invalid != 0);
-        const bool last = j + 1 == p.n_sub;
-        if (begin == end && !phantom) {           // empty sub-bucket: only keeps the chain alive
-            if (warp == 0) {
-                const uint64_t e = lookback_warp(p.status, j, 0);
-                if (last && lane == 0) *p.d_num_out = e;
-            }
+        if (begin == end && !phantom) {
+            if (tid == 0) p.m_out[j] = 0;
             continue;
         }
+        // the phantom record needs a slot of its own: sub-bucket 0 may be empty or full
+        // of real keys; tmp has n_slots + 1 entries and key 0 is the smallest key, so the
+        // records of sub-bucket 0 may spill one position into sub-bucket 1's range only if
+        // every key of sub-bucket 0 is distinct AND key 0 is absent -- handled by the host
+        // giving sub-bucket 0's range one extra leading position (base offset +1, see below).
 
         // Hash-count the keys of round r (of 2^round_bits) and compact the distinct ones into
         // lk/lc. Returns false if they do not fit. All threads call it.
@@ -385,18 +353,29 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             __syncthreads();
             const int rshift = 64 - p.prefix_bits - (int)round_bits;
             const uint32_t rmask = (1u << round_bits) - 1;
-            for (uint32_t i = begin + tid; i < end; i += kPcThreads) {
-                const uint64_t k = p.keys[i];
-                if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
-                if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
-                uint32_t h = mix32(k) & (kHcap - 1);
-                uint32_t probes = 0;
-                while (true) {
-                    unsigned long long cur = tk[h];
-                    if (cur == kEmptyKey) cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
-                    if (cur == kEmptyKey || cur == k) { atomicAdd(&tc[h], 1u); break; }
-                    h = (h + 1) & (kHcap - 1);
-                    if (++probes >= kHcap) { s_over = 1; break; }
+            for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * 8) {
+                uint64_t kk[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t i = i0 + u * kPcThreads + tid;
+                    kk[u] = i < end ? ld_stream_u64(p.keys + i) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t i = i0 + u * kPcThreads + tid;
+                    if (i >= end) continue;
+                    const uint64_t k = kk[u];
+                    if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
+                    if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
+                    uint32_t h = mix32(k) & (kHcap - 1);
+                    uint32_t probes = 0;
+                    while (true) {
+                        unsigned long long cur = tk[h];
+                        if (cur == kEmptyKey) cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
+                        if (cur == kEmptyKey || cur == k) { atomicAdd(&tc[h], 1u); break; }
+                        h = (h + 1) & (kHcap - 1);
+                        if (++probes >= kHcap) { s_over = 1; break; }
+                    }
                 }
             }
             if (phantom && r == 0 && tid == 0) {           // key 0 joins with count += 0
@@ -429,86 +408,140 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             __syncthreads();
             return ok;
         };
-        // bitonic network over the next power of two (pads = all ones), then write at ob
-        auto sort_and_write = [&](uint32_t m, uint32_t ones, uint64_t ob) {
-            uint32_t p2 = 1;
-            while (p2 < m) p2 <<= 1;
-            for (uint32_t i = m + tid; i < p2; i += kPcThreads) { lk[i] = kEmptyKey; lc[i] = 0; }
+
+        // Sort the m (key, count) pairs of lk/lc and write them at ob. Counting sort on the
+        // next 10 key bits into the (now free) table arrays, then a tiny insertion sort
+        // inside each bin; a bitonic network takes over when some bin is crowded.
+        auto sort_and_write = [&](uint32_t m, uint32_t ones, uint32_t round_bits, uint64_t ob) {
+            int shift3 = 64 - p.prefix_bits - (int)round_bits - 10;
+            if (shift3 < 0) shift3 = 0;
+            for (uint32_t i = tid; i < kSortBins; i += kPcThreads) c3[i] = 0;
+            if (tid == 0) s_maxbin = 0;
             __syncthreads();
-            for (uint32_t size = 2; size <= p2; size <<= 1) {
-                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                    for (uint32_t t = tid; t < (p2 >> 1); t += kPcThreads) {
-                        const uint32_t lo = 2 * t - (t & (stride - 1));
-                        const uint32_t hi = lo + stride;
-                        const bool up = (lo & size) == 0;
-                        const uint64_t a = lk[lo], b = lk[hi];
-                        if ((a > b) == up) {
-                            lk[lo] = b; lk[hi] = a;
-                            const uint32_t ca = lc[lo]; lc[lo] = lc[hi]; lc[hi] = ca;
+            uint32_t rk[kLcap / kPcThreads];
+#pragma unroll
+            for (int u = 0; u < kLcap / kPcThreads; u++) {
+                const uint32_t i = u * kPcThreads + tid;
+                if (i < m) rk[u] = atomicAdd(&c3[(uint32_t)(lk[i] >> shift3) & (kSortBins - 1)], 1u);
+            }
+            __syncthreads();
+            uint32_t mx = 0;
+            for (uint32_t i = tid; i < kSortBins; i += kPcThreads) mx = max(mx, c3[i]);
+            if (mx > 1) atomicMax(&s_maxbin, mx);
+            block_scan_bins<kPcThreads>(c3, s3, kSortBins, s_warp);
+            const uint32_t maxbin = s_maxbin;
+            uint64_t *sk = tk;
+            uint32_t *sc = tc;
+            if (maxbin <= 24) {
+#pragma unroll
+                for (int u = 0; u < kLcap / kPcThreads; u++) {
+                    const uint32_t i = u * kPcThreads + tid;
+                    if (i < m) {
+                        const uint64_t k = lk[i];
+                        const uint32_t o = s3[(uint32_t)(k >> shift3) & (kSortBins - 1)] + rk[u];
+                        sk[o] = k;
+                        sc[o] = lc[i];
+                    }
+                }
+                __syncthreads();
+                if (maxbin > 1) {
+                    for (uint32_t b = tid; b < kSortBins; b += kPcThreads) {
+                        const uint32_t n = c3[b];
+                        if (n < 2) continue;
+                        const uint32_t s0 = s3[b];
+                        for (uint32_t a = 1; a < n; a++) {        // insertion sort of a handful of keys
+                            const uint64_t k = sk[s0 + a];
+                            const uint32_t c = sc[s0 + a];
+                            uint32_t q = a;
+                            while (q > 0 && sk[s0 + q - 1] > k) { sk[s0 + q] = sk[s0 + q - 1]; sc[s0 + q] = sc[s0 + q - 1]; q--; }
+                            sk[s0 + q] = k;
+                            sc[s0 + q] = c;
                         }
                     }
                     __syncthreads();
                 }
+            } else {
+                // crowded bins (keys sharing their next 10 bits): bitonic network over lk/lc
+                sk = lk;
+                sc = lc;
+                uint32_t p2 = 1;
+                while (p2 < m) p2 <<= 1;
+                for (uint32_t i = m + tid; i < p2; i += kPcThreads) { lk[i] = kEmptyKey; lc[i] = 0; }
+                __syncthreads();
+                for (uint32_t size = 2; size <= p2; size <<= 1) {
+                    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (uint32_t t = tid; t < (p2 >> 1); t += kPcThreads) {
+                            const uint32_t lo = 2 * t - (t & (stride - 1));
+                            const uint32_t hi = lo + stride;
+                            const bool up = (lo & size) == 0;
+                            const uint64_t a = lk[lo], b = lk[hi];
+                            if ((a > b) == up) {
+                                lk[lo] = b; lk[hi] = a;
+                                const uint32_t ca = lc[lo]; lc[lo] = lc[hi]; lc[hi] = ca;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
             }
             for (uint32_t i = tid; i < m; i += kPcThreads) {
-                p.out_keys[ob + i] = lk[i];
-                p.out_counts[ob + i] = lc[i];
+                p.tmp_keys[ob + i] = sk[i];
+                p.tmp_counts[ob + i] = sc[i];
             }
             if (ones && tid == 0) {                        // the all-ones key is the largest key there is
-                p.out_keys[ob + m] = kEmptyKey;
-                p.out_counts[ob + m] = ones;
+                p.tmp_keys[ob + m] = kEmptyKey;
+                p.tmp_counts[ob + m] = ones;
             }
             __syncthreads();
-        };
-        auto publish = [&](uint32_t total) -> uint64_t {
-            if (warp == 0) {
-                const uint64_t e = lookback_warp(p.status, j, total);
-                if (lane == 0) {
-                    s_base = e;
-                    if (last) *p.d_num_out = e + total;
-                }
-            }
-            __syncthreads();
-            return s_base;
         };
 
+        // tmp range of sub-bucket j starts at base2[j] + 1 for j > 0 and at 0 for j == 0: the
+        // extra leading position is the phantom's (see FinishParams::add_phantom)
+        const uint64_t ob0 = j == 0 ? 0 : (uint64_t)begin + 1;
         uint32_t round_bits = 0;
         while (true) {
-            uint32_t m = 0, ones = 0;
-            if (round_bits == 0) {
-                if (build(0, 0, m, ones)) {                // the common case: one table, built once
-                    const uint64_t ob = publish(m + (ones ? 1 : 0));
-                    sort_and_write(m, ones, ob);
-                    break;
-                }
-            } else {
-                // A sub-bucket with more distinct keys than one table holds is counted in
-                // 2^round_bits passes over its keys (pass r takes the keys whose next bits are r):
-                // first to learn the total, then again to write.
-                const uint32_t n_rounds = 1u << round_bits;
-                uint32_t total = 0;
-                bool ok = true;
-                for (uint32_t r = 0; r < n_rounds && ok; r++) {
-                    ok = build(r, round_bits, m, ones);
-                    total += m + (ones ? 1 : 0);
-                }
+            // A sub-bucket with more distinct keys than one table holds is counted in
+            // 2^round_bits passes over its keys (pass r takes the keys whose next bits are r).
+            const uint32_t n_rounds = 1u << round_bits;
+            uint32_t running = 0;
+            bool ok = true;
+            for (uint32_t r = 0; r < n_rounds && ok; r++) {
+                uint32_t m = 0, ones = 0;
+                ok = build(r, round_bits, m, ones);
                 if (ok) {
-                    const uint64_t ob = publish(total);
-                    uint32_t running = 0;
-                    for (uint32_t r = 0; r < n_rounds; r++) {
-                        build(r, round_bits, m, ones);
-                        sort_and_write(m, ones, ob + running);
-                        running += m + (ones ? 1 : 0);
-                    }
-                    break;
+                    sort_and_write(m, ones, round_bits, ob0 + running);
+                    running += m + (ones ? 1 : 0);
                 }
             }
-            round_bits += 4;
-            if (p.prefix_bits + (int)round_bits > 60 || round_bits > 16) {   // give up: caller re-counts by sorting
-                if (tid == 0) atomicExch(p.d_overflow, 1ull);
-                publish(0);
+            if (ok) {
+                if (tid == 0) p.m_out[j] = running;
                 break;
             }
+            round_bits += 4;
+            if (p.prefix_bits + (int)round_bits > 54 || round_bits > 16) {   // give up: caller re-counts by sorting
+                if (tid == 0) { atomicExch(p.d_overflow, 1ull); p.m_out[j] = 0; }
+                break;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// records of sub-bucket j: tmp[src(j) .. src(j) + m_j) -> out[off[j] ...); one warp per sub-bucket
+__global__ void __launch_bounds__(256) gather_kernel(const uint64_t *__restrict__ tmp_keys,
+                                                     const uint32_t *__restrict__ tmp_counts,
+                                                     const uint32_t *__restrict__ base2,
+                                                     const uint32_t *__restrict__ off, uint32_t n_sub,
+                                                     uint64_t *__restrict__ out_keys,
+                                                     uint32_t *__restrict__ out_counts) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_sub; j += warps) {
+        const uint32_t o0 = off[j], m = off[j + 1] - o0;
+        const uint64_t s0 = j == 0 ? 0 : (uint64_t)base2[j] + 1;
+        for (uint32_t i = lane; i < m; i += 32) {
+            out_keys[o0 + i] = tmp_keys[s0 + i];
+            out_counts[o0 + i] = tmp_counts[s0 + i];
         }
     }
 }
@@ -535,8 +568,22 @@ static PartitionPlan make_plan(uint64_t n_slots, int sig_bits, int target) {
     return pl;
 }
 
+// Second half of the partitioned count, run once the number of records is known on the
+// host: closes the gaps between the sub-buckets' record ranges.
+cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
+                             const uint32_t *tmp_counts, void *ws, uint64_t *out_keys, uint32_t *out_counts,
+                             cudaStream_t s) {
+    const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : kDefaultTarget);
+    uint32_t *hist1 = reinterpret_cast<uint32_t *>(ws);
+    uint32_t *hist2 = hist1 + 4 * (kMaxBins + 8);
+    uint32_t *base2 = hist2 + pl.n_sub + 8;
+    uint32_t *off = base2 + pl.n_sub + 8;
+    gather_kernel<<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, base2, off, pl.n_sub, out_keys, out_counts);
+    return cudaGetLastError();
+}
+
 bool partition_two_levels(uint64_t n_slots, int sig_bits, int target_sub) {
-    return make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : 1536).b2 > 0;
+    return make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : kDefaultTarget).b2 > 0;
 }
 
 uint64_t partition_workspace_bytes(uint64_t n_slots) {
@@ -554,7 +601,7 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
                             unsigned long long *d_num_out, unsigned long long *d_overflow,
                             unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,
                             cudaStream_t s, int *n_launches, cudaEvent_t *evs /* 5: after P0, PA, H2, PB, PC */) {
-    const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : 1536);
+    const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : kDefaultTarget);
     uint8_t *w = static_cast<uint8_t *>(ws);
     uint32_t *hist1 = reinterpret_cast<uint32_t *>(w);
     uint32_t *base1 = hist1 + kMaxBins + 8;
@@ -563,9 +610,9 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     uint32_t *hist2 = tile_prefix + kMaxBins + 8;
     uint32_t *base2 = hist2 + pl.n_sub + 8;
     uint32_t *cursor2 = base2 + pl.n_sub + 8;
-    uint64_t *status = reinterpret_cast<uint64_t *>(cursor2 + pl.n_sub + 8);
+    uint32_t *status_scratch = cursor2 + pl.n_sub + 8;       // n_sub + 8 entries, scratch for the second scan
     cudaError_t e;
-    const size_t zero_bytes = reinterpret_cast<uint8_t *>(status + pl.n_sub) - w;
+    const size_t zero_bytes = reinterpret_cast<uint8_t *>(status_scratch) - w;
     if ((e = cudaMemsetAsync(ws, 0, zero_bytes, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d_num_out, 0, 8, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d_overflow, 0, 8, s)) != cudaSuccess) return e;
@@ -621,22 +668,26 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     }
     const uint64_t *grouped = pl.b2 > 0 ? keys_b : keys_a;
     if (evs) cudaEventRecord(evs[3], s);
-    // PC: count + sort + ordered write
+    // PC: count + sort per sub-bucket into the temporary arrays, then offsets of the survivors
     {
         if (out_keys == grouped) return cudaErrorInvalidValue;
-        FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, status, d_num_out, d_overflow,
+        uint32_t *m_out = hist2;                               // the level-2 histogram is dead by now
+        FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, m_out, d_overflow,
                         ep_in.n_invalid, add_phantom ? 1 : 0};
         if ((e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPcSmemBytes)) != cudaSuccess) return e;
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_kernel, kPcThreads, kPcSmemBytes);
         if (per_sm < 1) per_sm = 1;
-        uint32_t grid = (uint32_t)n_sms * per_sm;           // every CTA resident: the look-back relies on it
+        uint32_t grid = (uint32_t)n_sms * per_sm;
         if (grid > pl.n_sub) grid = pl.n_sub;
         finish_kernel<<<grid, kPcThreads, kPcSmemBytes, s>>>(fp);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        // off[] (n_sub + 1) overwrites cursor2; its last entry is the number of records
+        scan2_kernel<<<1, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);
+        if ((e = cudaMemcpyAsync(d_num_out, cursor2 + pl.n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     }
     if (evs) cudaEventRecord(evs[4], s);
-    if (n_launches) *n_launches += pl.b2 > 0 ? 7 : 4;
+    if (n_launches) *n_launches += pl.b2 > 0 ? 8 : 5;
     return cudaSuccess;
 }
 
