@@ -29,6 +29,7 @@ struct ExtractParams {
     uint32_t tile_reads;     // reads per tile, multiple of 16 -> tile bytes % 16 == 0
     uint32_t n_tiles;
     uint32_t nk_magic;       // floor(2^32 / nk) + 1
+    uint32_t segs_per_read, seg_len;   // rolling walk: a read's nk positions in segs_per_read runs of seg_len
     uint64_t last_mask;      // applied to key word W-1
     unsigned long long *n_invalid;  // += slots that hold no k-mer (the phantom of SURVEY F7)
     uint32_t stage_bytes, enc_off, bad_off, flag_off, bar_off, smem_total;  // shared-memory layout
@@ -56,6 +57,7 @@ constexpr int kExtractThreads = 256;
 // extra_smem starts at ExtractParams::smem_total (16-byte aligned); launch with that many more bytes.
 struct SinkBase {
     static constexpr int kSweeps = 1;
+    static constexpr bool kRolling = false;   // true: slot order is irrelevant, use the sliding-window walk
     __device__ __forceinline__ void begin(uint8_t *) {}
     __device__ __forceinline__ void sweep_begin(int, uint32_t) {}
     __device__ __forceinline__ void sweep_end(int) {}
@@ -134,23 +136,36 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         }
         const uint8_t *src_tile = stage0 + stage * stage_bytes;
 
-        // ---- phase A: one warp per read, 4 bases per lane per step ----
+        // ---- phase A: one warp per read; a lane turns 4 bases (one 32-bit shared load) into one
+        // byte of 2-bit codes with SIMD-in-register arithmetic ----
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src_tile);
         for (uint32_t r = warp; r < nreads; r += kWarps) {
-            const uint8_t *src = src_tile + r * p.L;
+            const uint32_t rbase = r * p.L;
             uint32_t any_bad = 0;
             const uint32_t span_bases = enc_row * 32;
             for (uint32_t j0 = lane * 4; j0 < span_bases; j0 += 128) {
                 uint32_t codes = 0, badn = 0;
+                if (j0 < p.L) {
+                    const uint32_t addr = rbase + j0;
+                    const uint32_t w0 = src32[addr >> 2], w1 = src32[(addr >> 2) + 1];
+                    uint32_t x = __funnelshift_r(w0, w1, (addr & 3u) * 8u);        // bytes addr .. addr+3
+                    const uint32_t left = p.L - j0;                                 // bases of this read in x
+                    if (left < 4) x = (x & (0xffffffffu >> (32 - 8 * left))) | (0x41414141u << (8 * left));  // pad with 'A'
+                    // code = ((c >> 1) ^ (c >> 2)) & 3 for A,C,G,T = 0,1,2,3 (GPUHandler.cu:42-78)
+                    uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                    // letter each byte should be, picked by (c >> 1) & 3 out of "ACTG": equal <=> valid
+                    const uint32_t i4 = (x >> 1) & 0x03030303u;
+                    const uint32_t sel = __byte_perm(i4 | (i4 >> 4), 0u, 0x4420u);   // nibble i = index of byte i
+                    const uint32_t diff = x ^ __byte_perm(0x47544341u, 0u, sel);
+                    if (diff) {                                                     // rare: some byte is not ACGT
 #pragma unroll
-                for (uint32_t b = 0; b < 4; b++) {
-                    uint32_t j = j0 + b;
-                    uint32_t code = 0, bad = 0;
-                    if (j < p.L) code = base_code(src[j], bad);
-                    codes = (codes << 2) | code;
-                    badn |= bad << b;
+                        for (uint32_t b = 0; b < 4; b++)
+                            if ((diff >> (8 * b)) & 0xffu) { badn |= 1u << b; t |= 3u << (8 * b); }   // code 3 + filter bit (:79-87)
+                    }
+                    codes = (t * 0x40100401u) >> 24;                                // b0<<6 | b1<<4 | b2<<2 | b3
                 }
                 // byte (j0/4) of the big-endian bit string -> little-endian byte inside its word
-                uint32_t q = j0 >> 2;
+                const uint32_t q = j0 >> 2;
                 enc_b[(r * enc_row + (q >> 3)) * 8 + (7 - (q & 7))] = (uint8_t)codes;
                 if (j0 < p.L) bad4[r * p.nb4 + q] = (uint8_t)badn;
                 any_bad |= badn;
@@ -160,42 +175,72 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         }
         __syncthreads();
 
-        // ---- phase B: one key per thread per step, slots are contiguous in the output ----
+        // ---- phase B ----
         const uint32_t total = nreads * p.nk;
         const uint64_t slot0 = (uint64_t)tile * p.tile_reads * p.nk;
+        // rare path: any bad base inside [pos, pos+k) kills the k-mer
+        auto kmer_valid = [&](uint32_t r, uint32_t pos) -> bool {
+            const uint8_t *bn = bad4 + r * p.nb4;
+            const uint32_t lo = pos, hi = pos + p.k;  // [lo, hi)
+            for (uint32_t q = lo >> 2; q <= (hi - 1) >> 2; q++) {
+                uint32_t m = bn[q];
+                const uint32_t b0 = q * 4;
+                if (b0 < lo) m &= 0xFu << (lo - b0);
+                if (b0 + 4 > hi) m &= 0xFu >> (b0 + 4 - hi);
+                if (m & 0xFu) return false;
+            }
+            return true;
+        };
 #pragma unroll
         for (int sw = 0; sw < Sink::kSweeps; sw++) {
             sink.sweep_begin(sw, total);
-            for (uint32_t s = tid; s < total; s += kExtractThreads) {
-                uint32_t r = p.nk == 1 ? s : __umulhi(s, p.nk_magic);
-                if (r * p.nk > s) r--;
-                const uint32_t pos = s - r * p.nk;
-                const uint64_t *e = enc + r * enc_row + (pos >> 5);
-                const uint32_t sh = (pos & 31u) * 2u;
-                Key<W> key;
-                uint64_t a = e[0];
-#pragma unroll
-                for (int q = 0; q < W; q++) {
-                    uint64_t b = e[q + 1];
-                    key.w[q] = sh ? ((a << sh) | (b >> (64 - sh))) : a;
-                    a = b;
-                }
-                key.w[W - 1] &= p.last_mask;
-                bool valid = true;
-                if (flag[r]) {
-                    // rare path: any bad base inside [pos, pos+k) kills the k-mer
-                    const uint8_t *bn = bad4 + r * p.nb4;
-                    uint32_t lo = pos, hi = pos + p.k;  // [lo, hi)
-                    for (uint32_t q = lo >> 2; q <= (hi - 1) >> 2; q++) {
-                        uint32_t m = bn[q];
-                        uint32_t b0 = q * 4;
-                        if (b0 < lo) m &= 0xFu << (lo - b0);
-                        if (b0 + 4 > hi) m &= 0xFu >> (b0 + 4 - hi);
-                        if (m & 0xFu) { valid = false; break; }
+            if constexpr (Sink::kRolling && W == 1) {
+                // Sinks that ignore the slot index: a thread walks a segment of consecutive
+                // positions of one read and slides the 32-base window by one base per key
+                // (two funnel shifts) instead of rebuilding it from the encoded words.
+                const uint32_t n_seg = nreads * p.segs_per_read;
+                for (uint32_t sg = tid; sg < n_seg; sg += kExtractThreads) {
+                    const uint32_t r = sg / p.segs_per_read;
+                    const uint32_t p0 = (sg - r * p.segs_per_read) * p.seg_len;
+                    const uint32_t p1 = min(p0 + p.seg_len, p.nk);
+                    const uint64_t *e = enc + r * enc_row + (p0 >> 5);
+                    const uint32_t sh = (p0 & 31u) * 2u;
+                    const uint64_t e0 = e[0], e1 = e[1];
+                    const uint64_t e2 = ((p0 >> 5) + 2 <= p.nw) ? e[2] : 0ull;
+                    uint64_t win = sh ? ((e0 << sh) | (e1 >> (64 - sh))) : e0;     // bases p0 .. p0+31
+                    uint64_t nxt = sh ? ((e1 << sh) | (e2 >> (64 - sh))) : e1;     // bases p0+32 .. p0+63
+                    const bool check = flag[r] != 0;
+                    for (uint32_t pos = p0; pos < p1; pos++) {
+                        Key<1> key;
+                        key.w[0] = win & p.last_mask;
+                        const bool valid = check ? kmer_valid(r, pos) : true;
+                        if (sw == 0 && !valid) invalid_local++;
+                        sink(sw, slot0 + r * p.nk + pos, key, valid);
+                        win = (win << 2) | (nxt >> 62);
+                        nxt <<= 2;
                     }
                 }
-                if (sw == 0 && !valid) invalid_local++;
-                sink(sw, slot0 + s, key, valid);
+            } else {
+                // one key per thread per step, slots are contiguous in the output
+                for (uint32_t s = tid; s < total; s += kExtractThreads) {
+                    uint32_t r = p.nk == 1 ? s : __umulhi(s, p.nk_magic);
+                    if (r * p.nk > s) r--;
+                    const uint32_t pos = s - r * p.nk;
+                    const uint64_t *e = enc + r * enc_row + (pos >> 5);
+                    const uint32_t sh = (pos & 31u) * 2u;
+                    Key<W> key;
+                    uint64_t a = e[0];
+#pragma unroll
+                    for (int q = 0; q < W; q++) {
+                        uint64_t b = e[q + 1];
+                        key.w[q] = sh ? ((a << sh) | (b >> (64 - sh))) : a;
+                        a = b;
+                    }
+                    key.w[W - 1] &= p.last_mask;
+                    const bool valid = flag[r] ? kmer_valid(r, pos) : true;
+                    if (sw == 0 && !valid) invalid_local++;
+                    sink(sw, slot0 + s, key, valid);
+                }
             }
             __syncthreads();
             sink.sweep_end(sw);

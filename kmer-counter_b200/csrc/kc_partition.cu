@@ -75,6 +75,7 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_
 
 // ------------------------------------------------------------------- P0: hist1
 struct Hist1Sink : SinkBase {
+    static constexpr bool kRolling = true;
     uint32_t *g_hist1;
     int shift1, nb1;
     uint32_t *sh;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(1024) scan1_kernel(const uint32_t *__restrict_
 // ---------------------------------------------------------------- PA: scatter1
 struct Scatter1Sink : SinkBase {
     static constexpr int kSweeps = 2;
+    static constexpr bool kRolling = true;
     uint32_t *g_cursor1;
     uint64_t *out;
     int shift1, nb1;
@@ -311,23 +313,29 @@ struct FinishParams {
     unsigned long long *d_overflow;
     const unsigned long long *d_n_invalid;
     int add_phantom;               // KC_COMPAT_REF: key 0 exists whenever a slot was empty
+    int cap_shift;                 // first table guess = pow2ceil(n >> cap_shift) slots
 };
 
-constexpr int kSortBins = 1024;    // bins of the in-table counting sort
-constexpr uint32_t kPcSmemBytes = kHcap * 12 + kLcap * 12 + 2 * kSortBins * 4;
+constexpr int kSortBins = 1024;    // most bins the in-table counting sort uses
+constexpr uint32_t kPcSmemBytes = kHcap * 12 + kLcap * 12;
+
+__device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 1u : 1u << (32 - __clz(x - 1)); }
 
 // One CTA per sub-bucket (round-robin over a persistent grid). Nothing here depends on
 // another CTA: a sub-bucket with n keys has at most n distinct keys, so its records are
-// written to the private range [base2[j], base2[j] + m) of a temporary array and a later
-// gather closes the gaps.
+// written to the private range [base2[j] + 1, ...) of a temporary array (position 0 is
+// the phantom's) and a later gather closes the gaps.
 __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     extern __shared__ __align__(16) uint8_t pc_smem[];
-    uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]; later: sorted keys
+    uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]
     uint64_t *lk = tk + kHcap;                                       // list keys    [kLcap]
-    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);         // table counts [kHcap]; later: sorted counts
+    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);         // table counts [kHcap]
     uint32_t *lc = tc + kHcap;                                       // list counts  [kLcap]
-    uint32_t *c3 = lc + kLcap;                                       // counting-sort bins [kSortBins]
-    uint32_t *s3 = c3 + kSortBins;                                   // their starts
+    // once the table has been compacted into the list its arrays are reused by the sort:
+    uint64_t *sk = tk;                                               // sorted keys   [kLcap]
+    uint32_t *sc = reinterpret_cast<uint32_t *>(tk + kLcap);         // sorted counts [kLcap]
+    uint32_t *c3 = tc;                                               // counting-sort bins [kSortBins]
+    uint32_t *s3 = tc + kSortBins;                                   // their starts
     __shared__ uint32_t s_m, s_ones, s_over, s_maxbin;
     __shared__ uint32_t s_warp[kPcThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -339,20 +347,29 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             if (tid == 0) p.m_out[j] = 0;
             continue;
         }
-        // the phantom record needs a slot of its own: sub-bucket 0 may be empty or full
-        // of real keys; tmp has n_slots + 1 entries and key 0 is the smallest key, so the
-        // records of sub-bucket 0 may spill one position into sub-bucket 1's range only if
-        // every key of sub-bucket 0 is distinct AND key 0 is absent -- handled by the host
-        // giving sub-bucket 0's range one extra leading position (base offset +1, see below).
 
-        // Hash-count the keys of round r (of 2^round_bits) and compact the distinct ones into
-        // lk/lc. Returns false if they do not fit. All threads call it.
-        auto build = [&](uint32_t r, uint32_t round_bits, uint32_t &m, uint32_t &ones) -> bool {
-            for (uint32_t i = tid; i < kHcap; i += kPcThreads) { tk[i] = kEmptyKey; tc[i] = 0; }
+        // Hash-count the keys of round r (of 2^round_bits) in a table of `cap` slots and compact
+        // the distinct ones into lk/lc. Returns false if more than cap/2 are distinct.
+        auto build = [&](uint32_t r, uint32_t round_bits, uint32_t cap, uint32_t &m, uint32_t &ones) -> bool {
+            for (uint32_t i = tid; i < cap; i += kPcThreads) { tk[i] = kEmptyKey; tc[i] = 0; }
             if (tid == 0) { s_m = 0; s_ones = 0; s_over = 0; }
             __syncthreads();
             const int rshift = 64 - p.prefix_bits - (int)round_bits;
             const uint32_t rmask = (1u << round_bits) - 1;
+            const uint32_t hshift = __clz(cap) + 1;                  // 32 - log2(cap)
+            auto insert = [&](uint64_t k, uint32_t add) {
+                uint32_t h = (((uint32_t)k ^ (uint32_t)(k >> 29)) * 0x9E3779B1u) >> hshift;
+                for (uint32_t probes = 0; probes < cap; probes++) {
+                    unsigned long long cur = tk[h];
+                    if (cur == kEmptyKey) {
+                        cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
+                        if (cur == kEmptyKey) atomicAdd(&s_m, 1u);     // claimed: one more distinct key
+                    }
+                    if (cur == kEmptyKey || cur == k) { if (add) atomicAdd(&tc[h], add); return; }
+                    h = (h + 1) & (cap - 1);
+                }
+                s_over = 1;
+            };
             for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * 8) {
                 uint64_t kk[8];
 #pragma unroll
@@ -367,27 +384,19 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                     const uint64_t k = kk[u];
                     if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
                     if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
-                    uint32_t h = mix32(k) & (kHcap - 1);
-                    uint32_t probes = 0;
-                    while (true) {
-                        unsigned long long cur = tk[h];
-                        if (cur == kEmptyKey) cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
-                        if (cur == kEmptyKey || cur == k) { atomicAdd(&tc[h], 1u); break; }
-                        h = (h + 1) & (kHcap - 1);
-                        if (++probes >= kHcap) { s_over = 1; break; }
-                    }
+                    insert(k, 1u);
                 }
             }
-            if (phantom && r == 0 && tid == 0) {           // key 0 joins with count += 0
-                uint32_t h = mix32(0ull) & (kHcap - 1);
-                for (uint32_t probes = 0; probes < kHcap; probes++) {
-                    const unsigned long long cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, 0ull);
-                    if (cur == kEmptyKey || cur == 0ull) break;
-                    h = (h + 1) & (kHcap - 1);
-                }
-            }
+            if (phantom && r == 0 && tid == 0) insert(0ull, 0u);      // key 0 joins with count += 0
             __syncthreads();
-            for (uint32_t i0 = 0; i0 < kHcap; i0 += kPcThreads) {
+            m = s_m;
+            ones = s_ones;
+            const bool ok = !s_over && 2 * m <= cap;
+            __syncthreads();
+            if (!ok) return false;
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            for (uint32_t i0 = 0; i0 < cap; i0 += kPcThreads) {
                 const uint32_t i = i0 + tid;
                 const uint64_t k = tk[i];
                 const bool live = k != kEmptyKey;
@@ -397,55 +406,56 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                     const int leader = __ffs(bal) - 1;
                     if ((int)lane == leader) b = atomicAdd(&s_m, (uint32_t)__popc(bal));
                     b = __shfl_sync(0xffffffffu, b, leader);
-                    const uint32_t o = b + __popc(bal & lanemask_lt());
-                    if (live && o < kLcap) { lk[o] = k; lc[o] = tc[i]; }
+                    if (live) {
+                        const uint32_t o = b + __popc(bal & lanemask_lt());
+                        lk[o] = k;
+                        lc[o] = tc[i];
+                    }
                 }
             }
             __syncthreads();
-            m = s_m;
-            ones = s_ones;
-            const bool ok = !s_over && m <= (uint32_t)kLcap;
-            __syncthreads();
-            return ok;
+            return true;
         };
 
-        // Sort the m (key, count) pairs of lk/lc and write them at ob. Counting sort on the
-        // next 10 key bits into the (now free) table arrays, then a tiny insertion sort
-        // inside each bin; a bitonic network takes over when some bin is crowded.
+        // Sort the m (key, count) pairs of lk/lc and write them at ob: counting sort on the
+        // next key bits into the (now free) table arrays, then a tiny insertion sort inside each
+        // bin; a bitonic network takes over when some bin is crowded.
         auto sort_and_write = [&](uint32_t m, uint32_t ones, uint32_t round_bits, uint64_t ob) {
-            int shift3 = 64 - p.prefix_bits - (int)round_bits - 10;
+            uint32_t nb3 = pow2_ceil_u32(m);
+            nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)kSortBins ? (uint32_t)kSortBins : nb3);
+            int shift3 = 64 - p.prefix_bits - (int)round_bits - (31 - __clz(nb3));
             if (shift3 < 0) shift3 = 0;
-            for (uint32_t i = tid; i < kSortBins; i += kPcThreads) c3[i] = 0;
+            for (uint32_t i = tid; i < nb3; i += kPcThreads) c3[i] = 0;
             if (tid == 0) s_maxbin = 0;
             __syncthreads();
             uint32_t rk[kLcap / kPcThreads];
 #pragma unroll
             for (int u = 0; u < kLcap / kPcThreads; u++) {
                 const uint32_t i = u * kPcThreads + tid;
-                if (i < m) rk[u] = atomicAdd(&c3[(uint32_t)(lk[i] >> shift3) & (kSortBins - 1)], 1u);
+                if (i < m) rk[u] = atomicAdd(&c3[(uint32_t)(lk[i] >> shift3) & (nb3 - 1)], 1u);
             }
             __syncthreads();
             uint32_t mx = 0;
-            for (uint32_t i = tid; i < kSortBins; i += kPcThreads) mx = max(mx, c3[i]);
+            for (uint32_t i = tid; i < nb3; i += kPcThreads) mx = max(mx, c3[i]);
             if (mx > 1) atomicMax(&s_maxbin, mx);
-            block_scan_bins<kPcThreads>(c3, s3, kSortBins, s_warp);
+            block_scan_bins<kPcThreads>(c3, s3, (int)nb3, s_warp);
             const uint32_t maxbin = s_maxbin;
-            uint64_t *sk = tk;
-            uint32_t *sc = tc;
+            const uint64_t *rk_keys = sk;
+            const uint32_t *rk_cnts = sc;
             if (maxbin <= 24) {
 #pragma unroll
                 for (int u = 0; u < kLcap / kPcThreads; u++) {
                     const uint32_t i = u * kPcThreads + tid;
                     if (i < m) {
                         const uint64_t k = lk[i];
-                        const uint32_t o = s3[(uint32_t)(k >> shift3) & (kSortBins - 1)] + rk[u];
+                        const uint32_t o = s3[(uint32_t)(k >> shift3) & (nb3 - 1)] + rk[u];
                         sk[o] = k;
                         sc[o] = lc[i];
                     }
                 }
                 __syncthreads();
                 if (maxbin > 1) {
-                    for (uint32_t b = tid; b < kSortBins; b += kPcThreads) {
+                    for (uint32_t b = tid; b < nb3; b += kPcThreads) {
                         const uint32_t n = c3[b];
                         if (n < 2) continue;
                         const uint32_t s0 = s3[b];
@@ -461,11 +471,10 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                     __syncthreads();
                 }
             } else {
-                // crowded bins (keys sharing their next 10 bits): bitonic network over lk/lc
-                sk = lk;
-                sc = lc;
-                uint32_t p2 = 1;
-                while (p2 < m) p2 <<= 1;
+                // crowded bins (keys sharing their next bits): bitonic network over lk/lc
+                rk_keys = lk;
+                rk_cnts = lc;
+                const uint32_t p2 = pow2_ceil_u32(m);
                 for (uint32_t i = m + tid; i < p2; i += kPcThreads) { lk[i] = kEmptyKey; lc[i] = 0; }
                 __syncthreads();
                 for (uint32_t size = 2; size <= p2; size <<= 1) {
@@ -485,8 +494,8 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                 }
             }
             for (uint32_t i = tid; i < m; i += kPcThreads) {
-                p.tmp_keys[ob + i] = sk[i];
-                p.tmp_counts[ob + i] = sc[i];
+                p.tmp_keys[ob + i] = rk_keys[i];
+                p.tmp_counts[ob + i] = rk_cnts[i];
             }
             if (ones && tid == 0) {                        // the all-ones key is the largest key there is
                 p.tmp_keys[ob + m] = kEmptyKey;
@@ -495,19 +504,21 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             __syncthreads();
         };
 
-        // tmp range of sub-bucket j starts at base2[j] + 1 for j > 0 and at 0 for j == 0: the
-        // extra leading position is the phantom's (see FinishParams::add_phantom)
         const uint64_t ob0 = j == 0 ? 0 : (uint64_t)begin + 1;
+        const uint32_t n = end - begin + (phantom ? 1u : 0u);
+        // first guess: about half of the keys are repeats; every failure quadruples the table,
+        // and once it is at its largest halves the keys per pass (pass r takes the keys whose
+        // next round_bits bits are r).
+        uint32_t cap = pow2_ceil_u32(n >> p.cap_shift);
+        cap = cap < 256 ? 256 : (cap > (uint32_t)kHcap ? (uint32_t)kHcap : cap);
         uint32_t round_bits = 0;
         while (true) {
-            // A sub-bucket with more distinct keys than one table holds is counted in
-            // 2^round_bits passes over its keys (pass r takes the keys whose next bits are r).
             const uint32_t n_rounds = 1u << round_bits;
             uint32_t running = 0;
             bool ok = true;
             for (uint32_t r = 0; r < n_rounds && ok; r++) {
                 uint32_t m = 0, ones = 0;
-                ok = build(r, round_bits, m, ones);
+                ok = build(r, round_bits, cap, m, ones);
                 if (ok) {
                     sort_and_write(m, ones, round_bits, ob0 + running);
                     running += m + (ones ? 1 : 0);
@@ -517,10 +528,14 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                 if (tid == 0) p.m_out[j] = running;
                 break;
             }
-            round_bits += 4;
-            if (p.prefix_bits + (int)round_bits > 54 || round_bits > 16) {   // give up: caller re-counts by sorting
-                if (tid == 0) { atomicExch(p.d_overflow, 1ull); p.m_out[j] = 0; }
-                break;
+            if (cap < (uint32_t)kHcap) {
+                cap = cap * 4 > (uint32_t)kHcap ? (uint32_t)kHcap : cap * 4;
+            } else {
+                round_bits += 1;
+                if (p.prefix_bits + (int)round_bits > 54 || round_bits > 20) {   // give up: caller re-counts by sorting
+                    if (tid == 0) { atomicExch(p.d_overflow, 1ull); p.m_out[j] = 0; }
+                    break;
+                }
             }
         }
         __syncthreads();
@@ -673,7 +688,7 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
         if (out_keys == grouped) return cudaErrorInvalidValue;
         uint32_t *m_out = hist2;                               // the level-2 histogram is dead by now
         FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, m_out, d_overflow,
-                        ep_in.n_invalid, add_phantom ? 1 : 0};
+                        ep_in.n_invalid, add_phantom ? 1 : 0, 1};
         if ((e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPcSmemBytes)) != cudaSuccess) return e;
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_kernel, kPcThreads, kPcSmemBytes);
