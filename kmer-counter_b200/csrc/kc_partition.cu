@@ -20,6 +20,8 @@
 //   PB  scatter2  keys grouped by the b1+b2 leading bits                 reads 8N, writes 8N
 //   PC  finish    per sub-bucket: shared-memory hash count, sort of the distinct keys,
 //                 ordered write via decoupled look-back                  reads 8N, writes 12U
+#include <stdlib.h>
+
 #include "kc_internal.h"
 
 namespace kc {
@@ -29,9 +31,6 @@ namespace {
 constexpr int kMaxBins = 1024;          // bins per level
 constexpr uint64_t kEmptyKey = ~0ull;   // the all-ones key (poly-T window) is the empty marker; counted aside
 constexpr int kPbThreads = 256, kPbItems = 16, kPbTile = kPbThreads * kPbItems;
-constexpr int kPcThreads = 256;
-constexpr int kHcap = 4096;             // hash slots per sub-bucket table
-constexpr int kLcap = 2048;             // distinct keys per round (load <= 0.5)
 constexpr int kDefaultTarget = 3072;    // keys per sub-bucket the plan aims for
 
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
@@ -295,12 +294,6 @@ __global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__
 }
 
 // ------------------------------------------------------------------ PC: finish
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
-    x ^= x >> 31; x *= 0x7fb5d329728ea185ull;
-    x ^= x >> 27; x *= 0x81dadef4bc2dd44dull;
-    x ^= x >> 33;
-    return (uint32_t)x;
-}
 
 struct FinishParams {
     const uint64_t *keys;          // grouped by sub-bucket
@@ -317,7 +310,6 @@ struct FinishParams {
 };
 
 constexpr int kSortBins = 1024;    // most bins the in-table counting sort uses
-constexpr uint32_t kPcSmemBytes = kHcap * 12 + kLcap * 12;
 
 __device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 1u : 1u << (32 - __clz(x - 1)); }
 
@@ -325,7 +317,9 @@ __device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 
 // another CTA: a sub-bucket with n keys has at most n distinct keys, so its records are
 // written to the private range [base2[j] + 1, ...) of a temporary array (position 0 is
 // the phantom's) and a later gather closes the gaps.
+template <int kPcThreads, int kHcap>
 __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
+    constexpr int kLcap = kHcap / 2;
     extern __shared__ __align__(16) uint8_t pc_smem[];
     uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]
     uint64_t *lk = tk + kHcap;                                       // list keys    [kLcap]
@@ -334,8 +328,9 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     // once the table has been compacted into the list its arrays are reused by the sort:
     uint64_t *sk = tk;                                               // sorted keys   [kLcap]
     uint32_t *sc = reinterpret_cast<uint32_t *>(tk + kLcap);         // sorted counts [kLcap]
-    uint32_t *c3 = tc;                                               // counting-sort bins [kSortBins]
-    uint32_t *s3 = tc + kSortBins;                                   // their starts
+    constexpr int kBins = kHcap / 2 < kSortBins ? kHcap / 2 : kSortBins;
+    uint32_t *c3 = tc;                                               // counting-sort bins [kBins]
+    uint32_t *s3 = tc + kBins;                                       // their starts
     __shared__ uint32_t s_m, s_ones, s_over, s_maxbin;
     __shared__ uint32_t s_warp[kPcThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -422,15 +417,16 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
         // bin; a bitonic network takes over when some bin is crowded.
         auto sort_and_write = [&](uint32_t m, uint32_t ones, uint32_t round_bits, uint64_t ob) {
             uint32_t nb3 = pow2_ceil_u32(m);
-            nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)kSortBins ? (uint32_t)kSortBins : nb3);
+            nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)kBins ? (uint32_t)kBins : nb3);
             int shift3 = 64 - p.prefix_bits - (int)round_bits - (31 - __clz(nb3));
             if (shift3 < 0) shift3 = 0;
             for (uint32_t i = tid; i < nb3; i += kPcThreads) c3[i] = 0;
             if (tid == 0) s_maxbin = 0;
             __syncthreads();
-            uint32_t rk[kLcap / kPcThreads];
+            constexpr int kPer = (kLcap + kPcThreads - 1) / kPcThreads;
+            uint32_t rk[kPer];
 #pragma unroll
-            for (int u = 0; u < kLcap / kPcThreads; u++) {
+            for (int u = 0; u < kPer; u++) {
                 const uint32_t i = u * kPcThreads + tid;
                 if (i < m) rk[u] = atomicAdd(&c3[(uint32_t)(lk[i] >> shift3) & (nb3 - 1)], 1u);
             }
@@ -444,7 +440,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             const uint32_t *rk_cnts = sc;
             if (maxbin <= 24) {
 #pragma unroll
-                for (int u = 0; u < kLcap / kPcThreads; u++) {
+                for (int u = 0; u < kPer; u++) {
                     const uint32_t i = u * kPcThreads + tid;
                     if (i < m) {
                         const uint64_t k = lk[i];
@@ -539,6 +535,42 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             }
         }
         __syncthreads();
+    }
+}
+
+template <int THREADS, int HCAP>
+cudaError_t launch_finish_v(const FinishParams &fp, int n_sms, uint32_t n_sub, cudaStream_t s) {
+    constexpr uint32_t smem = HCAP * 12 + (HCAP / 2) * 12;
+    auto kern = finish_kernel<THREADS, HCAP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)n_sms * per_sm;
+    if (grid > n_sub) grid = n_sub;
+    kern<<<grid, THREADS, smem, s>>>(fp);
+    return cudaGetLastError();
+}
+
+// KC_PC_VARIANT (development knob): CTA size / table size of the finish kernel
+cudaError_t launch_finish(const FinishParams &fp, int n_sms, uint32_t n_sub, cudaStream_t s) {
+    static int variant = -1;
+    if (variant < 0) {
+        const char *v = getenv("KC_PC_VARIANT");
+        variant = v ? atoi(v) : 0;
+    }
+    switch (variant) {
+        case 1: return launch_finish_v<128, 2048>(fp, n_sms, n_sub, s);
+        case 2: return launch_finish_v<128, 4096>(fp, n_sms, n_sub, s);
+        case 3: return launch_finish_v<64, 1024>(fp, n_sms, n_sub, s);
+        case 4: return launch_finish_v<256, 2048>(fp, n_sms, n_sub, s);
+        case 5: return launch_finish_v<256, 1024>(fp, n_sms, n_sub, s);
+        case 6: return launch_finish_v<512, 2048>(fp, n_sms, n_sub, s);
+        case 7: return launch_finish_v<512, 4096>(fp, n_sms, n_sub, s);
+        case 8: return launch_finish_v<384, 2048>(fp, n_sms, n_sub, s);
+        case 9: return launch_finish_v<256, 4096>(fp, n_sms, n_sub, s);
+        default: return launch_finish_v<256, 2048>(fp, n_sms, n_sub, s);   // best of the sweep in profiles/r1
     }
 }
 
@@ -689,14 +721,7 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
         uint32_t *m_out = hist2;                               // the level-2 histogram is dead by now
         FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, m_out, d_overflow,
                         ep_in.n_invalid, add_phantom ? 1 : 0, 1};
-        if ((e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPcSmemBytes)) != cudaSuccess) return e;
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_kernel, kPcThreads, kPcSmemBytes);
-        if (per_sm < 1) per_sm = 1;
-        uint32_t grid = (uint32_t)n_sms * per_sm;
-        if (grid > pl.n_sub) grid = pl.n_sub;
-        finish_kernel<<<grid, kPcThreads, kPcSmemBytes, s>>>(fp);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = launch_finish(fp, n_sms, pl.n_sub, s)) != cudaSuccess) return e;
         // off[] (n_sub + 1) overwrites cursor2; its last entry is the number of records
         scan2_kernel<<<1, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);
         if ((e = cudaMemcpyAsync(d_num_out, cursor2 + pl.n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;

@@ -227,3 +227,51 @@ def test_run_split_and_file_write(kc, tmp_path):
         assert open(p, "rb").read() == want
         run.write(p)                                   # truncates, unlike KMerFileMerger.cpp:129
         assert os.path.getsize(p) == len(want)
+
+
+def test_device_generator_matches_host_generator(kc):
+    import torch
+    from kmer_counter_b200 import synth
+    for kw in (dict(genome_len=50000, sub_rate=0.01, n_rate=0.002, seed=3),
+               dict(genome_len=0, sub_rate=0.0, n_rate=0.0, seed=4),
+               dict(genome_len=80000, sub_rate=0.001, n_rate=0.0, seed=5, zipf_loci=1000)):
+        R, L = 3000, 100
+        d = torch.empty(R * L, dtype=torch.uint8, device="cuda")
+        synth.synth_reads_device(d.data_ptr(), R, L, first_read=17, **kw)
+        torch.cuda.synchronize()
+        want = oracle.gen_reads(R, L, kw["genome_len"], kw["sub_rate"], kw["n_rate"], seed=kw["seed"], first_read=17,
+                                zipf_loci=kw.get("zipf_loci", 0))
+        assert bytes(d.cpu().numpy()) == bytes(want)
+
+
+def test_full_size_properties_config2(kc):
+    """BASELINE config 2 at full size (10M reads): size-independent properties -- strictly
+    ascending keys, counts sum to the number of k-mers, methods agree byte for byte, and a
+    2e5-read prefix is bit-exact against the oracle."""
+    import torch
+    from kmer_counter_b200 import synth
+    R, L, k = 10_000_000, 100, 31
+    d = torch.empty(R * L + 256, dtype=torch.uint8, device="cuda")
+    synth.synth_reads_device(d.data_ptr(), R, L, 100_000_000, 1e-3, 0.0, seed=2)
+    torch.cuda.synchronize()
+    digests = {}
+    for method in ("hash", "sort"):
+        with kc.Counter(k, L, method=method) as c:
+            run = c.count_device(d.data_ptr(), R * L)
+            kptr, cptr, n = run.device_arrays()
+            from kmer_counter_b200.multigpu import run_as_tensors
+            keys_t, counts_t = run_as_tensors(run, torch.device("cuda", 0))
+            ku = keys_t[:, 0]
+            # unsigned order on int64 storage: flip the sign bit
+            kk = ku ^ torch.tensor(-2**63, dtype=torch.int64, device="cuda")
+            assert bool((kk[1:] > kk[:-1]).all()), "keys not strictly ascending"
+            assert int(counts_t.to(torch.int64).sum()) == R * (L - k + 1)
+            digests[method] = (n, int(ku.sum()), int((ku * counts_t.to(torch.int64)).sum()))
+            if method == "hash":
+                pre = 200_000
+                r2 = c.count_device(d.data_ptr(), pre * L)
+                host = d[: pre * L].cpu().numpy()
+                assert r2.to_bytes() == oracle.count(host, L, k, threads=8)
+                r2.free()
+            run.free()
+    assert digests["hash"] == digests["sort"]
