@@ -34,9 +34,9 @@ constexpr int kPbThreads = 256, kPbItems = 16, kPbTile = kPbThreads * kPbItems;
 constexpr int kDefaultTarget = 3072;    // keys per sub-bucket the plan aims for
 
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
-template <int THREADS>
+template <int THREADS, int MAXBINS = kMaxBins>
 __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_t *start, int nb, uint32_t *s_warp) {
-    constexpr int PER = kMaxBins / THREADS > 0 ? kMaxBins / THREADS : 1;
+    constexpr int PER = MAXBINS / THREADS > 0 ? MAXBINS / THREADS : 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t v[PER];
     uint32_t sum = 0;
@@ -307,6 +307,8 @@ struct FinishParams {
     const unsigned long long *d_n_invalid;
     int add_phantom;               // KC_COMPAT_REF: key 0 exists whenever a slot was empty
     int cap_shift;                 // first table guess = pow2ceil(n >> cap_shift) slots
+    const uint32_t *list;          // optional: only these sub-buckets (NULL = all)
+    const uint32_t *list_count;
 };
 
 constexpr int kSortBins = 1024;    // most bins the in-table counting sort uses
@@ -335,7 +337,9 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     __shared__ uint32_t s_warp[kPcThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
-    for (uint32_t j = blockIdx.x; j < p.n_sub; j += gridDim.x) {
+    const uint32_t n_work = p.list ? *p.list_count : p.n_sub;
+    for (uint32_t jj = blockIdx.x; jj < n_work; jj += gridDim.x) {
+        const uint32_t j = p.list ? p.list[jj] : jj;
         const uint32_t begin = p.base2[j], end = p.base2[j + 1];
         const bool phantom = (j == 0) && p.add_phantom && (*p.d_n_invalid != 0);
         if (begin == end && !phantom) {
@@ -538,6 +542,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     }
 }
 
+
 template <int THREADS, int HCAP>
 cudaError_t launch_finish_v(const FinishParams &fp, int n_sms, uint32_t n_sub, cudaStream_t s) {
     constexpr uint32_t smem = HCAP * 12 + (HCAP / 2) * 12;
@@ -720,7 +725,7 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
         if (out_keys == grouped) return cudaErrorInvalidValue;
         uint32_t *m_out = hist2;                               // the level-2 histogram is dead by now
         FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, m_out, d_overflow,
-                        ep_in.n_invalid, add_phantom ? 1 : 0, 1};
+                        ep_in.n_invalid, add_phantom ? 1 : 0, 1, nullptr, nullptr};
         if ((e = launch_finish(fp, n_sms, pl.n_sub, s)) != cudaSuccess) return e;
         // off[] (n_sub + 1) overwrites cursor2; its last entry is the number of records
         scan2_kernel<<<1, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);
