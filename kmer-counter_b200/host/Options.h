@@ -1,0 +1,26 @@
+// Options.h -- the reference's key=value flags (main.cpp:25-70, Options.h:26-43).
+#pragma once
+
+#include <stdint.h>
+
+#include <string>
+
+struct Options {
+    std::string inputFileDirectory;           // inputFileLocation=
+    std::string tempFileLocation = "/tmp";    // tempFileLocation=   (run spill directory)
+    std::string outputFile = "output.bin";    // outputFile=
+    int64_t gpuMemoryLimit = 100000000;       // gpuMemoryLimit=     (main.cpp:28)
+    int64_t kmerLength = 32;                  // kmerLength=         (Options.cpp default)
+    uint32_t noOfMergersAtOnce = 2;           // noOfMergersAtOnce=
+    uint32_t noOfMergeThreads = 2;            // noOfMergeThreads=   (accepted; merging runs on the GPU)
+    // additions
+    std::string method = "auto";              // method=auto|sort|hash
+    std::string compat = "ref";               // compat=ref|strict
+    int device = 0;                           // device=
+    bool keepRuns = false;                    // keepRuns=1: also write every chunk's run to tempFileLocation/<id>
+
+    // Same prefix matching as the reference. Unknown tokens are ignored, as there.
+    static Options parse(int argc, char **argv);
+    // KMerCounter::GetChunkSize (KMerCounter.cpp:193-212): bytes of reads per chunk
+    int64_t chunkSize(int64_t lineLength) const;
+};

@@ -1,0 +1,127 @@
+// kc_main.cpp -- command line with the reference's flags (main.cpp:25-89).
+//
+//   kmer_counter_b200 kmerLength=31 inputFileLocation=<dir> outputFile=<file> [gpuMemoryLimit=..]
+//                     [tempFileLocation=..] [noOfMergersAtOnce=..] [noOfMergeThreads=..]
+//                     [method=auto|sort|hash] [compat=ref|strict] [device=N] [keepRuns=1]
+//   kmer_counter_b200 print <record file> <ignored> <k>       (KMerPrinter, main.cpp:78-82)
+//
+// What KMerCounter::Start does (KMerCounter.cpp:108-191), on the B200 path: read fixed
+// length reads into pinned chunks, count each chunk on the GPU into a sorted run
+// (double-buffered: the next chunk is parsed while the previous one is copied and
+// counted), merge the runs on the GPU, write the sorted unique records.
+#include <inttypes.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/kc_api.h"
+#include "FastqChunker.h"
+#include "Options.h"
+#include "RunMerger.h"
+
+// KMerPrinter::print (KMerPrinter.cpp:35-91): every word as 32 letters, then " count".
+static int print_records(const char *path, uint64_t k) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", path); return 1; }
+    const uint32_t W = kc_key_words((uint32_t)k), S = kc_record_size((uint32_t)k);
+    std::vector<unsigned char> buf((size_t)S * 10000);
+    std::string line;
+    size_t n;
+    while ((n = fread(buf.data(), 1, buf.size(), f)) >= S) {
+        for (size_t off = 0; off + S <= n; off += S) {
+            line.clear();
+            for (uint32_t w = 0; w < W; w++) {
+                uint64_t v;
+                memcpy(&v, &buf[off + 8 * w], 8);
+                for (int b = 0; b < 32; b++) line.push_back("ACGT"[(v >> (62 - 2 * b)) & 3]);
+            }
+            uint32_t c;
+            memcpy(&c, &buf[off + 8 * W], 4);
+            printf("%s %u\n", line.c_str(), c);
+        }
+    }
+    fclose(f);
+    return 0;
+}
+
+static uint32_t method_of(const std::string &m) {
+    if (m == "sort") return KC_COUNT_SORT;
+    if (m == "hash") return KC_COUNT_HASH;
+    if (m == "hash_global") return KC_COUNT_HASH_GLOBAL;
+    return KC_COUNT_AUTO;
+}
+
+int main(int argc, char **argv) {
+    if (argc == 5 && strncmp(argv[1], "print", 5) == 0) return print_records(argv[2], strtoull(argv[4], nullptr, 10));
+    Options opt = Options::parse(argc, argv);
+    if (opt.inputFileDirectory.empty()) {
+        fprintf(stderr, "usage: %s kmerLength=K inputFileLocation=DIR outputFile=FILE [gpuMemoryLimit=BYTES] ...\n", argv[0]);
+        return 2;
+    }
+    FastqChunker reader(opt.inputFileDirectory);
+    if (!reader.ok()) { fprintf(stderr, "no FASTQ input in %s\n", opt.inputFileDirectory.c_str()); return 1; }
+    const int64_t L = reader.getLineLength();
+    int64_t chunk = opt.chunkSize(L);
+    const int64_t max_chunk = (int64_t)((((1ull << 30) - 1) / (uint64_t)(L - opt.kmerLength + 1)) * (uint64_t)L);
+    if (chunk > max_chunk) chunk = max_chunk - max_chunk % (16 * L);
+
+    kc_config cfg = {};
+    cfg.struct_size = sizeof cfg;
+    cfg.k = (uint32_t)opt.kmerLength;
+    cfg.read_len = (uint32_t)L;
+    cfg.device = opt.device;
+    cfg.flags = opt.compat == "strict" ? KC_COMPAT_STRICT : KC_COMPAT_REF;
+    cfg.method = method_of(opt.method);
+    cfg.n_slots = 2;
+    cfg.max_chunk_bytes = (uint64_t)chunk;
+    kc_ctx *ctx = nullptr;
+    if (kc_create(&cfg, &ctx) != KC_OK) { fprintf(stderr, "kc_create: %s\n", kc_last_error(nullptr)); return 1; }
+
+    RunMerger merger(ctx, opt.noOfMergersAtOnce);
+    int rc = KC_OK;
+    uint32_t chunk_id = 0;
+    bool busy[2] = {false, false};
+    auto collect = [&](uint32_t slot) -> int {
+        kc_run *run = nullptr;
+        int r = kc_wait(ctx, slot, &run);
+        busy[slot] = false;
+        if (r != KC_OK) return r;
+        if (opt.keepRuns) {                                     // FileDump::dumpKmersToFile naming (FileDump.cpp:51-58)
+            std::string path = opt.tempFileLocation + "/" + std::to_string(++chunk_id);
+            if ((r = kc_run_write(ctx, run, path.c_str(), 0)) != KC_OK) return r;
+        }
+        return merger.AddRun(run);
+    };
+    for (uint32_t slot = 0; rc == KC_OK; slot ^= 1) {
+        if (busy[slot]) rc = collect(slot);                      // the other slot keeps the GPU busy meanwhile
+        if (rc != KC_OK) break;
+        void *buf = nullptr;
+        uint64_t cap = 0;
+        if ((rc = kc_slot_buffer(ctx, slot, &buf, &cap)) != KC_OK) break;
+        const int64_t n = reader.read(static_cast<char *>(buf), (int64_t)cap);
+        if (n == 0) break;
+        if ((rc = kc_submit(ctx, slot, (uint64_t)n)) != KC_OK) break;
+        busy[slot] = true;
+    }
+    for (uint32_t slot = 0; slot < 2 && rc == KC_OK; slot++)
+        if (busy[slot]) rc = collect(slot);
+    kc_run *final_run = nullptr;
+    if (rc == KC_OK) rc = merger.InputComplete(&final_run);
+    if (rc == KC_OK) rc = kc_run_write(ctx, final_run, opt.outputFile.c_str(), 0);   // truncates (KMerFileMerger.cpp:129 appends)
+    if (rc != KC_OK) {
+        fprintf(stderr, "kmer_counter_b200: %s\n", kc_last_error(ctx));
+    } else {
+        kc_stats st;
+        kc_stats_get(ctx, &st);
+        fprintf(stderr, "reads=%" PRIu64 " skipped=%" PRIu64 " kmers=%" PRIu64 " chunks=%" PRIu64 " merges=%" PRIu64
+                        " records=%" PRIu64 " -> %s\n",
+                reader.totalReads(), reader.skippedReads(), st.kmers_valid, st.chunks, merger.merges(),
+                kc_run_records(final_run), opt.outputFile.c_str());
+    }
+    if (final_run) kc_run_free(ctx, final_run);
+    kc_destroy(ctx);
+    return rc == KC_OK ? 0 : 1;
+}

@@ -1,0 +1,74 @@
+"""The C++ host surface over the C ABI: command line with the reference's flags, the
+reference-shaped PrepareGPU / processKMers / FreeGPU seam, and the printer."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "kmer-counter_b200", "host")
+CLI = os.path.join(HOST, "kmer_counter_b200")
+SELFTEST = os.path.join(HOST, "shim_selftest")
+
+
+def test_host_binaries_are_built():
+    assert os.path.exists(CLI) and os.path.exists(SELFTEST) and os.path.exists(os.path.join(HOST, "libkc_shim.so"))
+
+
+def test_printer_mode_matches_kmerprinter_format(tmp_path):
+    """`print <in> <out> <k>`: every word as 32 letters, then ' count' (KMerPrinter.cpp:35-91). No GPU needed."""
+    rec = np.zeros(3, dtype=[("w0", "<u8"), ("w1", "<u8"), ("cnt", "<u4")])
+    rec["w0"] = [0x1b1b1b1b1b1b1b1b, 0, 2**64 - 1]
+    rec["w1"] = [0xc000000000000000, 0, 1 << 62]
+    rec["cnt"] = [7, 0, 4000000000]
+    p = tmp_path / "r.bin"
+    p.write_bytes(rec.tobytes())
+    out = subprocess.run([CLI, "print", str(p), "ignored", "33"], capture_output=True, text=True, check=True).stdout
+    want = "".join("%s%s %d\n" % (oracle.print_word(int(r["w0"])), oracle.print_word(int(r["w1"])), int(r["cnt"])) for r in rec)
+    assert out == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,method", [(31, "auto"), (31, "sort"), (63, "auto"), (28, "hash")])
+def test_cli_counts_a_fastq_directory(tmp_path, k, method):
+    d = tmp_path / "in"
+    d.mkdir()
+    L, per = 100, 1500
+    for i in range(3):                                        # several files; a dot-file is ignored
+        (d / ("part%d.fastq" % i)).write_bytes(oracle.gen_fastq(per, L, 40000, 0.01, 0.002, seed=8, first_read=i * per))
+    (d / ".hidden").write_bytes(b"@x\nAAAA\n+\nIIII\n")
+    out = tmp_path / "out.bin"
+    out.write_bytes(b"stale")                                 # the output is truncated, not appended to
+    r = subprocess.run([CLI, "kmerLength=%d" % k, "inputFileLocation=%s" % d, "outputFile=%s" % out,
+                        "gpuMemoryLimit=2000000", "noOfMergersAtOnce=3", "method=%s" % method,
+                        "tempFileLocation=%s" % tmp_path, "keepRuns=1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    reads = oracle.gen_reads(3 * per, L, 40000, 0.01, 0.002, seed=8)
+    assert out.read_bytes() == oracle.count(reads, L, k)
+    assert "chunks=" in r.stderr and (tmp_path / "1").exists()   # several chunks went through, runs were dumped
+    # each dumped run is a valid sorted run; merging them with the oracle's merger gives the artefact too
+    runs = [(tmp_path / str(i)).read_bytes() for i in range(1, 50) if (tmp_path / str(i)).exists()]
+    assert len(runs) >= 2 and oracle.merge_runs(runs, k) == out.read_bytes()
+
+
+@pytest.mark.gpu
+def test_reference_shaped_seam_from_four_threads(tmp_path):
+    L, k, R, chunk = 100, 31, 6000, 1000
+    reads = oracle.gen_reads(R, L, 50000, 0.01, 0.002, seed=9)
+    src = tmp_path / "reads.bin"
+    src.write_bytes(reads.tobytes())
+    out = tmp_path / "runs.bin"
+    subprocess.run([SELFTEST, str(src), str(L), str(k), str(chunk), str(out)], check=True, timeout=300)
+    blob = out.read_bytes()
+    pos, c = 0, 0
+    while pos < len(blob):
+        (nb,) = struct.unpack_from("<Q", blob, pos)
+        run = blob[pos + 8: pos + 8 + nb]
+        assert run == oracle.process_chunk(reads[c * chunk * L:(c + 1) * chunk * L], L, k), c
+        pos += 8 + nb
+        c += 1
+    assert c == R // chunk
