@@ -67,21 +67,30 @@ def workload(a):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled through NVML every 20 ms while the timed region runs."""
 
     def __init__(self, index):
-        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons, self.stop, self.th = index, [], 0, set(), threading.Event(), None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            flags = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in flags.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.stop.wait(0.02)
+        except Exception as e:                      # no NVML: report that instead of inventing numbers
+            self.reasons.add("nvml_unavailable: %s" % type(e).__name__)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -90,22 +99,12 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        self.th.join(timeout=5)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for nme, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def measured_peak_gbs():
@@ -267,9 +266,13 @@ def run_ours(a, rank, world, local_rank):
         pinned_out = counter.host_alloc(out_cap)
         d2h = 0
 
+        e2e_parts = {"count": 0.0, "exchange_merge": 0.0, "records_d2h": 0.0}
+
         def e2e_step():
+            t_a = time.perf_counter()
             counter.submit(0, n_bytes)
             run = counter.wait(0)
+            t_b = time.perf_counter()
             if world > 1:
                 off = run.split(multigpu.range_splitters(world, counter.words))
                 keys_t, counts_t = multigpu.run_as_tensors(run, dev)
@@ -283,12 +286,17 @@ def run_ours(a, rank, world, local_rank):
                 run = counter.merge(parts)
                 for p in parts:
                     p.free()
+            t_c = time.perf_counter()
             nb = run.copy_into(pinned_out.ctypes.data, out_cap)
             run.free()
+            t_d = time.perf_counter()
+            e2e_parts["count"] += t_b - t_a; e2e_parts["exchange_merge"] += t_c - t_b; e2e_parts["records_d2h"] += t_d - t_c
             return nb
 
         for _ in range(min(a.warmup, 2)):
             e2e_step()
+        for kx in e2e_parts:
+            e2e_parts[kx] = 0.0
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
@@ -300,7 +308,8 @@ def run_ours(a, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
         e2e = {"value": kmers_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_dt * 1e3, "timing": "wall clock around K steps, sync on both sides, max over ranks"}
+               "ms_per_step": e2e_dt * 1e3, "timing": "wall clock around K steps, sync on both sides, max over ranks",
+               "ms_parts_rank0": {kx: v / a.steps * 1e3 for kx, v in e2e_parts.items()}}
         counter.host_free(pinned_out)
 
     clocks = clk.summary()
@@ -325,6 +334,7 @@ def run_ours(a, rank, world, local_rank):
             "path_roofline": {"bound": "hbm", "b_alg_bytes": b_alg, "achieved": path_ach, "peak": peak, "unit": "GB/s",
                               "frac": path_ach / peak if peak else None,
                               "definition": "SURVEY 8(d): B_in + N*(Kb+8) + U*S over the local counting time"},
+            "stages_last_step": {n: round(m, 4) for n, m in zip(st1["stage_names"], st1["ms_stage"])},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_ms_per_step": wall / a.steps * 1e3,
         }

@@ -45,6 +45,10 @@ struct Pending {                 // a chunk whose kernels are queued but whose r
     int n_passes = 0;
     uint32_t *counts = nullptr;              // partition path: counts next to the unique keys
     void *ws_part = nullptr;
+    // Chunk scratch arena: one grow-only device block per Pending, carved by a bump pointer.
+    // Chunk after chunk reuses it, so the big buffers never go through the allocator again.
+    uint8_t *arena = nullptr;
+    uint64_t arena_cap = 0, arena_used = 0;
 };
 
 struct Slot {
@@ -113,6 +117,7 @@ int pending_init(kc_ctx *c, Pending &p) {
     return KC_OK;
 }
 void pending_destroy(Pending &p) {
+    if (p.arena) cudaFree(p.arena);
     if (p.d_scal) cudaFree(p.d_scal);
     if (p.h_scal) cudaFreeHost(p.h_scal);
     for (auto &e : p.ev)
@@ -120,10 +125,32 @@ void pending_destroy(Pending &p) {
     p = Pending();
 }
 
-void pending_release(cudaStream_t s, Pending &p) {
-    dev_free(s, p.keys_a); dev_free(s, p.keys_b); dev_free(s, p.starts);
-    dev_free(s, p.ws_sort); dev_free(s, p.ws_rle); dev_free(s, p.table.slots);
-    dev_free(s, p.counts); dev_free(s, p.ws_part);
+// Reserve the scratch a chunk needs (call once per chunk, before arena_take). The stream
+// is drained before a grown arena replaces the old one.
+int arena_reserve(kc_ctx *c, Pending &p, uint64_t bytes, cudaStream_t s) {
+    p.arena_used = 0;
+    if (bytes <= p.arena_cap) return KC_OK;
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (p.arena) cudaFree(p.arena);
+    p.arena = nullptr;
+    p.arena_cap = 0;
+    bytes += bytes / 16;                           // a little headroom so that slightly larger chunks fit too
+    if (cudaMalloc((void **)&p.arena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes of chunk scratch failed", (unsigned long long)bytes);
+    }
+    p.arena_cap = bytes;
+    return KC_OK;
+}
+inline uint64_t arena_round(uint64_t b) { return (b + 511) & ~511ull; }
+void *arena_take(Pending &p, uint64_t bytes) {
+    void *r = p.arena + p.arena_used;
+    p.arena_used += arena_round(bytes);
+    return r;
+}
+
+void pending_release(cudaStream_t, Pending &p) {
+    p.arena_used = 0;
     p.keys_a = p.keys_b = p.sorted = p.uniq = nullptr;
     p.starts = nullptr;
     p.counts = nullptr;
@@ -183,11 +210,12 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
         ExtractParams ep64;
         if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep64, 6400))
             return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
-        void *mem = nullptr;
-        KC_TRY(dev_alloc(c, s, p.n_slots * 8 + 64, &mem)); p.keys_a = static_cast<uint64_t *>(mem);
-        KC_TRY(dev_alloc(c, s, p.n_slots * 8 + 64, &mem)); p.keys_b = static_cast<uint64_t *>(mem);
-        KC_TRY(dev_alloc(c, s, (p.n_slots + 2) * 4, &mem)); p.counts = static_cast<uint32_t *>(mem);
-        KC_TRY(dev_alloc(c, s, partition_workspace_bytes(p.n_slots), &p.ws_part));
+        const uint64_t kb = p.n_slots * 8 + 64, cb = (p.n_slots + 2) * 4, wb = partition_workspace_bytes(p.n_slots);
+        KC_TRY(arena_reserve(c, p, 2 * arena_round(kb) + arena_round(cb) + arena_round(wb), s));
+        p.keys_a = static_cast<uint64_t *>(arena_take(p, kb));
+        p.keys_b = static_cast<uint64_t *>(arena_take(p, kb));
+        p.counts = static_cast<uint32_t *>(arena_take(p, cb));
+        p.ws_part = arena_take(p, wb);
         const int sig = 64 - static_zero_bits(c);
         const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;   // keys per sub-bucket (0 = default)
         p.uniq = partition_two_levels(p.n_slots, sig, target) ? p.keys_a : p.keys_b;
@@ -199,9 +227,8 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
     } else if (method == KC_COUNT_HASH_GLOBAL) {
         uint64_t cap = c->cfg.table_slots ? pow2_ceil(c->cfg.table_slots) : pow2_ceil(p.n_slots / 2 + 1);
         if (cap < (1u << 16)) cap = 1u << 16;
-        void *mem = nullptr;
-        KC_TRY(dev_alloc(c, s, hash_table_bytes(cap), &mem));
-        p.table.slots = static_cast<uint64_t *>(mem);
+        KC_TRY(arena_reserve(c, p, arena_round(hash_table_bytes(cap)), s));
+        p.table.slots = static_cast<uint64_t *>(arena_take(p, hash_table_bytes(cap)));
         p.table.capacity = cap;
         p.table.side = &p.d_scal[SC_SIDE];
         KC_CUDA_TRY(c, hash_clear(p.table, s));
@@ -213,13 +240,14 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
         launches += 3;
         p.n_passes = 1;
     } else {
-        void *mem = nullptr;
-        KC_TRY(dev_alloc(c, s, p.n_slots * W * 8, &mem)); p.keys_a = static_cast<uint64_t *>(mem);
-        KC_TRY(dev_alloc(c, s, p.n_slots * W * 8, &mem)); p.keys_b = static_cast<uint64_t *>(mem);
-        KC_TRY(dev_alloc(c, s, (p.n_slots + 1) * 4, &mem)); p.starts = static_cast<uint32_t *>(mem);
         const uint64_t ws_bytes = sort_workspace_bytes(p.n_slots, W);
-        KC_TRY(dev_alloc(c, s, ws_bytes, &p.ws_sort));
-        KC_TRY(dev_alloc(c, s, rle_workspace_bytes(p.n_slots), &p.ws_rle));
+        const uint64_t kb = p.n_slots * W * 8, sb = (p.n_slots + 1) * 4, rb = rle_workspace_bytes(p.n_slots);
+        KC_TRY(arena_reserve(c, p, 2 * arena_round(kb) + arena_round(sb) + arena_round(ws_bytes) + arena_round(rb), s));
+        p.keys_a = static_cast<uint64_t *>(arena_take(p, kb));
+        p.keys_b = static_cast<uint64_t *>(arena_take(p, kb));
+        p.starts = static_cast<uint32_t *>(arena_take(p, sb));
+        p.ws_sort = arena_take(p, ws_bytes);
+        p.ws_rle = arena_take(p, rb);
         KC_CUDA_TRY(c, launch_extract_store(ep, W, p.keys_a, c->n_sms, s));
         KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));
         const int lo_bit = static_zero_bits(c);

@@ -208,7 +208,8 @@ def test_device_resident_input(kc):
         assert run.to_bytes() == want
         st = c.stats()
         assert st["reads"] == R and st["kmer_slots"] == R * (L - k + 1)
-        assert st["launches"] > 0 and st["dominant_launches"] == 8
+        assert st["launches"] > 0 and st["method_used"] == "sort"
+        assert st["stage_names"][2] == "radix_scatter_passes" and st["stage_launches"][2] == 8   # 64-bit key, 8-bit digits
 
 
 def test_run_split_and_file_write(kc, tmp_path):
