@@ -30,6 +30,7 @@ bool extract_plan(const void *d_reads, uint64_t n_reads, uint32_t L, uint32_t k,
     p.tile_reads = 16u * (groups ? groups : 1u);
     p.n_tiles = (uint32_t)((n_reads + p.tile_reads - 1) / p.tile_reads);
     p.nk_magic = (uint32_t)((1ull << 32) / p.nk + 1);
+    p.nb4_magic = p.nb4 == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / p.nb4 + 1);
     p.segs_per_read = (p.nk + 17) / 18;                    // ~18 positions per thread-segment (<= 32: one 64-bit lookahead word)
     p.seg_len = (p.nk + p.segs_per_read - 1) / p.segs_per_read;
     uint32_t m = k % 32;

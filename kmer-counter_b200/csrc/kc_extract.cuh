@@ -29,6 +29,7 @@ struct ExtractParams {
     uint32_t tile_reads;     // reads per tile, multiple of 16 -> tile bytes % 16 == 0
     uint32_t n_tiles;
     uint32_t nk_magic;       // floor(2^32 / nk) + 1
+    uint32_t nb4_magic;      // floor(2^32 / nb4) + 1
     uint32_t segs_per_read, seg_len;   // rolling walk: a read's nk positions in segs_per_read runs of seg_len
     uint64_t last_mask;      // applied to key word W-1
     unsigned long long *n_invalid;  // += slots that hold no k-mer (the phantom of SURVEY F7)
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
+    for (uint32_t i = tid; i < p.tile_reads * enc_row; i += kExtractThreads) enc[i] = 0;
+    for (uint32_t i = tid; i < p.tile_reads; i += kExtractThreads) flag[i] = 0;
     sink.begin(smem + p.smem_total);
     __syncthreads();
 
@@ -136,42 +139,37 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         }
         const uint8_t *src_tile = stage0 + stage * stage_bytes;
 
-        // ---- phase A: one warp per read; a lane turns 4 bases (one 32-bit shared load) into one
-        // byte of 2-bit codes with SIMD-in-register arithmetic ----
+        // ---- phase A: every thread turns groups of 4 bases (one 32-bit shared load) into one byte
+        // of 2-bit codes with SIMD-in-register arithmetic; the (read, group) pairs of the tile are
+        // spread over the whole CTA. The pad bytes of each encoded row were zeroed once, above. ----
         const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src_tile);
-        for (uint32_t r = warp; r < nreads; r += kWarps) {
-            const uint32_t rbase = r * p.L;
-            uint32_t any_bad = 0;
-            const uint32_t span_bases = enc_row * 32;
-            for (uint32_t j0 = lane * 4; j0 < span_bases; j0 += 128) {
-                uint32_t codes = 0, badn = 0;
-                if (j0 < p.L) {
-                    const uint32_t addr = rbase + j0;
-                    const uint32_t w0 = src32[addr >> 2], w1 = src32[(addr >> 2) + 1];
-                    uint32_t x = __funnelshift_r(w0, w1, (addr & 3u) * 8u);        // bytes addr .. addr+3
-                    const uint32_t left = p.L - j0;                                 // bases of this read in x
-                    if (left < 4) x = (x & (0xffffffffu >> (32 - 8 * left))) | (0x41414141u << (8 * left));  // pad with 'A'
-                    // code = ((c >> 1) ^ (c >> 2)) & 3 for A,C,G,T = 0,1,2,3 (GPUHandler.cu:42-78)
-                    uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
-                    // letter each byte should be, picked by (c >> 1) & 3 out of "ACTG": equal <=> valid
-                    const uint32_t i4 = (x >> 1) & 0x03030303u;
-                    const uint32_t sel = __byte_perm(i4 | (i4 >> 4), 0u, 0x4420u);   // nibble i = index of byte i
-                    const uint32_t diff = x ^ __byte_perm(0x47544341u, 0u, sel);
-                    if (diff) {                                                     // rare: some byte is not ACGT
+        const uint32_t n_groups = nreads * p.nb4;
+        for (uint32_t g = tid; g < n_groups; g += kExtractThreads) {
+            uint32_t r = p.nb4 == 1 ? g : __umulhi(g, p.nb4_magic);
+            if (r * p.nb4 > g) r--;
+            const uint32_t q = g - r * p.nb4;                                   // byte q of the read's bit string
+            const uint32_t j0 = q * 4;
+            const uint32_t addr = r * p.L + j0;
+            const uint32_t w0 = src32[addr >> 2], w1 = src32[(addr >> 2) + 1];
+            uint32_t x = __funnelshift_r(w0, w1, (addr & 3u) * 8u);             // bytes addr .. addr+3
+            const uint32_t left = p.L - j0;                                      // bases of this read in x
+            if (left < 4) x = (x & (0xffffffffu >> (32 - 8 * left))) | (0x41414141u << (8 * left));   // pad with 'A'
+            // code = ((c >> 1) ^ (c >> 2)) & 3 for A,C,G,T = 0,1,2,3 (GPUHandler.cu:42-78)
+            uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+            // letter each byte should be, picked by (c >> 1) & 3 out of "ACTG": equal <=> valid
+            const uint32_t i4 = (x >> 1) & 0x03030303u;
+            const uint32_t sel = __byte_perm(i4 | (i4 >> 4), 0u, 0x4420u);      // nibble i = index of byte i
+            const uint32_t diff = x ^ __byte_perm(0x47544341u, 0u, sel);
+            uint32_t badn = 0;
+            if (diff) {                                                          // rare: some byte is not ACGT
 #pragma unroll
-                        for (uint32_t b = 0; b < 4; b++)
-                            if ((diff >> (8 * b)) & 0xffu) { badn |= 1u << b; t |= 3u << (8 * b); }   // code 3 + filter bit (:79-87)
-                    }
-                    codes = (t * 0x40100401u) >> 24;                                // b0<<6 | b1<<4 | b2<<2 | b3
-                }
-                // byte (j0/4) of the big-endian bit string -> little-endian byte inside its word
-                const uint32_t q = j0 >> 2;
-                enc_b[(r * enc_row + (q >> 3)) * 8 + (7 - (q & 7))] = (uint8_t)codes;
-                if (j0 < p.L) bad4[r * p.nb4 + q] = (uint8_t)badn;
-                any_bad |= badn;
+                for (uint32_t b = 0; b < 4; b++)
+                    if ((diff >> (8 * b)) & 0xffu) { badn |= 1u << b; t |= 3u << (8 * b); }   // code 3 + filter bit (:79-87)
+                flag[r] = 1;
             }
-            any_bad = __any_sync(0xffffffffu, any_bad != 0);
-            if (lane == 0) flag[r] = (uint8_t)any_bad;
+            // byte q of the big-endian bit string -> little-endian byte inside its word
+            enc_b[(r * enc_row + (q >> 3)) * 8 + (7 - (q & 7))] = (uint8_t)((t * 0x40100401u) >> 24);   // b0<<6|b1<<4|b2<<2|b3
+            bad4[r * p.nb4 + q] = (uint8_t)badn;
         }
         __syncthreads();
 
@@ -245,6 +243,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
             __syncthreads();
             sink.sweep_end(sw);
         }
+        for (uint32_t i = tid; i < nreads; i += kExtractThreads) flag[i] = 0;       // for the next tile's phase A
         __syncthreads();
         stage ^= 1;
     }

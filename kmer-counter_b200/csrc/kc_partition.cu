@@ -127,6 +127,8 @@ struct Scatter1Sink : SinkBase {
     uint32_t *g_cursor1;
     uint64_t *out;
     int shift1, nb1;
+    uint32_t *g_hist2;     // non-NULL: count the (b1+b2)-bit prefix of every key on the way out
+    int shift2;
     // shared
     uint32_t *cnt, *start, *gbase, *s_warp;
     uint64_t *staging;
@@ -167,6 +169,7 @@ struct Scatter1Sink : SinkBase {
             for (uint32_t i = threadIdx.x; i < total; i += kExtractThreads) {
                 const uint64_t k = staging[i];
                 out[gbase[k >> shift1] + i] = k;
+                if (g_hist2) atomicAdd(&g_hist2[k >> shift2], 1u);
             }
             for (int b = threadIdx.x; b < nb1; b += kExtractThreads) cnt[b] = 0;
             __syncthreads();
@@ -222,32 +225,47 @@ __global__ void __launch_bounds__(kPbThreads) hist2_kernel(const uint64_t *__res
     }
 }
 
-// one block: exclusive scan over all sub-buckets -> base2 (n+1) and the mutable cursors
+// one block: exclusive scan over all sub-buckets -> base2 (n+1) and the mutable cursors.
+// Coalesced tiles of 4096 entries (4 per thread) with a running carry.
 __global__ void __launch_bounds__(1024) scan2_kernel(const uint32_t *__restrict__ hist2, uint32_t n,
                                                      uint32_t *__restrict__ base2, uint32_t *__restrict__ cursor2) {
     __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t b0 = tid * per, b1 = b0 + per < n ? b0 + per : n;
-    uint32_t sum = 0;
-    for (uint32_t i = b0; i < b1; i++) sum += hist2[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += t;
-    }
-    if (lane == 31) s_w[warp] = incl;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    uint32_t off = 0;
-    for (uint32_t w = 0; w < warp; w++) off += s_w[w];
-    uint32_t run = off + incl - sum;
-    for (uint32_t i = b0; i < b1; i++) {
-        base2[i] = run;
-        cursor2[i] = run;
-        run += hist2[i];
+    for (uint32_t t0 = 0; t0 < n; t0 += 4096) {
+        const uint32_t i0 = t0 + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = i0 + u < n ? hist2[i0 + u] : 0;
+        const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        uint32_t off = s_carry, tot = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 32; w++) {
+            const uint32_t x = s_w[w];
+            if (w < warp) off += x;
+            tot += x;
+        }
+        uint32_t run = off + incl - sum;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + u < n) { base2[i0 + u] = run; cursor2[i0 + u] = run; }
+            run += v[u];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
     }
-    if (tid == 1023) base2[n] = off + incl;
+    if (tid == 0) base2[n] = s_carry;
 }
 
 // ---------------------------------------------------------------- PB: scatter2
@@ -670,6 +688,8 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     if ((e = cudaMemsetAsync(d_overflow, 0, 8, s)) != cudaSuccess) return e;
 
     const int shift1 = 64 - pl.b1, shift2 = 64 - pl.b1 - pl.b2;
+    static int fuse_h2 = -1;                // KC_FUSE_H2=1 (development knob): level-2 histogram by REDs inside PA
+    if (fuse_h2 < 0) { const char *v = getenv("KC_FUSE_H2"); fuse_h2 = (v && v[0] == '1') ? 1 : 0; }
     // P0: level-1 histogram (invalid-slot count goes to a scratch counter: PA counts it for real)
     {
         ExtractParams ep = ep_in;
@@ -701,6 +721,8 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
         if (grid > ep_in.n_tiles) grid = ep_in.n_tiles;
         Scatter1Sink sink{};
         sink.g_cursor1 = cursor1; sink.out = keys_a; sink.shift1 = shift1; sink.nb1 = (int)pl.nb1;
+        sink.g_hist2 = (fuse_h2 && pl.b2 > 0) ? hist2 : nullptr;
+        sink.shift2 = shift2;
         kern<<<grid, kExtractThreads, smem, s>>>(ep_in, sink);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -708,7 +730,8 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     // H2 + PB over the level-1 buckets
     const uint32_t max_tiles = (uint32_t)(n_slots / kPbTile) + pl.nb1 + 1;
     if (pl.b2 > 0) {
-        hist2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, tile_prefix, base1, (int)pl.nb1, shift2, (int)pl.nb2, hist2);
+        if (!fuse_h2)
+            hist2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, tile_prefix, base1, (int)pl.nb1, shift2, (int)pl.nb2, hist2);
         scan2_kernel<<<1, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
         if (evs) cudaEventRecord(evs[2], s);
         scatter2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,

@@ -2,13 +2,18 @@
 import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+want = sys.argv[3] if len(sys.argv) > 3 else None      # substring of the kernel name to keep
+keep = True
 cur_file, hdr = None, None
 agg = collections.OrderedDict()
 line_key = None
 for r in rows:
     if not r: continue
     if r[0] == 'File Path': cur_file = r[1].split('/')[-1]; continue
-    if r[0] == 'Function Name': continue
+    if r[0] == 'Function Name':
+        keep = want is None or want in r[1]
+        continue
+    if not keep: continue
     if r[0] == 'Line No': hdr = r; continue
     if hdr is None: continue
     if r[0] != '':          # a source line row: the text may contain commas -> columns shift; take line no + text
