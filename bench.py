@@ -274,18 +274,7 @@ def run_ours(a, rank, world, local_rank):
             run = counter.wait(0)
             t_b = time.perf_counter()
             if world > 1:
-                off = run.split(multigpu.range_splitters(world, counter.words))
-                keys_t, counts_t = multigpu.run_as_tensors(run, dev)
-                rk, rc, sizes = multigpu.exchange_slices(keys_t, counts_t, off)
-                torch.cuda.current_stream().synchronize()
-                parts, pos = [], 0
-                for sz in sizes:
-                    parts.append(counter.run_from_device(rk.data_ptr() + pos * counter.words * 8, rc.data_ptr() + pos * 4, sz))
-                    pos += sz
-                run.free()
-                run = counter.merge(parts)
-                for p in parts:
-                    p.free()
+                run = multigpu.exchange_and_combine(counter, run, dev)
             t_c = time.perf_counter()
             nb = run.copy_into(pinned_out.ctypes.data, out_cap)
             run.free()

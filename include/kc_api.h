@@ -157,6 +157,19 @@ int  kc_run_write(kc_ctx *ctx, const kc_run *run, const char *path, int append);
 int  kc_run_split(kc_ctx *ctx, const kc_run *run, const uint64_t *splitters, uint32_t n_splitters,
                   uint64_t *offsets);
 
+/* Runs produced by KC_COUNT_HASH also carry their partition structure: the key space is cut
+ * into n_sub equal ranges on the leading prefix_bits of the key and d_offsets[j] (uint32,
+ * n_sub + 1 entries, device memory owned by the run) is the first record of range j. n_sub == 0
+ * for runs without it (sort path, uploads, merges). Used by the multi-GPU exchange. */
+int  kc_run_parts(const kc_run *run, void **d_offsets, uint32_t *n_sub, uint32_t *prefix_bits);
+/* Merge n_src (<= 8) pre-counted parts that cover the same n_sub consecutive key ranges:
+ * part s is n_records[s] sorted unique records (d_keys[s], d_counts[s]) with d_offsets[s]
+ * (uint32[n_sub + 1], relative to the part) marking the ranges. Equal keys are summed
+ * (uint32 wrap). One pass, independent of n_src: each range is combined in a shared-memory table. */
+int  kc_merge_parts(kc_ctx *ctx, uint32_t n_src, const void *const *d_keys, const void *const *d_counts,
+                    const void *const *d_offsets, const uint64_t *n_records, uint32_t n_sub,
+                    uint32_t prefix_bits, kc_run **out);
+
 /* ---- merge: replaces KMerFileMerger::Merge (KMerFileMerger.cpp:49-96) ---- */
 /* Merge n sorted runs into one, adding the counts of equal keys (uint32 wrap).
  * Inputs stay valid and owned by the caller. n may be 0 (empty run) or 1 (copy). */

@@ -4,6 +4,8 @@
 // There is no CPU compute path here; if the device cannot run a kernel the call
 // fails with KC_ERR_CUDA.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <time.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,6 +24,9 @@ struct kc_run {
     uint64_t skip = 0;       // leading records hidden (strict mode drops an empty key-0 record)
     uint64_t *d_keys = nullptr;
     uint32_t *d_counts = nullptr;
+    // partition structure (KC_COUNT_HASH runs only): record offsets of n_sub equal key ranges
+    uint32_t *d_sub_off = nullptr;
+    uint32_t n_sub = 0, prefix_bits = 0;
 };
 
 namespace {
@@ -372,6 +377,12 @@ int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) 
         const int sig = 64 - static_zero_bits(c);
         const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;
         KC_CUDA_TRY(c, partition_gather(p.n_slots, sig, target, p.uniq, p.counts, p.ws_part, r->d_keys, r->d_counts, s));
+        const uint32_t *d_off = nullptr;
+        partition_plan_info(p.n_slots, sig, target, p.ws_part, &r->n_sub, &r->prefix_bits, &d_off);
+        void *mem = nullptr;
+        KC_TRY(dev_alloc(c, s, (uint64_t)(r->n_sub + 1) * 4, &mem));
+        r->d_sub_off = static_cast<uint32_t *>(mem);
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_sub_off, d_off, (uint64_t)(r->n_sub + 1) * 4, cudaMemcpyDeviceToDevice, s));
         std::lock_guard<std::mutex> g(c->mu);
         c->stats.launches += 1;
     }
@@ -646,7 +657,79 @@ int kc_run_free(kc_ctx *c, kc_run *r) {
     if (!r) return KC_OK;
     dev_free(c->stream, r->d_keys);
     dev_free(c->stream, r->d_counts);
+    dev_free(c->stream, r->d_sub_off);
     delete r;
+    return KC_OK;
+}
+
+int kc_run_parts(const kc_run *r, void **d_offsets, uint32_t *n_sub, uint32_t *prefix_bits) {
+    if (!r) return KC_ERR_ARG;
+    const bool has = r->d_sub_off && r->skip == 0;
+    if (d_offsets) *d_offsets = has ? r->d_sub_off : nullptr;
+    if (n_sub) *n_sub = has ? r->n_sub : 0;
+    if (prefix_bits) *prefix_bits = has ? r->prefix_bits : 0;
+    return KC_OK;
+}
+
+int kc_merge_parts(kc_ctx *c, uint32_t n_src, const void *const *d_keys, const void *const *d_counts,
+                   const void *const *d_offsets, const uint64_t *n_records, uint32_t n_sub, uint32_t prefix_bits,
+                   kc_run **out) {
+    KC_TRY(check_ctx(c));
+    if (!out || n_src == 0 || n_src > 8 || !d_keys || !d_counts || !d_offsets || !n_records || n_sub == 0)
+        return c->set_error(KC_ERR_ARG, "kc_merge_parts: bad argument");
+    if (c->W != 1) return c->set_error(KC_ERR_ARG, "kc_merge_parts: 64-bit keys only");
+    cudaSetDevice(c->cfg.device);
+    cudaStream_t s = c->stream;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_src; i++) total += n_records[i];
+    if (total >= (1ull << 32) - 2) return c->set_error(KC_ERR_CAPACITY, "kc_merge_parts: too many records");
+    // temporaries come from the chunk scratch arena (idle between chunks), not from the allocator
+    Pending &ar = c->direct;
+    if (ar.active) return c->set_error(KC_ERR_STATE, "kc_merge_parts: a chunk is in flight on this context");
+    KC_TRY(arena_reserve(c, ar, arena_round((total + 2) * 8) + arena_round((total + 2) * 4) +
+                                    arena_round(merge_parts_workspace_bytes(n_sub)) + 512, s));
+    void *tk = arena_take(ar, (total + 2) * 8), *tc = arena_take(ar, (total + 2) * 4);
+    void *ws = arena_take(ar, merge_parts_workspace_bytes(n_sub));
+    unsigned long long *d_sc = static_cast<unsigned long long *>(arena_take(ar, 16));
+    int launches = 0;
+    const bool dbg = getenv("KC_DEBUG_TIMING") != nullptr;
+    auto now = [&]() { cudaStreamSynchronize(s); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t0 = dbg ? now() : 0;
+    KC_CUDA_TRY(c, merge_parts_count(n_src, reinterpret_cast<const uint64_t *const *>(d_keys),
+                                     reinterpret_cast<const uint32_t *const *>(d_counts),
+                                     reinterpret_cast<const uint32_t *const *>(d_offsets), n_sub, (int)prefix_bits,
+                                     static_cast<uint64_t *>(tk), static_cast<uint32_t *>(tc), &d_sc[0], &d_sc[1], ws,
+                                     c->n_sms, s, &launches));
+    unsigned long long h[2] = {0, 0};
+    KC_CUDA_TRY(c, cudaMemcpyAsync(h, d_sc, 16, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    int rc = KC_OK;
+    kc_run *r = nullptr;
+    double t1 = dbg ? now() : 0;
+    if (h[1]) rc = c->set_error(KC_ERR_CAPACITY, "kc_merge_parts: a key range could not be combined in shared memory");
+    if (rc == KC_OK) rc = make_run(c, s, h[0], &r);
+    double t2 = dbg ? now() : 0;
+    if (rc == KC_OK) {
+        void *mem = nullptr;
+        rc = dev_alloc(c, s, (uint64_t)(n_sub + 1) * 4, &mem);
+        if (rc == KC_OK) {
+            r->d_sub_off = static_cast<uint32_t *>(mem);
+            r->n_sub = n_sub;
+            r->prefix_bits = prefix_bits;
+            cudaError_t e = merge_parts_gather(n_sub, static_cast<uint64_t *>(tk), static_cast<uint32_t *>(tc), ws,
+                                               r->d_keys, r->d_counts, r->d_sub_off, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = c->set_error(KC_ERR_CUDA, "kc_merge_parts: %s", cudaGetErrorString(e));
+        }
+    }
+    ar.arena_used = 0;
+    if (dbg) fprintf(stderr, "kc_merge_parts: count %.2f ms, alloc %.2f ms, gather %.2f ms\n", t1 - t0, t2 - t1, now() - t2);
+    if (rc != KC_OK) { if (r) kc_run_free(c, r); return rc; }
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += launches + 1;
+    }
+    *out = r;
     return KC_OK;
 }
 

@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
     uint8_t *bad4 = smem + p.bad_off;
     uint8_t *flag = smem + p.flag_off;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.bar_off);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr uint32_t kWarps = kExtractThreads / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);

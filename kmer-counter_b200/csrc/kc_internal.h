@@ -81,6 +81,15 @@ bool partition_two_levels(uint64_t n_slots, int sig_bits, int target_sub);
 cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
                              const uint32_t *tmp_counts, void *ws, uint64_t *out_keys, uint32_t *out_counts,
                              cudaStream_t s);
+void partition_plan_info(uint64_t n_slots, int sig_bits, int target_sub, void *ws, uint32_t *n_sub,
+                         uint32_t *prefix_bits, const uint32_t **d_offsets);
+uint64_t merge_parts_workspace_bytes(uint32_t n_sub);
+cudaError_t merge_parts_count(uint32_t n_src, const uint64_t *const *src_keys, const uint32_t *const *src_counts,
+                              const uint32_t *const *src_off, uint32_t n_sub, int prefix_bits, uint64_t *tmp_keys,
+                              uint32_t *tmp_counts, unsigned long long *d_num_out, unsigned long long *d_overflow,
+                              void *ws, int n_sms, cudaStream_t s, int *n_launches);
+cudaError_t merge_parts_gather(uint32_t n_sub, const uint64_t *tmp_keys, const uint32_t *tmp_counts, void *ws,
+                               uint64_t *out_keys, uint32_t *out_counts, uint32_t *out_offsets, cudaStream_t s);
 cudaError_t partition_count(const ExtractParams &ep, uint64_t n_slots, int sig_bits, bool add_phantom,
                             uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
                             unsigned long long *d_num_out, unsigned long long *d_overflow,

@@ -327,6 +327,13 @@ struct FinishParams {
     int cap_shift;                 // first table guess = pow2ceil(n >> cap_shift) slots
     const uint32_t *list;          // optional: only these sub-buckets (NULL = all)
     const uint32_t *list_count;
+    uint32_t *tmp_start;           // [n_sub] where sub-bucket j's records start in tmp (written here, read by the gather)
+    // MULTI mode (merging pre-counted parts from several ranks): source s holds sorted unique
+    // (key, count) records, src_off[s][j] .. src_off[s][j+1] are those of sub-bucket j
+    uint32_t n_src;
+    const uint64_t *src_keys[8];
+    const uint32_t *src_counts[8];
+    const uint32_t *src_off[8];
 };
 
 constexpr int kSortBins = 1024;    // most bins the in-table counting sort uses
@@ -337,7 +344,7 @@ __device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 
 // another CTA: a sub-bucket with n keys has at most n distinct keys, so its records are
 // written to the private range [base2[j] + 1, ...) of a temporary array (position 0 is
 // the phantom's) and a later gather closes the gaps.
-template <int kPcThreads, int kHcap>
+template <int kPcThreads, int kHcap, bool MULTI>
 __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     constexpr int kLcap = kHcap / 2;
     extern __shared__ __align__(16) uint8_t pc_smem[];
@@ -356,11 +363,26 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
     const uint32_t n_work = p.list ? *p.list_count : p.n_sub;
+    float ratio = 0.5f;            // distinct / total of the sub-buckets finished so far (uniform across the CTA)
     for (uint32_t jj = blockIdx.x; jj < n_work; jj += gridDim.x) {
         const uint32_t j = p.list ? p.list[jj] : jj;
-        const uint32_t begin = p.base2[j], end = p.base2[j + 1];
-        const bool phantom = (j == 0) && p.add_phantom && (*p.d_n_invalid != 0);
-        if (begin == end && !phantom) {
+        uint32_t begin = 0, end = 0, n_in = 0, start_out = 0, floor_m = 0;
+        if constexpr (MULTI) {
+            for (uint32_t sidx = 0; sidx < p.n_src; sidx++) {
+                const uint32_t ns = p.src_off[sidx][j + 1] - p.src_off[sidx][j];
+                n_in += ns;
+                floor_m = ns > floor_m ? ns : floor_m;        // every part is key-unique already
+                start_out += p.src_off[sidx][j];
+            }
+        } else {
+            begin = p.base2[j];
+            end = p.base2[j + 1];
+            n_in = end - begin;
+            start_out = j == 0 ? 0 : begin + 1;       // position 0 of the temporary array is the phantom's
+        }
+        const bool phantom = !MULTI && (j == 0) && p.add_phantom && (*p.d_n_invalid != 0);
+        if (tid == 0) p.tmp_start[j] = start_out;
+        if (n_in == 0 && !phantom) {
             if (tid == 0) p.m_out[j] = 0;
             continue;
         }
@@ -374,37 +396,58 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             const int rshift = 64 - p.prefix_bits - (int)round_bits;
             const uint32_t rmask = (1u << round_bits) - 1;
             const uint32_t hshift = __clz(cap) + 1;                  // 32 - log2(cap)
+            uint32_t claims = 0;                                     // slots this thread claimed = new distinct keys
+            // a probe sequence longer than this means the table is far beyond half full: abandon the attempt
+            const uint32_t max_probes = cap < 64 ? cap : 64;
             auto insert = [&](uint64_t k, uint32_t add) {
                 uint32_t h = (((uint32_t)k ^ (uint32_t)(k >> 29)) * 0x9E3779B1u) >> hshift;
-                for (uint32_t probes = 0; probes < cap; probes++) {
+                for (uint32_t probes = 0; probes < max_probes; probes++) {
                     unsigned long long cur = tk[h];
                     if (cur == kEmptyKey) {
                         cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
-                        if (cur == kEmptyKey) atomicAdd(&s_m, 1u);     // claimed: one more distinct key
+                        if (cur == kEmptyKey) claims++;
                     }
                     if (cur == kEmptyKey || cur == k) { if (add) atomicAdd(&tc[h], add); return; }
                     h = (h + 1) & (cap - 1);
                 }
                 s_over = 1;
             };
-            for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * 8) {
-                uint64_t kk[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const uint32_t i = i0 + u * kPcThreads + tid;
-                    kk[u] = i < end ? ld_stream_u64(p.keys + i) : 0;
+            if constexpr (MULTI) {
+                for (uint32_t sidx = 0; sidx < p.n_src; sidx++) {
+                    const uint32_t b = p.src_off[sidx][j], e = p.src_off[sidx][j + 1];
+                    for (uint32_t i = b + tid; i < e; i += kPcThreads) {
+                        if (*reinterpret_cast<volatile uint32_t *>(&s_over)) break;
+                        const uint64_t k = p.src_keys[sidx][i];
+                        const uint32_t w = p.src_counts[sidx][i];
+                        if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
+                        if (k == kEmptyKey) { atomicAdd(&s_ones, w); continue; }
+                        insert(k, w);
+                    }
                 }
+            } else {
+                for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * 8) {
+                    if (*reinterpret_cast<volatile uint32_t *>(&s_over)) break;
+                    uint64_t kk[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const uint32_t i = i0 + u * kPcThreads + tid;
-                    if (i >= end) continue;
-                    const uint64_t k = kk[u];
-                    if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
-                    if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
-                    insert(k, 1u);
+                    for (int u = 0; u < 8; u++) {
+                        const uint32_t i = i0 + u * kPcThreads + tid;
+                        kk[u] = i < end ? ld_stream_u64(p.keys + i) : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const uint32_t i = i0 + u * kPcThreads + tid;
+                        if (i >= end) continue;
+                        const uint64_t k = kk[u];
+                        if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
+                        if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
+                        insert(k, 1u);
+                    }
                 }
             }
             if (phantom && r == 0 && tid == 0) insert(0ull, 0u);      // key 0 joins with count += 0
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, o);
+            if (lane == 0 && claims) atomicAdd(&s_m, claims);
             __syncthreads();
             m = s_m;
             ones = s_ones;
@@ -522,14 +565,19 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             __syncthreads();
         };
 
-        const uint64_t ob0 = j == 0 ? 0 : (uint64_t)begin + 1;
-        const uint32_t n = end - begin + (phantom ? 1u : 0u);
-        // first guess: about half of the keys are repeats; every failure quadruples the table,
-        // and once it is at its largest halves the keys per pass (pass r takes the keys whose
-        // next round_bits bits are r).
-        uint32_t cap = pow2_ceil_u32(n >> p.cap_shift);
-        cap = cap < 256 ? 256 : (cap > (uint32_t)kHcap ? (uint32_t)kHcap : cap);
+        const uint64_t ob0 = start_out;
+        const uint32_t n = n_in + (phantom ? 1u : 0u);
+        // First guess from the distinct/total ratio of the sub-buckets this CTA has finished so
+        // far (starts at 1/2): table = twice the expected distinct keys; if that exceeds the
+        // largest table the keys are taken in 2^round_bits passes (pass r = keys whose next bits
+        // are r). A failed attempt is abandoned early, quadruples the table, then halves the pass.
+        uint32_t expect = (uint32_t)((float)n * ratio * 1.25f) + 16;
+        if (expect < floor_m) expect = floor_m;
+        if (expect > n) expect = n;
         uint32_t round_bits = 0;
+        while ((expect >> round_bits) > (uint32_t)kLcap && round_bits < 16) round_bits++;
+        uint32_t cap = pow2_ceil_u32(2 * (expect >> round_bits));
+        cap = cap < 256 ? 256 : (cap > (uint32_t)kHcap ? (uint32_t)kHcap : cap);
         while (true) {
             const uint32_t n_rounds = 1u << round_bits;
             uint32_t running = 0;
@@ -544,6 +592,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             }
             if (ok) {
                 if (tid == 0) p.m_out[j] = running;
+                ratio = 0.5f * ratio + 0.5f * (float)running / (float)n;
                 break;
             }
             if (cap < (uint32_t)kHcap) {
@@ -561,10 +610,10 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
 }
 
 
-template <int THREADS, int HCAP>
+template <int THREADS, int HCAP, bool MULTI = false>
 cudaError_t launch_finish_v(const FinishParams &fp, int n_sms, uint32_t n_sub, cudaStream_t s) {
     constexpr uint32_t smem = HCAP * 12 + (HCAP / 2) * 12;
-    auto kern = finish_kernel<THREADS, HCAP>;
+    auto kern = finish_kernel<THREADS, HCAP, MULTI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -600,7 +649,7 @@ cudaError_t launch_finish(const FinishParams &fp, int n_sms, uint32_t n_sub, cud
 // records of sub-bucket j: tmp[src(j) .. src(j) + m_j) -> out[off[j] ...); one warp per sub-bucket
 __global__ void __launch_bounds__(256) gather_kernel(const uint64_t *__restrict__ tmp_keys,
                                                      const uint32_t *__restrict__ tmp_counts,
-                                                     const uint32_t *__restrict__ base2,
+                                                     const uint32_t *__restrict__ tmp_start,
                                                      const uint32_t *__restrict__ off, uint32_t n_sub,
                                                      uint64_t *__restrict__ out_keys,
                                                      uint32_t *__restrict__ out_counts) {
@@ -608,7 +657,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint64_t *__restrict_
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_sub; j += warps) {
         const uint32_t o0 = off[j], m = off[j + 1] - o0;
-        const uint64_t s0 = j == 0 ? 0 : (uint64_t)base2[j] + 1;
+        const uint64_t s0 = tmp_start[j];
         for (uint32_t i = lane; i < m; i += 32) {
             out_keys[o0 + i] = tmp_keys[s0 + i];
             out_counts[o0 + i] = tmp_counts[s0 + i];
@@ -648,7 +697,70 @@ cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, con
     uint32_t *hist2 = hist1 + 4 * (kMaxBins + 8);
     uint32_t *base2 = hist2 + pl.n_sub + 8;
     uint32_t *off = base2 + pl.n_sub + 8;
-    gather_kernel<<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, base2, off, pl.n_sub, out_keys, out_counts);
+    uint32_t *tmp_start = off + pl.n_sub + 8 + pl.n_sub + 8;
+    gather_kernel<<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
+    return cudaGetLastError();
+}
+
+// The plan a chunk of n_slots k-mer slots is counted with, and where the per-sub-bucket
+// record offsets (n_sub + 1 entries, valid after partition_count) live inside ws.
+void partition_plan_info(uint64_t n_slots, int sig_bits, int target_sub, void *ws, uint32_t *n_sub,
+                         uint32_t *prefix_bits, const uint32_t **d_offsets) {
+    const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : kDefaultTarget);
+    *n_sub = pl.n_sub;
+    *prefix_bits = (uint32_t)(pl.b1 + pl.b2);
+    if (d_offsets) {
+        const uint32_t *hist1 = reinterpret_cast<const uint32_t *>(ws);
+        *d_offsets = hist1 + 4 * (kMaxBins + 8) + 2 * (pl.n_sub + 8);
+    }
+}
+
+uint64_t merge_parts_workspace_bytes(uint32_t n_sub) { return (uint64_t)(4 * (n_sub + 8)) * 4 + 256; }
+
+// Merge pre-counted parts: n_src sources of sorted unique (key, count) records covering the
+// same n_sub consecutive sub-buckets (src_off[s] = n_sub + 1 offsets into source s). Equal keys
+// are summed in shared-memory tables, sub-bucket by sub-bucket; records land in tmp arrays
+// (capacity = total input records + 1), *d_num_out = records. Finish with merge_parts_gather.
+cudaError_t merge_parts_count(uint32_t n_src, const uint64_t *const *src_keys, const uint32_t *const *src_counts,
+                              const uint32_t *const *src_off, uint32_t n_sub, int prefix_bits, uint64_t *tmp_keys,
+                              uint32_t *tmp_counts, unsigned long long *d_num_out, unsigned long long *d_overflow,
+                              void *ws, int n_sms, cudaStream_t s, int *n_launches) {
+    if (n_src == 0 || n_src > 8) return cudaErrorInvalidValue;
+    uint32_t *m_out = reinterpret_cast<uint32_t *>(ws);
+    uint32_t *off = m_out + n_sub + 8;
+    uint32_t *tmp_start = off + n_sub + 8;
+    uint32_t *scratch = tmp_start + n_sub + 8;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(d_num_out, 0, 8, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(d_overflow, 0, 8, s)) != cudaSuccess) return e;
+    FinishParams fp{};
+    fp.n_sub = n_sub;
+    fp.prefix_bits = prefix_bits;
+    fp.tmp_keys = tmp_keys;
+    fp.tmp_counts = tmp_counts;
+    fp.m_out = m_out;
+    fp.d_overflow = d_overflow;
+    fp.cap_shift = 1;
+    fp.tmp_start = tmp_start;
+    fp.n_src = n_src;
+    for (uint32_t i = 0; i < n_src; i++) { fp.src_keys[i] = src_keys[i]; fp.src_counts[i] = src_counts[i]; fp.src_off[i] = src_off[i]; }
+    if ((e = launch_finish_v<256, 2048, true>(fp, n_sms, n_sub, s)) != cudaSuccess) return e;
+    scan2_kernel<<<1, 1024, 0, s>>>(m_out, n_sub, off, scratch);
+    if ((e = cudaMemcpyAsync(d_num_out, off + n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    if (n_launches) *n_launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t merge_parts_gather(uint32_t n_sub, const uint64_t *tmp_keys, const uint32_t *tmp_counts, void *ws,
+                               uint64_t *out_keys, uint32_t *out_counts, uint32_t *out_offsets, cudaStream_t s) {
+    uint32_t *m_out = reinterpret_cast<uint32_t *>(ws);
+    uint32_t *off = m_out + n_sub + 8;
+    uint32_t *tmp_start = off + n_sub + 8;
+    gather_kernel<<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, n_sub, out_keys, out_counts);
+    if (out_offsets) {
+        cudaError_t e = cudaMemcpyAsync(out_offsets, off, (size_t)(n_sub + 1) * 4, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+    }
     return cudaGetLastError();
 }
 
@@ -747,8 +859,11 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     {
         if (out_keys == grouped) return cudaErrorInvalidValue;
         uint32_t *m_out = hist2;                               // the level-2 histogram is dead by now
-        FinishParams fp{grouped, base2, pl.n_sub, pl.b1 + pl.b2, out_keys, out_counts, m_out, d_overflow,
-                        ep_in.n_invalid, add_phantom ? 1 : 0, 1, nullptr, nullptr};
+        FinishParams fp{};
+        fp.keys = grouped; fp.base2 = base2; fp.n_sub = pl.n_sub; fp.prefix_bits = pl.b1 + pl.b2;
+        fp.tmp_keys = out_keys; fp.tmp_counts = out_counts; fp.m_out = m_out; fp.d_overflow = d_overflow;
+        fp.d_n_invalid = ep_in.n_invalid; fp.add_phantom = add_phantom ? 1 : 0; fp.cap_shift = 1;
+        fp.tmp_start = status_scratch + pl.n_sub + 8;
         if ((e = launch_finish(fp, n_sms, pl.n_sub, s)) != cudaSuccess) return e;
         // off[] (n_sub + 1) overwrites cursor2; its last entry is the number of records
         scan2_kernel<<<1, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);

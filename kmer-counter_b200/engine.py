@@ -63,6 +63,12 @@ class Run:
         self._c._check(self._c._lib.kc_run_device(self._h, C.byref(k), C.byref(c), C.byref(n)))
         return k.value or 0, c.value or 0, n.value
 
+    def parts(self):
+        """(offsets_ptr, n_sub, prefix_bits): the run's partition structure, n_sub == 0 if it has none."""
+        o, n, b = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._c._check(self._c._lib.kc_run_parts(self._h, C.byref(o), C.byref(n), C.byref(b)))
+        return o.value or 0, n.value, b.value
+
     def split(self, splitters):
         """Lower-bound offsets of the splitter keys ([n_split, W] uint64) -> n_split+2 offsets."""
         sp = np.ascontiguousarray(splitters, dtype=np.uint64).reshape(-1, self._c.words)
@@ -196,6 +202,17 @@ class Counter:
     def run_from_device(self, keys_ptr, counts_ptr, n) -> Run:
         h = C.c_void_p()
         self._check(self._lib.kc_run_from_device(self._ctx, keys_ptr, counts_ptr, n, C.byref(h)))
+        return Run(self, h)
+
+    def merge_parts(self, key_ptrs, count_ptrs, offset_ptrs, n_records, n_sub, prefix_bits) -> Run:
+        """Combine pre-counted parts covering the same n_sub key ranges (kc_merge_parts)."""
+        n = len(key_ptrs)
+        ka = (C.c_void_p * n)(*key_ptrs)
+        ca = (C.c_void_p * n)(*count_ptrs)
+        oa = (C.c_void_p * n)(*offset_ptrs)
+        na = (C.c_uint64 * n)(*n_records)
+        h = C.c_void_p()
+        self._check(self._lib.kc_merge_parts(self._ctx, n, ka, ca, oa, na, n_sub, prefix_bits, C.byref(h)))
         return Run(self, h)
 
     def merge(self, runs) -> Run:

@@ -123,17 +123,57 @@ def run_as_tensors(run, device):
 
 def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, splitters=None):
     """This rank's share of the distributed count.  Returns the Run holding the final
-    records of this rank's key range.  Collective: every rank of `group` must call it."""
+    records of this rank's key range.  Collective: every rank of `group` must call it.
+
+    Runs of the partitioned hash path carry their partition structure (n_sub equal key ranges
+    with record offsets); when all ranks agree on it, rank r owns ranges [r*n_sub/P, (r+1)*n_sub/P),
+    receives each peer's records and offsets for them, and combines the P parts range by range in
+    shared-memory tables (kc_merge_parts): one pass whose cost does not grow with P.  Otherwise
+    (sort path, k > 32) slices are cut at key splitters and merged by the merge-path tree."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     local = counter.count_device(d_reads_ptr, n_bytes)
     if world == 1:
         return local
+    return exchange_and_combine(counter, local, device, group, splitters)
+
+
+def exchange_and_combine(counter, local, device, group=None, splitters=None):
+    """Second half of count_shard: `local` is this rank's run; returns the run of this rank's
+    key range. Frees `local`."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    off_ptr, n_sub, pbits = local.parts()
+    plan = torch.tensor([n_sub, pbits], dtype=torch.int64, device=device)
+    plans = [torch.empty_like(plan) for _ in range(world)]
+    dist.all_gather(plans, plan, group=group)
+    agreed = n_sub >= world and n_sub % world == 0 and all(bool((q == plan).all()) for q in plans)
+    keys_t, counts_t = run_as_tensors(local, device)
+    if agreed:
+        per = n_sub // world
+        off_t = torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=device)
+        bounds = off_t[::per].to(torch.int64)                      # record boundaries of the owners' ranges
+        rel = torch.stack([off_t[p * per:(p + 1) * per + 1] - off_t[p * per] for p in range(world)]).contiguous()
+        recv_rel = torch.empty_like(rel)
+        if dist.get_backend(group) == "nccl":
+            dist.all_to_all_single(recv_rel, rel, group=group)
+        else:
+            _p2p_all_to_all(recv_rel, rel, [1] * world, [1] * world, group)
+        rk, rc, sizes = exchange_slices(keys_t, counts_t, bounds.tolist(), group)
+        torch.cuda.current_stream().synchronize()
+        local.free()
+        kp, cp, op, pos = [], [], [], 0
+        for src, sz in enumerate(sizes):
+            kp.append(rk.data_ptr() + pos * 8 if sz else 0)
+            cp.append(rc.data_ptr() + pos * 4 if sz else 0)
+            op.append(recv_rel[src].data_ptr())
+            pos += sz
+        return counter.merge_parts(kp, cp, op, sizes, per, pbits)
     if splitters is None:
         splitters = range_splitters(world, counter.words)
     off = local.split(splitters)
-    keys_t, counts_t = run_as_tensors(local, device)
     # the run was produced on the counter's stream and is complete (count_device synchronises)
     rk, rc, sizes = exchange_slices(keys_t, counts_t, off, group)
     torch.cuda.current_stream().synchronize()
