@@ -154,14 +154,45 @@ def exchange_and_combine(counter, local, device, group=None, splitters=None):
     if agreed:
         per = n_sub // world
         off_t = torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=device)
-        bounds = off_t[::per].to(torch.int64)                      # record boundaries of the owners' ranges
-        rel = torch.stack([off_t[p * per:(p + 1) * per + 1] - off_t[p * per] for p in range(world)]).contiguous()
+        # offsets of every owner's ranges, relative to the start of its slice; the last entry of a
+        # row is the slice length, so this one small all-to-all also tells the receiver the sizes
+        rel = (off_t.unfold(0, per + 1, per) - off_t[0:n_sub:per].unsqueeze(1)).contiguous()
         recv_rel = torch.empty_like(rel)
-        if dist.get_backend(group) == "nccl":
+        nccl = dist.get_backend(group) == "nccl"
+        if nccl:
             dist.all_to_all_single(recv_rel, rel, group=group)
         else:
             _p2p_all_to_all(recv_rel, rel, [1] * world, [1] * world, group)
-        rk, rc, sizes = exchange_slices(keys_t, counts_t, bounds.tolist(), group)
+        send = rel[:, per].tolist()
+        sizes = recv_rel[:, per].tolist()
+        starts = off_t[0:n_sub:per].tolist()
+        rk = torch.empty((sum(sizes), 1), dtype=keys_t.dtype, device=device)
+        rc = torch.empty((sum(sizes),), dtype=counts_t.dtype, device=device)
+        if nccl:
+            # keys and counts of all peers in ONE grouped launch
+            rank = dist.get_rank(group)
+            ops, pos = [], 0
+            for p in range(world):
+                peer = dist.get_global_rank(group, p) if group else p
+                a, b = starts[p], starts[p] + send[p]
+                if p == rank:
+                    rk[pos:pos + sizes[p]].copy_(keys_t[a:b])
+                    rc[pos:pos + sizes[p]].copy_(counts_t[a:b])
+                else:
+                    if send[p]:
+                        ops.append(dist.P2POp(dist.isend, keys_t[a:b], peer, group))
+                        ops.append(dist.P2POp(dist.isend, counts_t[a:b], peer, group))
+                    if sizes[p]:
+                        ops.append(dist.P2POp(dist.irecv, rk[pos:pos + sizes[p]], peer, group))
+                        ops.append(dist.P2POp(dist.irecv, rc[pos:pos + sizes[p]], peer, group))
+                pos += sizes[p]
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        else:
+            bounds = [starts[p] for p in range(world)] + [starts[-1] + send[-1]]
+            _p2p_all_to_all(rk, keys_t, sizes, [bounds[p + 1] - bounds[p] for p in range(world)], group)
+            _p2p_all_to_all(rc, counts_t, sizes, [bounds[p + 1] - bounds[p] for p in range(world)], group)
         torch.cuda.current_stream().synchronize()
         local.free()
         kp, cp, op, pos = [], [], [], 0

@@ -18,21 +18,10 @@ def T():
 for it in range(4):
     dist.barrier(); t0 = T()
     local = c.count_device(d.data_ptr(), R * L); t1 = T()
-    off_ptr, n_sub, pbits = local.parts()
-    keys_t, counts_t = multigpu.run_as_tensors(local, dev)
-    per = n_sub // world
-    off_t = torch.as_tensor(multigpu._CudaView(off_ptr, (n_sub + 1,), "<i4"), device=dev)
-    bounds = off_t[::per].to(torch.int64)
-    rel = torch.stack([off_t[p * per:(p + 1) * per + 1] - off_t[p * per] for p in range(world)]).contiguous()
-    recv_rel = torch.empty_like(rel); dist.all_to_all_single(recv_rel, rel); t2 = T()
-    rk, rc, sizes = multigpu.exchange_slices(keys_t, counts_t, bounds.tolist()); t3 = T()
-    local.free()
-    kp, cp, op, pos = [], [], [], 0
-    for src, sz in enumerate(sizes):
-        kp.append(rk.data_ptr() + pos * 8); cp.append(rc.data_ptr() + pos * 4); op.append(recv_rel[src].data_ptr()); pos += sz
-    m = c.merge_parts(kp, cp, op, sizes, per, pbits); t4 = T()
+    t2 = t3 = t1
+    m = multigpu.exchange_and_combine(c, local, dev); t4 = T()
     n = len(m); m.free(); t5 = T()
     if rank == 0:
         print("it %d: count %.2f  offsets+a2a %.2f  exchange %.2f (%.0f MB sent)  merge_parts %.2f  free %.2f  total %.2f ms  records %d" %
-              (it, (t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3, keys_t.numel()*12/1e6*(world-1)/world, (t4-t3)*1e3, (t5-t4)*1e3, (t5-t0)*1e3, n), flush=True)
+              (it, (t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3, 0, (t4-t3)*1e3, (t5-t4)*1e3, (t5-t0)*1e3, n), flush=True)
 dist.destroy_process_group()
