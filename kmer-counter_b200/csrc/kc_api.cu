@@ -182,7 +182,8 @@ constexpr uint64_t kMaxSortKeys = (1ull << 30) - 1;
 
 uint32_t pick_method(const kc_ctx *c) {
     uint32_t m = c->cfg.method;
-    if (c->W != 1) return KC_COUNT_SORT;           // 128-bit+ keys: sort + run-length (config 3)
+    if (c->W > 2) return KC_COUNT_SORT;            // 192/256-bit keys: sort + run-length
+    if (c->W == 2) return (m == KC_COUNT_AUTO || m == KC_COUNT_HASH) ? KC_COUNT_HASH : KC_COUNT_SORT;
     // 64-bit keys: partitioned shared-memory hashing unless the key has too few significant
     // bits to partition on (tiny k); see DESIGN.md "method selection"
     if (m == KC_COUNT_AUTO) return (64 - static_zero_bits(c)) >= 24 ? KC_COUNT_HASH : KC_COUNT_SORT;
@@ -215,16 +216,16 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
         ExtractParams ep64;
         if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep64, 6400))
             return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
-        const uint64_t kb = p.n_slots * 8 + 64, cb = (p.n_slots + 2) * 4, wb = partition_workspace_bytes(p.n_slots);
+        const uint64_t kb = p.n_slots * 8 * W + 64, cb = (p.n_slots + 2) * 4, wb = partition_workspace_bytes(p.n_slots);
         KC_TRY(arena_reserve(c, p, 2 * arena_round(kb) + arena_round(cb) + arena_round(wb), s));
         p.keys_a = static_cast<uint64_t *>(arena_take(p, kb));
         p.keys_b = static_cast<uint64_t *>(arena_take(p, kb));
         p.counts = static_cast<uint32_t *>(arena_take(p, cb));
         p.ws_part = arena_take(p, wb);
-        const int sig = 64 - static_zero_bits(c);
+        const int sig = W == 1 ? 64 - static_zero_bits(c) : 64;        // significant bits of key word 0
         const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;   // keys per sub-bucket (0 = default)
         p.uniq = partition_two_levels(p.n_slots, sig, target) ? p.keys_a : p.keys_b;
-        KC_CUDA_TRY(c, partition_count(ep64, p.n_slots, sig, !c->strict, p.keys_a, p.keys_b, p.uniq, p.counts,
+        KC_CUDA_TRY(c, partition_count(W, ep64, p.n_slots, sig, !c->strict, p.keys_a, p.keys_b, p.uniq, p.counts,
                                        &p.d_scal[SC_UNIQUE], &p.d_scal[SC_SIDE + 1], &p.d_scal[SC_COUNT - 2],
                                        p.ws_part, c->n_sms, target, s, &launches, &p.ev[1]));
         p.n_ev = 6;
@@ -344,11 +345,11 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
             st.stage_bytes[4] = U * (2 * Kb + 8);                          st.stage_launches[4] = 1;
         } else if (used == KC_COUNT_HASH && p.n_slots) {
             st.stage_bytes[0] = in_bytes;                                  st.stage_launches[0] = 2;
-            st.stage_bytes[1] = in_bytes + 8 * nv;                         st.stage_launches[1] = 1;
-            st.stage_bytes[2] = 8 * nv;                                    st.stage_launches[2] = 2;
-            st.stage_bytes[3] = 16 * nv;                                   st.stage_launches[3] = 1;
-            st.stage_bytes[4] = 8 * nv + 12 * U;                           st.stage_launches[4] = 2;
-            st.stage_bytes[5] = 24 * U;                                    st.stage_launches[5] = 1;
+            st.stage_bytes[1] = in_bytes + Kb * nv;                        st.stage_launches[1] = 1;
+            st.stage_bytes[2] = Kb * nv;                                   st.stage_launches[2] = 2;
+            st.stage_bytes[3] = 2 * Kb * nv;                               st.stage_launches[3] = 1;
+            st.stage_bytes[4] = Kb * nv + (Kb + 4) * U;                    st.stage_launches[4] = 2;
+            st.stage_bytes[5] = 2 * (Kb + 4) * U;                          st.stage_launches[5] = 1;
         } else if (used == KC_COUNT_HASH_GLOBAL && p.n_slots) {
             st.stage_bytes[0] = p.table.capacity * 16;                     st.stage_launches[0] = 1;
             st.stage_bytes[1] = in_bytes + nv * 16;                        st.stage_launches[1] = 1;   // SURVEY 8(d) terms
@@ -374,9 +375,9 @@ int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) 
     kc_run *r = nullptr;
     KC_TRY(make_run(c, s, U, &r));
     if (U) {
-        const int sig = 64 - static_zero_bits(c);
+        const int sig = c->W == 1 ? 64 - static_zero_bits(c) : 64;
         const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;
-        KC_CUDA_TRY(c, partition_gather(p.n_slots, sig, target, p.uniq, p.counts, p.ws_part, r->d_keys, r->d_counts, s));
+        KC_CUDA_TRY(c, partition_gather(c->W, p.n_slots, sig, target, p.uniq, p.counts, p.ws_part, r->d_keys, r->d_counts, s));
         const uint32_t *d_off = nullptr;
         partition_plan_info(p.n_slots, sig, target, p.ws_part, &r->n_sub, &r->prefix_bits, &d_off);
         void *mem = nullptr;
@@ -464,7 +465,8 @@ int kc_create(const kc_config *cfg, kc_ctx **out) {
     if (c0.k < 1 || c0.k > 128) { g_create_error = "kc_create: k must be in 1..128 (KMerSizes.h holds 4 words)"; return KC_ERR_ARG; }
     if (c0.read_len < c0.k || c0.read_len > 4096) { g_create_error = "kc_create: read_len must be in k..4096"; return KC_ERR_ARG; }
     if (c0.method > KC_COUNT_HASH_GLOBAL) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
-    if ((c0.method == KC_COUNT_HASH || c0.method == KC_COUNT_HASH_GLOBAL) && c0.k > 32) { g_create_error = "kc_create: hash counting needs k <= 32"; return KC_ERR_ARG; }
+    if (c0.method == KC_COUNT_HASH && c0.k > 64) { g_create_error = "kc_create: hash counting needs k <= 64"; return KC_ERR_ARG; }
+    if (c0.method == KC_COUNT_HASH_GLOBAL && c0.k > 32) { g_create_error = "kc_create: the HBM-resident table needs k <= 32"; return KC_ERR_ARG; }
     cudaError_t e = cudaSetDevice(c0.device);
     if (e != cudaSuccess) { g_create_error = std::string("kc_create: cudaSetDevice failed: ") + cudaGetErrorString(e); return KC_ERR_CUDA; }
     kc_ctx *c = new kc_ctx();

@@ -191,30 +191,36 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
 #pragma unroll
         for (int sw = 0; sw < Sink::kSweeps; sw++) {
             sink.sweep_begin(sw, total);
-            if constexpr (Sink::kRolling && W == 1) {
+            if constexpr (Sink::kRolling) {
                 // Sinks that ignore the slot index: a thread walks a segment of consecutive
-                // positions of one read and slides the 32-base window by one base per key
-                // (two funnel shifts) instead of rebuilding it from the encoded words.
+                // positions of one read and slides the 32W-base window by one base per key
+                // (funnel shifts) instead of rebuilding it from the encoded words.
                 const uint32_t n_seg = nreads * p.segs_per_read;
                 for (uint32_t sg = tid; sg < n_seg; sg += kExtractThreads) {
                     const uint32_t r = sg / p.segs_per_read;
                     const uint32_t p0 = (sg - r * p.segs_per_read) * p.seg_len;
                     const uint32_t p1 = min(p0 + p.seg_len, p.nk);
-                    const uint64_t *e = enc + r * enc_row + (p0 >> 5);
+                    const uint32_t wi = p0 >> 5;
+                    const uint64_t *e = enc + r * enc_row + wi;
                     const uint32_t sh = (p0 & 31u) * 2u;
-                    const uint64_t e0 = e[0], e1 = e[1];
-                    const uint64_t e2 = ((p0 >> 5) + 2 <= p.nw) ? e[2] : 0ull;
-                    uint64_t win = sh ? ((e0 << sh) | (e1 >> (64 - sh))) : e0;     // bases p0 .. p0+31
-                    uint64_t nxt = sh ? ((e1 << sh) | (e2 >> (64 - sh))) : e1;     // bases p0+32 .. p0+63
+                    uint64_t ew[W + 2];
+#pragma unroll
+                    for (int q = 0; q < W + 2; q++) ew[q] = (wi + q <= p.nw) ? e[q] : 0ull;
+                    uint64_t win[W + 1];                                           // win[W] = lookahead word
+#pragma unroll
+                    for (int q = 0; q <= W; q++) win[q] = sh ? ((ew[q] << sh) | (ew[q + 1] >> (64 - sh))) : ew[q];
                     const bool check = flag[r] != 0;
                     for (uint32_t pos = p0; pos < p1; pos++) {
-                        Key<1> key;
-                        key.w[0] = win & p.last_mask;
+                        Key<W> key;
+#pragma unroll
+                        for (int q = 0; q < W; q++) key.w[q] = win[q];
+                        key.w[W - 1] &= p.last_mask;
                         const bool valid = check ? kmer_valid(r, pos) : true;
                         if (sw == 0 && !valid) invalid_local++;
                         sink(sw, slot0 + r * p.nk + pos, key, valid);
-                        win = (win << 2) | (nxt >> 62);
-                        nxt <<= 2;
+#pragma unroll
+                        for (int q = 0; q < W; q++) win[q] = (win[q] << 2) | (win[q + 1] >> 62);
+                        win[W] <<= 2;
                     }
                 }
             } else {

@@ -74,11 +74,11 @@ cudaError_t hash_touch_zero(HashTable t, const unsigned long long *d_n_invalid, 
 cudaError_t hash_compact(HashTable t, uint64_t *out_keys, uint32_t *out_counts, unsigned long long *d_num,
                          cudaStream_t s, int *n_launches);
 
-// ---- partitioned shared-memory hash counting (kc_partition.cu), W == 1 only
+// ---- partitioned shared-memory hash counting (kc_partition.cu), W = 1 or 2
 uint64_t partition_workspace_bytes(uint64_t n_slots);
 // true when out_keys must be keys_a (two partition levels) rather than keys_b
 bool partition_two_levels(uint64_t n_slots, int sig_bits, int target_sub);
-cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
+cudaError_t partition_gather(int W, uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
                              const uint32_t *tmp_counts, void *ws, uint64_t *out_keys, uint32_t *out_counts,
                              cudaStream_t s);
 void partition_plan_info(uint64_t n_slots, int sig_bits, int target_sub, void *ws, uint32_t *n_sub,
@@ -90,7 +90,7 @@ cudaError_t merge_parts_count(uint32_t n_src, const uint64_t *const *src_keys, c
                               void *ws, int n_sms, cudaStream_t s, int *n_launches);
 cudaError_t merge_parts_gather(uint32_t n_sub, const uint64_t *tmp_keys, const uint32_t *tmp_counts, void *ws,
                                uint64_t *out_keys, uint32_t *out_counts, uint32_t *out_offsets, cudaStream_t s);
-cudaError_t partition_count(const ExtractParams &ep, uint64_t n_slots, int sig_bits, bool add_phantom,
+cudaError_t partition_count(int W, const ExtractParams &ep, uint64_t n_slots, int sig_bits, bool add_phantom,
                             uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
                             unsigned long long *d_num_out, unsigned long long *d_overflow,
                             unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,

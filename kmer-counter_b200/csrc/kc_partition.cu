@@ -1,4 +1,4 @@
-// kc_partition.cu -- partitioned hash counting for 64-bit keys (k <= 32), sm_100a.
+// kc_partition.cu -- partitioned hash counting for 64- and 128-bit keys (k <= 64), sm_100a.
 //
 // This is the B200 replacement for the reference's counting step (one TBB hash
 // insert per k-mer occurrence on the host, KMerCounter.cpp:61-82) AND for its
@@ -29,8 +29,8 @@ namespace kc {
 namespace {
 
 constexpr int kMaxBins = 1024;          // bins per level
-constexpr uint64_t kEmptyKey = ~0ull;   // the all-ones key (poly-T window) is the empty marker; counted aside
-constexpr int kPbThreads = 256, kPbItems = 16, kPbTile = kPbThreads * kPbItems;
+constexpr int kPbThreads = 256;
+template <int W> struct PbCfg { static constexpr int ITEMS = 16 / W, TILE = kPbThreads * ITEMS; };
 constexpr int kDefaultTarget = 3072;    // keys per sub-bucket the plan aims for
 
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
@@ -73,6 +73,7 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_
 }
 
 // ------------------------------------------------------------------- P0: hist1
+template <int W>
 struct Hist1Sink : SinkBase {
     static constexpr bool kRolling = true;
     uint32_t *g_hist1;
@@ -82,7 +83,7 @@ struct Hist1Sink : SinkBase {
         sh = reinterpret_cast<uint32_t *>(extra);
         for (int i = threadIdx.x; i < nb1; i += kExtractThreads) sh[i] = 0;
     }
-    __device__ __forceinline__ void operator()(int, uint64_t, const Key<1> &key, bool valid) {
+    __device__ __forceinline__ void operator()(int, uint64_t, const Key<W> &key, bool valid) {
         if (valid) atomicAdd(&sh[key.w[0] >> shift1], 1u);
     }
     __device__ __forceinline__ void finish() {
@@ -95,13 +96,13 @@ struct Hist1Sink : SinkBase {
 };
 
 // one block: bucket bases, the mutable cursors, and the tile map for H2 / PB
-__global__ void __launch_bounds__(1024) scan1_kernel(const uint32_t *__restrict__ hist1, int nb1,
+__global__ void __launch_bounds__(1024) scan1_kernel(const uint32_t *__restrict__ hist1, int nb1, uint32_t tile_keys,
                                                      uint32_t *__restrict__ base1, uint32_t *__restrict__ cursor1,
                                                      uint32_t *__restrict__ tile_prefix) {
     __shared__ uint32_t s_a[32], s_b[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = tid < nb1 ? hist1[tid] : 0;
-    const uint32_t t = (c + kPbTile - 1) / kPbTile;
+    const uint32_t t = (c + tile_keys - 1) / tile_keys;
     uint32_t ia = c, ib = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(1024) scan1_kernel(const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------- PA: scatter1
+template <int W>
 struct Scatter1Sink : SinkBase {
     static constexpr int kSweeps = 2;
     static constexpr bool kRolling = true;
@@ -131,29 +133,29 @@ struct Scatter1Sink : SinkBase {
     int shift2;
     // shared
     uint32_t *cnt, *start, *gbase, *s_warp;
-    uint64_t *staging;
+    Key<W> *staging;
     uint32_t total;
 
     static __host__ __device__ uint32_t smem_bytes(uint32_t max_tile_keys) {
-        return 3 * kMaxBins * 4 + 64 + max_tile_keys * 8;
+        return 3 * kMaxBins * 4 + 64 + max_tile_keys * 8 * W;
     }
     __device__ __forceinline__ void begin(uint8_t *extra) {
         cnt = reinterpret_cast<uint32_t *>(extra);
         start = cnt + kMaxBins;
         gbase = start + kMaxBins;
         s_warp = gbase + kMaxBins;
-        staging = reinterpret_cast<uint64_t *>(s_warp + 16);
+        staging = reinterpret_cast<Key<W> *>(s_warp + 16);
         for (int i = threadIdx.x; i < nb1; i += kExtractThreads) cnt[i] = 0;
         total = 0;
     }
-    __device__ __forceinline__ void operator()(int sw, uint64_t, const Key<1> &key, bool valid) {
+    __device__ __forceinline__ void operator()(int sw, uint64_t, const Key<W> &key, bool valid) {
         if (!valid) return;
         const uint32_t d = (uint32_t)(key.w[0] >> shift1);
         if (sw == 0) {
             atomicAdd(&cnt[d], 1u);
         } else {
             const uint32_t pos = start[d] + atomicAdd(&cnt[d], 1u);
-            staging[pos] = key.w[0];
+            staging[pos] = key;
         }
     }
     __device__ __forceinline__ void sweep_end(int sw) {
@@ -167,9 +169,9 @@ struct Scatter1Sink : SinkBase {
             __syncthreads();
         } else {
             for (uint32_t i = threadIdx.x; i < total; i += kExtractThreads) {
-                const uint64_t k = staging[i];
-                out[gbase[k >> shift1] + i] = k;
-                if (g_hist2) atomicAdd(&g_hist2[k >> shift2], 1u);
+                const Key<W> k = staging[i];
+                st_key<W>(out, gbase[k.w[0] >> shift1] + i, k);
+                if (g_hist2) atomicAdd(&g_hist2[k.w[0] >> shift2], 1u);
             }
             for (int b = threadIdx.x; b < nb1; b += kExtractThreads) cnt[b] = 0;
             __syncthreads();
@@ -179,8 +181,8 @@ struct Scatter1Sink : SinkBase {
 
 // -------------------------------------------------------------- tile map (H2 / PB)
 __device__ __forceinline__ bool map_tile(const uint32_t *__restrict__ tile_prefix, const uint32_t *__restrict__ base1,
-                                         int nb1, uint32_t tile, uint32_t *s_map, uint32_t &bucket, uint32_t &begin,
-                                         uint32_t &end) {
+                                         int nb1, uint32_t tile, uint32_t tile_keys, uint32_t *s_map, uint32_t &bucket,
+                                         uint32_t &begin, uint32_t &end) {
     if (threadIdx.x == 0) {
         uint32_t b = 0xffffffffu, lo_i = 0, hi_i = 0;
         if (tile < tile_prefix[nb1]) {
@@ -191,9 +193,9 @@ __device__ __forceinline__ bool map_tile(const uint32_t *__restrict__ tile_prefi
             }
             b = lo;
             const uint32_t t = tile - tile_prefix[b];
-            lo_i = base1[b] + t * kPbTile;
+            lo_i = base1[b] + t * tile_keys;
             hi_i = base1[b + 1];
-            if (hi_i - lo_i > (uint32_t)kPbTile) hi_i = lo_i + kPbTile;
+            if (hi_i - lo_i > tile_keys) hi_i = lo_i + tile_keys;
         }
         s_map[0] = b; s_map[1] = lo_i; s_map[2] = hi_i;
     }
@@ -203,6 +205,7 @@ __device__ __forceinline__ bool map_tile(const uint32_t *__restrict__ tile_prefi
 }
 
 // ------------------------------------------------------------------- H2: hist2
+template <int W>
 __global__ void __launch_bounds__(kPbThreads) hist2_kernel(const uint64_t *__restrict__ keys,
                                                            const uint32_t *__restrict__ tile_prefix,
                                                            const uint32_t *__restrict__ base1, int nb1, int shift2,
@@ -211,12 +214,12 @@ __global__ void __launch_bounds__(kPbThreads) hist2_kernel(const uint64_t *__res
     __shared__ uint32_t s_map[4];
     uint32_t bucket, begin, end;
     for (int i = threadIdx.x; i < nb2; i += kPbThreads) sh[i] = 0;
-    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, s_map, bucket, begin, end)) return;
+    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, PbCfg<W>::TILE, s_map, bucket, begin, end)) return;
     const uint32_t m2 = (uint32_t)nb2 - 1;
 #pragma unroll 4
-    for (int i = 0; i < kPbItems; i++) {
+    for (int i = 0; i < PbCfg<W>::ITEMS; i++) {
         const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        if (idx < end) atomicAdd(&sh[(uint32_t)(keys[idx] >> shift2) & m2], 1u);
+        if (idx < end) atomicAdd(&sh[(uint32_t)(keys[(size_t)idx * W] >> shift2) & m2], 1u);   // word 0 holds the prefix
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nb2; i += kPbThreads) {
@@ -269,29 +272,32 @@ __global__ void __launch_bounds__(1024) scan2_kernel(const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------- PB: scatter2
+template <int W>
 __global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__restrict__ keys,
                                                               uint64_t *__restrict__ out,
                                                               const uint32_t *__restrict__ tile_prefix,
                                                               const uint32_t *__restrict__ base1, int nb1, int shift2,
                                                               int nb2, uint32_t *__restrict__ g_cursor2) {
+    constexpr int ITEMS = PbCfg<W>::ITEMS, TILE = PbCfg<W>::TILE;
     __shared__ uint32_t cnt[kMaxBins], start[kMaxBins], gbase[kMaxBins];
     __shared__ uint32_t s_warp[kPbThreads / 32], s_map[4];
-    __shared__ uint64_t staging[kPbTile];
+    __shared__ Key<W> staging[TILE];
     uint32_t bucket, begin, end;
     for (int i = threadIdx.x; i < nb2; i += kPbThreads) cnt[i] = 0;
-    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, s_map, bucket, begin, end)) return;
+    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, TILE, s_map, bucket, begin, end)) return;
     const uint32_t m2 = (uint32_t)nb2 - 1;
-    uint64_t key[kPbItems];
-    uint16_t rank[kPbItems];
+    Key<W> key[ITEMS];
+    uint16_t rank[ITEMS];
 #pragma unroll
-    for (int i = 0; i < kPbItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        key[i] = idx < end ? keys[idx] : 0;
+        if (idx < end) key[i] = ld_key<W>(keys, idx);
+        else key[i].w[0] = 0;
     }
 #pragma unroll
-    for (int i = 0; i < kPbItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        if (idx < end) rank[i] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key[i] >> shift2) & m2], 1u);
+        if (idx < end) rank[i] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key[i].w[0] >> shift2) & m2], 1u);
     }
     __syncthreads();
     const uint32_t total = block_scan_bins<kPbThreads>(cnt, start, nb2, s_warp);
@@ -300,14 +306,14 @@ __global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__
         if (c) gbase[b] = atomicAdd(&g_cursor2[(size_t)bucket * nb2 + b], c) - start[b];
     }
 #pragma unroll
-    for (int i = 0; i < kPbItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        if (idx < end) staging[start[(uint32_t)(key[i] >> shift2) & m2] + rank[i]] = key[i];
+        if (idx < end) staging[start[(uint32_t)(key[i].w[0] >> shift2) & m2] + rank[i]] = key[i];
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < total; i += kPbThreads) {
-        const uint64_t k = staging[i];
-        out[gbase[(uint32_t)(k >> shift2) & m2] + i] = k;
+        const Key<W> k = staging[i];
+        st_key<W>(out, gbase[(uint32_t)(k.w[0] >> shift2) & m2] + i, k);
     }
 }
 
@@ -340,24 +346,69 @@ constexpr int kSortBins = 1024;    // most bins the in-table counting sort uses
 
 __device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 1u : 1u << (32 - __clz(x - 1)); }
 
+// ---- table slot primitives: 64-bit keys use a 64-bit shared CAS, 128-bit keys ATOMS.CAS.128
+template <int W> __device__ __forceinline__ bool key_all_ones(const Key<W> &k) {
+    uint64_t a = ~0ull;
+#pragma unroll
+    for (int i = 0; i < W; i++) a &= k.w[i];
+    return a == ~0ull;
+}
+template <int W> __device__ __forceinline__ bool key_any_word_ones(const Key<W> &k) {
+    bool r = false;
+#pragma unroll
+    for (int i = 0; i < W; i++) r = r || (k.w[i] == ~0ull);
+    return r;
+}
+template <int W> __device__ __forceinline__ void key_set_ones(Key<W> &k) {
+#pragma unroll
+    for (int i = 0; i < W; i++) k.w[i] = ~0ull;
+}
+__device__ __forceinline__ Key<1> slot_claim(Key<1> *slot, const Key<1> &k) {      // returns the previous content
+    Key<1> o;
+    o.w[0] = atomicCAS(reinterpret_cast<unsigned long long *>(slot), ~0ull, (unsigned long long)k.w[0]);
+    return o;
+}
+__device__ __forceinline__ Key<2> slot_claim(Key<2> *slot, const Key<2> &k) {
+    Key<2> o;
+    const uint32_t a = smem_u32(slot);
+    asm volatile(
+        "{\n"
+        ".reg .b128 c, n, o;\n"
+        "mov.b128 c, {%3, %3};\n"
+        "mov.b128 n, {%4, %5};\n"
+        "atom.shared.cas.b128 o, [%2], c, n;\n"
+        "mov.b128 {%0, %1}, o;\n"
+        "}\n"
+        : "=l"(o.w[0]), "=l"(o.w[1])
+        : "r"(a), "l"(~0ull), "l"(k.w[0]), "l"(k.w[1])
+        : "memory");
+    return o;
+}
+template <int W> __device__ __forceinline__ uint32_t key_hash(const Key<W> &k) {
+    uint32_t x = (uint32_t)k.w[0] ^ (uint32_t)(k.w[0] >> 29);
+    if constexpr (W > 1) x ^= ((uint32_t)k.w[W - 1] ^ (uint32_t)(k.w[W - 1] >> 31)) * 0x85EBCA6Bu;
+    return x * 0x9E3779B1u;
+}
+
 // One CTA per sub-bucket (round-robin over a persistent grid). Nothing here depends on
 // another CTA: a sub-bucket with n keys has at most n distinct keys, so its records are
-// written to the private range [base2[j] + 1, ...) of a temporary array (position 0 is
-// the phantom's) and a later gather closes the gaps.
-template <int kPcThreads, int kHcap, bool MULTI>
+// written to a private range of a temporary array (position 0 is the phantom's) and a later
+// gather closes the gaps.
+template <int kPcThreads, int kHcap, bool MULTI, int W>
 __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
+    static_assert(!MULTI || W == 1, "merging pre-counted parts is implemented for 64-bit keys");
     constexpr int kLcap = kHcap / 2;
     extern __shared__ __align__(16) uint8_t pc_smem[];
-    uint64_t *tk = reinterpret_cast<uint64_t *>(pc_smem);            // table keys   [kHcap]
-    uint64_t *lk = tk + kHcap;                                       // list keys    [kLcap]
-    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);         // table counts [kHcap]
-    uint32_t *lc = tc + kHcap;                                       // list counts  [kLcap]
+    Key<W> *tk = reinterpret_cast<Key<W> *>(pc_smem);               // table keys   [kHcap]
+    Key<W> *lk = tk + kHcap;                                        // list keys    [kLcap]
+    uint32_t *tc = reinterpret_cast<uint32_t *>(lk + kLcap);        // table counts [kHcap]
+    uint32_t *lc = tc + kHcap;                                      // list counts  [kLcap]
     // once the table has been compacted into the list its arrays are reused by the sort:
-    uint64_t *sk = tk;                                               // sorted keys   [kLcap]
-    uint32_t *sc = reinterpret_cast<uint32_t *>(tk + kLcap);         // sorted counts [kLcap]
+    Key<W> *sk = tk;                                                // sorted keys   [kLcap]
+    uint32_t *sc = reinterpret_cast<uint32_t *>(tk + kLcap);        // sorted counts [kLcap]
     constexpr int kBins = kHcap / 2 < kSortBins ? kHcap / 2 : kSortBins;
-    uint32_t *c3 = tc;                                               // counting-sort bins [kBins]
-    uint32_t *s3 = tc + kBins;                                       // their starts
+    uint32_t *c3 = tc;                                              // counting-sort bins [kBins]
+    uint32_t *s3 = tc + kBins;                                      // their starts
     __shared__ uint32_t s_m, s_ones, s_over, s_maxbin;
     __shared__ uint32_t s_warp[kPcThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -390,7 +441,9 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
         // Hash-count the keys of round r (of 2^round_bits) in a table of `cap` slots and compact
         // the distinct ones into lk/lc. Returns false if more than cap/2 are distinct.
         auto build = [&](uint32_t r, uint32_t round_bits, uint32_t cap, uint32_t &m, uint32_t &ones) -> bool {
-            for (uint32_t i = tid; i < cap; i += kPcThreads) { tk[i] = kEmptyKey; tc[i] = 0; }
+            Key<W> empty;
+            key_set_ones<W>(empty);
+            for (uint32_t i = tid; i < cap; i += kPcThreads) { tk[i] = empty; tc[i] = 0; }
             if (tid == 0) { s_m = 0; s_ones = 0; s_over = 0; }
             __syncthreads();
             const int rshift = 64 - p.prefix_bits - (int)round_bits;
@@ -399,15 +452,16 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             uint32_t claims = 0;                                     // slots this thread claimed = new distinct keys
             // a probe sequence longer than this means the table is far beyond half full: abandon the attempt
             const uint32_t max_probes = cap < 64 ? cap : 64;
-            auto insert = [&](uint64_t k, uint32_t add) {
-                uint32_t h = (((uint32_t)k ^ (uint32_t)(k >> 29)) * 0x9E3779B1u) >> hshift;
+            auto insert = [&](const Key<W> &k, uint32_t add) {
+                uint32_t h = key_hash<W>(k) >> hshift;
                 for (uint32_t probes = 0; probes < max_probes; probes++) {
-                    unsigned long long cur = tk[h];
-                    if (cur == kEmptyKey) {
-                        cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tk[h]), kEmptyKey, k);
-                        if (cur == kEmptyKey) claims++;
+                    Key<W> cur = tk[h];
+                    // a slot that looks (even partly: a 128-bit read may tear) empty is settled by the CAS
+                    if (key_any_word_ones<W>(cur)) {
+                        cur = slot_claim(&tk[h], k);
+                        if (key_all_ones<W>(cur)) { claims++; if (add) atomicAdd(&tc[h], add); return; }
                     }
-                    if (cur == kEmptyKey || cur == k) { if (add) atomicAdd(&tc[h], add); return; }
+                    if (key_eq<W>(cur, k)) { if (add) atomicAdd(&tc[h], add); return; }
                     h = (h + 1) & (cap - 1);
                 }
                 s_over = 1;
@@ -417,34 +471,42 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                     const uint32_t b = p.src_off[sidx][j], e = p.src_off[sidx][j + 1];
                     for (uint32_t i = b + tid; i < e; i += kPcThreads) {
                         if (*reinterpret_cast<volatile uint32_t *>(&s_over)) break;
-                        const uint64_t k = p.src_keys[sidx][i];
+                        Key<W> k;
+                        k.w[0] = p.src_keys[sidx][i];
                         const uint32_t w = p.src_counts[sidx][i];
-                        if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
-                        if (k == kEmptyKey) { atomicAdd(&s_ones, w); continue; }
+                        if (round_bits && ((uint32_t)(k.w[0] >> rshift) & rmask) != r) continue;
+                        if (key_all_ones<W>(k)) { atomicAdd(&s_ones, w); continue; }
                         insert(k, w);
                     }
                 }
             } else {
-                for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * 8) {
+                constexpr int kBatch = 8 / W;
+                for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * kBatch) {
                     if (*reinterpret_cast<volatile uint32_t *>(&s_over)) break;
-                    uint64_t kk[8];
+                    Key<W> kk[kBatch];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < kBatch; u++) {
                         const uint32_t i = i0 + u * kPcThreads + tid;
-                        kk[u] = i < end ? ld_stream_u64(p.keys + i) : 0;
+                        if (i < end) kk[u] = ld_key<W>(p.keys, i);
+                        else kk[u].w[0] = 0;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < kBatch; u++) {
                         const uint32_t i = i0 + u * kPcThreads + tid;
                         if (i >= end) continue;
-                        const uint64_t k = kk[u];
-                        if (round_bits && ((uint32_t)(k >> rshift) & rmask) != r) continue;
-                        if (k == kEmptyKey) { atomicAdd(&s_ones, 1u); continue; }
+                        const Key<W> k = kk[u];
+                        if (round_bits && ((uint32_t)(k.w[0] >> rshift) & rmask) != r) continue;
+                        if (key_all_ones<W>(k)) { atomicAdd(&s_ones, 1u); continue; }
                         insert(k, 1u);
                     }
                 }
             }
-            if (phantom && r == 0 && tid == 0) insert(0ull, 0u);      // key 0 joins with count += 0
+            if (phantom && r == 0 && tid == 0) {                      // key 0 joins with count += 0
+                Key<W> zero;
+#pragma unroll
+                for (int i = 0; i < W; i++) zero.w[i] = 0;
+                insert(zero, 0u);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, o);
             if (lane == 0 && claims) atomicAdd(&s_m, claims);
@@ -458,8 +520,8 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             __syncthreads();
             for (uint32_t i0 = 0; i0 < cap; i0 += kPcThreads) {
                 const uint32_t i = i0 + tid;
-                const uint64_t k = tk[i];
-                const bool live = k != kEmptyKey;
+                const Key<W> k = tk[i];
+                const bool live = !key_all_ones<W>(k);
                 const uint32_t bal = __ballot_sync(0xffffffffu, live);
                 if (bal) {
                     uint32_t b = 0;
@@ -493,7 +555,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
 #pragma unroll
             for (int u = 0; u < kPer; u++) {
                 const uint32_t i = u * kPcThreads + tid;
-                if (i < m) rk[u] = atomicAdd(&c3[(uint32_t)(lk[i] >> shift3) & (nb3 - 1)], 1u);
+                if (i < m) rk[u] = atomicAdd(&c3[(uint32_t)(lk[i].w[0] >> shift3) & (nb3 - 1)], 1u);
             }
             __syncthreads();
             uint32_t mx = 0;
@@ -501,15 +563,15 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             if (mx > 1) atomicMax(&s_maxbin, mx);
             block_scan_bins<kPcThreads>(c3, s3, (int)nb3, s_warp);
             const uint32_t maxbin = s_maxbin;
-            const uint64_t *rk_keys = sk;
+            const Key<W> *rk_keys = sk;
             const uint32_t *rk_cnts = sc;
             if (maxbin <= 24) {
 #pragma unroll
                 for (int u = 0; u < kPer; u++) {
                     const uint32_t i = u * kPcThreads + tid;
                     if (i < m) {
-                        const uint64_t k = lk[i];
-                        const uint32_t o = s3[(uint32_t)(k >> shift3) & (nb3 - 1)] + rk[u];
+                        const Key<W> k = lk[i];
+                        const uint32_t o = s3[(uint32_t)(k.w[0] >> shift3) & (nb3 - 1)] + rk[u];
                         sk[o] = k;
                         sc[o] = lc[i];
                     }
@@ -521,10 +583,10 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                         if (n < 2) continue;
                         const uint32_t s0 = s3[b];
                         for (uint32_t a = 1; a < n; a++) {        // insertion sort of a handful of keys
-                            const uint64_t k = sk[s0 + a];
+                            const Key<W> k = sk[s0 + a];
                             const uint32_t c = sc[s0 + a];
                             uint32_t q = a;
-                            while (q > 0 && sk[s0 + q - 1] > k) { sk[s0 + q] = sk[s0 + q - 1]; sc[s0 + q] = sc[s0 + q - 1]; q--; }
+                            while (q > 0 && key_lt<W>(k, sk[s0 + q - 1])) { sk[s0 + q] = sk[s0 + q - 1]; sc[s0 + q] = sc[s0 + q - 1]; q--; }
                             sk[s0 + q] = k;
                             sc[s0 + q] = c;
                         }
@@ -536,7 +598,9 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                 rk_keys = lk;
                 rk_cnts = lc;
                 const uint32_t p2 = pow2_ceil_u32(m);
-                for (uint32_t i = m + tid; i < p2; i += kPcThreads) { lk[i] = kEmptyKey; lc[i] = 0; }
+                Key<W> pad;
+                key_set_ones<W>(pad);
+                for (uint32_t i = m + tid; i < p2; i += kPcThreads) { lk[i] = pad; lc[i] = 0; }
                 __syncthreads();
                 for (uint32_t size = 2; size <= p2; size <<= 1) {
                     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -544,8 +608,8 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                             const uint32_t lo = 2 * t - (t & (stride - 1));
                             const uint32_t hi = lo + stride;
                             const bool up = (lo & size) == 0;
-                            const uint64_t a = lk[lo], b = lk[hi];
-                            if ((a > b) == up) {
+                            const Key<W> a = lk[lo], b = lk[hi];
+                            if (key_lt<W>(b, a) == up) {
                                 lk[lo] = b; lk[hi] = a;
                                 const uint32_t ca = lc[lo]; lc[lo] = lc[hi]; lc[hi] = ca;
                             }
@@ -555,11 +619,13 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                 }
             }
             for (uint32_t i = tid; i < m; i += kPcThreads) {
-                p.tmp_keys[ob + i] = rk_keys[i];
+                st_key<W>(p.tmp_keys, ob + i, rk_keys[i]);
                 p.tmp_counts[ob + i] = rk_cnts[i];
             }
             if (ones && tid == 0) {                        // the all-ones key is the largest key there is
-                p.tmp_keys[ob + m] = kEmptyKey;
+                Key<W> top;
+                key_set_ones<W>(top);
+                st_key<W>(p.tmp_keys, ob + m, top);
                 p.tmp_counts[ob + m] = ones;
             }
             __syncthreads();
@@ -609,11 +675,10 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
     }
 }
 
-
-template <int THREADS, int HCAP, bool MULTI = false>
+template <int THREADS, int HCAP, bool MULTI = false, int W = 1>
 cudaError_t launch_finish_v(const FinishParams &fp, int n_sms, uint32_t n_sub, cudaStream_t s) {
-    constexpr uint32_t smem = HCAP * 12 + (HCAP / 2) * 12;
-    auto kern = finish_kernel<THREADS, HCAP, MULTI>;
+    constexpr uint32_t smem = HCAP * (8 * W + 4) + (HCAP / 2) * (8 * W + 4);
+    auto kern = finish_kernel<THREADS, HCAP, MULTI, W>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -647,6 +712,7 @@ cudaError_t launch_finish(const FinishParams &fp, int n_sms, uint32_t n_sub, cud
 }
 
 // records of sub-bucket j: tmp[src(j) .. src(j) + m_j) -> out[off[j] ...); one warp per sub-bucket
+template <int W>
 __global__ void __launch_bounds__(256) gather_kernel(const uint64_t *__restrict__ tmp_keys,
                                                      const uint32_t *__restrict__ tmp_counts,
                                                      const uint32_t *__restrict__ tmp_start,
@@ -659,7 +725,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint64_t *__restrict_
         const uint32_t o0 = off[j], m = off[j + 1] - o0;
         const uint64_t s0 = tmp_start[j];
         for (uint32_t i = lane; i < m; i += 32) {
-            out_keys[o0 + i] = tmp_keys[s0 + i];
+            st_key<W>(out_keys, o0 + i, ld_key<W>(tmp_keys, s0 + i));
             out_counts[o0 + i] = tmp_counts[s0 + i];
         }
     }
@@ -689,7 +755,7 @@ static PartitionPlan make_plan(uint64_t n_slots, int sig_bits, int target) {
 
 // Second half of the partitioned count, run once the number of records is known on the
 // host: closes the gaps between the sub-buckets' record ranges.
-cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
+cudaError_t partition_gather(int W, uint64_t n_slots, int sig_bits, int target_sub, const uint64_t *tmp_keys,
                              const uint32_t *tmp_counts, void *ws, uint64_t *out_keys, uint32_t *out_counts,
                              cudaStream_t s) {
     const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : kDefaultTarget);
@@ -698,7 +764,8 @@ cudaError_t partition_gather(uint64_t n_slots, int sig_bits, int target_sub, con
     uint32_t *base2 = hist2 + pl.n_sub + 8;
     uint32_t *off = base2 + pl.n_sub + 8;
     uint32_t *tmp_start = off + pl.n_sub + 8 + pl.n_sub + 8;
-    gather_kernel<<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
+    if (W == 1) gather_kernel<1><<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
+    else gather_kernel<2><<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
     return cudaGetLastError();
 }
 
@@ -744,7 +811,7 @@ cudaError_t merge_parts_count(uint32_t n_src, const uint64_t *const *src_keys, c
     fp.tmp_start = tmp_start;
     fp.n_src = n_src;
     for (uint32_t i = 0; i < n_src; i++) { fp.src_keys[i] = src_keys[i]; fp.src_counts[i] = src_counts[i]; fp.src_off[i] = src_off[i]; }
-    if ((e = launch_finish_v<256, 2048, true>(fp, n_sms, n_sub, s)) != cudaSuccess) return e;
+    if ((e = launch_finish_v<256, 2048, true, 1>(fp, n_sms, n_sub, s)) != cudaSuccess) return e;
     scan2_kernel<<<1, 1024, 0, s>>>(m_out, n_sub, off, scratch);
     if ((e = cudaMemcpyAsync(d_num_out, off + n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     if (n_launches) *n_launches += 2;
@@ -756,7 +823,7 @@ cudaError_t merge_parts_gather(uint32_t n_sub, const uint64_t *tmp_keys, const u
     uint32_t *m_out = reinterpret_cast<uint32_t *>(ws);
     uint32_t *off = m_out + n_sub + 8;
     uint32_t *tmp_start = off + n_sub + 8;
-    gather_kernel<<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, n_sub, out_keys, out_counts);
+    gather_kernel<1><<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, n_sub, out_keys, out_counts);
     if (out_offsets) {
         cudaError_t e = cudaMemcpyAsync(out_offsets, off, (size_t)(n_sub + 1) * 4, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
@@ -775,14 +842,15 @@ uint64_t partition_workspace_bytes(uint64_t n_slots) {
     return 4 * (kMaxBins + 8) * 4 + 3 * (nsub + 8) * 4 + nsub * 8 + 256;
 }
 
-// Counts the k-mers of `ep` (W == 1) into sorted unique (out_keys, out_counts).
+// Counts the k-mers of `ep` (W = 1 or 2 words per key) into sorted unique (out_keys, out_counts).
 // keys_a / keys_b: scratch of n_slots keys each. *d_num_out = records; *d_overflow != 0
 // means a sub-bucket could not be counted (caller falls back to sort + run-length).
-cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int sig_bits, bool add_phantom,
-                            uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
-                            unsigned long long *d_num_out, unsigned long long *d_overflow,
-                            unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,
-                            cudaStream_t s, int *n_launches, cudaEvent_t *evs /* 5: after P0, PA, H2, PB, PC */) {
+template <int W>
+static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slots, int sig_bits, bool add_phantom,
+                                     uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
+                                     unsigned long long *d_num_out, unsigned long long *d_overflow,
+                                     unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,
+                                     cudaStream_t s, int *n_launches, cudaEvent_t *evs) {
     const PartitionPlan pl = make_plan(n_slots, sig_bits, target_sub > 0 ? target_sub : kDefaultTarget);
     uint8_t *w = static_cast<uint8_t *>(ws);
     uint32_t *hist1 = reinterpret_cast<uint32_t *>(w);
@@ -806,7 +874,7 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     {
         ExtractParams ep = ep_in;
         ep.n_invalid = d_scratch_invalid;
-        auto kern = extract_kernel<1, Hist1Sink>;
+        auto kern = extract_kernel<W, Hist1Sink<W>>;
         const uint32_t smem = ep.smem_total + kMaxBins * 4;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int per_sm = 1;
@@ -814,24 +882,25 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
         per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
         uint32_t grid = (uint32_t)n_sms * per_sm;
         if (grid > ep.n_tiles) grid = ep.n_tiles;
-        Hist1Sink sink{{}, hist1, shift1, (int)pl.nb1, nullptr};
+        Hist1Sink<W> sink{};
+        sink.g_hist1 = hist1; sink.shift1 = shift1; sink.nb1 = (int)pl.nb1;
         kern<<<grid, kExtractThreads, smem, s>>>(ep, sink);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    scan1_kernel<<<1, 1024, 0, s>>>(hist1, (int)pl.nb1, base1, cursor1, tile_prefix);
+    scan1_kernel<<<1, 1024, 0, s>>>(hist1, (int)pl.nb1, (uint32_t)PbCfg<W>::TILE, base1, cursor1, tile_prefix);
     if (evs) cudaEventRecord(evs[0], s);
     // PA: keys grouped by level-1 digit
     {
-        auto kern = extract_kernel<1, Scatter1Sink>;
+        auto kern = extract_kernel<W, Scatter1Sink<W>>;
         const uint32_t max_tile_keys = ep_in.tile_reads * ep_in.nk;
-        const uint32_t smem = ep_in.smem_total + Scatter1Sink::smem_bytes(max_tile_keys);
+        const uint32_t smem = ep_in.smem_total + Scatter1Sink<W>::smem_bytes(max_tile_keys);
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kExtractThreads, smem);
         per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
         uint32_t grid = (uint32_t)n_sms * per_sm;
         if (grid > ep_in.n_tiles) grid = ep_in.n_tiles;
-        Scatter1Sink sink{};
+        Scatter1Sink<W> sink{};
         sink.g_cursor1 = cursor1; sink.out = keys_a; sink.shift1 = shift1; sink.nb1 = (int)pl.nb1;
         sink.g_hist2 = (fuse_h2 && pl.b2 > 0) ? hist2 : nullptr;
         sink.shift2 = shift2;
@@ -840,14 +909,14 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     }
     if (evs) cudaEventRecord(evs[1], s);
     // H2 + PB over the level-1 buckets
-    const uint32_t max_tiles = (uint32_t)(n_slots / kPbTile) + pl.nb1 + 1;
+    const uint32_t max_tiles = (uint32_t)(n_slots / PbCfg<W>::TILE) + pl.nb1 + 1;
     if (pl.b2 > 0) {
         if (!fuse_h2)
-            hist2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, tile_prefix, base1, (int)pl.nb1, shift2, (int)pl.nb2, hist2);
+            hist2_kernel<W><<<max_tiles, kPbThreads, 0, s>>>(keys_a, tile_prefix, base1, (int)pl.nb1, shift2, (int)pl.nb2, hist2);
         scan2_kernel<<<1, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
         if (evs) cudaEventRecord(evs[2], s);
-        scatter2_kernel<<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,
-                                                         (int)pl.nb2, cursor2);
+        scatter2_kernel<W><<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,
+                                                            (int)pl.nb2, cursor2);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else {
         if ((e = cudaMemcpyAsync(base2, base1, (pl.nb1 + 1) * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
@@ -864,7 +933,9 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
         fp.tmp_keys = out_keys; fp.tmp_counts = out_counts; fp.m_out = m_out; fp.d_overflow = d_overflow;
         fp.d_n_invalid = ep_in.n_invalid; fp.add_phantom = add_phantom ? 1 : 0; fp.cap_shift = 1;
         fp.tmp_start = status_scratch + pl.n_sub + 8;
-        if ((e = launch_finish(fp, n_sms, pl.n_sub, s)) != cudaSuccess) return e;
+        if constexpr (W == 1) e = launch_finish(fp, n_sms, pl.n_sub, s);
+        else e = launch_finish_v<256, 2048, false, W>(fp, n_sms, pl.n_sub, s);
+        if (e != cudaSuccess) return e;
         // off[] (n_sub + 1) overwrites cursor2; its last entry is the number of records
         scan2_kernel<<<1, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);
         if ((e = cudaMemcpyAsync(d_num_out, cursor2 + pl.n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
@@ -872,6 +943,20 @@ cudaError_t partition_count(const ExtractParams &ep_in, uint64_t n_slots, int si
     if (evs) cudaEventRecord(evs[4], s);
     if (n_launches) *n_launches += pl.b2 > 0 ? 8 : 5;
     return cudaSuccess;
+}
+
+cudaError_t partition_count(int W, const ExtractParams &ep, uint64_t n_slots, int sig_bits, bool add_phantom,
+                            uint64_t *keys_a, uint64_t *keys_b, uint64_t *out_keys, uint32_t *out_counts,
+                            unsigned long long *d_num_out, unsigned long long *d_overflow,
+                            unsigned long long *d_scratch_invalid, void *ws, int n_sms, int target_sub,
+                            cudaStream_t s, int *n_launches, cudaEvent_t *evs /* 5: after P0, PA, H2, PB, PC */) {
+    if (W == 1)
+        return partition_count_w<1>(ep, n_slots, sig_bits, add_phantom, keys_a, keys_b, out_keys, out_counts, d_num_out,
+                                    d_overflow, d_scratch_invalid, ws, n_sms, target_sub, s, n_launches, evs);
+    if (W == 2)
+        return partition_count_w<2>(ep, n_slots, sig_bits, add_phantom, keys_a, keys_b, out_keys, out_counts, d_num_out,
+                                    d_overflow, d_scratch_invalid, ws, n_sms, target_sub, s, n_launches, evs);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace kc

@@ -149,7 +149,7 @@ def exchange_and_combine(counter, local, device, group=None, splitters=None):
     plan = torch.tensor([n_sub, pbits], dtype=torch.int64, device=device)
     plans = [torch.empty_like(plan) for _ in range(world)]
     dist.all_gather(plans, plan, group=group)
-    agreed = n_sub >= world and n_sub % world == 0 and all(bool((q == plan).all()) for q in plans)
+    agreed = counter.words == 1 and n_sub >= world and n_sub % world == 0 and all(bool((q == plan).all()) for q in plans)
     keys_t, counts_t = run_as_tensors(local, device)
     if agreed:
         per = n_sub // world

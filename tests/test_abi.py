@@ -61,7 +61,9 @@ def test_bad_arguments_are_rejected_before_touching_the_device():
             kc.Counter(k, L)
         assert ei.value.code == -1
     with pytest.raises(kc.KcError):
-        kc.Counter(63, 100, method="hash")            # hash counting is for k <= 32
+        kc.Counter(65, 100, method="hash")            # partitioned hash counting is for k <= 64
+    with pytest.raises(kc.KcError):
+        kc.Counter(63, 100, method="hash_global")     # the HBM-resident table is for k <= 32
 
 
 def test_product_package_does_not_import_the_oracle():
