@@ -71,26 +71,32 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.sm, self.mx, self.reasons, self.stop, self.th = index, [], 0, set(), threading.Event(), None
-
-    def _run(self):
-        try:
+        self.nv = self.h = None
+        try:                                        # NVML is initialised before the timed region starts
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            flags = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
-                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
-                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-            while not self.stop.is_set():
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in flags.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self.stop.wait(0.02)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.flags = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                          "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                          "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         except Exception as e:                      # no NVML: report that instead of inventing numbers
             self.reasons.add("nvml_unavailable: %s" % type(e).__name__)
+
+    def _sample(self):
+        if self.h is None:
+            return
+        self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.flags.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self.stop.is_set():
+            self._sample()
+            self.stop.wait(0.005)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -98,6 +104,7 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        self._sample()                              # one sample is taken while the last step is still in flight
         self.stop.set()
         self.th.join(timeout=5)
 
@@ -305,6 +312,18 @@ def run_ours(a, rank, world, local_rank):
     peak, peak_src = measured_peak_gbs()
     if rank == 0:
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        dom_name = st1["stage_names"][st1["dominant_stage"]] if st1["stage_names"] else "none"
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this
+        # workload (bytes per launch), if there is one for this method and size
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            ent = tj.get("%s/%s/%d" % (method_used, dom_name, R))
+            if ent:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+        except Exception:
+            pass
         Kb, S = 8 * counter.words, counter.record_size
         b_alg = R * L + R * nk * (Kb + 8) + distinct * S
         path_ach = b_alg / (tot_ms / a.steps * 1e-3) / 1e9 if tot_ms > 0 else 0.0
@@ -314,12 +333,13 @@ def run_ours(a, rank, world, local_rank):
             "dtype": "u64", "data": "synthetic", "config": dict(workload(a), method=method_used),
             "bases_per_s": R * L * world / (ms_per_step * 1e-3),
             "distinct_per_gpu": distinct,
-            "roofline": {"bound": "hbm", "kernel": "onesweep radix scatter pass" if method_used == "sort" else "fused extract + hash insert",
+            "roofline": {"bound": "hbm", "kernel": dom_name,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src + " HBM copy bandwidth (MEASURED_PEAKS.json)",
                          "bytes_per_launch": dom_bytes / max(dom_launch, 1), "launches_per_step": dom_launch / a.steps,
                          "ms_per_launch": dom_ms / max(dom_launch, 1),
-                         "share_of_step": dom_ms / tot_ms if tot_ms else None, "traffic": None},
+                         "share_of_step": dom_ms / tot_ms if tot_ms else None, "traffic": traffic,
+                         "traffic_source": traffic_src},
             "path_roofline": {"bound": "hbm", "b_alg_bytes": b_alg, "achieved": path_ach, "peak": peak, "unit": "GB/s",
                               "frac": path_ach / peak if peak else None,
                               "definition": "SURVEY 8(d): B_in + N*(Kb+8) + U*S over the local counting time"},

@@ -344,11 +344,11 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
             st.stage_bytes[3] = Kb * N + U * (Kb + 4);                     st.stage_launches[3] = 1;
             st.stage_bytes[4] = U * (2 * Kb + 8);                          st.stage_launches[4] = 1;
         } else if (used == KC_COUNT_HASH && p.n_slots) {
-            st.stage_bytes[0] = in_bytes;                                  st.stage_launches[0] = 2;
+            st.stage_bytes[0] = in_bytes;                                  st.stage_launches[0] = 1;   // + a one-block scan
             st.stage_bytes[1] = in_bytes + Kb * nv;                        st.stage_launches[1] = 1;
-            st.stage_bytes[2] = Kb * nv;                                   st.stage_launches[2] = 2;
+            st.stage_bytes[2] = Kb * nv;                                   st.stage_launches[2] = 1;   // + a one-block scan
             st.stage_bytes[3] = 2 * Kb * nv;                               st.stage_launches[3] = 1;
-            st.stage_bytes[4] = Kb * nv + (Kb + 4) * U;                    st.stage_launches[4] = 2;
+            st.stage_bytes[4] = Kb * nv + (Kb + 4) * U;                    st.stage_launches[4] = 1;   // + a one-block scan
             st.stage_bytes[5] = 2 * (Kb + 4) * U;                          st.stage_launches[5] = 1;
         } else if (used == KC_COUNT_HASH_GLOBAL && p.n_slots) {
             st.stage_bytes[0] = p.table.capacity * 16;                     st.stage_launches[0] = 1;
