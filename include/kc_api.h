@@ -138,6 +138,22 @@ int  kc_wait(kc_ctx *ctx, uint32_t slot, kc_run **run);   /* caller owns *run (m
 /* Device-resident input (d_reads: device pointer, 16-byte aligned). */
 int  kc_count_device(kc_ctx *ctx, const void *d_reads, uint64_t n_bytes, kc_run **run);
 
+/* ---- raw FASTQ chunks: replaces FASTQFileReader::readData (FASTQFileReader.cpp:49-89) ----
+ * The text must start at a record boundary and be well formed (4 lines per record, the
+ * line after the sequence starts with '+', every sequence read_len long); the parse runs
+ * on the device.  *consumed = bytes of whole records taken (carry the rest into the next
+ * chunk; at end of file terminate the last line with '\n').  *flags != 0 (KC_FASTQ_*) means
+ * the text is not of that shape: nothing was counted, use a host parser for this input. */
+#define KC_FASTQ_MALFORMED  0x1u   /* a record's third line does not start with '+'   */
+#define KC_FASTQ_RAGGED     0x2u   /* a sequence is not read_len long                 */
+/* parse only: d_text (16-byte aligned, < 4 GiB) -> d_reads (packed lines) */
+int  kc_parse_fastq_device(kc_ctx *ctx, const void *d_text, uint64_t n_bytes, void *d_reads,
+                           uint64_t reads_cap_bytes, uint64_t *n_reads, uint64_t *consumed, uint32_t *flags);
+/* host text -> H2D -> parse -> count on `slot` (as kc_submit; collect with kc_wait).  The
+ * reads parsed must fit the slot (max_chunk_bytes); text beyond that is left unconsumed. */
+int  kc_submit_fastq(kc_ctx *ctx, uint32_t slot, const void *host_text, uint64_t n_bytes,
+                     uint64_t *consumed, uint32_t *flags);
+
 /* ---- runs: the sorted-run dump (FileDump.cpp:51-58) and its consumers ---- */
 uint64_t kc_run_records(const kc_run *run);
 int  kc_run_free(kc_ctx *ctx, kc_run *run);

@@ -59,6 +59,8 @@ SYMBOLS = {
     "kc_submit": (_i, [_vp, _u32, _u64]),
     "kc_wait": (_i, [_vp, _u32, _pp]),
     "kc_count_device": (_i, [_vp, _vp, _u64, _pp]),
+    "kc_parse_fastq_device": (_i, [_vp, _vp, _u64, _vp, _u64, _pu64, _pu64, C.POINTER(C.c_uint32)]),
+    "kc_submit_fastq": (_i, [_vp, _u32, _vp, _u64, _pu64, C.POINTER(C.c_uint32)]),
     "kc_run_records": (_u64, [_vp]),
     "kc_run_free": (_i, [_vp, _vp]),
     "kc_run_copy_records": (_i, [_vp, _vp, _vp, _u64, _pu64]),

@@ -63,6 +63,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     Pending pend;
     uint64_t n_bytes = 0;
+    void *d_text = nullptr;      // raw FASTQ staging (kc_submit_fastq), grown on demand
+    uint64_t text_cap = 0;
 };
 
 }  // namespace
@@ -516,6 +518,7 @@ void kc_destroy(kc_ctx *c) {
         pending_destroy(sl.pend);
         if (sl.h_in) cudaFreeHost(sl.h_in);
         if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.d_text) cudaFree(sl.d_text);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     pending_release(c->stream, c->direct);
@@ -587,6 +590,80 @@ int kc_count_device(kc_ctx *c, const void *d_reads, uint64_t n_bytes, kc_run **r
     if (rc == KC_OK) rc = kc_merge_runs(c, parts.data(), (uint32_t)parts.size(), run);
     for (auto *p : parts) kc_run_free(c, p);
     return rc;
+}
+
+static int parse_fastq_impl(kc_ctx *c, Pending &ar, const void *d_text, uint64_t n_bytes, void *d_reads,
+                            uint64_t reads_cap_bytes, cudaStream_t s, uint64_t *n_reads, uint64_t *consumed,
+                            uint32_t *flags) {
+    if (n_bytes >= (1ull << 32)) return c->set_error(KC_ERR_CAPACITY, "FASTQ chunks must be smaller than 4 GiB");
+    if (n_bytes && (reinterpret_cast<uintptr_t>(d_text) & 15)) return c->set_error(KC_ERR_ARG, "d_text must be 16-byte aligned");
+    KC_TRY(pending_init(c, ar));
+    const uint64_t wsb = fastq_workspace_bytes(n_bytes);
+    KC_TRY(arena_reserve(c, ar, arena_round(wsb) + 512, s));
+    void *ws = arena_take(ar, wsb);
+    unsigned long long *d_out = static_cast<unsigned long long *>(arena_take(ar, 32));
+    int launches = 0;
+    KC_CUDA_TRY(c, fastq_parse(d_text, n_bytes, c->cfg.read_len, d_reads, reads_cap_bytes / c->cfg.read_len, d_out, ws,
+                               s, &launches));
+    unsigned long long h[3] = {0, 0, 0};
+    KC_CUDA_TRY(c, cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    ar.arena_used = 0;
+    if (n_reads) *n_reads = h[0];
+    if (consumed) *consumed = h[1];
+    if (flags) *flags = (uint32_t)h[2];
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stats.launches += launches;
+    return KC_OK;
+}
+
+int kc_parse_fastq_device(kc_ctx *c, const void *d_text, uint64_t n_bytes, void *d_reads, uint64_t reads_cap_bytes,
+                          uint64_t *n_reads, uint64_t *consumed, uint32_t *flags) {
+    KC_TRY(check_ctx(c));
+    if ((n_bytes && (!d_text || !d_reads))) return c->set_error(KC_ERR_ARG, "null argument");
+    if (c->direct.active) return c->set_error(KC_ERR_STATE, "a chunk is in flight on this context");
+    cudaSetDevice(c->cfg.device);
+    return parse_fastq_impl(c, c->direct, d_text, n_bytes, d_reads, reads_cap_bytes, c->stream, n_reads, consumed, flags);
+}
+
+int kc_submit_fastq(kc_ctx *c, uint32_t slot, const void *host_text, uint64_t n_bytes, uint64_t *consumed,
+                    uint32_t *flags) {
+    KC_TRY(check_ctx(c));
+    if (consumed) *consumed = 0;
+    if (flags) *flags = 0;
+    if (slot >= c->slots.size() || !c->slots[slot].d_in) return c->set_error(KC_ERR_ARG, "slot %u not available", slot);
+    if (n_bytes && !host_text) return c->set_error(KC_ERR_ARG, "null text");
+    Slot &sl = c->slots[slot];
+    if (sl.pend.active) return c->set_error(KC_ERR_STATE, "slot %u already has a chunk in flight", slot);
+    cudaSetDevice(c->cfg.device);
+    if (n_bytes + 64 > sl.text_cap) {                    // device staging for the raw text, grown on demand
+        KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+        if (sl.d_text) cudaFree(sl.d_text);
+        sl.d_text = nullptr;
+        sl.text_cap = 0;
+        const uint64_t want = n_bytes + n_bytes / 8 + 4096;
+        if (cudaMalloc(&sl.d_text, want) != cudaSuccess) {
+            cudaGetLastError();
+            return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes for FASTQ text failed", (unsigned long long)want);
+        }
+        sl.text_cap = want;
+    }
+    if (n_bytes) KC_CUDA_TRY(c, cudaMemcpyAsync(sl.d_text, host_text, n_bytes, cudaMemcpyHostToDevice, sl.stream));
+    uint64_t n_reads = 0, used = 0;
+    uint32_t fl = 0;
+    KC_TRY(parse_fastq_impl(c, sl.pend, sl.d_text, n_bytes, sl.d_in, c->cfg.max_chunk_bytes, sl.stream, &n_reads, &used, &fl));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.h2d_bytes += n_bytes;
+    }
+    if (flags) *flags = fl;
+    if (fl) return KC_OK;                                // not the shape the device parser handles: nothing submitted
+    if (consumed) *consumed = used;
+    const uint64_t nk = c->cfg.read_len - c->cfg.k + 1;
+    if (n_reads * nk > kMaxSortKeys)
+        return c->set_error(KC_ERR_CAPACITY, "chunk holds more than %llu k-mer slots; use a smaller max_chunk_bytes", (unsigned long long)kMaxSortKeys);
+    sl.n_bytes = n_reads * c->cfg.read_len;
+    return count_enqueue(c, sl.pend, sl.d_in, sl.n_bytes, sl.stream, pick_method(c));
 }
 
 int kc_slot_buffer(kc_ctx *c, uint32_t slot, void **ptr, uint64_t *cap) {

@@ -74,6 +74,11 @@ cudaError_t hash_touch_zero(HashTable t, const unsigned long long *d_n_invalid, 
 cudaError_t hash_compact(HashTable t, uint64_t *out_keys, uint32_t *out_counts, unsigned long long *d_num,
                          cudaStream_t s, int *n_launches);
 
+// ---- raw FASTQ text -> packed reads (kc_fastq.cu)
+uint64_t fastq_workspace_bytes(uint64_t n_bytes);
+cudaError_t fastq_parse(const void *d_text, uint64_t n_bytes, uint32_t L, void *d_reads, uint64_t max_reads,
+                        unsigned long long *d_out, void *ws, cudaStream_t s, int *n_launches);
+
 // ---- partitioned shared-memory hash counting (kc_partition.cu), W = 1 or 2
 uint64_t partition_workspace_bytes(uint64_t n_slots);
 // true when out_keys must be keys_a (two partition levels) rather than keys_b

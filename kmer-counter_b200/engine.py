@@ -186,6 +186,48 @@ class Counter:
         self._check(self._lib.kc_wait(self._ctx, slot, C.byref(h)))
         return Run(self, h)
 
+    def submit_fastq(self, slot, text) -> tuple:
+        """Raw FASTQ text (host bytes / uint8 array, starting at a record boundary) -> H2D ->
+        device parse -> count on `slot`.  Returns (consumed_bytes, flags); flags != 0 means the
+        text is not plain 4-line fixed-length FASTQ and nothing was submitted."""
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else \
+            np.ascontiguousarray(text, dtype=np.uint8)
+        used, fl = C.c_uint64(), C.c_uint32()
+        self._check(self._lib.kc_submit_fastq(self._ctx, slot, a.ctypes.data, a.size, C.byref(used), C.byref(fl)))
+        return used.value, fl.value
+
+    def parse_fastq_device(self, d_text, n_bytes, d_reads, reads_cap) -> tuple:
+        """(n_reads, consumed_bytes, flags) of a device-resident FASTQ chunk parsed into d_reads."""
+        n, used, fl = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        self._check(self._lib.kc_parse_fastq_device(self._ctx, d_text, n_bytes, d_reads, reads_cap, C.byref(n),
+                                                    C.byref(used), C.byref(fl)))
+        return n.value, used.value, fl.value
+
+    def count_fastq(self, text, block_bytes=0) -> Run:
+        """A whole FASTQ file image through the device parser in blocks with carry-over, counted
+        and merged. Raises KcError(-1) if the text is not of the shape the device parser handles."""
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else \
+            np.ascontiguousarray(text, dtype=np.uint8)
+        if a.size and a[-1] != 10:
+            a = np.concatenate([a, np.array([10], dtype=np.uint8)])
+        if block_bytes <= 0:
+            block_bytes = 2 * self.max_chunk_bytes + 4096
+        runs, pos = [], 0
+        while pos < a.size:
+            used, fl = self.submit_fastq(0, a[pos:pos + block_bytes])
+            if fl:
+                for r in runs:
+                    r.free()
+                raise KcError(-1, "FASTQ text is not plain 4-line fixed-length (flags=%d)" % fl)
+            if used == 0:
+                raise KcError(-4, "no whole record fits a block of %d bytes" % block_bytes)
+            runs.append(self.wait(0))
+            pos += used
+        out = self.merge(runs)
+        for r in runs:
+            r.free()
+        return out
+
     def count_device(self, d_ptr, n_bytes) -> Run:
         h = C.c_void_p()
         self._check(self._lib.kc_count_device(self._ctx, d_ptr, n_bytes, C.byref(h)))

@@ -25,6 +25,7 @@ public:
     int64_t getLineLength() const { return _lineLength; }
     // Fills dst (capacity bytes) with whole reads; returns bytes written, 0 at end of input.
     int64_t read(char *dst, int64_t capacity);
+    const std::vector<std::string> &files() const { return _files; }
     uint64_t skippedReads() const { return _skipped; }
     uint64_t totalReads() const { return _reads; }
 

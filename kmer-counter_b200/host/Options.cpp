@@ -25,6 +25,7 @@ Options Options::parse(int argc, char **argv) {
         else if (take(argv[i], "compat=", &v)) o.compat = v;
         else if (take(argv[i], "device=", &v)) o.device = atoi(v);
         else if (take(argv[i], "keepRuns=", &v)) o.keepRuns = atoi(v) != 0;
+        else if (take(argv[i], "parser=", &v)) o.parser = v;
     }
     if (o.noOfMergersAtOnce < 2) o.noOfMergersAtOnce = 2;
     return o;

@@ -18,6 +18,8 @@ struct Options {
     std::string compat = "ref";               // compat=ref|strict
     int device = 0;                           // device=
     bool keepRuns = false;                    // keepRuns=1: also write every chunk's run to tempFileLocation/<id>
+    std::string parser = "gpu";               // parser=gpu|host: where FASTQ text is parsed (gpu falls back to host
+                                              // for input that is not plain 4-line fixed-length FASTQ)
 
     // Same prefix matching as the reference. Unknown tokens are ignored, as there.
     static Options parse(int argc, char **argv);

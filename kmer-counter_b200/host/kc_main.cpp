@@ -2,7 +2,7 @@
 //
 //   kmer_counter_b200 kmerLength=31 inputFileLocation=<dir> outputFile=<file> [gpuMemoryLimit=..]
 //                     [tempFileLocation=..] [noOfMergersAtOnce=..] [noOfMergeThreads=..]
-//                     [method=auto|sort|hash] [compat=ref|strict] [device=N] [keepRuns=1]
+//                     [method=auto|sort|hash] [compat=ref|strict] [device=N] [keepRuns=1] [parser=gpu|host]
 //   kmer_counter_b200 print <record file> <ignored> <k>       (KMerPrinter, main.cpp:78-82)
 //
 // What KMerCounter::Start does (KMerCounter.cpp:108-191), on the B200 path: read fixed
@@ -80,47 +80,110 @@ int main(int argc, char **argv) {
     kc_ctx *ctx = nullptr;
     if (kc_create(&cfg, &ctx) != KC_OK) { fprintf(stderr, "kc_create: %s\n", kc_last_error(nullptr)); return 1; }
 
-    RunMerger merger(ctx, opt.noOfMergersAtOnce);
     int rc = KC_OK;
     uint32_t chunk_id = 0;
-    bool busy[2] = {false, false};
-    auto collect = [&](uint32_t slot) -> int {
-        kc_run *run = nullptr;
-        int r = kc_wait(ctx, slot, &run);
-        busy[slot] = false;
-        if (r != KC_OK) return r;
-        if (opt.keepRuns) {                                     // FileDump::dumpKmersToFile naming (FileDump.cpp:51-58)
-            std::string path = opt.tempFileLocation + "/" + std::to_string(++chunk_id);
-            if ((r = kc_run_write(ctx, run, path.c_str(), 0)) != KC_OK) return r;
-        }
-        return merger.AddRun(run);
-    };
-    for (uint32_t slot = 0; rc == KC_OK; slot ^= 1) {
-        if (busy[slot]) rc = collect(slot);                      // the other slot keeps the GPU busy meanwhile
-        if (rc != KC_OK) break;
-        void *buf = nullptr;
-        uint64_t cap = 0;
-        if ((rc = kc_slot_buffer(ctx, slot, &buf, &cap)) != KC_OK) break;
-        const int64_t n = reader.read(static_cast<char *>(buf), (int64_t)cap);
-        if (n == 0) break;
-        if ((rc = kc_submit(ctx, slot, (uint64_t)n)) != KC_OK) break;
-        busy[slot] = true;
-    }
-    for (uint32_t slot = 0; slot < 2 && rc == KC_OK; slot++)
-        if (busy[slot]) rc = collect(slot);
+    uint64_t gpu_parsed_bytes = 0;
     kc_run *final_run = nullptr;
-    if (rc == KC_OK) rc = merger.InputComplete(&final_run);
-    if (rc == KC_OK) rc = kc_run_write(ctx, final_run, opt.outputFile.c_str(), 0);   // truncates (KMerFileMerger.cpp:129 appends)
-    if (rc != KC_OK) {
-        fprintf(stderr, "kmer_counter_b200: %s\n", kc_last_error(ctx));
-    } else {
-        kc_stats st;
-        kc_stats_get(ctx, &st);
-        fprintf(stderr, "reads=%" PRIu64 " skipped=%" PRIu64 " kmers=%" PRIu64 " chunks=%" PRIu64 " merges=%" PRIu64
-                        " records=%" PRIu64 " -> %s\n",
-                reader.totalReads(), reader.skippedReads(), st.kmers_valid, st.chunks, merger.merges(),
-                kc_run_records(final_run), opt.outputFile.c_str());
+    // attempt 0: FASTQ text goes to the GPU as it is and is parsed there (kc_submit_fastq);
+    // attempt 1: the host chunker, for input the device parser refuses (or parser=host)
+    for (int attempt = opt.parser == "host" ? 1 : 0; attempt < 2; attempt++) {
+        RunMerger merger(ctx, opt.noOfMergersAtOnce);
+        bool busy[2] = {false, false};
+        bool refused = false;
+        chunk_id = 0;
+        auto collect = [&](uint32_t slot) -> int {
+            kc_run *run = nullptr;
+            int r = kc_wait(ctx, slot, &run);
+            busy[slot] = false;
+            if (r != KC_OK) return r;
+            if (opt.keepRuns) {                                 // FileDump::dumpKmersToFile naming (FileDump.cpp:51-58)
+                std::string path = opt.tempFileLocation + "/" + std::to_string(++chunk_id);
+                if ((r = kc_run_write(ctx, run, path.c_str(), 0)) != KC_OK) return r;
+            }
+            return merger.AddRun(run);
+        };
+        if (attempt == 0) {
+            const uint64_t raw_cap = (uint64_t)chunk * 23 / 10 + (1u << 20);
+            void *raw[2] = {nullptr, nullptr};
+            if (kc_host_alloc(ctx, raw_cap, &raw[0]) != KC_OK || kc_host_alloc(ctx, raw_cap, &raw[1]) != KC_OK) rc = KC_ERR_NOMEM;
+            uint32_t slot = 0;
+            for (const std::string &path : reader.files()) {
+                if (rc != KC_OK || refused) break;
+                FILE *f = fopen(path.c_str(), "rb");
+                if (!f) continue;                               // the reference ignores unreadable files too
+                uint64_t carry = 0;
+                bool eof = false;
+                while (rc == KC_OK && !refused) {
+                    char *buf = static_cast<char *>(raw[slot]);
+                    uint64_t total = carry;
+                    if (!eof) {
+                        const size_t n = fread(buf + carry, 1, raw_cap - carry - 1, f);
+                        total += n;
+                        eof = n < raw_cap - carry - 1;
+                    }
+                    if (eof && total > 0 && buf[total - 1] != '\n') buf[total++] = '\n';
+                    if (total == 0) break;
+                    if (busy[slot] && (rc = collect(slot)) != KC_OK) break;
+                    uint64_t used = 0;
+                    uint32_t flags = 0;
+                    if ((rc = kc_submit_fastq(ctx, slot, buf, total, &used, &flags)) != KC_OK) break;
+                    if (flags) { refused = true; break; }
+                    if (used == 0) {
+                        // fewer than four lines are left: at end of file that is a truncated record, ignored
+                        if (eof) { kc_run *empty = nullptr; rc = kc_wait(ctx, slot, &empty); if (empty) kc_run_free(ctx, empty); break; }
+                        rc = KC_ERR_CAPACITY;
+                        fprintf(stderr, "a FASTQ record does not fit %llu bytes\n", (unsigned long long)raw_cap);
+                        break;
+                    }
+                    busy[slot] = true;
+                    gpu_parsed_bytes += used;
+                    carry = total - used;
+                    memcpy(raw[slot ^ 1], buf + used, carry);   // the tail opens the next block
+                    slot ^= 1;
+                    if (eof && carry == 0) break;
+                }
+                fclose(f);
+            }
+            for (uint32_t sl = 0; sl < 2 && rc == KC_OK; sl++)
+                if (busy[sl]) rc = collect(sl);
+            if (raw[0]) kc_host_free(ctx, raw[0]);
+            if (raw[1]) kc_host_free(ctx, raw[1]);
+            if (refused && rc == KC_OK) {
+                for (uint32_t sl = 0; sl < 2; sl++)
+                    if (busy[sl]) collect(sl);
+                fprintf(stderr, "input is not plain 4-line fixed-length FASTQ: parsing on the host instead\n");
+                gpu_parsed_bytes = 0;
+                continue;                                       // merger (and its runs) is dropped, start over
+            }
+        } else {
+            for (uint32_t slot = 0; rc == KC_OK; slot ^= 1) {
+                if (busy[slot]) rc = collect(slot);             // the other slot keeps the GPU busy meanwhile
+                if (rc != KC_OK) break;
+                void *buf = nullptr;
+                uint64_t cap = 0;
+                if ((rc = kc_slot_buffer(ctx, slot, &buf, &cap)) != KC_OK) break;
+                const int64_t n = reader.read(static_cast<char *>(buf), (int64_t)cap);
+                if (n == 0) break;
+                if ((rc = kc_submit(ctx, slot, (uint64_t)n)) != KC_OK) break;
+                busy[slot] = true;
+            }
+            for (uint32_t slot = 0; slot < 2 && rc == KC_OK; slot++)
+                if (busy[slot]) rc = collect(slot);
+        }
+        if (rc == KC_OK) rc = merger.InputComplete(&final_run);
+        if (rc == KC_OK) {
+            kc_stats st;
+            kc_stats_get(ctx, &st);
+            fprintf(stderr, "parser=%s reads=%" PRIu64 " skipped=%" PRIu64 " kmers=%" PRIu64 " chunks=%" PRIu64
+                            " merges=%" PRIu64 "\n",
+                    attempt == 0 ? "gpu" : "host", attempt == 0 ? st.reads : reader.totalReads(), reader.skippedReads(),
+                    st.kmers_valid, st.chunks, merger.merges());
+        }
+        break;
     }
+    if (rc == KC_OK) rc = kc_run_write(ctx, final_run, opt.outputFile.c_str(), 0);   // truncates (KMerFileMerger.cpp:129 appends)
+    if (rc != KC_OK) fprintf(stderr, "kmer_counter_b200: %s\n", kc_last_error(ctx));
+    else fprintf(stderr, "records=%" PRIu64 " -> %s\n", kc_run_records(final_run), opt.outputFile.c_str());
     if (final_run) kc_run_free(ctx, final_run);
     kc_destroy(ctx);
     return rc == KC_OK ? 0 : 1;

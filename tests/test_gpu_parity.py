@@ -291,3 +291,36 @@ def test_full_size_properties_config2(kc):
                 r2.free()
             run.free()
     assert digests["hash"] == digests["sort"]
+
+
+def test_fastq_parse_on_device(kc):
+    """N1: raw FASTQ text parsed on the GPU, in blocks with carry-over, against the oracle's
+    restatement of the reference reader + counter."""
+    import torch
+    L, k, R = 100, 31, 5000
+    fq = oracle.gen_fastq(R, L, 60000, 0.01, 0.002, seed=31)
+    assert oracle.parse_fastq(fq) == oracle.gen_reads(R, L, 60000, 0.01, 0.002, seed=31).tobytes()
+    want = oracle.count(oracle.parse_fastq(fq), L, k)
+    with _counter(kc, k, L, method="auto", cap=1 << 20) as c:
+        for block in (0, 50_000, 7_777, 1_000_003):
+            run = c.count_fastq(fq, block_bytes=block)
+            assert run.to_bytes() == want, block
+            run.free()
+        # no trailing newline, CRLF line ends
+        run = c.count_fastq(fq[:-1]); assert run.to_bytes() == want; run.free()
+        run = c.count_fastq(fq.replace(b"\n", b"\r\n")); assert run.to_bytes() == want; run.free()
+        # parse only, device buffers
+        d_text = torch.from_numpy(np.frombuffer(fq, dtype=np.uint8).copy()).cuda()
+        d_reads = torch.empty(R * L, dtype=torch.uint8, device="cuda")
+        n, used, fl = c.parse_fastq_device(d_text.data_ptr(), d_text.numel(), d_reads.data_ptr(), d_reads.numel())
+        assert (n, used, fl) == (R, len(fq), 0)
+        assert bytes(d_reads.cpu().numpy()) == oracle.parse_fastq(fq)
+        n, used, fl = c.parse_fastq_device(d_text.data_ptr(), len(fq) - 150, d_reads.data_ptr(), d_reads.numel())
+        assert (n, fl) == (R - 1, 0) and used == len(fq) - 220                 # the cut record is left to the caller
+        # shapes the device parser refuses (the host chunker handles them)
+        ragged = fq[:220] + b"@x\nACGT\n+\nIIII\n" + fq[220:]
+        assert c.submit_fastq(0, ragged)[1] == 2
+        multi = b"@r\nACGT\nACGT\n+\nIIIIIIII\n" * 4
+        assert c.submit_fastq(0, multi)[1] & 1
+        with pytest.raises(kc.KcError):
+            c.count_fastq(ragged)

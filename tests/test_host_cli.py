@@ -56,6 +56,34 @@ def test_cli_counts_a_fastq_directory(tmp_path, k, method):
 
 
 @pytest.mark.gpu
+def test_cli_gpu_parser_host_parser_and_fallback(tmp_path):
+    L, k, R = 100, 31, 4000
+    fq = oracle.gen_fastq(R, L, 50000, 0.01, 0.002, seed=12)
+    want = oracle.count(oracle.gen_reads(R, L, 50000, 0.01, 0.002, seed=12), L, k)
+
+    def run(dirname, text, *extra):
+        d = tmp_path / dirname
+        d.mkdir()
+        (d / "reads.fastq").write_bytes(text)
+        out = tmp_path / (dirname + ".bin")
+        r = subprocess.run([CLI, "kmerLength=%d" % k, "inputFileLocation=%s" % d, "outputFile=%s" % out,
+                            "gpuMemoryLimit=3000000", *extra], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return out.read_bytes(), r.stderr
+
+    got, err = run("gpu", fq)
+    assert got == want and "parser=gpu" in err
+    got, err = run("host", fq, "parser=host")
+    assert got == want and "parser=host" in err
+    got, err = run("nonl", fq[:-1])                              # no final newline
+    assert got == want
+    # a read of another length in the middle: the device parser refuses, the host chunker skips it
+    odd = fq[:2200] + b"@odd\nACGTACGT\n+\nIIIIIIII\n" + fq[2200:]
+    got, err = run("odd", odd)
+    assert got == want and "parsing on the host" in err and "skipped=1" in err
+
+
+@pytest.mark.gpu
 def test_reference_shaped_seam_from_four_threads(tmp_path):
     L, k, R, chunk = 100, 31, 6000, 1000
     reads = oracle.gen_reads(R, L, 50000, 0.01, 0.002, seed=9)
