@@ -30,7 +30,10 @@ namespace {
 
 constexpr int kMaxBins = 1024;          // bins per level
 constexpr int kPbThreads = 256;
-template <int W> struct PbCfg { static constexpr int ITEMS = 16 / W, TILE = kPbThreads * ITEMS; };
+#ifndef KC_PB_ITEMS
+#define KC_PB_ITEMS 16
+#endif
+template <int W> struct PbCfg { static constexpr int ITEMS = KC_PB_ITEMS / W, TILE = kPbThreads * ITEMS; };
 constexpr int kDefaultTarget = 3072;    // keys per sub-bucket the plan aims for
 
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
