@@ -333,7 +333,8 @@ struct FinishParams {
     unsigned long long *d_overflow;
     const unsigned long long *d_n_invalid;
     int add_phantom;               // KC_COMPAT_REF: key 0 exists whenever a slot was empty
-    int cap_shift;                 // first table guess = pow2ceil(n >> cap_shift) slots
+    int cap_shift;                 // (unused)
+    float cap_factor;              // table slots per expected distinct key (first guess)
     const uint32_t *list;          // optional: only these sub-buckets (NULL = all)
     const uint32_t *list_count;
     uint32_t *tmp_start;           // [n_sub] where sub-bucket j's records start in tmp (written here, read by the gather)
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
         if (expect > n) expect = n;
         uint32_t round_bits = 0;
         while ((expect >> round_bits) > (uint32_t)kLcap && round_bits < 16) round_bits++;
-        uint32_t cap = pow2_ceil_u32(2 * (expect >> round_bits));
+        uint32_t cap = pow2_ceil_u32((uint32_t)(p.cap_factor * (float)(expect >> round_bits)));
         cap = cap < 256 ? 256 : (cap > (uint32_t)kHcap ? (uint32_t)kHcap : cap);
         while (true) {
             const uint32_t n_rounds = 1u << round_bits;
@@ -811,6 +812,7 @@ cudaError_t merge_parts_count(uint32_t n_src, const uint64_t *const *src_keys, c
     fp.m_out = m_out;
     fp.d_overflow = d_overflow;
     fp.cap_shift = 1;
+    fp.cap_factor = 2.0f;
     fp.tmp_start = tmp_start;
     fp.n_src = n_src;
     for (uint32_t i = 0; i < n_src; i++) { fp.src_keys[i] = src_keys[i]; fp.src_counts[i] = src_counts[i]; fp.src_off[i] = src_off[i]; }
@@ -935,6 +937,9 @@ static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slot
         fp.keys = grouped; fp.base2 = base2; fp.n_sub = pl.n_sub; fp.prefix_bits = pl.b1 + pl.b2;
         fp.tmp_keys = out_keys; fp.tmp_counts = out_counts; fp.m_out = m_out; fp.d_overflow = d_overflow;
         fp.d_n_invalid = ep_in.n_invalid; fp.add_phantom = add_phantom ? 1 : 0; fp.cap_shift = 1;
+        static float cap_factor = -1.f;             // KC_PC_LOAD (development knob): slots per expected distinct key
+        if (cap_factor < 0) { const char *v = getenv("KC_PC_LOAD"); cap_factor = v ? (float)atof(v) : 2.0f; }
+        fp.cap_factor = cap_factor;
         fp.tmp_start = status_scratch + pl.n_sub + 8;
         if constexpr (W == 1) e = launch_finish(fp, n_sms, pl.n_sub, s);
         else e = launch_finish_v<256, 2048, false, W>(fp, n_sms, pl.n_sub, s);
