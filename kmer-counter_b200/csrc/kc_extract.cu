@@ -36,6 +36,7 @@ bool extract_plan(const void *d_reads, uint64_t n_reads, uint32_t L, uint32_t k,
     uint32_t m = k % 32;
     bool masked = strict ? (m != 0) : (m >= 1 && m <= 28);
     p.last_mask = masked ? (~0ull << (64 - 2 * m)) : ~0ull;
+    p.last_mask_strict = strict ? 1u : 0u;
     p.n_invalid = d_n_invalid;
     extract_smem_layout(p);
     if (p.smem_total > 200 * 1024) return false;

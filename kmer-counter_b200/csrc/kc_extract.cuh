@@ -32,6 +32,7 @@ struct ExtractParams {
     uint32_t nb4_magic;      // floor(2^32 / nb4) + 1
     uint32_t segs_per_read, seg_len;   // rolling walk: a read's nk positions in segs_per_read runs of seg_len
     uint64_t last_mask;      // applied to key word W-1
+    uint32_t last_mask_strict;   // the plan was made for KC_COMPAT_STRICT (kept so that a plan can be re-made)
     unsigned long long *n_invalid;  // += slots that hold no k-mer (the phantom of SURVEY F7)
     uint32_t stage_bytes, enc_off, bad_off, flag_off, bar_off, smem_total;  // shared-memory layout
 };
@@ -46,6 +47,7 @@ inline void extract_smem_layout(ExtractParams &p) {
 }
 
 constexpr int kExtractThreads = 256;
+constexpr uint32_t kMaxSegLen = 18;      // positions a thread walks in the sliding-window mode (plan: seg_len <= 18)
 
 // Sink protocol (all members __device__; every thread of the CTA calls every hook):
 //   static constexpr int kSweeps      phase-B sweeps over a tile's slots (1, or 2 for rank-then-place)
@@ -59,7 +61,9 @@ constexpr int kExtractThreads = 256;
 struct SinkBase {
     static constexpr int kSweeps = 1;
     static constexpr bool kRolling = false;   // true: slot order is irrelevant, use the sliding-window walk
+    static constexpr bool kTopOnlySweep0 = false;   // true: sweep 0 only needs the top 32 bits of key word 0 (top())
     __device__ __forceinline__ void begin(uint8_t *) {}
+    __device__ __forceinline__ void top(uint32_t, bool) {}
     __device__ __forceinline__ void sweep_begin(int, uint32_t) {}
     __device__ __forceinline__ void sweep_end(int) {}
     __device__ __forceinline__ void finish() {}
@@ -210,6 +214,21 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
 #pragma unroll
                     for (int q = 0; q <= W; q++) win[q] = sh ? ((ew[q] << sh) | (ew[q + 1] >> (64 - sh))) : ew[q];
                     const bool check = flag[r] != 0;
+                    if (Sink::kTopOnlySweep0 && sw == 0) {
+                        // the sink only wants leading key bits here (a digit histogram): they all come
+                        // from the 64-bit window at p0, one constant funnel shift per position
+                        const uint64_t x = win[0];
+#pragma unroll
+                        for (uint32_t i = 0; i < kMaxSegLen; i++) {
+                            const uint32_t pos = p0 + i;
+                            if (pos < p1) {
+                                const bool valid = check ? kmer_valid(r, pos) : true;
+                                if (!valid) invalid_local++;
+                                sink.top((uint32_t)((x << (2 * i)) >> 32), valid);
+                            }
+                        }
+                        continue;
+                    }
                     for (uint32_t pos = p0; pos < p1; pos++) {
                         Key<W> key;
 #pragma unroll

@@ -79,6 +79,10 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_
 template <int W>
 struct Hist1Sink : SinkBase {
     static constexpr bool kRolling = true;
+    static constexpr bool kTopOnlySweep0 = true;
+    __device__ __forceinline__ void top(uint32_t top32, bool valid) {
+        if (valid) atomicAdd(&sh[top32 >> (shift1 - 32)], 1u);
+    }
     uint32_t *g_hist1;
     int shift1, nb1;
     uint32_t *sh;
@@ -129,6 +133,10 @@ template <int W>
 struct Scatter1Sink : SinkBase {
     static constexpr int kSweeps = 2;
     static constexpr bool kRolling = true;
+    static constexpr bool kTopOnlySweep0 = true;
+    __device__ __forceinline__ void top(uint32_t top32, bool valid) {      // sweep 0: count the level-1 digit
+        if (valid) atomicAdd(&cnt[top32 >> (shift1 - 32)], 1u);
+    }
     uint32_t *g_cursor1;
     uint64_t *out;
     int shift1, nb1;
@@ -877,7 +885,13 @@ static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slot
     if (fuse_h2 < 0) { const char *v = getenv("KC_FUSE_H2"); fuse_h2 = (v && v[0] == '1') ? 1 : 0; }
     // P0: level-1 histogram (invalid-slot count goes to a scratch counter: PA counts it for real)
     {
+        // the histogram pass keeps nothing per tile, so it takes larger tiles than PA (fewer barriers per read)
         ExtractParams ep = ep_in;
+        static int p0_stage = -1;               // KC_P0_STAGE (development knob): bytes of reads per P0 tile
+        if (p0_stage < 0) { const char *v = getenv("KC_P0_STAGE"); p0_stage = v ? atoi(v) : 12800; }
+        if (!extract_plan(ep_in.reads, ep_in.n_reads, ep_in.L, ep_in.k, ep_in.last_mask_strict != 0, d_scratch_invalid, &ep,
+                          (uint32_t)p0_stage))
+            ep = ep_in;
         ep.n_invalid = d_scratch_invalid;
         auto kern = extract_kernel<W, Hist1Sink<W>>;
         const uint32_t smem = ep.smem_total + kMaxBins * 4;
