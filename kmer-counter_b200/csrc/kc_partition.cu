@@ -493,23 +493,48 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                 }
             } else {
                 constexpr int kBatch = 8 / W;
-                for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * kBatch) {
-                    if (*reinterpret_cast<volatile uint32_t *>(&s_over)) break;
-                    Key<W> kk[kBatch];
+                // A sub-bucket far larger than the plan's target holds heavy hitters (skewed input):
+                // there the lanes of a warp that carry the same key are combined first (MATCH.ANY) and
+                // one of them adds their number, instead of 32 atomics serialising on one counter.
+                const bool hot = (end - begin) > 16384u;
+                if (!hot) {
+                    for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads * kBatch) {
+                        if (*reinterpret_cast<volatile uint32_t *>(&s_over)) break;
+                        Key<W> kk[kBatch];
 #pragma unroll
-                    for (int u = 0; u < kBatch; u++) {
-                        const uint32_t i = i0 + u * kPcThreads + tid;
-                        if (i < end) kk[u] = ld_key<W>(p.keys, i);
-                        else kk[u].w[0] = 0;
+                        for (int u = 0; u < kBatch; u++) {
+                            const uint32_t i = i0 + u * kPcThreads + tid;
+                            if (i < end) kk[u] = ld_key<W>(p.keys, i);
+                            else kk[u].w[0] = 0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kBatch; u++) {
+                            const uint32_t i = i0 + u * kPcThreads + tid;
+                            if (i >= end) continue;
+                            const Key<W> k = kk[u];
+                            if (round_bits && ((uint32_t)(k.w[0] >> rshift) & rmask) != r) continue;
+                            if (key_all_ones<W>(k)) { atomicAdd(&s_ones, 1u); continue; }
+                            insert(k, 1u);
+                        }
                     }
-#pragma unroll
-                    for (int u = 0; u < kBatch; u++) {
-                        const uint32_t i = i0 + u * kPcThreads + tid;
-                        if (i >= end) continue;
-                        const Key<W> k = kk[u];
-                        if (round_bits && ((uint32_t)(k.w[0] >> rshift) & rmask) != r) continue;
-                        if (key_all_ones<W>(k)) { atomicAdd(&s_ones, 1u); continue; }
-                        insert(k, 1u);
+                } else {
+                    for (uint32_t i0 = begin; i0 < end; i0 += kPcThreads) {
+                        uint32_t ov = *reinterpret_cast<volatile uint32_t *>(&s_over);
+                        ov = __shfl_sync(0xffffffffu, ov, 0);           // the whole warp leaves together
+                        if (ov) break;
+                        const uint32_t i = i0 + tid;
+                        Key<W> k;
+                        k.w[0] = 0;
+                        bool act = i < end;
+                        if (act) k = ld_key<W>(p.keys, i);
+                        if (act && round_bits && ((uint32_t)(k.w[0] >> rshift) & rmask) != r) act = false;
+                        if (act && key_all_ones<W>(k)) { atomicAdd(&s_ones, 1u); act = false; }
+                        const uint32_t am = __ballot_sync(0xffffffffu, act);
+                        if (act) {
+                            uint32_t peers = __match_any_sync(am, (unsigned long long)k.w[0]);
+                            if constexpr (W > 1) peers &= __match_any_sync(am, (unsigned long long)k.w[W - 1]);
+                            if ((int)lane == __ffs(peers) - 1) insert(k, (uint32_t)__popc(peers));
+                        }
                     }
                 }
             }
@@ -652,8 +677,10 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
         uint32_t expect = (uint32_t)((float)n * ratio * 1.25f) + 16;
         if (expect < floor_m) expect = floor_m;
         if (expect > n) expect = n;
+        // (at most 4 passes to begin with: an oversized sub-bucket is usually a few heavy hitters, not
+        // many distinct keys, and a wrong optimistic guess is abandoned after a couple of thousand keys)
         uint32_t round_bits = 0;
-        while ((expect >> round_bits) > (uint32_t)kLcap && round_bits < 16) round_bits++;
+        while ((expect >> round_bits) > (uint32_t)kLcap && round_bits < 2) round_bits++;
         uint32_t cap = pow2_ceil_u32((uint32_t)(p.cap_factor * (float)(expect >> round_bits)));
         cap = cap < 256 ? 256 : (cap > (uint32_t)kHcap ? (uint32_t)kHcap : cap);
         while (true) {

@@ -96,10 +96,11 @@ def test_partitioned_hash_heavy_hitters(kc):
     """A few keys with huge counts (skew): they stream through one table without overflowing it."""
     L, k = 100, 31
     hot = oracle.gen_reads(3, L, 0, 0, 0, seed=5)
-    reads = np.concatenate([np.tile(hot, 4000), oracle.gen_reads(2000, L, 50000, 0.01, 0.001, seed=6)])
-    want = oracle.process_chunk(reads, L, k)
-    with _counter(kc, k, L, method="hash", cap=1 << 26) as c:
-        assert c.process_chunk(reads) == want
+    for reps, kk in ((4000, 31), (30000, 31), (30000, 63)):       # 30000 copies: the warp-aggregated path of hot sub-buckets
+        reads = np.concatenate([np.tile(hot, reps), oracle.gen_reads(2000, L, 50000, 0.01, 0.001, seed=6)])
+        want = oracle.process_chunk(reads, L, kk)
+        with _counter(kc, kk, L, method="hash", cap=1 << 26) as c:
+            assert c.process_chunk(reads) == want, (reps, kk)
 
 
 def test_empty_and_ragged_inputs(kc):
