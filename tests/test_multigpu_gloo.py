@@ -107,13 +107,14 @@ def _gpu_worker(rank, world, port, k, L, R, q):
 @pytest.mark.gpu
 @pytest.mark.parametrize("k", [31, 63])
 def test_two_gpu_count_matches_oracle(k):
-    """Needs two devices (gpurun --gpus 2); skipped on a one-GPU box."""
+    """Needs at least two devices (gpurun --gpus 2/4/8); uses all of them, up to 8. Skipped on a one-GPU box."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     import oracle
-    R, L, world = 4000, 100, 2
+    world = min(8, 1 << (torch.cuda.device_count().bit_length() - 1))
+    R, L = 8000, 100
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
