@@ -186,6 +186,17 @@ int  kc_merge_parts(kc_ctx *ctx, uint32_t n_src, const void *const *d_keys, cons
                     const void *const *d_offsets, const uint64_t *n_records, uint32_t n_sub,
                     uint32_t prefix_bits, kc_run **out);
 
+/* Peer staging memory (same node, NVLink / NVSwitch): a rank keeps its run in a kc_peer_alloc'd
+ * buffer, its peers map it once with kc_peer_open (the 64-byte handle travels by any host
+ * channel) and hand the mapped pointers to kc_merge_parts, whose kernel then loads the parts
+ * straight from the peers' HBM: the exchange happens inside the combine kernel.
+ * d_offsets[s] may hold absolute record indices into part s's arrays (only differences and the
+ * first entry are used), n_records[s] = the records of the n_sub ranges read from it. */
+int  kc_peer_alloc(kc_ctx *ctx, uint64_t n_bytes, void **d_ptr, void *handle64);
+int  kc_peer_open(kc_ctx *ctx, const void *handle64, void **d_ptr);
+int  kc_peer_close(kc_ctx *ctx, void *d_ptr);
+int  kc_peer_free(kc_ctx *ctx, void *d_ptr);
+
 /* ---- merge: replaces KMerFileMerger::Merge (KMerFileMerger.cpp:49-96) ---- */
 /* Merge n sorted runs into one, adding the counts of equal keys (uint32 wrap).
  * Inputs stay valid and owned by the caller. n may be 0 (empty run) or 1 (copy). */

@@ -741,6 +741,50 @@ int kc_run_free(kc_ctx *c, kc_run *r) {
     return KC_OK;
 }
 
+// Staging memory a peer process can map: plain cudaMalloc (CUDA IPC does not export pool or
+// VMM allocations), handle = the 64-byte cudaIpcMemHandle_t.
+int kc_peer_alloc(kc_ctx *c, uint64_t n_bytes, void **d_ptr, void *handle64) {
+    KC_TRY(check_ctx(c));
+    if (!d_ptr || !handle64 || n_bytes == 0) return c->set_error(KC_ERR_ARG, "kc_peer_alloc: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaSetDevice(c->cfg.device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, n_bytes) != cudaSuccess) { cudaGetLastError(); return c->set_error(KC_ERR_NOMEM, "kc_peer_alloc: %llu bytes", (unsigned long long)n_bytes); }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return c->set_error(KC_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return KC_OK;
+}
+
+// Map a peer's staging memory into this context's device: opened with this device current, so
+// the mapping is one its kernels can load from (peer access is enabled on the way).
+int kc_peer_open(kc_ctx *c, const void *handle64, void **d_ptr) {
+    KC_TRY(check_ctx(c));
+    if (!d_ptr || !handle64) return c->set_error(KC_ERR_ARG, "kc_peer_open: null argument");
+    cudaSetDevice(c->cfg.device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return c->set_error(KC_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+    return KC_OK;
+}
+
+int kc_peer_close(kc_ctx *c, void *d_ptr) {
+    KC_TRY(check_ctx(c));
+    cudaSetDevice(c->cfg.device);
+    KC_CUDA_TRY(c, cudaIpcCloseMemHandle(d_ptr));
+    return KC_OK;
+}
+
+int kc_peer_free(kc_ctx *c, void *d_ptr) {
+    KC_TRY(check_ctx(c));
+    cudaSetDevice(c->cfg.device);
+    KC_CUDA_TRY(c, cudaFree(d_ptr));
+    return KC_OK;
+}
+
 int kc_run_parts(const kc_run *r, void **d_offsets, uint32_t *n_sub, uint32_t *prefix_bits) {
     if (!r) return KC_ERR_ARG;
     const bool has = r->d_sub_off && r->skip == 0;

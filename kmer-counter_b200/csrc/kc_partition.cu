@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                 const uint32_t ns = p.src_off[sidx][j + 1] - p.src_off[sidx][j];
                 n_in += ns;
                 floor_m = ns > floor_m ? ns : floor_m;        // every part is key-unique already
-                start_out += p.src_off[sidx][j];
+                start_out += p.src_off[sidx][j] - p.src_off[sidx][0];   // offsets may be absolute (peer arrays) or slice-relative
             }
         } else {
             begin = p.base2[j];

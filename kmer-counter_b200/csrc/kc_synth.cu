@@ -82,3 +82,24 @@ extern "C" int kc_synth_reads(void *d_out, uint64_t first_read, uint64_t n_reads
         static_cast<uint8_t *>(d_out), first_read, n_reads, read_len, genome_len, sub_rate, n_rate, seed, zipf_loci);
     return cudaGetLastError() == cudaSuccess ? KC_OK : KC_ERR_CUDA;
 }
+
+
+// Development aid: can a kernel on the current device read n 64-bit words at d_ptr (e.g. a
+// peer rank's buffer mapped through CUDA IPC)? Returns their sum in *out.
+namespace kc { namespace {
+__global__ void probe_sum_kernel(const unsigned long long *p, uint64_t n, unsigned long long *out) {
+    unsigned long long s = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += p[i];
+    atomicAdd(out, s);
+}
+} }
+extern "C" int kc_debug_probe_read(const void *d_ptr, uint64_t n_words, unsigned long long *out) {
+    unsigned long long *d = nullptr;
+    if (cudaMalloc((void **)&d, 8) != cudaSuccess) return KC_ERR_NOMEM;
+    cudaMemset(d, 0, 8);
+    kc::probe_sum_kernel<<<64, 256>>>(static_cast<const unsigned long long *>(d_ptr), n_words, d);
+    cudaError_t e = cudaMemcpy(out, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { fprintf(stderr, "kc_debug_probe_read: %s\n", cudaGetErrorString(e)); return KC_ERR_CUDA; }
+    return KC_OK;
+}

@@ -246,6 +246,23 @@ class Counter:
         self._check(self._lib.kc_run_from_device(self._ctx, keys_ptr, counts_ptr, n, C.byref(h)))
         return Run(self, h)
 
+    def peer_alloc(self, n_bytes):
+        """Staging memory peers can map (kc_peer_alloc): returns (device pointer, 64-byte handle)."""
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        self._check(self._lib.kc_peer_alloc(self._ctx, int(n_bytes), C.byref(p), h))
+        return p.value, h.raw
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        self._check(self._lib.kc_peer_open(self._ctx, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr):
+        self._check(self._lib.kc_peer_close(self._ctx, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        self._check(self._lib.kc_peer_free(self._ctx, C.c_void_p(ptr)))
+
     def merge_parts(self, key_ptrs, count_ptrs, offset_ptrs, n_records, n_sub, prefix_bits) -> Run:
         """Combine pre-counted parts covering the same n_sub key ranges (kc_merge_parts)."""
         n = len(key_ptrs)

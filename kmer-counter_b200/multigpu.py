@@ -121,7 +121,7 @@ def run_as_tensors(run, device):
     return keys, counts
 
 
-def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, splitters=None):
+def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, splitters=None, peer=None):
     """This rank's share of the distributed count.  Returns the Run holding the final
     records of this rank's key range.  Collective: every rank of `group` must call it.
 
@@ -136,6 +136,10 @@ def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, splitters=Non
     local = counter.count_device(d_reads_ptr, n_bytes)
     if world == 1:
         return local
+    if peer is not None:
+        merged = peer.combine(local)                # the exchange happens inside the combine kernel
+        if merged is not None:
+            return merged
     return exchange_and_combine(counter, local, device, group, splitters)
 
 
@@ -217,3 +221,84 @@ def exchange_and_combine(counter, local, device, group=None, splitters=None):
     for p in parts:
         p.free()
     return merged
+
+
+# ------------------------------------------------ exchange fused into the combine kernel (peer memory)
+class PeerCombine:
+    """The all-to-all fused into the combine kernel over NVLink peer memory.
+
+    Every rank keeps its run (keys, counts, range offsets) in a staging buffer whose CUDA IPC
+    handle its peers have opened once.  A step is then: count locally -> copy the run into the
+    staging buffer -> barrier -> kc_merge_parts reads, for every key range this rank owns, the
+    P parts straight out of the peers' staging buffers (P2P loads through NVSwitch) while it
+    combines them in shared memory -> barrier.  No exchange kernel, no receive buffer: the
+    transfer happens inside the kernel that consumes it.  Needs partition-structured runs
+    (64-bit keys); exchange_and_combine() over NCCL is the general path."""
+
+    def __init__(self, counter, device, max_records, n_sub_max=1 << 20, group=None):
+        import torch
+        import torch.distributed as dist
+        self.c, self.dev, self.group = counter, device, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap, self.n_sub_max = int(max_records), int(n_sub_max)
+        # one allocation: keys u64[cap] | counts u32[cap] | range offsets u32[n_sub_max + 1]
+        self._o_counts = 8 * self.cap
+        self._o_offs = (12 * self.cap + 255) // 256 * 256
+        self.base, handle = counter.peer_alloc(self._o_offs + 4 * (self.n_sub_max + 1))
+        self.keys = torch.as_tensor(_CudaView(self.base, (self.cap,), "<i8"), device=device)
+        self.counts = torch.as_tensor(_CudaView(self.base + self._o_counts, (self.cap,), "<i4"), device=device)
+        self.offs = torch.as_tensor(_CudaView(self.base + self._o_offs, (self.n_sub_max + 1,), "<i4"), device=device)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handle, group=group)
+        # per rank: base pointer of its staging buffer as mapped into this process
+        self.peer_base = [self.base if r == self.rank else counter.peer_open(h) for r, h in enumerate(everyone)]
+        dist.barrier(group=group)
+
+    def close(self):
+        import torch.distributed as dist
+        if self.base is None:
+            return
+        dist.barrier(group=self.group)                  # nobody is still reading
+        for r, p in enumerate(self.peer_base):
+            if r != self.rank:
+                self.c.peer_close(p)
+        dist.barrier(group=self.group)                  # every mapping is gone before the memory is
+        self.keys = self.counts = self.offs = None
+        self.c.peer_free(self.base)
+        self.base = None
+
+    def combine(self, local):
+        """`local`: this rank's run (freed here). Returns the run of this rank's key range, or None
+        if the runs have no common partition structure (caller falls back to NCCL)."""
+        import torch
+        import torch.distributed as dist
+        off_ptr, n_sub, pbits = local.parts()
+        kptr, cptr, n = local.device_arrays()
+        P = self.world
+        usable = self.c.words == 1 and n_sub >= P and n_sub % P == 0 and n_sub <= self.n_sub_max and n <= self.cap
+        per = n_sub // P if usable else 1
+        # one small all-gather: plan, size, and the record boundaries of the owners' ranges
+        info = torch.zeros(4 + P + 1, dtype=torch.int64, device=self.dev)
+        info[0], info[1], info[2], info[3] = n_sub, pbits, n, int(usable)
+        if usable:
+            off_t = torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=self.dev)
+            info[4:] = off_t[::per].to(torch.int64)
+        infos = [torch.empty_like(info) for _ in range(P)]
+        dist.all_gather(infos, info, group=self.group)
+        infos = [t.tolist() for t in infos]
+        if not all(i[3] == 1 and i[0] == n_sub and i[1] == pbits for i in infos):
+            return None
+        keys_t, counts_t = run_as_tensors(local, self.dev)
+        self.keys[:n].copy_(keys_t[:, 0])
+        self.counts[:n].copy_(counts_t)
+        self.offs[:n_sub + 1].copy_(torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=self.dev))
+        torch.cuda.current_stream().synchronize()
+        local.free()
+        dist.barrier(group=self.group)                  # every rank's staging buffer is complete
+        kp = list(self.peer_base)                       # absolute offsets index the peer's whole array
+        cp = [b + self._o_counts for b in self.peer_base]
+        op = [b + self._o_offs + 4 * self.rank * per for b in self.peer_base]
+        sizes = [i[4 + self.rank + 1] - i[4 + self.rank] for i in infos]    # records this rank reads from each peer
+        merged = self.c.merge_parts(kp, cp, op, sizes, per, pbits)
+        dist.barrier(group=self.group)                  # nobody overwrites a buffer that is still being read
+        return merged

@@ -97,6 +97,14 @@ def _gpu_worker(rank, world, port, k, L, R, q):
     with kc.Counter(k, L, device=rank) as c:
         run = multigpu.count_shard(c, d.data_ptr(), per * L, dev)
         mine = run.to_bytes()
+        run.free()
+        if k <= 32:                                    # the same through the peer-memory fused combine
+            peer = multigpu.PeerCombine(c, dev, max_records=per * (L - k + 1) + 16, n_sub_max=1 << 16)
+            for _ in range(2):                         # twice: the staging buffers are reused
+                run = multigpu.count_shard(c, d.data_ptr(), per * L, dev, peer=peer)
+                assert run.to_bytes() == mine, "peer-memory combine differs from the NCCL path"
+                run.free()
+            peer.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     if rank == 0:
