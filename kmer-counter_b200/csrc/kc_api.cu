@@ -76,6 +76,11 @@ struct kc_ctx {
     int n_sms = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // records D2H (kc_run_copy_records): its own stream, so that reading
+                                          // one run back overlaps the kernels of the next on `stream`
+    std::mutex copy_mu;                   // one read-back at a time (the link is the limit anyway)
+    void *copy_buf = nullptr;             // packed records staged for D2H: grow-only, not from the pool
+    uint64_t copy_cap = 0;
     std::vector<Slot> slots;
     Pending direct;              // kc_count_device / kc_process_chunk without slots use this
     std::mutex mu;
@@ -491,6 +496,9 @@ int kc_create(const kc_config *cfg, kc_ctx **out) {
         if (e != cudaSuccess) { g_create_error = std::string("kc_create: stream: ") + cudaGetErrorString(e); delete c; return KC_ERR_CUDA; }
         c->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "kc_create: copy stream"; kc_destroy(c); return KC_ERR_CUDA;
+    }
     uint32_t ns = c0.n_slots ? c0.n_slots : 2;
     if (ns > 64) ns = 64;
     c->slots.resize(ns);
@@ -524,6 +532,8 @@ void kc_destroy(kc_ctx *c) {
     pending_release(c->stream, c->direct);
     pending_destroy(c->direct);
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_buf) cudaFree(c->copy_buf);
     delete c;
 }
 
@@ -872,12 +882,26 @@ int kc_run_copy_records(kc_ctx *c, const kc_run *r, void *dst, uint64_t cap, uin
     if (nb > cap || (nb && !dst)) return c->set_error(KC_ERR_CAPACITY, "run needs %llu bytes, buffer holds %llu", (unsigned long long)nb, (unsigned long long)cap);
     if (n == 0) return KC_OK;
     cudaSetDevice(c->cfg.device);
-    void *d_rec = nullptr;
-    KC_TRY(dev_alloc(c, c->stream, nb, &d_rec));
-    KC_CUDA_TRY(c, pack_records(r->d_keys + r->skip * r->W, r->d_counts + r->skip, n, r->W, d_rec, c->stream));
-    KC_CUDA_TRY(c, cudaMemcpyAsync(dst, d_rec, nb, cudaMemcpyDeviceToHost, c->stream));
-    KC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    dev_free(c->stream, d_rec);
+    std::lock_guard<std::mutex> cg(c->copy_mu);
+    cudaStream_t cs = c->copy_stream;
+    if (nb > c->copy_cap) {
+        cudaStreamSynchronize(cs);
+        if (c->copy_buf) cudaFree(c->copy_buf);
+        c->copy_buf = nullptr; c->copy_cap = 0;
+        const uint64_t want = nb + nb / 8 + (1u << 20);
+        if (cudaMalloc(&c->copy_buf, want) != cudaSuccess) { cudaGetLastError(); return c->set_error(KC_ERR_NOMEM, "record staging buffer: %llu bytes", (unsigned long long)want); }
+        c->copy_cap = want;
+    }
+    // everything queued on `stream` so far (the run's producer) is ordered before the copy; what
+    // is queued later is not waited for
+    cudaEvent_t ready;
+    KC_CUDA_TRY(c, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventRecord(ready, c->stream);
+    cudaStreamWaitEvent(cs, ready, 0);
+    cudaEventDestroy(ready);
+    KC_CUDA_TRY(c, pack_records(r->d_keys + r->skip * r->W, r->d_counts + r->skip, n, r->W, c->copy_buf, cs));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(dst, c->copy_buf, nb, cudaMemcpyDeviceToHost, cs));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(cs));
     std::lock_guard<std::mutex> g(c->mu);
     c->stats.d2h_bytes += nb;
     c->stats.launches += 1;
