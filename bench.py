@@ -56,7 +56,7 @@ def parse_args():
     return ap.parse_args()
 
 
-E2E_SLOTS = 3           # pinned input slots of the end-to-end pipeline: H2D | kernels | D2H of three consecutive chunks
+E2E_SLOTS = 2           # pinned input slots of the end-to-end pipeline (chunks whose H2D / kernels are in flight)
 
 
 def workload(a):
@@ -66,6 +66,22 @@ def workload(a):
             "sub_rate": a.sub_rate, "n_rate": a.n_rate, "seed": a.seed, "zipf_loci": a.zipf_loci,
             "kmers_per_step_per_gpu": a.reads * (a.read_len - a.k + 1),
             "l2_policy": "inputs larger than L2 (1 GB of reads, 5.6 GB of keys per step vs 126 MB L2)"}
+
+
+def bind_near_gpu(index):
+    """Run this process on the CPUs next to GPU `index` (NVML's ideal affinity) before anything is
+    allocated: the pinned buffers of the end-to-end path then live in that NUMA node's memory, which is
+    what the GPU's PCIe link reaches without crossing the socket interconnect. Returns the CPU count
+    bound to, or None when NVML has no answer (KC_NO_BIND=1 skips it)."""
+    if os.environ.get("KC_NO_BIND") == "1":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------ clocks
@@ -196,6 +212,7 @@ def run_ours(a, rank, world, local_rank):
     import kmer_counter_b200 as kc
     from kmer_counter_b200 import multigpu, synth
 
+    numa = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -203,7 +220,9 @@ def run_ours(a, rank, world, local_rank):
     L, k, R = a.read_len, a.k, a.reads
     nk = L - k + 1
     n_bytes = R * L
-    stream = torch.cuda.Stream(device=dev)
+    # high priority: the combine step and the record read-back of chunk i are queued while the
+    # kernels of chunks i+1, i+2 occupy the SMs on the (default-priority) slot streams
+    stream = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(stream)
     counter = kc.Counter(k, L, device=local_rank, method=a.method, n_slots=E2E_SLOTS, max_chunk_bytes=0 if a.no_e2e else n_bytes,
                          stream=stream.cuda_stream)
@@ -320,34 +339,56 @@ def run_ours(a, rank, world, local_rank):
         import queue
         todo, res = queue.Queue(maxsize=1), {"nb": 0, "err": None}
 
+        trace = [] if os.environ.get("KC_E2E_TRACE") == "1" and rank == 0 else None   # (what, start ms, ms) per call
+
+        def timed(what, fn, *args):
+            if trace is None:
+                return fn(*args)
+            t_s = time.perf_counter()
+            out = fn(*args)
+            trace.append((what, t_s * 1e3, (time.perf_counter() - t_s) * 1e3))
+            return out
+
         def reader():
             while True:
                 run = todo.get()
                 if run is None:
                     return
                 try:
-                    res["nb"] = run.copy_into(pinned_out.ctypes.data, out_cap)
+                    res["nb"] = timed("copy", run.copy_into, pinned_out.ctypes.data, out_cap)
                     run.free()
                 except Exception as e:                       # surfaced after the join
                     res["err"] = e
 
-        def take(sl):
-            run = counter.wait(sl)
+        def combine(run):
+            merged = peer.combine(run) if peer is not None else None
+            return merged if merged is not None else multigpu.exchange_and_combine(counter, run, dev)
+
+        def emit(run):
+            """[exchange + combine of a finished chunk], then hand its records to the reader"""
             if world > 1:
-                merged = peer.combine(run) if peer is not None else None
-                run = merged if merged is not None else multigpu.exchange_and_combine(counter, run, dev)
-            todo.put(run)
+                run = timed("combine", combine, run)
+            timed("put", todo.put, run)
 
         def pipelined(n_steps):
+            # Steady state of iteration i: H2D of chunk i is in flight, chunk i-1 is being counted, chunk
+            # i-2 is combined with the peers' parts as soon as i-1's kernels have drained (so the combine
+            # runs in the shadow of i's H2D instead of fighting i-1's kernels for SMs), and the reader
+            # thread copies the records of chunk i-3 to the host.
             th = threading.Thread(target=reader, daemon=True)
             th.start()
-            depth = E2E_SLOTS - 1                           # chunks in flight behind the one being submitted
-            for i in range(n_steps):
-                counter.submit(i % E2E_SLOTS, n_bytes)
-                if i >= depth:
-                    take((i - depth) % E2E_SLOTS)
-            for i in range(max(n_steps - depth, 0), n_steps):
-                take(i % E2E_SLOTS)
+            held = None                                     # counted, not yet combined
+            for i in range(n_steps + 1):
+                if i < n_steps:
+                    timed("submit%d" % (i % E2E_SLOTS), counter.submit, i % E2E_SLOTS, n_bytes)
+                if i >= 1:
+                    sl = (i - 1) % E2E_SLOTS
+                    run = timed("wait%d" % sl, counter.wait, sl)
+                    if held is not None:
+                        emit(held)
+                    held = run
+            if held is not None:
+                emit(held)
             todo.put(None)
             th.join()
             if res["err"] is not None:
@@ -356,9 +397,15 @@ def run_ours(a, rank, world, local_rank):
         pipelined(max(a.warmup, 2 * E2E_SLOTS))             # untimed: every slot's arena and the run pool reach their steady size
         barrier()
         t0 = time.perf_counter()
+        if trace is not None:
+            del trace[:]
         pipelined(a.steps)
         d2h = res["nb"]
         barrier()
+        if trace:
+            t_first = min(t for _, t, _ in trace)
+            for what, t_s, dur in sorted(trace, key=lambda x: x[1]):
+                sys.stderr.write("e2e-trace %8.1f  %-9s %7.2f\n" % (t_s - t_first, what, dur))
         e2e_dt = (time.perf_counter() - t0) / a.steps
         t = torch.tensor([e2e_dt, single_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -370,7 +417,7 @@ def run_ours(a, rank, world, local_rank):
                          "by a consumer thread), sync on both sides, max over ranks; every step copies its reads H2D "
                          "and its records D2H" % E2E_SLOTS,
                "single_step_ms": single_ms, "single_step_value": kmers_step / (single_ms * 1e-3),
-               "single_step_parts_ms_rank0": parts}
+               "single_step_parts_ms_rank0": parts, "cpus_bound_near_gpu": numa}
         counter.host_free(pinned_out)
 
     clocks = clk.summary()

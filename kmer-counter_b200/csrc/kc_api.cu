@@ -489,14 +489,18 @@ int kc_create(const kc_config *cfg, kc_ctx **out) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    // merges, combines and read-backs run while later chunks' kernels fill the SMs from the slot
+    // streams (default = least priority): give them the greatest priority so they are not queued behind
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (c0.stream) {
         c->stream = static_cast<cudaStream_t>(c0.stream);
     } else {
-        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
         if (e != cudaSuccess) { g_create_error = std::string("kc_create: stream: ") + cudaGetErrorString(e); delete c; return KC_ERR_CUDA; }
         c->own_stream = true;
     }
-    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         g_create_error = "kc_create: copy stream"; kc_destroy(c); return KC_ERR_CUDA;
     }
     uint32_t ns = c0.n_slots ? c0.n_slots : 2;
