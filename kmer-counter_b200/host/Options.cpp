@@ -26,6 +26,7 @@ Options Options::parse(int argc, char **argv) {
         else if (take(argv[i], "device=", &v)) o.device = atoi(v);
         else if (take(argv[i], "keepRuns=", &v)) o.keepRuns = atoi(v) != 0;
         else if (take(argv[i], "parser=", &v)) o.parser = v;
+        else if (take(argv[i], "runBudget=", &v)) o.runBudget = strtoll(v, nullptr, 10);
     }
     if (o.noOfMergersAtOnce < 2) o.noOfMergersAtOnce = 2;
     return o;

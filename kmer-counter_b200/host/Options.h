@@ -18,6 +18,8 @@ struct Options {
     std::string compat = "ref";               // compat=ref|strict
     int device = 0;                           // device=
     bool keepRuns = false;                    // keepRuns=1: also write every chunk's run to tempFileLocation/<id>
+    int64_t runBudget = 0;                    // runBudget=BYTES: a merged run larger than this is spilled to pinned host
+                                              // memory and the final merge runs out of core, range by range (0 = never)
     std::string parser = "gpu";               // parser=gpu|host: where FASTQ text is parsed (gpu falls back to host
                                               // for input that is not plain 4-line fixed-length FASTQ)
 

@@ -1,38 +1,86 @@
-// RunMerger.h -- merge scheduling over device-resident runs.
+// RunMerger.h -- merge scheduling over sorted runs, with spill to host memory.
 //
 // Replaces KMerFileMergeHandler (KMerFileMergeHandler.cpp:23-123), whose polling thread
 // hangs when InputComplete() arrives late or when there is a single run.
 // Same shape -- AddRun / InputComplete / result -- but synchronous and terminating for
 // 0, 1 or N runs: whenever noOfMergersAtOnce runs are pending they are merged on the GPU
 // (kc_merge_runs, the merge-path kernel), and InputComplete() merges whatever is left.
+//
+// Spill (the reference spills every chunk's run to tempFileLocation and merges files,
+// FileDump.cpp:51-58 + KMerFileMerger.cpp:49-135): with a run budget, a merged run that
+// outgrows it is copied to pinned host memory as packed records and leaves the device.
+// Finish() then merges out of core: the key space is cut at sampled splitters into ranges
+// whose records fit the budget, and range by range the matching slice of every spilled run
+// is uploaded (kc_run_upload), merged (kc_merge_runs) and appended to the output file --
+// ranges are key-disjoint and ascending, so the file is the sorted unique artefact.
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/kc_api.h"
 
 class RunMerger {
 public:
-    RunMerger(kc_ctx *ctx, uint32_t noOfMergersAtOnce) : _ctx(ctx), _fanIn(noOfMergersAtOnce < 2 ? 2 : noOfMergersAtOnce) {}
-    ~RunMerger() { for (kc_run *r : _pending) kc_run_free(_ctx, r); }
+    // runBudgetBytes = packed-record bytes a merged run may hold on the device (0 = no limit, never spill)
+    RunMerger(kc_ctx *ctx, uint32_t noOfMergersAtOnce, uint32_t k = 0, uint64_t runBudgetBytes = 0)
+        : _ctx(ctx), _fanIn(noOfMergersAtOnce < 2 ? 2 : noOfMergersAtOnce), _budget(runBudgetBytes),
+          _W(k ? kc_key_words(k) : 1), _S(k ? kc_record_size(k) : 12) {}
+    ~RunMerger() {
+        for (kc_run *r : _pending) kc_run_free(_ctx, r);
+        for (HostRun &h : _spilled) kc_host_free(_ctx, h.data);
+    }
     int AddRun(kc_run *run) {                       // takes ownership
         _pending.push_back(run);
-        return _pending.size() >= _fanIn ? mergePending() : KC_OK;
+        if (_pending.size() < _fanIn) return KC_OK;
+        int rc = mergePending();
+        if (rc != KC_OK) return rc;
+        if (_budget && !_pending.empty() && kc_run_records(_pending[0]) * _S > _budget) rc = spill();
+        return rc;
     }
     // Merges everything that is left; *out is the final run (an empty run for no input).
+    // Only valid when nothing was spilled (spills() == 0); use Finish() otherwise.
     int InputComplete(kc_run **out) {
         int rc = mergePending();
         if (rc != KC_OK) return rc;
+        if (!_spilled.empty()) return KC_ERR_STATE;
         if (_pending.empty()) return kc_merge_runs(_ctx, nullptr, 0, out);
         *out = _pending[0];
         _pending.clear();
         return KC_OK;
     }
+    // Merges everything that is left and writes the artefact to `path` (truncating; the reference
+    // appends to whatever is there, KMerFileMerger.cpp:129). *n_records = records written.
+    int Finish(const char *path, uint64_t *n_records) {
+        int rc = mergePending();
+        if (rc != KC_OK) return rc;
+        if (_spilled.empty()) {
+            kc_run *out = nullptr;
+            if ((rc = InputComplete(&out)) != KC_OK) return rc;
+            if (n_records) *n_records = kc_run_records(out);
+            rc = kc_run_write(_ctx, out, path, 0);
+            kc_run_free(_ctx, out);
+            return rc;
+        }
+        if (!_pending.empty() && (rc = spill()) != KC_OK) return rc;
+        return mergeOutOfCore(path, n_records);
+    }
     uint64_t merges() const { return _merges; }
+    uint64_t spills() const { return _spills; }
+    uint64_t ranges() const { return _ranges; }
 
 private:
+    struct HostRun {
+        void *data;
+        uint64_t n;                                 // records
+    };
+    struct KeyRef {                                 // W words, most significant first
+        uint64_t w[4];
+    };
+
     int mergePending() {
         if (_pending.size() < 2) return KC_OK;
         kc_run *merged = nullptr;
@@ -43,8 +91,99 @@ private:
         _merges++;
         return KC_OK;
     }
+    // the (single) pending run goes to pinned host memory as packed records
+    int spill() {
+        kc_run *r = _pending[0];
+        const uint64_t n = kc_run_records(r), nb = n * _S;
+        void *buf = nullptr;
+        int rc = kc_host_alloc(_ctx, nb ? nb : 1, &buf);
+        if (rc != KC_OK) return rc;
+        uint64_t got = 0;
+        rc = kc_run_copy_records(_ctx, r, buf, nb, &got);
+        if (rc != KC_OK) { kc_host_free(_ctx, buf); return rc; }
+        _spilled.push_back(HostRun{buf, n});
+        kc_run_free(_ctx, r);
+        _pending.clear();
+        _spills++;
+        return KC_OK;
+    }
+    KeyRef keyAt(const HostRun &h, uint64_t i) const {
+        KeyRef k = {{0, 0, 0, 0}};
+        memcpy(k.w, static_cast<const uint8_t *>(h.data) + i * _S, 8 * _W);
+        return k;
+    }
+    bool less(const KeyRef &a, const KeyRef &b) const {
+        for (uint32_t i = 0; i < _W; i++)
+            if (a.w[i] != b.w[i]) return a.w[i] < b.w[i];
+        return false;
+    }
+    uint64_t lowerBound(const HostRun &h, const KeyRef &k) const {  // first record whose key is >= k
+        uint64_t lo = 0, hi = h.n;
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (less(keyAt(h, mid), k)) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    }
+    int mergeOutOfCore(const char *path, uint64_t *n_records) {
+        uint64_t total = 0;
+        for (const HostRun &h : _spilled) total += h.n * _S;
+        const uint64_t per_range = _budget > 2 * _S ? _budget / 2 : _S;
+        const uint64_t G = std::max<uint64_t>(1, (total + per_range - 1) / per_range);
+        // splitters: 16 evenly spaced keys per range from every run, sorted, then every n_runs*16-th
+        std::vector<KeyRef> samples;
+        const uint64_t per_run = 16 * G;
+        for (const HostRun &h : _spilled)
+            for (uint64_t i = 1; i <= per_run && h.n; i++) samples.push_back(keyAt(h, (h.n - 1) * i / per_run));
+        std::sort(samples.begin(), samples.end(), [this](const KeyRef &a, const KeyRef &b) { return less(a, b); });
+        std::vector<uint64_t> lo(_spilled.size(), 0);
+        uint64_t written = 0;
+        bool first = true;
+        int rc = KC_OK;
+        for (uint64_t g = 0; g < G && rc == KC_OK; g++) {
+            std::vector<kc_run *> parts;
+            for (size_t r = 0; r < _spilled.size() && rc == KC_OK; r++) {
+                const HostRun &h = _spilled[r];
+                const uint64_t hi = (g + 1 == G || samples.empty()) ? h.n
+                                                                   : lowerBound(h, samples[(g + 1) * samples.size() / G - 1]);
+                if (hi > lo[r]) {
+                    kc_run *part = nullptr;
+                    rc = kc_run_upload(_ctx, static_cast<const uint8_t *>(h.data) + lo[r] * _S, (hi - lo[r]) * _S, &part);
+                    if (rc == KC_OK) parts.push_back(part);
+                    lo[r] = hi;
+                }
+            }
+            if (rc == KC_OK && !parts.empty()) {
+                kc_run *out = nullptr;
+                rc = kc_merge_runs(_ctx, parts.data(), (uint32_t)parts.size(), &out);
+                if (rc == KC_OK) {
+                    rc = kc_run_write(_ctx, out, path, first ? 0 : 1);
+                    written += kc_run_records(out);
+                    first = false;
+                    _merges++;
+                    _ranges++;
+                    kc_run_free(_ctx, out);
+                }
+            }
+            for (kc_run *p : parts) kc_run_free(_ctx, p);
+        }
+        if (rc == KC_OK && first) {                 // nothing at all: still leave an (empty) artefact behind
+            kc_run *empty = nullptr;
+            if ((rc = kc_merge_runs(_ctx, nullptr, 0, &empty)) == KC_OK) {
+                rc = kc_run_write(_ctx, empty, path, 0);
+                kc_run_free(_ctx, empty);
+            }
+        }
+        if (n_records) *n_records = written;
+        return rc;
+    }
+
     kc_ctx *_ctx;
     size_t _fanIn;
+    uint64_t _budget;
+    uint32_t _W, _S;
     std::vector<kc_run *> _pending;
-    uint64_t _merges = 0;
+    std::vector<HostRun> _spilled;
+    uint64_t _merges = 0, _spills = 0, _ranges = 0;
 };

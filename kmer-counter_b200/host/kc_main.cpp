@@ -3,6 +3,7 @@
 //   kmer_counter_b200 kmerLength=31 inputFileLocation=<dir> outputFile=<file> [gpuMemoryLimit=..]
 //                     [tempFileLocation=..] [noOfMergersAtOnce=..] [noOfMergeThreads=..]
 //                     [method=auto|sort|hash] [compat=ref|strict] [device=N] [keepRuns=1] [parser=gpu|host]
+//                     [runBudget=BYTES]
 //   kmer_counter_b200 print <record file> <ignored> <k>       (KMerPrinter, main.cpp:78-82)
 //
 // What KMerCounter::Start does (KMerCounter.cpp:108-191), on the B200 path: read fixed
@@ -83,11 +84,11 @@ int main(int argc, char **argv) {
     int rc = KC_OK;
     uint32_t chunk_id = 0;
     uint64_t gpu_parsed_bytes = 0;
-    kc_run *final_run = nullptr;
+    uint64_t n_records = 0;
     // attempt 0: FASTQ text goes to the GPU as it is and is parsed there (kc_submit_fastq);
     // attempt 1: the host chunker, for input the device parser refuses (or parser=host)
     for (int attempt = opt.parser == "host" ? 1 : 0; attempt < 2; attempt++) {
-        RunMerger merger(ctx, opt.noOfMergersAtOnce);
+        RunMerger merger(ctx, opt.noOfMergersAtOnce, (uint32_t)opt.kmerLength, opt.runBudget > 0 ? (uint64_t)opt.runBudget : 0);
         bool busy[2] = {false, false};
         bool refused = false;
         chunk_id = 0;
@@ -170,21 +171,19 @@ int main(int argc, char **argv) {
             for (uint32_t slot = 0; slot < 2 && rc == KC_OK; slot++)
                 if (busy[slot]) rc = collect(slot);
         }
-        if (rc == KC_OK) rc = merger.InputComplete(&final_run);
+        if (rc == KC_OK) rc = merger.Finish(opt.outputFile.c_str(), &n_records);     // truncates (KMerFileMerger.cpp:129 appends)
         if (rc == KC_OK) {
             kc_stats st;
             kc_stats_get(ctx, &st);
             fprintf(stderr, "parser=%s reads=%" PRIu64 " skipped=%" PRIu64 " kmers=%" PRIu64 " chunks=%" PRIu64
-                            " merges=%" PRIu64 "\n",
+                            " merges=%" PRIu64 " spills=%" PRIu64 " ranges=%" PRIu64 "\n",
                     attempt == 0 ? "gpu" : "host", attempt == 0 ? st.reads : reader.totalReads(), reader.skippedReads(),
-                    st.kmers_valid, st.chunks, merger.merges());
+                    st.kmers_valid, st.chunks, merger.merges(), merger.spills(), merger.ranges());
         }
         break;
     }
-    if (rc == KC_OK) rc = kc_run_write(ctx, final_run, opt.outputFile.c_str(), 0);   // truncates (KMerFileMerger.cpp:129 appends)
     if (rc != KC_OK) fprintf(stderr, "kmer_counter_b200: %s\n", kc_last_error(ctx));
-    else fprintf(stderr, "records=%" PRIu64 " -> %s\n", kc_run_records(final_run), opt.outputFile.c_str());
-    if (final_run) kc_run_free(ctx, final_run);
+    else fprintf(stderr, "records=%" PRIu64 " -> %s\n", n_records, opt.outputFile.c_str());
     kc_destroy(ctx);
     return rc == KC_OK ? 0 : 1;
 }

@@ -84,6 +84,28 @@ def test_cli_gpu_parser_host_parser_and_fallback(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k", [31, 63, 100])
+def test_cli_spills_runs_and_merges_out_of_core(tmp_path, k):
+    """SURVEY N2 / C5's forced multi-run configuration: a run budget far below the distinct set, so
+    merged runs leave the device for pinned host memory and the artefact is put together range by
+    range (upload slices, merge-path, append)."""
+    d = tmp_path / "in"
+    d.mkdir()
+    L, R = 100 if k < 100 else 150, 24000
+    (d / "reads.fastq").write_bytes(oracle.gen_fastq(R, L, 300000, 0.01, 0.002, seed=21))
+    out = tmp_path / "out.bin"
+    r = subprocess.run([CLI, "kmerLength=%d" % k, "inputFileLocation=%s" % d, "outputFile=%s" % out,
+                        "gpuMemoryLimit=1200000", "noOfMergersAtOnce=2", "runBudget=400000"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    stats = dict(t.split("=") for t in r.stderr.split() if "=" in t and t.split("=")[1].isdigit())
+    assert int(stats["chunks"]) >= 16 and int(stats["spills"]) >= 4 and int(stats["ranges"]) >= 8, r.stderr
+    want = oracle.count(oracle.gen_reads(R, L, 300000, 0.01, 0.002, seed=21), L, k)
+    assert out.read_bytes() == want
+    assert int(stats["records"]) * (8 * ((k + 31) // 32) + 4) == len(want)
+
+
+@pytest.mark.gpu
 def test_reference_shaped_seam_from_four_threads(tmp_path):
     L, k, R, chunk = 100, 31, 6000, 1000
     reads = oracle.gen_reads(R, L, 50000, 0.01, 0.002, seed=9)
