@@ -216,26 +216,49 @@ __device__ __forceinline__ bool map_tile(const uint32_t *__restrict__ tile_prefi
 }
 
 // ------------------------------------------------------------------- H2: hist2
+// Level-2 histogram of the grouped keys. The grouped array is dense and a key's own leading
+// bits name its sub-bucket, so no tile map is needed: a CTA takes a flat chunk of kH2Chunk keys,
+// counts those of the chunk's first bucket (all of them, except where the chunk straddles a
+// bucket boundary) in shared memory and flushes nb2 counters once per chunk; stragglers add to
+// the global counter directly.
+constexpr uint32_t kH2Chunk = 32768;
 template <int W>
 __global__ void __launch_bounds__(kPbThreads) hist2_kernel(const uint64_t *__restrict__ keys,
-                                                           const uint32_t *__restrict__ tile_prefix,
-                                                           const uint32_t *__restrict__ base1, int nb1, int shift2,
-                                                           int nb2, uint32_t *__restrict__ g_hist2) {
+                                                           const uint32_t *__restrict__ n_keys_ptr, int b2, int shift2,
+                                                           uint32_t *__restrict__ g_hist2) {
     __shared__ uint32_t sh[kMaxBins];
-    __shared__ uint32_t s_map[4];
-    uint32_t bucket, begin, end;
-    for (int i = threadIdx.x; i < nb2; i += kPbThreads) sh[i] = 0;
-    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, PbCfg<W>::TILE, s_map, bucket, begin, end)) return;
-    const uint32_t m2 = (uint32_t)nb2 - 1;
+    const uint32_t n = *n_keys_ptr;
+    const uint32_t begin = blockIdx.x * kH2Chunk;
+    if (begin >= n) return;
+    const uint32_t end = begin + kH2Chunk < n ? begin + kH2Chunk : n;
+    const uint32_t nb2 = 1u << b2, m2 = nb2 - 1;
+    for (uint32_t i = threadIdx.x; i < nb2; i += kPbThreads) sh[i] = 0;
+    const uint32_t b0 = (uint32_t)(keys[(size_t)begin * W] >> shift2) >> b2;      // word 0 holds the prefix
+    __syncthreads();
+    auto add = [&](uint64_t w0) {
+        const uint32_t pfx = (uint32_t)(w0 >> shift2);
+        if ((pfx >> b2) == b0) atomicAdd(&sh[pfx & m2], 1u);
+        else atomicAdd(&g_hist2[pfx], 1u);
+    };
+    if constexpr (W == 1) {
+        // begin is a multiple of the chunk: 16-byte loads of two keys
+        const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys + begin);
+        const uint32_t pairs = (end - begin) >> 1;
 #pragma unroll 4
-    for (int i = 0; i < PbCfg<W>::ITEMS; i++) {
-        const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        if (idx < end) atomicAdd(&sh[(uint32_t)(keys[(size_t)idx * W] >> shift2) & m2], 1u);   // word 0 holds the prefix
+        for (uint32_t i = threadIdx.x; i < pairs; i += kPbThreads) {
+            const ulonglong2 v = k2[i];
+            add(v.x);
+            add(v.y);
+        }
+        if (((end - begin) & 1u) && threadIdx.x == 0) add(keys[end - 1]);
+    } else {
+#pragma unroll 4
+        for (uint32_t i = begin + threadIdx.x; i < end; i += kPbThreads) add(keys[(size_t)i * W]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nb2; i += kPbThreads) {
+    for (uint32_t i = threadIdx.x; i < nb2; i += kPbThreads) {
         const uint32_t c = sh[i];
-        if (c) atomicAdd(&g_hist2[(size_t)bucket * nb2 + i], c);
+        if (c) atomicAdd(&g_hist2[(size_t)b0 * nb2 + i], c);
     }
 }
 
@@ -958,7 +981,7 @@ static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slot
     const uint32_t max_tiles = (uint32_t)(n_slots / PbCfg<W>::TILE) + pl.nb1 + 1;
     if (pl.b2 > 0) {
         if (!fuse_h2)
-            hist2_kernel<W><<<max_tiles, kPbThreads, 0, s>>>(keys_a, tile_prefix, base1, (int)pl.nb1, shift2, (int)pl.nb2, hist2);
+            hist2_kernel<W><<<(uint32_t)div_up(n_slots, (uint64_t)kH2Chunk), kPbThreads, 0, s>>>(keys_a, base1 + pl.nb1, pl.b2, shift2, hist2);
         scan2_kernel<<<1, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
         if (evs) cudaEventRecord(evs[2], s);
         scatter2_kernel<W><<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,
