@@ -262,47 +262,58 @@ __global__ void __launch_bounds__(kPbThreads) hist2_kernel(const uint64_t *__res
     }
 }
 
-// one block: exclusive scan over all sub-buckets -> base2 (n+1) and the mutable cursors.
-// Coalesced tiles of 4096 entries (4 per thread) with a running carry.
+// Exclusive scan over all sub-buckets -> base2 (n+1) and the mutable cursors. One CTA per tile of
+// 4096 entries; a CTA gets its offset by summing the entries before its tile itself (at most
+// 2 MB out of L2), so there is neither a carried dependency between tiles nor scratch memory.
+// The input must not alias the outputs.
+constexpr uint32_t kScan2Tile = 4096;
 __global__ void __launch_bounds__(1024) scan2_kernel(const uint32_t *__restrict__ hist2, uint32_t n,
                                                      uint32_t *__restrict__ base2, uint32_t *__restrict__ cursor2) {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    const uint32_t t0 = blockIdx.x * kScan2Tile;
+    uint32_t acc = 0;
+#pragma unroll 8
+    for (uint32_t i = tid; i < t0; i += 1024) acc += hist2[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_w[warp] = acc;
     __syncthreads();
-    for (uint32_t t0 = 0; t0 < n; t0 += 4096) {
-        const uint32_t i0 = t0 + tid * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = i0 + u < n ? hist2[i0 + u] : 0;
-        const uint32_t sum = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        uint32_t off = s_carry, tot = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < 32; w++) {
-            const uint32_t x = s_w[w];
-            if (w < warp) off += x;
-            tot += x;
-        }
-        uint32_t run = off + incl - sum;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (i0 + u < n) { base2[i0 + u] = run; cursor2[i0 + u] = run; }
-            run += v[u];
-        }
-        __syncthreads();
-        if (tid == 0) s_carry += tot;
-        __syncthreads();
+    if (tid == 0) {
+        uint32_t c = 0;
+        for (int w = 0; w < 32; w++) c += s_w[w];
+        s_carry = c;
     }
-    if (tid == 0) base2[n] = s_carry;
+    __syncthreads();
+    const uint32_t i0 = t0 + tid * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = i0 + u < n ? hist2[i0 + u] : 0;
+    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();                        // s_w is reused
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = s_carry, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 32; w++) {
+        const uint32_t x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    uint32_t run = off + incl - sum;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (i0 + u < n) { base2[i0 + u] = run; cursor2[i0 + u] = run; }
+        run += v[u];
+    }
+    if (tid == 0 && t0 + kScan2Tile >= n) base2[n] = s_carry + tot;    // the last tile closes the scan
 }
 
 // ---------------------------------------------------------------- PB: scatter2
@@ -875,7 +886,7 @@ cudaError_t merge_parts_count(uint32_t n_src, const uint64_t *const *src_keys, c
     fp.n_src = n_src;
     for (uint32_t i = 0; i < n_src; i++) { fp.src_keys[i] = src_keys[i]; fp.src_counts[i] = src_counts[i]; fp.src_off[i] = src_off[i]; }
     if ((e = launch_finish_v<256, 2048, true, 1>(fp, n_sms, n_sub, s)) != cudaSuccess) return e;
-    scan2_kernel<<<1, 1024, 0, s>>>(m_out, n_sub, off, scratch);
+    scan2_kernel<<<(n_sub + kScan2Tile - 1) / kScan2Tile, 1024, 0, s>>>(m_out, n_sub, off, scratch);
     if ((e = cudaMemcpyAsync(d_num_out, off + n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     if (n_launches) *n_launches += 2;
     return cudaGetLastError();
@@ -982,7 +993,7 @@ static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slot
     if (pl.b2 > 0) {
         if (!fuse_h2)
             hist2_kernel<W><<<(uint32_t)div_up(n_slots, (uint64_t)kH2Chunk), kPbThreads, 0, s>>>(keys_a, base1 + pl.nb1, pl.b2, shift2, hist2);
-        scan2_kernel<<<1, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
+        scan2_kernel<<<(pl.n_sub + kScan2Tile - 1) / kScan2Tile, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
         if (evs) cudaEventRecord(evs[2], s);
         scatter2_kernel<W><<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,
                                                             (int)pl.nb2, cursor2);
@@ -1009,7 +1020,7 @@ static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slot
         else e = launch_finish_v<256, 2048, false, W>(fp, n_sms, pl.n_sub, s);
         if (e != cudaSuccess) return e;
         // off[] (n_sub + 1) overwrites cursor2; its last entry is the number of records
-        scan2_kernel<<<1, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);
+        scan2_kernel<<<(pl.n_sub + kScan2Tile - 1) / kScan2Tile, 1024, 0, s>>>(m_out, pl.n_sub, cursor2, status_scratch);
         if ((e = cudaMemcpyAsync(d_num_out, cursor2 + pl.n_sub, 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     }
     if (evs) cudaEventRecord(evs[4], s);
