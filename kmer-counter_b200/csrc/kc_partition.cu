@@ -190,31 +190,6 @@ struct Scatter1Sink : SinkBase {
     }
 };
 
-// -------------------------------------------------------------- tile map (H2 / PB)
-__device__ __forceinline__ bool map_tile(const uint32_t *__restrict__ tile_prefix, const uint32_t *__restrict__ base1,
-                                         int nb1, uint32_t tile, uint32_t tile_keys, uint32_t *s_map, uint32_t &bucket,
-                                         uint32_t &begin, uint32_t &end) {
-    if (threadIdx.x == 0) {
-        uint32_t b = 0xffffffffu, lo_i = 0, hi_i = 0;
-        if (tile < tile_prefix[nb1]) {
-            int lo = 0, hi = nb1 - 1;                 // last b with tile_prefix[b] <= tile
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
-            }
-            b = lo;
-            const uint32_t t = tile - tile_prefix[b];
-            lo_i = base1[b] + t * tile_keys;
-            hi_i = base1[b + 1];
-            if (hi_i - lo_i > tile_keys) hi_i = lo_i + tile_keys;
-        }
-        s_map[0] = b; s_map[1] = lo_i; s_map[2] = hi_i;
-    }
-    __syncthreads();
-    bucket = s_map[0]; begin = s_map[1]; end = s_map[2];
-    return bucket != 0xffffffffu;
-}
-
 // ------------------------------------------------------------------- H2: hist2
 // Level-2 histogram of the grouped keys. The grouped array is dense and a key's own leading
 // bits name its sub-bucket, so no tile map is needed: a CTA takes a flat chunk of kH2Chunk keys,
@@ -317,20 +292,24 @@ __global__ void __launch_bounds__(1024) scan2_kernel(const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------- PB: scatter2
+// Level-2 scatter over flat tiles of the grouped array (dense, bucket after bucket): the keys'
+// own leading bits name bucket and sub-bucket, so a CTA needs no tile map and its loads are in
+// flight from the first instruction. Bins are relative to the bucket of the tile's first key
+// and span two buckets when the tile straddles a boundary; a key even further away (tiles
+// crossing a bucket of fewer than TILE keys) is placed on its own.
 template <int W>
 __global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__restrict__ keys,
                                                               uint64_t *__restrict__ out,
-                                                              const uint32_t *__restrict__ tile_prefix,
-                                                              const uint32_t *__restrict__ base1, int nb1, int shift2,
-                                                              int nb2, uint32_t *__restrict__ g_cursor2) {
+                                                              const uint32_t *__restrict__ n_keys_ptr, int b2, int shift2,
+                                                              uint32_t *__restrict__ g_cursor2) {
     constexpr int ITEMS = PbCfg<W>::ITEMS, TILE = PbCfg<W>::TILE;
     __shared__ uint32_t cnt[kMaxBins], start[kMaxBins], gbase[kMaxBins];
-    __shared__ uint32_t s_warp[kPbThreads / 32], s_map[4];
+    __shared__ uint32_t s_warp[kPbThreads / 32];
     __shared__ Key<W> staging[TILE];
-    uint32_t bucket, begin, end;
-    for (int i = threadIdx.x; i < nb2; i += kPbThreads) cnt[i] = 0;
-    if (!map_tile(tile_prefix, base1, nb1, blockIdx.x, TILE, s_map, bucket, begin, end)) return;
-    const uint32_t m2 = (uint32_t)nb2 - 1;
+    const uint32_t n = *n_keys_ptr;
+    const uint32_t begin = blockIdx.x * (uint32_t)TILE;
+    if (begin >= n) return;
+    const uint32_t end = begin + TILE < n ? begin + TILE : n;
     Key<W> key[ITEMS];
     uint16_t rank[ITEMS];
 #pragma unroll
@@ -339,26 +318,36 @@ __global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__
         if (idx < end) key[i] = ld_key<W>(keys, idx);
         else key[i].w[0] = 0;
     }
+    const uint32_t nb2 = 1u << b2;
+    const uint32_t p0 = ((uint32_t)(keys[(size_t)begin * W] >> shift2) >> b2) << b2;     // first sub-bucket of the first key's bucket
+    const uint32_t pl = (uint32_t)(keys[(size_t)(end - 1) * W] >> shift2);
+    const uint32_t nb = (pl >> b2) == (p0 >> b2) ? nb2 : 2 * nb2;                         // 2 * nb2 <= kMaxBins
+    for (uint32_t i = threadIdx.x; i < nb; i += kPbThreads) cnt[i] = 0;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        if (idx < end) rank[i] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key[i].w[0] >> shift2) & m2], 1u);
+        rank[i] = 0xffffu;
+        if (idx < end) {
+            const uint32_t pfx = (uint32_t)(key[i].w[0] >> shift2);
+            const uint32_t rel = pfx - p0;
+            if (rel < nb) rank[i] = (uint16_t)atomicAdd(&cnt[rel], 1u);
+            else st_key<W>(out, atomicAdd(&g_cursor2[pfx], 1u), key[i]);
+        }
     }
     __syncthreads();
-    const uint32_t total = block_scan_bins<kPbThreads>(cnt, start, nb2, s_warp);
-    for (int b = threadIdx.x; b < nb2; b += kPbThreads) {
+    const uint32_t total = block_scan_bins<kPbThreads>(cnt, start, (int)nb, s_warp);
+    for (uint32_t b = threadIdx.x; b < nb; b += kPbThreads) {
         const uint32_t c = cnt[b];
-        if (c) gbase[b] = atomicAdd(&g_cursor2[(size_t)bucket * nb2 + b], c) - start[b];
+        if (c) gbase[b] = atomicAdd(&g_cursor2[p0 + b], c) - start[b];
     }
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const uint32_t idx = begin + i * kPbThreads + threadIdx.x;
-        if (idx < end) staging[start[(uint32_t)(key[i].w[0] >> shift2) & m2] + rank[i]] = key[i];
-    }
+    for (int i = 0; i < ITEMS; i++)
+        if (rank[i] != 0xffffu) staging[start[(uint32_t)(key[i].w[0] >> shift2) - p0] + rank[i]] = key[i];
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < total; i += kPbThreads) {
         const Key<W> k = staging[i];
-        st_key<W>(out, gbase[(uint32_t)(k.w[0] >> shift2) & m2] + i, k);
+        st_key<W>(out, gbase[(uint32_t)(k.w[0] >> shift2) - p0] + i, k);
     }
 }
 
@@ -989,14 +978,13 @@ static cudaError_t partition_count_w(const ExtractParams &ep_in, uint64_t n_slot
     }
     if (evs) cudaEventRecord(evs[1], s);
     // H2 + PB over the level-1 buckets
-    const uint32_t max_tiles = (uint32_t)(n_slots / PbCfg<W>::TILE) + pl.nb1 + 1;
     if (pl.b2 > 0) {
         if (!fuse_h2)
             hist2_kernel<W><<<(uint32_t)div_up(n_slots, (uint64_t)kH2Chunk), kPbThreads, 0, s>>>(keys_a, base1 + pl.nb1, pl.b2, shift2, hist2);
         scan2_kernel<<<(pl.n_sub + kScan2Tile - 1) / kScan2Tile, 1024, 0, s>>>(hist2, pl.n_sub, base2, cursor2);
         if (evs) cudaEventRecord(evs[2], s);
-        scatter2_kernel<W><<<max_tiles, kPbThreads, 0, s>>>(keys_a, keys_b, tile_prefix, base1, (int)pl.nb1, shift2,
-                                                            (int)pl.nb2, cursor2);
+        scatter2_kernel<W><<<(uint32_t)div_up(n_slots, (uint64_t)PbCfg<W>::TILE), kPbThreads, 0, s>>>(
+            keys_a, keys_b, base1 + pl.nb1, pl.b2, shift2, cursor2);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else {
         if ((e = cudaMemcpyAsync(base2, base1, (pl.nb1 + 1) * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
