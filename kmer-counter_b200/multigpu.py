@@ -251,8 +251,25 @@ class PeerCombine:
         everyone = [None] * self.world
         dist.all_gather_object(everyone, handle, group=group)
         # per rank: base pointer of its staging buffer as mapped into this process
-        self.peer_base = [self.base if r == self.rank else counter.peer_open(h) for r, h in enumerate(everyone)]
-        dist.barrier(group=group)
+        self.peer_base, err = [], None
+        for r, h in enumerate(everyone):
+            try:
+                self.peer_base.append(self.base if r == self.rank else counter.peer_open(h))
+            except Exception as e:                      # no peer access to that GPU
+                err = e
+                break
+        # all ranks or none: a rank that cannot map a peer makes everybody fall back together
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            for r, p in enumerate(self.peer_base):
+                if r != self.rank:
+                    counter.peer_close(p)
+            dist.barrier(group=group)
+            self.keys = self.counts = self.offs = None
+            counter.peer_free(self.base)
+            self.base = None
+            raise RuntimeError("peer staging buffers cannot be mapped on every rank: %s" % (err or "a peer failed"))
 
     def close(self):
         import torch.distributed as dist
