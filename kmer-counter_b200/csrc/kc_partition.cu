@@ -146,6 +146,7 @@ struct Scatter1Sink : SinkBase {
     uint32_t *cnt, *start, *gbase, *s_warp;
     Key<W> *staging;
     uint32_t total;
+    uint32_t reserved[kMaxBins / kExtractThreads];     // answers of this thread's reservations (registers)
 
     static __host__ __device__ uint32_t smem_bytes(uint32_t max_tile_keys) {
         return 3 * kMaxBins * 4 + 64 + max_tile_keys * 8 * W;
@@ -172,13 +173,25 @@ struct Scatter1Sink : SinkBase {
     __device__ __forceinline__ void sweep_end(int sw) {
         if (sw == 0) {
             total = block_scan_bins<kExtractThreads>(cnt, start, nb1, s_warp);
-            for (int b = threadIdx.x; b < nb1; b += kExtractThreads) {
-                const uint32_t c = cnt[b];
-                if (c) gbase[b] = atomicAdd(&g_cursor1[b], c) - start[b];   // dst = gbase[d] + staging index
-                cnt[b] = 0;
+            // reserve the bins' ranges now, look at the answers after the placing sweep: the
+            // round trips of the global atomics are hidden behind it
+#pragma unroll
+            for (int u = 0; u < kMaxBins / kExtractThreads; u++) {
+                const int b = u * kExtractThreads + threadIdx.x;
+                if (b < nb1) {
+                    const uint32_t c = cnt[b];
+                    if (c) reserved[u] = atomicAdd(&g_cursor1[b], c);
+                    cnt[b] = 0;
+                }
             }
             __syncthreads();
         } else {
+#pragma unroll
+            for (int u = 0; u < kMaxBins / kExtractThreads; u++) {
+                const int b = u * kExtractThreads + threadIdx.x;
+                if (b < nb1) gbase[b] = reserved[u] - start[b];            // dst = gbase[d] + staging index
+            }
+            __syncthreads();
             for (uint32_t i = threadIdx.x; i < total; i += kExtractThreads) {
                 const Key<W> k = staging[i];
                 st_key<W>(out, gbase[k.w[0] >> shift1] + i, k);
@@ -337,13 +350,25 @@ __global__ void __launch_bounds__(kPbThreads) scatter2_kernel(const uint64_t *__
     }
     __syncthreads();
     const uint32_t total = block_scan_bins<kPbThreads>(cnt, start, (int)nb, s_warp);
-    for (uint32_t b = threadIdx.x; b < nb; b += kPbThreads) {
-        const uint32_t c = cnt[b];
-        if (c) gbase[b] = atomicAdd(&g_cursor2[p0 + b], c) - start[b];
+    // reserve the bins' ranges, stage the keys while the atomics are in flight, then look at the answers
+    uint32_t reserved[kMaxBins / kPbThreads];
+#pragma unroll
+    for (int u = 0; u < kMaxBins / kPbThreads; u++) {
+        const uint32_t b = u * kPbThreads + threadIdx.x;
+        reserved[u] = 0;
+        if (b < nb) {
+            const uint32_t c = cnt[b];
+            if (c) reserved[u] = atomicAdd(&g_cursor2[p0 + b], c);
+        }
     }
 #pragma unroll
     for (int i = 0; i < ITEMS; i++)
         if (rank[i] != 0xffffu) staging[start[(uint32_t)(key[i].w[0] >> shift2) - p0] + rank[i]] = key[i];
+#pragma unroll
+    for (int u = 0; u < kMaxBins / kPbThreads; u++) {
+        const uint32_t b = u * kPbThreads + threadIdx.x;
+        if (b < nb) gbase[b] = reserved[u] - start[b];
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < total; i += kPbThreads) {
         const Key<W> k = staging[i];
