@@ -221,7 +221,9 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
     if (method == KC_COUNT_HASH) {
         // partitioned shared-memory hash counting (kc_partition.cu)
         ExtractParams ep64;
-        if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep64, 6400))
+        static int pa_stage = -1;               // KC_PA_STAGE (development knob): bytes of reads per PA tile
+        if (pa_stage < 0) { const char *v = getenv("KC_PA_STAGE"); pa_stage = v ? atoi(v) : 6400; }
+        if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep64, (uint32_t)pa_stage))
             return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
         const uint64_t kb = p.n_slots * 8 * W + 64, cb = (p.n_slots + 2) * 4, wb = partition_workspace_bytes(p.n_slots);
         KC_TRY(arena_reserve(c, p, 2 * arena_round(kb) + arena_round(cb) + arena_round(wb), s));
