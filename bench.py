@@ -384,6 +384,9 @@ def run_ours(a, rank, world, local_rank):
                 if i >= 1:
                     sl = (i - 1) % E2E_SLOTS
                     run = timed("wait%d" % sl, counter.wait, sl)
+                    if world == 1:                          # nothing to combine: straight to the reader
+                        emit(run)
+                        continue
                     if held is not None:
                         emit(held)
                     held = run

@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
             }
             if (ok) {
                 if (tid == 0) p.m_out[j] = running;
-                ratio = 0.5f * ratio + 0.5f * (float)running / (float)n;
+                ratio = 0.5f * ratio + 0.5f * __fdividef((float)running, (float)n);      // steers a guess only
                 break;
             }
             if (cap < (uint32_t)kHcap) {
