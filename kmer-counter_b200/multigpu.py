@@ -241,6 +241,7 @@ class PeerCombine:
         self.c, self.dev, self.group = counter, device, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.cap, self.n_sub_max = int(max_records), int(n_sub_max)
+        self.loc_offs = None
         # one allocation: keys u64[cap] | counts u32[cap] | range offsets u32[n_sub_max + 1]
         self._o_counts = 8 * self.cap
         self._o_offs = (12 * self.cap + 255) // 256 * 256
@@ -314,7 +315,19 @@ class PeerCombine:
         dist.barrier(group=self.group)                  # every rank's staging buffer is complete
         kp = list(self.peer_base)                       # absolute offsets index the peer's whole array
         cp = [b + self._o_counts for b in self.peer_base]
-        op = [b + self._o_offs + 4 * self.rank * per for b in self.peer_base]
+        # The range offsets are read twice per range and part: bring this rank's slice of every
+        # peer's offsets over once (per + 1 integers each) instead of paying a link round trip per read.
+        if self.loc_offs is None or self.loc_offs.shape[1] < per + 1:
+            self.loc_offs = torch.empty((P, per + 1), dtype=torch.int32, device=self.dev)
+        op = []
+        for r, b in enumerate(self.peer_base):
+            src = b + self._o_offs + 4 * self.rank * per
+            if r == self.rank:
+                op.append(src)
+            else:
+                self.loc_offs[r, :per + 1].copy_(torch.as_tensor(_CudaView(src, (per + 1,), "<i4"), device=self.dev))
+                op.append(self.loc_offs[r].data_ptr())
+        torch.cuda.current_stream().synchronize()
         sizes = [i[4 + self.rank + 1] - i[4 + self.rank] for i in infos]    # records this rank reads from each peer
         merged = self.c.merge_parts(kp, cp, op, sizes, per, pbits)
         dist.barrier(group=self.group)                  # nobody overwrites a buffer that is still being read
