@@ -186,6 +186,15 @@ int  kc_merge_parts(kc_ctx *ctx, uint32_t n_src, const void *const *d_keys, cons
                     const void *const *d_offsets, const uint64_t *n_records, uint32_t n_sub,
                     uint32_t prefix_bits, kc_run **out);
 
+/* Place the next run: the next run the partitioned path finishes on this context (kc_count_device,
+ * kc_wait) is written into caller-owned device arrays -- keys (8W bytes each), counts (uint32) and
+ * n_sub + 1 range offsets -- if it has at most cap_records records and cap_ranges offsets;
+ * otherwise it is allocated as usual. One-shot; NULL pointers clear it. The run does not own placed
+ * arrays (kc_run_free leaves them alone); kc_run_device tells where a run ended up. Used to count
+ * straight into peer staging memory. */
+int  kc_place_next_run(kc_ctx *ctx, void *d_keys, void *d_counts, void *d_offsets, uint64_t cap_records,
+                       uint32_t cap_ranges);
+
 /* Peer staging memory (same node, NVLink / NVSwitch): a rank keeps its run in a kc_peer_alloc'd
  * buffer, its peers map it once with kc_peer_open (the 64-byte handle travels by any host
  * channel) and hand the mapped pointers to kc_merge_parts, whose kernel then loads the parts

@@ -27,6 +27,7 @@ struct kc_run {
     // partition structure (KC_COUNT_HASH runs only): record offsets of n_sub equal key ranges
     uint32_t *d_sub_off = nullptr;
     uint32_t n_sub = 0, prefix_bits = 0;
+    bool placed = false;     // arrays belong to the caller (kc_place_next_run): never freed here
 };
 
 namespace {
@@ -78,6 +79,7 @@ struct kc_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // records D2H (kc_run_copy_records): its own stream, so that reading
                                           // one run back overlaps the kernels of the next on `stream`
+    struct { uint64_t *keys = nullptr; uint32_t *counts = nullptr, *offs = nullptr; uint64_t cap = 0; uint32_t cap_ranges = 0; bool set = false; } place;
     std::mutex copy_mu;                   // one read-back at a time (the link is the limit anyway)
     void *copy_buf = nullptr;             // packed records staged for D2H: grow-only, not from the pool
     uint64_t copy_cap = 0;
@@ -381,18 +383,41 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
 
 int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
     const uint64_t U = p.h_scal[SC_UNIQUE];
+    const int sig = c->W == 1 ? 64 - static_zero_bits(c) : 64;
+    const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;
+    uint32_t n_sub = 0, prefix_bits = 0;
+    const uint32_t *d_off = nullptr;
+    if (U) partition_plan_info(p.n_slots, sig, target, p.ws_part, &n_sub, &prefix_bits, &d_off);
     kc_run *r = nullptr;
-    KC_TRY(make_run(c, s, U, &r));
+    bool placed = false;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (c->place.set) {                      // one-shot, whether it fits or not
+            placed = U > 0 && U <= c->place.cap && n_sub + 1 <= c->place.cap_ranges;
+            c->place.set = false;
+        }
+    }
+    if (placed) {
+        r = new kc_run();
+        r->W = c->W;
+        r->n = U;
+        r->d_keys = c->place.keys;
+        r->d_counts = c->place.counts;
+        r->d_sub_off = c->place.offs;
+        r->placed = true;
+    } else {
+        KC_TRY(make_run(c, s, U, &r));
+    }
     if (U) {
-        const int sig = c->W == 1 ? 64 - static_zero_bits(c) : 64;
-        const int target = c->cfg.table_slots ? (int)c->cfg.table_slots : 0;
         KC_CUDA_TRY(c, partition_gather(c->W, p.n_slots, sig, target, p.uniq, p.counts, p.ws_part, r->d_keys, r->d_counts, s));
-        const uint32_t *d_off = nullptr;
-        partition_plan_info(p.n_slots, sig, target, p.ws_part, &r->n_sub, &r->prefix_bits, &d_off);
-        void *mem = nullptr;
-        KC_TRY(dev_alloc(c, s, (uint64_t)(r->n_sub + 1) * 4, &mem));
-        r->d_sub_off = static_cast<uint32_t *>(mem);
-        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_sub_off, d_off, (uint64_t)(r->n_sub + 1) * 4, cudaMemcpyDeviceToDevice, s));
+        r->n_sub = n_sub;
+        r->prefix_bits = prefix_bits;
+        if (!placed) {
+            void *mem = nullptr;
+            KC_TRY(dev_alloc(c, s, (uint64_t)(n_sub + 1) * 4, &mem));
+            r->d_sub_off = static_cast<uint32_t *>(mem);
+        }
+        KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_sub_off, d_off, (uint64_t)(n_sub + 1) * 4, cudaMemcpyDeviceToDevice, s));
         std::lock_guard<std::mutex> g(c->mu);
         c->stats.launches += 1;
     }
@@ -750,10 +775,24 @@ uint64_t kc_run_records(const kc_run *r) { return r ? r->n - r->skip : 0; }
 int kc_run_free(kc_ctx *c, kc_run *r) {
     KC_TRY(check_ctx(c));
     if (!r) return KC_OK;
-    dev_free(c->stream, r->d_keys);
-    dev_free(c->stream, r->d_counts);
-    dev_free(c->stream, r->d_sub_off);
+    if (!r->placed) {
+        dev_free(c->stream, r->d_keys);
+        dev_free(c->stream, r->d_counts);
+        dev_free(c->stream, r->d_sub_off);
+    }
     delete r;
+    return KC_OK;
+}
+
+int kc_place_next_run(kc_ctx *c, void *d_keys, void *d_counts, void *d_offsets, uint64_t cap_records, uint32_t cap_ranges) {
+    KC_TRY(check_ctx(c));
+    std::lock_guard<std::mutex> g(c->mu);
+    c->place.keys = static_cast<uint64_t *>(d_keys);
+    c->place.counts = static_cast<uint32_t *>(d_counts);
+    c->place.offs = static_cast<uint32_t *>(d_offsets);
+    c->place.cap = cap_records;
+    c->place.cap_ranges = cap_ranges;
+    c->place.set = d_keys && d_counts && d_offsets && cap_records;
     return KC_OK;
 }
 

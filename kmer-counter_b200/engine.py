@@ -246,6 +246,11 @@ class Counter:
         self._check(self._lib.kc_run_from_device(self._ctx, keys_ptr, counts_ptr, n, C.byref(h)))
         return Run(self, h)
 
+    def place_next_run(self, d_keys, d_counts, d_offsets, cap_records, cap_ranges):
+        """The next partitioned-path run is written into these device arrays if it fits (kc_place_next_run)."""
+        self._check(self._lib.kc_place_next_run(self._ctx, C.c_void_p(d_keys), C.c_void_p(d_counts), C.c_void_p(d_offsets),
+                                                int(cap_records), int(cap_ranges)))
+
     def peer_alloc(self, n_bytes):
         """Staging memory peers can map (kc_peer_alloc): returns (device pointer, 64-byte handle)."""
         p, h = C.c_void_p(), C.create_string_buffer(64)

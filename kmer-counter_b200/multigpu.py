@@ -133,6 +133,8 @@ def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, splitters=Non
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if peer is not None and world > 1:
+        peer.place()                                # count straight into the staging buffer the peers read
     local = counter.count_device(d_reads_ptr, n_bytes)
     if world == 1:
         return local
@@ -242,6 +244,7 @@ class PeerCombine:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.cap, self.n_sub_max = int(max_records), int(n_sub_max)
         self.loc_offs = None
+        self._readers_pending = False
         # one allocation: keys u64[cap] | counts u32[cap] | range offsets u32[n_sub_max + 1]
         self._o_counts = 8 * self.cap
         self._o_offs = (12 * self.cap + 255) // 256 * 256
@@ -285,6 +288,20 @@ class PeerCombine:
         self.c.peer_free(self.base)
         self.base = None
 
+    def _settle(self):
+        """Peers may still be reading this rank's staging buffer for the previous step: wait for them
+        before it is written again. Deferred to here so that it overlaps the local count."""
+        import torch.distributed as dist
+        if self._readers_pending:
+            dist.barrier(group=self.group)
+            self._readers_pending = False
+
+    def place(self):
+        """Have the next run of the partitioned path written straight into the staging buffer
+        (kc_place_next_run): saves the copy. Call right before the count whose run goes to combine()."""
+        self._settle()
+        self.c.place_next_run(self.base, self.base + self._o_counts, self.base + self._o_offs, self.cap, self.n_sub_max + 1)
+
     def combine(self, local):
         """`local`: this rank's run (freed here). Returns the run of this rank's key range, or None
         if the runs have no common partition structure (caller falls back to NCCL)."""
@@ -295,24 +312,26 @@ class PeerCombine:
         P = self.world
         usable = self.c.words == 1 and n_sub >= P and n_sub % P == 0 and n_sub <= self.n_sub_max and n <= self.cap
         per = n_sub // P if usable else 1
-        # one small all-gather: plan, size, and the record boundaries of the owners' ranges
+        placed = usable and kptr == self.base               # the count already wrote it here (place())
+        if usable and not placed:
+            self._settle()
+            keys_t, counts_t = run_as_tensors(local, self.dev)
+            self.keys[:n].copy_(keys_t[:, 0])
+            self.counts[:n].copy_(counts_t)
+            self.offs[:n_sub + 1].copy_(torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=self.dev))
+        # One small all-gather: plan, size, and the record boundaries of the owners' ranges. It is
+        # queued behind the copies above on this stream, so a peer that has received this rank's
+        # entry knows that its staging buffer is complete: no separate barrier.
         info = torch.zeros(4 + P + 1, dtype=torch.int64, device=self.dev)
         info[0], info[1], info[2], info[3] = n_sub, pbits, n, int(usable)
         if usable:
-            off_t = torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=self.dev)
-            info[4:] = off_t[::per].to(torch.int64)
+            info[4:] = self.offs[:n_sub + 1:per].to(torch.int64)
         infos = [torch.empty_like(info) for _ in range(P)]
         dist.all_gather(infos, info, group=self.group)
         infos = [t.tolist() for t in infos]
         if not all(i[3] == 1 and i[0] == n_sub and i[1] == pbits for i in infos):
-            return None
-        keys_t, counts_t = run_as_tensors(local, self.dev)
-        self.keys[:n].copy_(keys_t[:, 0])
-        self.counts[:n].copy_(counts_t)
-        self.offs[:n_sub + 1].copy_(torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=self.dev))
-        torch.cuda.current_stream().synchronize()
+            return None                                 # (a placed run is still a valid run for the NCCL exchange)
         local.free()
-        dist.barrier(group=self.group)                  # every rank's staging buffer is complete
         kp = list(self.peer_base)                       # absolute offsets index the peer's whole array
         cp = [b + self._o_counts for b in self.peer_base]
         # The range offsets are read twice per range and part: bring this rank's slice of every
@@ -330,5 +349,5 @@ class PeerCombine:
         torch.cuda.current_stream().synchronize()
         sizes = [i[4 + self.rank + 1] - i[4 + self.rank] for i in infos]    # records this rank reads from each peer
         merged = self.c.merge_parts(kp, cp, op, sizes, per, pbits)
-        dist.barrier(group=self.group)                  # nobody overwrites a buffer that is still being read
+        self._readers_pending = True                    # settled (barrier) before the staging buffer is written again
         return merged
