@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--check", action="store_true", help="verify a prefix against the oracle before timing")
+    ap.add_argument("--target", type=int, default=0, help="keys per sub-bucket the partition plan aims for (0 = library default)")
     return ap.parse_args()
 
 
@@ -224,7 +225,7 @@ def run_ours(a, rank, world, local_rank):
     # kernels of chunks i+1, i+2 occupy the SMs on the (default-priority) slot streams
     stream = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(stream)
-    counter = kc.Counter(k, L, device=local_rank, method=a.method, n_slots=E2E_SLOTS, max_chunk_bytes=0 if a.no_e2e else n_bytes,
+    counter = kc.Counter(k, L, device=local_rank, method=a.method, n_slots=E2E_SLOTS, max_chunk_bytes=0 if a.no_e2e else n_bytes, table_slots=a.target,
                          stream=stream.cuda_stream)
     d_reads = torch.empty(n_bytes + 256, dtype=torch.uint8, device=dev)
     synth.synth_reads_device(d_reads.data_ptr(), R, L, a.genome, a.sub_rate, a.n_rate, a.seed,

@@ -228,6 +228,41 @@ def test_device_resident_input(kc):
         assert st["stage_names"][2] == "radix_scatter_passes" and st["stage_launches"][2] == 8   # 64-bit key, 8-bit digits
 
 
+def test_run_placed_in_caller_arrays_and_peer_staging(kc):
+    """kc_place_next_run: the next partitioned-path run lands in caller-owned arrays (here: staging
+    memory from kc_peer_alloc, as the multi-GPU combine uses it) if it fits, and is allocated as
+    usual if it does not; a placed run does not own its arrays."""
+    import torch
+    from kmer_counter_b200 import multigpu
+    R, L, k = 4000, 100, 31
+    reads = oracle.gen_reads(R, L, 30000, 0.01, 0.001, seed=15)
+    d = torch.from_numpy(reads).cuda()
+    want = oracle.process_chunk(reads, L, k)
+    n_want = len(want) // 12
+    with kc.Counter(k, L, method="hash") as c:
+        cap, ranges = n_want + 10, 1 << 16
+        o_counts, o_offs = 8 * cap, (12 * cap + 255) // 256 * 256
+        base, handle = c.peer_alloc(o_offs + 4 * ranges)
+        assert len(handle) == 64
+        c.place_next_run(base, base + o_counts, base + o_offs, cap, ranges)
+        run = c.count_device(d.data_ptr(), d.numel())
+        kptr, cptr, n = run.device_arrays()
+        off_ptr, n_sub, pbits = run.parts()
+        assert (kptr, cptr, off_ptr, n) == (base, base + o_counts, base + o_offs, n_want)
+        assert run.to_bytes() == want
+        run.free()                                           # leaves the staging memory alone:
+        keys = torch.as_tensor(multigpu._CudaView(base, (n_want,), "<i8"), device=d.device).cpu().numpy()
+        assert keys.view(np.uint64).tolist() == np.frombuffer(want, dtype=[("k", "<u8"), ("c", "<u4")])["k"].tolist()
+        run = c.count_device(d.data_ptr(), d.numel())        # one-shot: the next run is allocated normally
+        assert run.device_arrays()[0] != base and run.to_bytes() == want
+        run.free()
+        c.place_next_run(base, base + o_counts, base + o_offs, n_want - 1, ranges)   # one record too small
+        run = c.count_device(d.data_ptr(), d.numel())
+        assert run.device_arrays()[0] != base and run.to_bytes() == want
+        run.free()
+        c.peer_free(base)
+
+
 def test_run_split_and_file_write(kc, tmp_path):
     R, L, k = 2000, 100, 31
     reads = oracle.gen_reads(R, L, 20000, 0.0, 0.0, seed=6)
