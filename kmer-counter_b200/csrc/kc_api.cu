@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1070,6 +1071,48 @@ int kc_merge_runs(kc_ctx *c, kc_run *const *runs, uint32_t n, kc_run **out) {
     if (n == 1) {
         const kc_run *r = runs[0];
         return kc_run_from_device(c, r->d_keys + r->skip * r->W, r->d_counts + r->skip, r->n - r->skip, out);
+    }
+    // Three or more runs of the partitioned path with the same plan (chunks of equal size): combine
+    // them range by range in shared-memory tables, up to 8 at a time (kc_merge_parts: one pass over
+    // the records instead of log2(n) merge-path passes; 4 runs of C2: 11.9 ms against 16.8 ms).
+    // Two runs, or runs without a common plan, take the merge-path tree below.
+    if (c->W == 1 && n >= 3 && !c->direct.active) {
+        bool same = true;
+        for (uint32_t i = 0; i < n && same; i++)
+            same = runs[i]->d_sub_off && runs[i]->skip == 0 && runs[i]->n_sub == runs[0]->n_sub &&
+                   runs[i]->prefix_bits == runs[0]->prefix_bits;
+        if (same) {
+            std::vector<kc_run *> cur(runs, runs + n);
+            std::vector<bool> mine(n, false);
+            int prc = KC_OK;
+            while (cur.size() > 1 && prc == KC_OK) {
+                std::vector<kc_run *> nxt;
+                std::vector<bool> nxt_mine;
+                for (size_t i = 0; i < cur.size() && prc == KC_OK; i += 8) {
+                    const uint32_t g = (uint32_t)std::min<size_t>(8, cur.size() - i);
+                    if (g == 1) { nxt.push_back(cur[i]); nxt_mine.push_back(mine[i]); mine[i] = false; continue; }
+                    const void *kp[8], *cp[8], *op[8];
+                    uint64_t sz[8];
+                    for (uint32_t j = 0; j < g; j++) {
+                        kp[j] = cur[i + j]->d_keys; cp[j] = cur[i + j]->d_counts; op[j] = cur[i + j]->d_sub_off;
+                        sz[j] = cur[i + j]->n;
+                    }
+                    kc_run *m = nullptr;
+                    prc = kc_merge_parts(c, g, kp, cp, op, sz, cur[0]->n_sub, cur[0]->prefix_bits, &m);
+                    if (prc == KC_OK) { nxt.push_back(m); nxt_mine.push_back(true); }
+                }
+                if (prc != KC_OK) {
+                    for (size_t i = 0; i < nxt.size(); i++) if (nxt_mine[i]) kc_run_free(c, nxt[i]);
+                    for (size_t i = 0; i < cur.size(); i++) if (mine[i]) kc_run_free(c, cur[i]);
+                    break;
+                }
+                for (size_t i = 0; i < cur.size(); i++) if (mine[i]) kc_run_free(c, cur[i]);
+                cur.swap(nxt);
+                mine.swap(nxt_mine);
+            }
+            if (prc == KC_OK) { *out = cur[0]; return KC_OK; }
+            // a range too large for a shared-memory table (or too many records): the tree handles anything
+        }
     }
     unsigned long long *d_num = nullptr;
     KC_TRY(dev_alloc(c, s, 8, (void **)&d_num));

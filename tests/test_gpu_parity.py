@@ -163,6 +163,30 @@ def test_chunking_invariance_and_merge(kc):
             run.free()
 
 
+def test_merge_of_same_plan_hash_runs(kc):
+    """Three or more partitioned-path runs with one plan (equal chunks) are combined range by range in
+    shared-memory tables, up to 8 at a time (kc_merge_runs' fast path); the result is the merge-path
+    tree's. 11 equal chunks exercise two levels (8 + 3), the ragged count the mixed case (tree)."""
+    L, k, per = 100, 31, 1200
+    reads = oracle.gen_reads(11 * per + 500, L, 40000, 0.01, 0.002, seed=31)
+    with _counter(kc, k, L, method="hash") as c:
+        def chunk_run(part):
+            c.slot_buffer(0)[:part.size] = part
+            c.submit(0, part.size)
+            return c.wait(0)
+        d_runs = [chunk_run(reads[i * per * L:(i + 1) * per * L]) for i in range(11)]
+        assert len({r.parts()[1:] for r in d_runs}) == 1 and d_runs[0].parts()[1] > 0        # one plan
+        for n in (3, 8, 11):
+            m = c.merge(d_runs[:n])
+            assert m.to_bytes() == oracle.count(reads[:n * per * L], L, k), n
+            assert m.parts()[1] == d_runs[0].parts()[1]                                      # structure is kept
+            m.free()
+        tail = chunk_run(reads[11 * per * L:])
+        m = c.merge(d_runs + [tail])                                                         # another plan: the tree
+        assert m.to_bytes() == oracle.count(reads, L, k)
+        m.free()
+
+
 def test_merge_runs_against_oracle_merger(kc):
     L, k = 100, 63
     parts = [oracle.gen_reads(400 + 37 * i, L, 6000, 0.01, 0.003, seed=100 + i) for i in range(5)]
