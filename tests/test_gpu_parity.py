@@ -142,6 +142,29 @@ def test_lowercase_is_invalid(kc):
         assert c.process_chunk(reads) == want
 
 
+def test_random_shapes_and_hostile_alphabet(kc):
+    """Random (L, k, R) over an alphabet with lower case, N, IUPAC letters, digits and bytes >= 0x80:
+    validity runs start and stop everywhere. Sort path for every k, partitioned hash for k <= 64."""
+    rng = np.random.default_rng(20261019)
+    alphabet = np.frombuffer(b"ACGT" * 12 + b"acgtNnRYKM-.*0" + bytes([0, 127, 128, 255]), dtype=np.uint8)
+    done = 0
+    while done < 24:
+        L = int(rng.integers(10, 201))
+        if L % 32 == 0 or 2 + 8 * ((L + 31) // 32) > L:            # shapes the reference corrupts (SURVEY F8)
+            continue
+        k = int(rng.integers(1, min(L, 128) + 1))
+        R = int(rng.integers(1, 400))
+        reads = np.ascontiguousarray(alphabet[rng.integers(0, alphabet.size, size=R * L)])
+        if done % 2 == 0:
+            reads = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=R * L)].copy()
+            reads[rng.integers(0, R * L, size=max(1, R * L // 40))] = rng.choice(alphabet, size=max(1, R * L // 40))
+        want = oracle.process_chunk(reads, L, k)
+        for method in (("sort", "hash") if k <= 64 else ("sort",)):
+            with _counter(kc, k, L, method=method) as c:
+                assert c.process_chunk(reads) == want, (L, k, R, method)
+        done += 1
+
+
 def test_strict_mode_matches_naive_model(kc):
     for (R, L, k) in [(800, 100, 31), (500, 80, 63), (500, 60, 28)]:
         reads = oracle.gen_reads(R, L, 9000, 0.005, 0.003, seed=k)

@@ -98,6 +98,31 @@ def test_oracle_equals_reference_build(R, L, k, G, e, n, tmp_path):
     assert oracle.naive_count(reads, L, k) == want
 
 
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+def test_random_shapes_and_alphabets_three_way():
+    """60 random shapes (k 1..128, L up to 200, L % 32 != 0) over a hostile alphabet -- lower case,
+    N, IUPAC letters, digits, bytes >= 0x80 -- so that validity runs start and stop everywhere:
+    restatement == reference build == independent window model, sorted and unsorted."""
+    rng = np.random.default_rng(20261018)
+    alphabet = np.frombuffer(b"ACGT" * 12 + b"acgtNnRYKM-.*0" + bytes([0, 127, 128, 255]), dtype=np.uint8)
+    done = 0
+    while done < 60:
+        L = int(rng.integers(10, 201))
+        if L % 32 == 0 or 2 + 8 * ((L + 31) // 32) > L:            # shapes the reference corrupts (SURVEY F8)
+            continue
+        k = int(rng.integers(1, min(L, 128) + 1))
+        R = int(rng.integers(1, 60))
+        reads = alphabet[rng.integers(0, alphabet.size, size=R * L)]
+        if done % 3 == 0:                                           # mostly valid reads with a few bad letters
+            reads = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=R * L)].copy()
+            reads[rng.integers(0, R * L, size=max(1, R * L // 50))] = ord("N")
+        reads = np.ascontiguousarray(reads)
+        for do_sort in (True, False):
+            assert oracle.process_chunk(reads, L, k, do_sort) == oracle.ref_process_chunk(reads, L, k, do_sort), (L, k, R)
+        assert oracle.count(reads, L, k, chunk_reads=7) == oracle.naive_count(reads, L, k), (L, k, R)
+        done += 1
+
+
 def test_merge_semantics():
     k = 31
     mk = lambda pairs: np.array(pairs, dtype=[("key", "<u8"), ("cnt", "<u4")]).tobytes()
