@@ -157,7 +157,10 @@ int  kc_submit_fastq(kc_ctx *ctx, uint32_t slot, const void *host_text, uint64_t
 /* ---- runs: the sorted-run dump (FileDump.cpp:51-58) and its consumers ---- */
 uint64_t kc_run_records(const kc_run *run);
 int  kc_run_free(kc_ctx *ctx, kc_run *run);
-/* packed records out (D2H), into pageable or pinned memory */
+/* Packed records out (D2H), into pageable or pinned memory. Runs on the context's own copy
+ * stream and staging buffer, so a consumer thread may read one run back while the producer thread
+ * submits and waits for later chunks (calls are serialised among themselves; returns when the bytes
+ * are in dst). */
 int  kc_run_copy_records(kc_ctx *ctx, const kc_run *run, void *dst, uint64_t cap, uint64_t *out_bytes);
 /* packed records in: a run file's bytes (must be sorted; adjacent equal keys are
  * folded like SortedKMerFile::ReadKmer does, SortedKMerFile.cpp:57-82) */
@@ -208,7 +211,10 @@ int  kc_peer_free(kc_ctx *ctx, void *d_ptr);
 
 /* ---- merge: replaces KMerFileMerger::Merge (KMerFileMerger.cpp:49-96) ---- */
 /* Merge n sorted runs into one, adding the counts of equal keys (uint32 wrap).
- * Inputs stay valid and owned by the caller. n may be 0 (empty run) or 1 (copy). */
+ * Inputs stay valid and owned by the caller. n may be 0 (empty run) or 1 (copy).
+ * Two runs: merge path. More: a pairwise merge-path tree, except that three or more runs of the
+ * partitioned path with one plan (chunks of equal size, 64-bit keys) are combined range by range
+ * in shared memory, up to 8 per pass (kc_merge_parts). */
 int  kc_merge_runs(kc_ctx *ctx, kc_run *const *runs, uint32_t n, kc_run **out);
 
 /* ---- measurement support (not a reference interface): deterministic synthetic reads
