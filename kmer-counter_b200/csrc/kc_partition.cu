@@ -402,6 +402,9 @@ struct FinishParams {
     const uint32_t *src_off[8];
 };
 
+#ifndef KC_PC_BATCH
+#define KC_PC_BATCH 4      // keys a thread loads before it starts inserting them (sweep: 16 -> 7.35 ms, 8 -> 6.41, 4 -> 6.03, 2 -> 6.04)
+#endif
 constexpr int kSortBins = 1024;    // most bins the in-table counting sort uses
 
 __device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 1u : 1u << (32 - __clz(x - 1)); }
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(kPcThreads) finish_kernel(FinishParams p) {
                     }
                 }
             } else {
-                constexpr int kBatch = 8 / W;
+                constexpr int kBatch = W == 1 ? KC_PC_BATCH : 4;     // 128-bit keys: 4 measured better than 2
                 // A sub-bucket far larger than the plan's target holds heavy hitters (skewed input):
                 // there the lanes of a warp that carry the same key are combined first (MATCH.ANY) and
                 // one of them adds their number, instead of 32 atomics serialising on one counter.
