@@ -391,10 +391,13 @@ int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) 
     if (U) partition_plan_info(p.n_slots, sig, target, p.ws_part, &n_sub, &prefix_bits, &d_off);
     kc_run *r = nullptr;
     bool placed = false;
+    uint64_t *pk = nullptr;
+    uint32_t *pc = nullptr, *po = nullptr;
     {
         std::lock_guard<std::mutex> g(c->mu);
         if (c->place.set) {                      // one-shot, whether it fits or not
             placed = U > 0 && U <= c->place.cap && n_sub + 1 <= c->place.cap_ranges;
+            pk = c->place.keys; pc = c->place.counts; po = c->place.offs;
             c->place.set = false;
         }
     }
@@ -402,9 +405,9 @@ int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) 
         r = new kc_run();
         r->W = c->W;
         r->n = U;
-        r->d_keys = c->place.keys;
-        r->d_counts = c->place.counts;
-        r->d_sub_off = c->place.offs;
+        r->d_keys = pk;
+        r->d_counts = pc;
+        r->d_sub_off = po;
         r->placed = true;
     } else {
         KC_TRY(make_run(c, s, U, &r));
