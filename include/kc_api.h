@@ -52,9 +52,14 @@ extern "C" {
                                      GPUHandler.cu:300-360)                                */
 #define KC_COUNT_HASH       2u    /* open-addressing hash tables in shared memory over key-range
                                      partitions (replaces the TBB accumulate, KMerCounter.cpp:61-82);
-                                     k <= 32                                                 */
+                                     k <= 64                                                 */
 #define KC_COUNT_HASH_GLOBAL 3u   /* one open-addressing table in HBM, then a sort of the distinct
                                      set; kept as the measured baseline for KC_COUNT_HASH      */
+
+#define KC_COUNT_SUPER      4u    /* super-window records (consecutive k-mers of a read that share a
+                                     minimizer bin, 2 bits per base) binned by minimizer, counted per bin in
+                                     shared-memory tables, distinct records then placed in key order;
+                                     k <= 64 with windows of >= 22 bases. What KC_COUNT_AUTO picks there. */
 
 typedef struct kc_ctx kc_ctx;
 typedef struct kc_run kc_run;
@@ -71,7 +76,9 @@ typedef struct kc_config {
     uint32_t reserved0;
     uint64_t max_chunk_bytes;  /* capacity of each slot = largest chunk submitted;
                                   replaces PrepareGPU's inputSize (GPUHandler.cu:479)      */
-    uint64_t table_slots;      /* hash capacity hint, 0 = derive from the chunk            */
+    uint64_t table_slots;      /* sizing hint, 0 = default. KC_COUNT_HASH_GLOBAL: table capacity;
+                                  KC_COUNT_HASH: k-mer occurrences per sub-bucket; KC_COUNT_SUPER:
+                                  k-mer occurrences per minimizer bin                      */
     void    *stream;           /* cudaStream_t to run on, NULL = a stream owned by the ctx */
 } kc_config;
 
@@ -94,7 +101,10 @@ typedef struct kc_stats {
      *   KC_COUNT_SORT : 0 extract, 1 digit histogram, 2 radix scatter passes, 3 run-length, 4 emit
      *   KC_COUNT_HASH : 0 level-1 histogram, 1 extract+scatter1, 2 level-2 histogram, 3 scatter2,
      *                   4 shared-memory count+sort+write, 5 emit
-     *   KC_COUNT_HASH_GLOBAL : 0 table clear, 1 extract+insert, 2 compact+sort, 3 emit          */
+     *   KC_COUNT_HASH_GLOBAL : 0 table clear, 1 extract+insert, 2 compact+sort, 3 emit
+     *   KC_COUNT_SUPER : 0 encode+minimizer+record scatter, 1 shared-memory count per bin,
+     *                    2 record scatter level 1, 3 level-2 histogram, 4 record scatter level 2,
+     *                    5 shared-memory sort + write                                             */
     uint32_t n_stages;
     uint32_t dominant_stage;
     float    ms_stage[8];
@@ -115,6 +125,10 @@ void kc_destroy(kc_ctx *ctx);
 const char *kc_last_error(const kc_ctx *ctx);   /* ctx may be NULL: last create error      */
 int  kc_sync(kc_ctx *ctx);                      /* wait for everything queued on the ctx   */
 int  kc_stats_get(kc_ctx *ctx, kc_stats *out);
+
+/* the 16 device scalars of the most recent chunk (diagnostics for tests; layout = the SW_* / SC_*
+ * enums of the implementation, not a stable interface) */
+int  kc_debug_scalars(kc_ctx *ctx, uint64_t *out16);
 
 /* pinned host memory for callers that want zero-copy staging (e2e path) */
 int  kc_host_alloc(kc_ctx *ctx, uint64_t bytes, void **out);

@@ -13,8 +13,9 @@ CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 KC_OK = 0
 KC_COMPAT_REF, KC_COMPAT_STRICT = 0, 1
-KC_COUNT_AUTO, KC_COUNT_SORT, KC_COUNT_HASH, KC_COUNT_HASH_GLOBAL = 0, 1, 2, 3
-METHODS = {"auto": KC_COUNT_AUTO, "sort": KC_COUNT_SORT, "hash": KC_COUNT_HASH, "hash_global": KC_COUNT_HASH_GLOBAL}
+KC_COUNT_AUTO, KC_COUNT_SORT, KC_COUNT_HASH, KC_COUNT_HASH_GLOBAL, KC_COUNT_SUPER = 0, 1, 2, 3, 4
+METHODS = {"auto": KC_COUNT_AUTO, "sort": KC_COUNT_SORT, "hash": KC_COUNT_HASH, "hash_global": KC_COUNT_HASH_GLOBAL,
+           "super": KC_COUNT_SUPER}
 METHOD_NAMES = {v: k for k, v in METHODS.items()}
 
 
@@ -52,6 +53,7 @@ SYMBOLS = {
     "kc_last_error": (C.c_char_p, [_vp]),
     "kc_sync": (_i, [_vp]),
     "kc_stats_get": (_i, [_vp, C.POINTER(KcStats)]),
+    "kc_debug_scalars": (_i, [_vp, _pu64]),
     "kc_host_alloc": (_i, [_vp, _u64, _pp]),
     "kc_host_free": (_i, [_vp, _vp]),
     "kc_process_chunk": (_i, [_vp, _u32, _vp, _u64, _vp, _u64, _pu64]),

@@ -52,6 +52,8 @@ struct Pending {                 // a chunk whose kernels are queued but whose r
     int n_passes = 0;
     uint32_t *counts = nullptr;              // partition path: counts next to the unique keys
     void *ws_part = nullptr;
+    SuperPlan splan{};                       // super-window path: plan + workspace (arena)
+    void *ws_super = nullptr;
     // Chunk scratch arena: one grow-only device block per Pending, carved by a bump pointer.
     // Chunk after chunk reuses it, so the big buffers never go through the allocator again.
     uint8_t *arena = nullptr;
@@ -88,6 +90,7 @@ struct kc_ctx {
     Pending direct;              // kc_count_device / kc_process_chunk without slots use this
     std::mutex mu;
     kc_stats stats{};
+    unsigned long long last_scal[SC_COUNT] = {0};   // device scalars of the most recent chunk (kc_debug_scalars)
     int last_code = 0;
     char err[512] = {0};
 
@@ -169,7 +172,7 @@ void pending_release(cudaStream_t, Pending &p) {
     p.keys_a = p.keys_b = p.sorted = p.uniq = nullptr;
     p.starts = nullptr;
     p.counts = nullptr;
-    p.ws_sort = p.ws_rle = p.ws_part = nullptr;
+    p.ws_sort = p.ws_rle = p.ws_part = p.ws_super = nullptr;
     p.table = HashTable{nullptr, 0, nullptr};
     p.active = false;
 }
@@ -190,8 +193,16 @@ int static_zero_bits(const kc_ctx *c) {
 
 constexpr uint64_t kMaxSortKeys = (1ull << 30) - 1;
 
+// the super-window path takes 64/128-bit keys whose windows span at least 22 bases
+bool super_ok(const kc_ctx *c) {
+    SuperPlan pl;
+    return c->W <= 2 && super_plan(c->cfg.k, c->cfg.read_len, c->strict, 1, 0, &pl) && super_supported(pl);
+}
+
 uint32_t pick_method(const kc_ctx *c) {
     uint32_t m = c->cfg.method;
+    if (m == KC_COUNT_SUPER) return super_ok(c) ? KC_COUNT_SUPER : (c->W > 2 ? KC_COUNT_SORT : KC_COUNT_HASH);
+    if (m == KC_COUNT_AUTO && super_ok(c)) return KC_COUNT_SUPER;
     if (c->W > 2) return KC_COUNT_SORT;            // 192/256-bit keys: sort + run-length
     if (c->W == 2) return (m == KC_COUNT_AUTO || m == KC_COUNT_HASH) ? KC_COUNT_HASH : KC_COUNT_SORT;
     // 64-bit keys: partitioned shared-memory hashing unless the key has too few significant
@@ -221,7 +232,20 @@ int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, 
     if (!extract_plan(d_reads, p.n_reads, L, k, c->strict, &p.d_scal[SC_INVALID], &ep))
         return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
 
-    if (method == KC_COUNT_HASH) {
+    if (method == KC_COUNT_SUPER) {
+        // super-window records binned by minimizer, counted in shared memory (kc_super.cu)
+        if (!super_plan(k, L, c->strict, p.n_slots, (uint32_t)c->cfg.table_slots, &p.splan))
+            return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
+        KC_TRY(arena_reserve(c, p, arena_round(p.splan.ws_bytes), s));
+        p.ws_super = arena_take(p, p.splan.ws_bytes);
+        KC_CUDA_TRY(c, super_reset(p.splan, p.ws_super, p.d_scal, s));
+        KC_CUDA_TRY(c, super_scatter(p.splan, d_reads, p.n_reads, c->strict, p.ws_super, p.d_scal, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));
+        KC_CUDA_TRY(c, super_count(p.splan, !c->strict, p.ws_super, p.d_scal, c->n_sms, s, &p.ev[2]));
+        p.n_ev = 6;
+        p.n_passes = 1;
+        launches += 8;
+    } else if (method == KC_COUNT_HASH) {
         // partitioned shared-memory hash counting (kc_partition.cu)
         ExtractParams ep64;
         static int pa_stage = -1;               // KC_PA_STAGE (development knob): bytes of reads per PA tile
@@ -307,6 +331,7 @@ int make_run(kc_ctx *c, cudaStream_t s, uint64_t n, kc_run **out) {
 int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_hash_global(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
+int count_finish_super(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool *failed);
 
 // Wait for the queued kernels, build the run, record stage timings.
 int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, kc_run **out) {
@@ -315,7 +340,22 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
     KC_CUDA_TRY(c, cudaStreamSynchronize(s));
     int rc;
     uint32_t used = p.method;
-    const bool overflow = p.n_slots && (p.method == KC_COUNT_HASH || p.method == KC_COUNT_HASH_GLOBAL) &&
+    memcpy(c->last_scal, p.h_scal, sizeof c->last_scal);
+    if (p.n_slots && p.method == KC_COUNT_SUPER) {
+        // a list or a sub-bucket overflowed (input far from the plan's assumptions): the chunk is
+        // re-counted by the partitioned path, which sizes everything from exact histograms
+        bool failed = false;
+        rc = count_finish_super(c, p, s, out, &failed);
+        if (rc != KC_OK) { pending_release(s, p); return rc; }
+        if (failed) {
+            if (*out) { kc_run_free(c, *out); *out = nullptr; }
+            pending_release(s, p);
+            used = c->W <= 2 ? KC_COUNT_HASH : KC_COUNT_SORT;
+            KC_TRY(count_enqueue(c, p, d_reads, n_bytes, s, used));
+            KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
+    }
+    const bool overflow = p.n_slots && (used == KC_COUNT_HASH || used == KC_COUNT_HASH_GLOBAL) &&
                           p.h_scal[SC_SIDE + 1];
     if (overflow) {                               // table(s) full: redo this chunk with sort + run-length
         pending_release(s, p);
@@ -323,7 +363,8 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
         used = KC_COUNT_SORT;
     }
-    if (p.n_slots == 0) rc = make_run(c, s, 0, out);
+    if (used == KC_COUNT_SUPER && p.n_slots) rc = KC_OK;     // the run was built above
+    else if (p.n_slots == 0) rc = make_run(c, s, 0, out);
     else if (used == KC_COUNT_HASH) rc = count_finish_partition(c, p, s, out);
     else if (used == KC_COUNT_HASH_GLOBAL) rc = count_finish_hash_global(c, p, s, out);
     else rc = count_finish_sort(c, p, s, out);
@@ -362,14 +403,27 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
             st.stage_bytes[3] = 2 * Kb * nv;                               st.stage_launches[3] = 1;
             st.stage_bytes[4] = Kb * nv + (Kb + 4) * U;                    st.stage_launches[4] = 1;   // + a one-block scan
             st.stage_bytes[5] = 2 * (Kb + 4) * U;                          st.stage_launches[5] = 1;
+        } else if (used == KC_COUNT_SUPER && p.n_slots) {
+            const uint64_t rec = c->last_scal[SW_RECORDS] * 16ull * c->W, ub = U * (Kb + 4);
+            st.stage_bytes[0] = in_bytes + rec;                            st.stage_launches[0] = 1;   // S1 scatter
+            st.stage_bytes[1] = rec + ub;                                  st.stage_launches[1] = 1;   // S2 count
+            st.stage_bytes[2] = 2 * ub;                                    st.stage_launches[2] = 1;   // S3a (+ plan)
+            st.stage_bytes[3] = U * Kb;                                    st.stage_launches[3] = 1;   // level-2 histogram (+ scan)
+            st.stage_bytes[4] = 2 * ub;                                    st.stage_launches[4] = 1;   // S3b
+            st.stage_bytes[5] = 2 * ub;                                    st.stage_launches[5] = 1;   // S3c
         } else if (used == KC_COUNT_HASH_GLOBAL && p.n_slots) {
             st.stage_bytes[0] = p.table.capacity * 16;                     st.stage_launches[0] = 1;
             st.stage_bytes[1] = in_bytes + nv * 16;                        st.stage_launches[1] = 1;   // SURVEY 8(d) terms
             st.stage_bytes[2] = p.table.capacity * 16 + U * 12 * 17;       st.stage_launches[2] = 10;
         }
         int dom = 0;
-        for (int i = 1; i + 1 < n_stages; i++)
-            if (st.ms_stage[i] > st.ms_stage[dom]) dom = i;
+        if (used == KC_COUNT_SUPER) {             // every stage is a kernel of the path
+            for (int i = 1; i < n_stages; i++)
+                if (st.ms_stage[i] > st.ms_stage[dom]) dom = i;
+        } else {
+            for (int i = 1; i + 1 < n_stages; i++)
+                if (st.ms_stage[i] > st.ms_stage[dom]) dom = i;
+        }
         st.dominant_stage = (uint32_t)dom;
         st.ms_dominant = st.ms_stage[dom];
         st.dominant_bytes = st.stage_bytes[dom];
@@ -379,6 +433,49 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
         st.ms_count = st.ms_total - st.ms_extract - st.ms_emit;
     }
     pending_release(s, p);
+    return KC_OK;
+}
+
+// Super-window path, after S1..S3b have drained: the host knows |D| now, allocates the run and
+// lets S3c sort every sub-bucket straight into it. If records may repeat (overflow list in use)
+// S3c folds them into a temporary and a gather closes the gaps.
+int count_finish_super(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool *failed) {
+    *failed = false;
+    *out = nullptr;
+    const SuperPlan &pl = p.splan;
+    if (p.h_scal[SW_FAIL]) { *failed = true; return KC_OK; }
+    const uint64_t n_d = p.h_scal[SW_D];
+    static int force_dup = -1;                  // KC_SW_FORCE_DUP=1 (test knob): always take the folding path
+    if (force_dup < 0) { const char *v = getenv("KC_SW_FORCE_DUP"); force_dup = (v && v[0] == '1') ? 1 : 0; }
+    const bool dup = p.h_scal[SW_OVF] != 0 || force_dup;
+    kc_run *r = nullptr;
+    if (!dup) {
+        KC_TRY(make_run(c, s, n_d, &r));
+        if (n_d) {
+            KC_CUDA_TRY(c, super_finish(pl, false, p.ws_super, p.d_scal, r->d_keys, r->d_counts, c->n_sms, s));
+            KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+            KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
+    } else {
+        uint64_t *tk = nullptr;
+        uint32_t *tc = nullptr;
+        super_tmp_buffers(pl, p.ws_super, &tk, &tc);
+        KC_CUDA_TRY(c, super_finish(pl, true, p.ws_super, p.d_scal, tk, tc, c->n_sms, s));
+        KC_CUDA_TRY(c, super_fold_offsets(pl, p.ws_super, p.d_scal, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (!p.h_scal[SW_FAIL]) {
+            KC_TRY(make_run(c, s, p.h_scal[SW_OUT], &r));
+            if (r->n) KC_CUDA_TRY(c, super_gather(pl, p.ws_super, tk, tc, r->d_keys, r->d_counts, c->n_sms, s));
+        }
+    }
+    memcpy(c->last_scal, p.h_scal, sizeof c->last_scal);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += dup ? 3 : 1;
+    }
+    if (p.h_scal[SW_FAIL]) { *failed = true; if (r) kc_run_free(c, r); return KC_OK; }
+    *out = r;
     return KC_OK;
 }
 
@@ -502,7 +599,7 @@ int kc_create(const kc_config *cfg, kc_ctx **out) {
     memcpy(&c0, cfg, cfg->struct_size && cfg->struct_size < sizeof(kc_config) ? cfg->struct_size : sizeof(kc_config));
     if (c0.k < 1 || c0.k > 128) { g_create_error = "kc_create: k must be in 1..128 (KMerSizes.h holds 4 words)"; return KC_ERR_ARG; }
     if (c0.read_len < c0.k || c0.read_len > 4096) { g_create_error = "kc_create: read_len must be in k..4096"; return KC_ERR_ARG; }
-    if (c0.method > KC_COUNT_HASH_GLOBAL) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
+    if (c0.method > KC_COUNT_SUPER) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
     if (c0.method == KC_COUNT_HASH && c0.k > 64) { g_create_error = "kc_create: hash counting needs k <= 64"; return KC_ERR_ARG; }
     if (c0.method == KC_COUNT_HASH_GLOBAL && c0.k > 32) { g_create_error = "kc_create: the HBM-resident table needs k <= 32"; return KC_ERR_ARG; }
     cudaError_t e = cudaSetDevice(c0.device);
@@ -587,6 +684,14 @@ int kc_stats_get(kc_ctx *c, kc_stats *out) {
     if (!out) return c->set_error(KC_ERR_ARG, "null stats");
     std::lock_guard<std::mutex> g(c->mu);
     *out = c->stats;
+    return KC_OK;
+}
+
+int kc_debug_scalars(kc_ctx *c, uint64_t *out16) {
+    KC_TRY(check_ctx(c));
+    if (!out16) return c->set_error(KC_ERR_ARG, "null out");
+    std::lock_guard<std::mutex> g(c->mu);
+    for (int i = 0; i < SC_COUNT; i++) out16[i] = c->last_scal[i];
     return KC_OK;
 }
 

@@ -77,6 +77,59 @@ __device__ __forceinline__ uint32_t base_code(uint32_t c, uint32_t &bad) {
     return ok ? code : 3u;
 }
 
+// Phase A of every extraction kernel: the CTA turns the ASCII reads of one tile (shared
+// memory, stride L) into 2-bit codes. Every thread takes groups of 4 bases (one 32-bit shared
+// load) and produces one byte of codes with SIMD-in-register arithmetic; the (read, group)
+// pairs of the tile are spread over the whole CTA. enc_b = rows of (nw + 1) 64-bit words per
+// read whose pad bytes were zeroed once; bad4 = one nibble of "not ACGT" bits per group;
+// flag[r] != 0 if read r has any such base. Follows bitEncode (GPUHandler.cu:42-101).
+__device__ __forceinline__ void encode_tile(const ExtractParams &p, const uint8_t *src_tile, uint32_t nreads,
+                                            uint8_t *enc_b, uint8_t *bad4, uint8_t *flag) {
+    const uint32_t enc_row = p.nw + 1;
+    const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src_tile);
+    const uint32_t n_groups = nreads * p.nb4;
+    for (uint32_t g = threadIdx.x; g < n_groups; g += blockDim.x) {
+        uint32_t r = p.nb4 == 1 ? g : __umulhi(g, p.nb4_magic);
+        if (r * p.nb4 > g) r--;
+        const uint32_t q = g - r * p.nb4;                                   // byte q of the read's bit string
+        const uint32_t j0 = q * 4;
+        const uint32_t addr = r * p.L + j0;
+        const uint32_t w0 = src32[addr >> 2], w1 = src32[(addr >> 2) + 1];
+        uint32_t x = __funnelshift_r(w0, w1, (addr & 3u) * 8u);             // bytes addr .. addr+3
+        const uint32_t left = p.L - j0;                                      // bases of this read in x
+        if (left < 4) x = (x & (0xffffffffu >> (32 - 8 * left))) | (0x41414141u << (8 * left));   // pad with 'A'
+        // code = ((c >> 1) ^ (c >> 2)) & 3 for A,C,G,T = 0,1,2,3 (GPUHandler.cu:42-78)
+        uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+        // letter each byte should be, picked by (c >> 1) & 3 out of "ACTG": equal <=> valid
+        const uint32_t i4 = (x >> 1) & 0x03030303u;
+        const uint32_t sel = __byte_perm(i4 | (i4 >> 4), 0u, 0x4420u);      // nibble i = index of byte i
+        const uint32_t diff = x ^ __byte_perm(0x47544341u, 0u, sel);
+        uint32_t badn = 0;
+        if (diff) {                                                          // rare: some byte is not ACGT
+#pragma unroll
+            for (uint32_t b = 0; b < 4; b++)
+                if ((diff >> (8 * b)) & 0xffu) { badn |= 1u << b; t |= 3u << (8 * b); }   // code 3 + filter bit (:79-87)
+            flag[r] = 1;
+        }
+        // byte q of the big-endian bit string -> little-endian byte inside its word
+        enc_b[(r * enc_row + (q >> 3)) * 8 + (7 - (q & 7))] = (uint8_t)((t * 0x40100401u) >> 24);   // b0<<6|b1<<4|b2<<2|b3
+        bad4[r * p.nb4 + q] = (uint8_t)badn;
+    }
+}
+
+// rare path: any bad base inside [pos, pos+k) kills the k-mer (bad4 row of the read)
+__device__ __forceinline__ bool kmer_window_valid(const uint8_t *bn, uint32_t pos, uint32_t k) {
+    const uint32_t lo = pos, hi = pos + k;  // [lo, hi)
+    for (uint32_t q = lo >> 2; q <= (hi - 1) >> 2; q++) {
+        uint32_t m = bn[q];
+        const uint32_t b0 = q * 4;
+        if (b0 < lo) m &= 0xFu << (lo - b0);
+        if (b0 + 4 > hi) m &= 0xFu >> (b0 + 4 - hi);
+        if (m & 0xFu) return false;
+    }
+    return true;
+}
+
 template <int W, class Sink>
 __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams p, Sink sink) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -142,38 +195,8 @@ __global__ void __launch_bounds__(kExtractThreads) extract_kernel(ExtractParams 
         }
         const uint8_t *src_tile = stage0 + stage * stage_bytes;
 
-        // ---- phase A: every thread turns groups of 4 bases (one 32-bit shared load) into one byte
-        // of 2-bit codes with SIMD-in-register arithmetic; the (read, group) pairs of the tile are
-        // spread over the whole CTA. The pad bytes of each encoded row were zeroed once, above. ----
-        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src_tile);
-        const uint32_t n_groups = nreads * p.nb4;
-        for (uint32_t g = tid; g < n_groups; g += kExtractThreads) {
-            uint32_t r = p.nb4 == 1 ? g : __umulhi(g, p.nb4_magic);
-            if (r * p.nb4 > g) r--;
-            const uint32_t q = g - r * p.nb4;                                   // byte q of the read's bit string
-            const uint32_t j0 = q * 4;
-            const uint32_t addr = r * p.L + j0;
-            const uint32_t w0 = src32[addr >> 2], w1 = src32[(addr >> 2) + 1];
-            uint32_t x = __funnelshift_r(w0, w1, (addr & 3u) * 8u);             // bytes addr .. addr+3
-            const uint32_t left = p.L - j0;                                      // bases of this read in x
-            if (left < 4) x = (x & (0xffffffffu >> (32 - 8 * left))) | (0x41414141u << (8 * left));   // pad with 'A'
-            // code = ((c >> 1) ^ (c >> 2)) & 3 for A,C,G,T = 0,1,2,3 (GPUHandler.cu:42-78)
-            uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
-            // letter each byte should be, picked by (c >> 1) & 3 out of "ACTG": equal <=> valid
-            const uint32_t i4 = (x >> 1) & 0x03030303u;
-            const uint32_t sel = __byte_perm(i4 | (i4 >> 4), 0u, 0x4420u);      // nibble i = index of byte i
-            const uint32_t diff = x ^ __byte_perm(0x47544341u, 0u, sel);
-            uint32_t badn = 0;
-            if (diff) {                                                          // rare: some byte is not ACGT
-#pragma unroll
-                for (uint32_t b = 0; b < 4; b++)
-                    if ((diff >> (8 * b)) & 0xffu) { badn |= 1u << b; t |= 3u << (8 * b); }   // code 3 + filter bit (:79-87)
-                flag[r] = 1;
-            }
-            // byte q of the big-endian bit string -> little-endian byte inside its word
-            enc_b[(r * enc_row + (q >> 3)) * 8 + (7 - (q & 7))] = (uint8_t)((t * 0x40100401u) >> 24);   // b0<<6|b1<<4|b2<<2|b3
-            bad4[r * p.nb4 + q] = (uint8_t)badn;
-        }
+        // ---- phase A: 2-bit encode of the tile's reads (encode_tile, above) ----
+        encode_tile(p, src_tile, nreads, enc_b, bad4, flag);
         __syncthreads();
 
         // ---- phase B ----

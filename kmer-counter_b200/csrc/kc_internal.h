@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "kc_extract.cuh"
+#include "kc_super.cuh"
 
 namespace kc {
 

@@ -1,0 +1,1448 @@
+// kc_super.cu -- super-window counting path (sm_100a). See kc_super.cuh for the design.
+//
+// What it replaces in the reference: extractKMers' one-record-per-occurrence output
+// (GPUHandler.cu:129-233, 8.4x the input), the host hash accumulate (KMerCounter.cpp:61-82)
+// and sortKmers + reduceKMers (GPUHandler.cu:300-360). Key semantics are those of
+// kc_extract.cuh: the key of window p is the 2-bit codes of s[p .. p+span).
+#include <stdlib.h>
+
+#include "kc_internal.h"
+#include "kc_super.cuh"
+
+namespace kc {
+
+namespace {
+
+constexpr uint32_t kNoBin = 0xffffffffu;
+constexpr int kSwThreads = 256;
+constexpr int kSwMaxSeg = 18;           // windows one thread derives minimizers for
+constexpr int kNb1Max = 1024;
+
+// ---------------------------------------------------------------- minimizer -> bin
+// Order of m-mers = order of a 32-bit bijective hash of their 2-bit codes (no ties between
+// different m-mers); the bin of a window is a second hash of its smallest m-mer hash. Both are
+// functions of the key's bases only, so equal keys always meet in the same bin.
+template <uint32_t X> struct ILog2 { static constexpr uint32_t v = 1 + ILog2<(X >> 1)>::v; };
+template <> struct ILog2<1> { static constexpr uint32_t v = 0; };
+
+__host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t mm) {
+    uint32_t h = mm * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA6Bu;
+    return h;
+}
+__device__ __forceinline__ uint32_t bin_of_min(uint32_t mn, uint32_t n_bins) {
+    return __umulhi(mn * 0xC2B2AE35u, n_bins);
+}
+
+// ===================================================================== S1: scatter
+struct SwScatterParams {
+    ExtractParams ep;
+    uint32_t m, w, nh, nh_stride, seg_len, segs_per_read, cmax;
+    uint32_t h_off, bin_off, bits_off;  // shared-memory offsets: m-mer hashes, window bins, boundary bitmask
+    uint32_t n_bins, bin_cap;
+    uint64_t ovf_cap;
+    uint32_t *cursor;                   // [n_bins] records appended to each bin so far
+    uint8_t *bins;                      // n_bins x bin_cap records of 16W bytes
+    uint8_t *ovf;                       // ovf_cap records
+    unsigned long long *sc;
+};
+
+template <int W>
+__global__ void __launch_bounds__(kSwThreads) sw_scatter_kernel(SwScatterParams q) {
+    const ExtractParams &p = q.ep;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t stage_bytes = p.stage_bytes;
+    uint8_t *stage0 = smem;
+    uint64_t *enc = reinterpret_cast<uint64_t *>(smem + p.enc_off);
+    uint8_t *enc_b = reinterpret_cast<uint8_t *>(enc);
+    const uint32_t enc_row = p.nw + 1;
+    uint8_t *bad4 = smem + p.bad_off;
+    uint8_t *flag = smem + p.flag_off;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.bar_off);
+    uint32_t *hh = reinterpret_cast<uint32_t *>(smem + q.h_off);
+    uint32_t *bid = reinterpret_cast<uint32_t *>(smem + q.bin_off);
+    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + q.bits_off);
+    __shared__ uint32_t s_nstart;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+    if (tid == 0) {
+        s_nstart = 0;
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    for (uint32_t i = tid; i < p.tile_reads * enc_row; i += kSwThreads) enc[i] = 0;
+    for (uint32_t i = tid; i < p.tile_reads; i += kSwThreads) flag[i] = 0;
+    __syncthreads();
+
+    auto tile_reads_of = [&](uint32_t t) -> uint32_t {
+        uint64_t first = (uint64_t)t * p.tile_reads;
+        uint64_t left = p.n_reads - first;
+        return left < p.tile_reads ? (uint32_t)left : p.tile_reads;
+    };
+    auto issue_load = [&](uint32_t t, uint32_t s) {
+        uint32_t bytes = tile_reads_of(t) * p.L;
+        const uint8_t *src = p.reads + (uint64_t)t * p.tile_reads * p.L;
+        uint8_t *dst = stage0 + s * stage_bytes;
+        if ((bytes & 15u) == 0) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[s], bytes);
+                tma_load_1d(dst, src, bytes, &bars[s]);
+            }
+        } else {
+            for (uint32_t i = tid; i < bytes; i += kSwThreads) dst[i] = src[i];
+        }
+    };
+
+    uint32_t phase_bits = 0, stage = 0;
+    unsigned long long invalid_local = 0, windows_local = 0, records_local = 0;
+    const uint32_t mmask = q.m >= 16 ? 0xffffffffu : ((1u << (2 * q.m)) - 1u);
+    const uint32_t mshift = 64 - 2 * q.m;
+    const uint32_t ng = (q.nh + 7) >> 3;
+
+    uint32_t tile = blockIdx.x;
+    if (tile < p.n_tiles) issue_load(tile, 0);
+
+    for (; tile < p.n_tiles; tile += gridDim.x) {
+        const uint32_t next = tile + gridDim.x;
+        if (next < p.n_tiles) issue_load(next, stage ^ 1);
+        const uint32_t nreads = tile_reads_of(tile);
+        if (((nreads * p.L) & 15u) == 0) {
+            mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
+            phase_bits ^= 1u << stage;
+        } else {
+            __syncthreads();
+        }
+        const uint8_t *src_tile = stage0 + stage * stage_bytes;
+
+        // ---- A: 2-bit encode
+        encode_tile(p, src_tile, nreads, enc_b, bad4, flag);
+        __syncthreads();
+        if (tid == 0) s_nstart = 0;                      // (read by D2 of the previous tile two barriers ago)
+
+        // ---- B: hash of the m-mer starting at every code position j < nh; a thread takes 8
+        // consecutive positions out of one 64-bit funnel of the encoded words
+        for (uint32_t g = tid; g < nreads * ng; g += kSwThreads) {
+            const uint32_t r = g / ng, j0 = (g - r * ng) * 8;
+            const uint32_t wi = j0 >> 5, sh = (j0 & 31u) * 2u;
+            const uint64_t *e = enc + r * enc_row;
+            const uint64_t a = wi <= p.nw ? e[wi] : 0ull;
+            const uint64_t b = wi + 1 <= p.nw ? e[wi + 1] : 0ull;
+            const uint64_t x = sh ? ((a << sh) | (b >> (64 - sh))) : a;
+            uint32_t *row = hh + r * q.nh_stride + j0;
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++)
+                if (j0 + i < q.nh) row[i] = mmer_hash((uint32_t)(x >> (mshift - 2 * i)) & mmask);
+        }
+        __syncthreads();
+
+        // ---- C: minimum over the w m-mers of each window -> bin of the window. A thread takes a
+        // segment of s <= min(18, w) consecutive windows: they all contain m-mers [s-1, w) of the
+        // segment (the core); window i adds a suffix of [i, s-1) and a prefix of [w, w+i).
+        const uint32_t n_seg = nreads * q.segs_per_read;
+        for (uint32_t sg = tid; sg < n_seg; sg += kSwThreads) {
+            const uint32_t r = sg / q.segs_per_read;
+            const uint32_t p0 = (sg - r * q.segs_per_read) * q.seg_len;
+            if (p0 >= p.nk) continue;
+            const uint32_t s = min(q.seg_len, p.nk - p0);
+            const uint32_t *g = hh + r * q.nh_stride + p0;
+            uint32_t S[kSwMaxSeg];
+            S[kSwMaxSeg - 1] = 0xffffffffu;
+#pragma unroll
+            for (int i = kSwMaxSeg - 2; i >= 0; i--) {
+                const uint32_t v = (uint32_t)i + 1 < s ? g[i] : 0xffffffffu;
+                S[i] = min(v, S[i + 1]);
+            }
+            uint32_t core = 0xffffffffu;
+            for (uint32_t t = s - 1; t < q.w; t++) core = min(core, g[t]);
+            uint32_t pm = 0xffffffffu;
+            const bool check = flag[r] != 0;
+            uint32_t *brow = bid + r * p.nk + p0;
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kSwMaxSeg; i++) {
+                if (i < s) {
+                    const uint32_t mn = min(min(S[i], core), pm);
+                    const bool valid = check ? kmer_window_valid(bad4 + r * p.nb4, p0 + i, p.k) : true;
+                    if (!valid) invalid_local++;
+                    brow[i] = valid ? bin_of_min(mn, q.n_bins) : kNoBin;
+                    if (i + 1 < s) pm = min(pm, g[q.w + i]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- D: a run of equal bins becomes records of at most cmax windows: 64W bases from the
+        // run's first base (the first key and the bases that follow it), the window count in the
+        // low byte of the last word.
+        // D1: boundary bitmask over the tile's windows (a run start, or a slot without a k-mer) and
+        // a compact list of the run starts; window indices are flat (bid rows are nk long).
+        const uint32_t total = nreads * p.nk;
+        const uint32_t n_words = (total + 31) >> 5;
+        uint32_t *list = hh;                            // the m-mer hashes are dead: tile_reads * nh_stride >= total words
+        for (uint32_t base = (tid >> 5) << 5; base < n_words * 32; base += kSwThreads) {
+            const uint32_t sidx = base + lane;
+            bool st = false, bd = true;                 // past the tile: a boundary that closes the last run
+            if (sidx < total) {
+                uint32_t r = p.nk == 1 ? sidx : __umulhi(sidx, p.nk_magic);
+                if (r * p.nk > sidx) r--;
+                const uint32_t b = bid[sidx];
+                st = b != kNoBin && (sidx == r * p.nk || bid[sidx - 1] != b);
+                bd = st || b == kNoBin;
+            }
+            const uint32_t bm = __ballot_sync(0xffffffffu, bd), sm = __ballot_sync(0xffffffffu, st);
+            uint32_t off = 0;
+            if (lane == 0) {
+                bits[base >> 5] = bm;
+                if (sm) off = atomicAdd(&s_nstart, (uint32_t)__popc(sm));
+            }
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (st) list[off + __popc(sm & lanemask_lt())] = sidx;
+        }
+        if (tid == 0) bits[n_words] = 0xffffffffu;
+        __syncthreads();
+        // D2: one thread per run. The bin's cursor is bumped first; the record is assembled while
+        // that atomic is in flight.
+        const uint32_t n_start = s_nstart;
+        for (uint32_t en = tid; en < n_start; en += kSwThreads) {
+            const uint32_t sidx = list[en];
+            uint32_t wd = sidx >> 5;
+            uint32_t mk = bits[wd] & ~(0xffffffffu >> (31 - (sidx & 31u)));      // boundaries after sidx in its word
+            while (mk == 0) mk = bits[++wd];
+            const uint32_t len = wd * 32 + (uint32_t)__ffs(mk) - 1 - sidx;
+            uint32_t r = p.nk == 1 ? sidx : __umulhi(sidx, p.nk_magic);
+            if (r * p.nk > sidx) r--;
+            const uint32_t pos = sidx - r * p.nk;
+            const uint32_t b = bid[sidx];
+            const uint64_t *e = enc + r * enc_row;
+            for (uint32_t q0 = 0; q0 < len; q0 += q.cmax) {
+                const uint32_t idx = atomicAdd(&q.cursor[b], 1u);
+                const uint32_t c = min(q.cmax, len - q0);
+                const uint32_t wi = (pos + q0) >> 5, sh = ((pos + q0) & 31u) * 2u;
+                uint64_t ew[2 * W + 1];
+#pragma unroll
+                for (int t = 0; t < 2 * W + 1; t++) ew[t] = wi + t <= p.nw ? e[wi + t] : 0ull;
+                uint64_t rec[2 * W];
+#pragma unroll
+                for (int t = 0; t < 2 * W; t++) rec[t] = sh ? ((ew[t] << sh) | (ew[t + 1] >> (64 - sh))) : ew[t];
+                rec[2 * W - 1] = (rec[2 * W - 1] & ~0xffull) | c;
+                ulonglong2 *dst = nullptr;
+                if (idx < q.bin_cap) {
+                    dst = reinterpret_cast<ulonglong2 *>(q.bins) + ((uint64_t)b * q.bin_cap + idx) * W;
+                } else {
+                    const unsigned long long oi = atomicAdd(&q.sc[SW_OVF], 1ull);
+                    if (oi < q.ovf_cap) dst = reinterpret_cast<ulonglong2 *>(q.ovf) + oi * W;
+                    else atomicOr(&q.sc[SW_FAIL], 1ull);
+                }
+                if (dst) {
+#pragma unroll
+                    for (int t = 0; t < W; t++) dst[t] = make_ulonglong2(rec[2 * t], rec[2 * t + 1]);
+                }
+                windows_local += c;
+                records_local++;
+            }
+        }
+        for (uint32_t i = tid; i < nreads; i += kSwThreads) flag[i] = 0;
+        __syncthreads();
+        stage ^= 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        invalid_local += __shfl_xor_sync(0xffffffffu, invalid_local, o);
+        windows_local += __shfl_xor_sync(0xffffffffu, windows_local, o);
+        records_local += __shfl_xor_sync(0xffffffffu, records_local, o);
+    }
+    if (lane == 0) {
+        if (invalid_local) atomicAdd(&q.sc[SW_INVALID], invalid_local);
+        if (windows_local) atomicAdd(&q.sc[SW_WINDOWS], windows_local);
+        if (records_local) atomicAdd(&q.sc[SW_RECORDS], records_local);
+    }
+}
+
+// ======================================================================= S2: count
+template <int W> __device__ __forceinline__ bool key_all_ones(const Key<W> &k) {
+    uint64_t a = ~0ull;
+#pragma unroll
+    for (int i = 0; i < W; i++) a &= k.w[i];
+    return a == ~0ull;
+}
+template <int W> __device__ __forceinline__ bool key_any_word_ones(const Key<W> &k) {
+    bool r = false;
+#pragma unroll
+    for (int i = 0; i < W; i++) r = r || (k.w[i] == ~0ull);
+    return r;
+}
+template <int W> __device__ __forceinline__ void key_set_ones(Key<W> &k) {
+#pragma unroll
+    for (int i = 0; i < W; i++) k.w[i] = ~0ull;
+}
+__device__ __forceinline__ Key<1> slot_claim(Key<1> *slot, const Key<1> &k) {      // returns the previous content
+    Key<1> o;
+    o.w[0] = atomicCAS(reinterpret_cast<unsigned long long *>(slot), ~0ull, (unsigned long long)k.w[0]);
+    return o;
+}
+__device__ __forceinline__ Key<2> slot_claim(Key<2> *slot, const Key<2> &k) {
+    Key<2> o;
+    const uint32_t a = smem_u32(slot);
+    asm volatile(
+        "{\n"
+        ".reg .b128 c, n, o;\n"
+        "mov.b128 c, {%3, %3};\n"
+        "mov.b128 n, {%4, %5};\n"
+        "atom.shared.cas.b128 o, [%2], c, n;\n"
+        "mov.b128 {%0, %1}, o;\n"
+        "}\n"
+        : "=l"(o.w[0]), "=l"(o.w[1])
+        : "r"(a), "l"(~0ull), "l"(k.w[0]), "l"(k.w[1])
+        : "memory");
+    return o;
+}
+template <int W> __device__ __forceinline__ uint32_t key_hash(const Key<W> &k) {
+    uint32_t x = (uint32_t)k.w[0] ^ (uint32_t)(k.w[0] >> 29);
+    if constexpr (W > 1) x ^= ((uint32_t)k.w[W - 1] ^ (uint32_t)(k.w[W - 1] >> 31)) * 0x85EBCA6Bu;
+    return x * 0x9E3779B1u;
+}
+// a second, independent hash: which of the 2^bits passes over a bin a key belongs to
+__device__ __forceinline__ uint32_t pass_hash(uint32_t h) { return (h ^ (h >> 15)) * 0x2C1B3C6Du; }
+
+struct SwCountParams {
+    const uint32_t *cursor;
+    const uint8_t *bins, *ovf;
+    uint32_t n_bins, bin_cap, ovf_slice;
+    uint64_t ovf_cap;
+    uint64_t last_mask;
+    uint64_t *d_keys;
+    uint32_t *d_counts;
+    uint64_t d_cap;
+    uint32_t *hist1;
+    int shift1, nb1;
+    int add_phantom;
+    unsigned long long *sc;
+};
+
+// One work unit = one bin, or one slice of the overflow list. The CTA stages RPT * THREADS records
+// at a time, splits their windows evenly over its threads (a thread takes a contiguous range of
+// the flattened window sequence, so it slides the window inside a record and every lane has the
+// same number of keys), and counts them in a shared-memory table. The insert loop is a per-lane
+// state machine -- one probe of the lane's current key per iteration, a lane that is done with a
+// key fetches its next one in the same loop -- so lanes with short and long probe sequences do not
+// wait for each other. A unit with more distinct keys than the table takes is redone in 2, 4, ...
+// passes, pass v counting the keys whose pass hash starts with v: the records a unit emits are
+// always key-distinct.
+template <int W, int THREADS, int TSLOTS, int RPT>
+__global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
+    constexpr int RB = THREADS * RPT;                                       // records per round
+    extern __shared__ __align__(16) uint8_t cs_smem[];
+    Key<W> *tk = reinterpret_cast<Key<W> *>(cs_smem);                       // [TSLOTS]
+    ulonglong2 *recs = reinterpret_cast<ulonglong2 *>(tk + TSLOTS);         // [RB * W]
+    uint32_t *tc = reinterpret_cast<uint32_t *>(recs + RB * W);             // [TSLOTS]
+    uint32_t *pre = tc + TSLOTS;                                            // [RB + 8]
+    uint32_t *s_hist = pre + RB + 8;                                        // [nb1]
+    __shared__ uint32_t s_unit, s_m, s_ones, s_abort, s_off;
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t kLimit = TSLOTS / 4 * 3;
+    constexpr uint32_t hshift = 32 - ILog2<(uint32_t)TSLOTS>::v;
+
+    {
+        Key<W> empty;
+        key_set_ones<W>(empty);
+        for (uint32_t i = tid; i < (uint32_t)TSLOTS; i += THREADS) { tk[i] = empty; tc[i] = 0; }
+        for (uint32_t i = tid; i < (uint32_t)p.nb1; i += THREADS) s_hist[i] = 0;
+        if (tid == 0) { s_m = 0; s_ones = 0; s_abort = 0; }
+    }
+    unsigned long long n_ovf = p.sc[SW_OVF];
+    if (n_ovf > p.ovf_cap) n_ovf = p.ovf_cap;
+    const uint32_t n_ovf_units = (uint32_t)((n_ovf + p.ovf_slice - 1) / p.ovf_slice);
+    const uint32_t n_units = p.n_bins + n_ovf_units;
+    unsigned long long occ_local = 0;
+    uint32_t aborts_local = 0;
+    // thread 0 draws the ticket of the NEXT unit while the current one is counted
+    uint32_t next_ticket = 0;
+    if (tid == 0) next_ticket = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
+    __syncthreads();
+
+    while (true) {
+        if (tid == 0) {
+            s_unit = next_ticket;
+            if (next_ticket < n_units) next_ticket = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
+        }
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units) break;
+        const ulonglong2 *src;
+        uint32_t n_rec;
+        if (u < p.n_bins) {
+            const uint32_t c = p.cursor[u];
+            n_rec = c < p.bin_cap ? c : p.bin_cap;
+            src = reinterpret_cast<const ulonglong2 *>(p.bins) + (uint64_t)u * p.bin_cap * W;
+        } else {
+            const uint64_t o0 = (uint64_t)(u - p.n_bins) * p.ovf_slice;
+            n_rec = (uint32_t)min((unsigned long long)p.ovf_slice, n_ovf - o0);
+            src = reinterpret_cast<const ulonglong2 *>(p.ovf) + o0 * W;
+        }
+        // key 0 joins with count += 0 whenever a slot held no k-mer: its bin is bin 0
+        const bool phantom = u == 0 && p.add_phantom && p.sc[SW_INVALID] != 0;
+        if (n_rec == 0 && !phantom) { __syncthreads(); continue; }
+
+        uint32_t bits = 0, val = 0;
+        while (true) {                                   // passes over the unit
+            uint32_t claims = 0;
+            auto in_pass = [&](uint32_t h) -> bool { return bits == 0 || (pass_hash(h) >> (32 - bits)) == val; };
+            if (phantom && tid == 0) {
+                Key<W> zero;
+#pragma unroll
+                for (int i = 0; i < W; i++) zero.w[i] = 0;
+                const uint32_t hv = key_hash<W>(zero);
+                if (in_pass(hv)) {
+                    uint32_t h = hv >> hshift;
+#pragma unroll 1
+                    for (uint32_t probes = 0; probes < 64u; probes++) {
+                        Key<W> cur = tk[h];
+                        if (key_any_word_ones<W>(cur)) {
+                            cur = slot_claim(&tk[h], zero);
+                            if (key_all_ones<W>(cur)) { claims++; break; }
+                        }
+                        if (key_eq<W>(cur, zero)) break;
+                        h = (h + 1) & (TSLOTS - 1);
+                        if (probes == 63u) s_abort = 1;
+                    }
+                }
+            }
+            bool aborted = false;
+            // the first round's records travel while the pass is set up
+            ulonglong2 pf[RPT][W];
+#pragma unroll
+            for (int u2 = 0; u2 < RPT; u2++) {
+                const uint32_t i = u2 * THREADS + tid;
+                if (i < n_rec) {
+#pragma unroll
+                    for (int t = 0; t < W; t++) pf[u2][t] = src[(uint64_t)i * W + t];
+                }
+            }
+            for (uint32_t r0 = 0; r0 < n_rec; r0 += RB) {
+                const uint32_t nr = min((uint32_t)RB, n_rec - r0);
+                // stage the records, exclusive scan of their window counts
+                uint32_t c[RPT];
+                uint32_t csum = 0;
+                // records were fetched with a stride of THREADS (coalesced); their place in the round keeps that order
+#pragma unroll
+                for (int u2 = 0; u2 < RPT; u2++) {
+                    const uint32_t i = u2 * THREADS + tid;
+                    c[u2] = 0;
+                    if (i < nr) {
+#pragma unroll
+                        for (int t = 0; t < W; t++) recs[i * W + t] = pf[u2][t];
+                        c[u2] = (uint32_t)(pf[u2][W - 1].y & 0xffull);
+                    }
+                }
+                // prefetch the next round
+#pragma unroll
+                for (int u2 = 0; u2 < RPT; u2++) {
+                    const uint32_t i = r0 + RB + u2 * THREADS + tid;
+                    if (i < n_rec) {
+#pragma unroll
+                        for (int t = 0; t < W; t++) pf[u2][t] = src[(uint64_t)i * W + t];
+                    }
+                }
+                // exclusive scan over the round in record order i = u2 * THREADS + tid: scan each stripe
+                // u2 across the CTA, stripes one after the other
+                uint32_t stripe_base = 0;
+#pragma unroll
+                for (int u2 = 0; u2 < RPT; u2++) {
+                    uint32_t incl = c[u2];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (uint32_t)o) incl += t;
+                    }
+                    if (lane == 31) s_warp[warp] = incl;
+                    __syncthreads();
+                    uint32_t woff = 0, tot = 0;
+#pragma unroll
+                    for (int wq = 0; wq < THREADS / 32; wq++) {
+                        const uint32_t t = s_warp[wq];
+                        if ((uint32_t)wq < warp) woff += t;
+                        tot += t;
+                    }
+                    pre[u2 * THREADS + tid] = stripe_base + woff + incl - c[u2];
+                    stripe_base += tot;
+                    csum = stripe_base;
+                    __syncthreads();
+                }
+                const uint32_t tot = csum;
+                // this thread's share of the tot windows: [f0, f1)
+                const uint32_t per = (tot + THREADS - 1) / THREADS;
+                const uint32_t f0 = tid * per, f1 = min(f0 + per, tot);
+                if (f0 < f1) {
+                    uint32_t lo = 0, hi = nr;                      // last record whose first window is <= f0
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (pre[mid] <= f0) lo = mid; else hi = mid;
+                    }
+                    uint32_t ri = lo;                              // next record to open
+                    uint32_t rem = f1 - f0;                        // windows this lane still has to fetch
+                    occ_local += rem;
+                    uint64_t rw[2 * W];
+                    uint32_t in_rec;                               // windows left in the open record
+                    {   // open the first record at window j
+                        const uint32_t j = f0 - pre[lo];
+#pragma unroll
+                        for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
+                        const uint32_t cnt = (uint32_t)(rw[2 * W - 1] & 0xffull);
+                        uint32_t sh = 2 * j;
+                        if constexpr (W > 1) {
+                            while (sh >= 64) {
+#pragma unroll
+                                for (int t = 0; t < 2 * W - 1; t++) rw[t] = rw[t + 1];
+                                rw[2 * W - 1] = 0;
+                                sh -= 64;
+                            }
+                        }
+                        if (sh) {
+#pragma unroll
+                            for (int t = 0; t < 2 * W - 1; t++) rw[t] = (rw[t] << sh) | (rw[t + 1] >> (64 - sh));
+                            rw[2 * W - 1] <<= sh;
+                        }
+                        in_rec = min(rem, cnt - j);
+                        ri++;
+                    }
+                    Key<W> key;
+                    uint32_t h = 0, probes = 0;
+                    bool need = true, active = true;
+#pragma unroll 1
+                    while (active) {
+                        if (need) {                                // fetch this lane's next window
+                            if (rem == 0) {
+                                active = false;
+                            } else {
+                                if (in_rec == 0) {
+#pragma unroll
+                                    for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
+                                    in_rec = min(rem, (uint32_t)(rw[2 * W - 1] & 0xffull));
+                                    ri++;
+                                }
+#pragma unroll
+                                for (int t = 0; t < W; t++) key.w[t] = rw[t];
+                                key.w[W - 1] &= p.last_mask;
+                                in_rec--;
+                                rem--;
+#pragma unroll
+                                for (int t = 0; t < 2 * W - 1; t++) rw[t] = (rw[t] << 2) | (rw[t + 1] >> 62);
+                                rw[2 * W - 1] <<= 2;
+                                if (key_all_ones<W>(key)) {        // the table's empty marker: counted on the side
+                                    if (in_pass(0x9E3779B1u)) atomicAdd(&s_ones, 1u);
+                                } else {
+                                    const uint32_t hv = key_hash<W>(key);
+                                    if (in_pass(hv)) { h = hv >> hshift; probes = 0; need = false; }
+                                }
+                            }
+                        }
+                        if (!need) {                               // one probe
+                            Key<W> cur = tk[h];
+                            bool done = key_eq<W>(cur, key);
+                            // a slot that looks (even partly: a 128-bit read may tear) empty is settled by the CAS
+                            if (!done && key_any_word_ones<W>(cur)) {
+                                cur = slot_claim(&tk[h], key);
+                                if (key_all_ones<W>(cur)) { claims++; done = true; }
+                                else done = key_eq<W>(cur, key);
+                            }
+                            if (done) {
+                                atomicAdd(&tc[h], 1u);
+                                need = true;
+                            } else {
+                                h = (h + 1) & (TSLOTS - 1);
+                                if (++probes >= 64u) { s_abort = 1; need = true; }   // table (nearly) full: the pass is abandoned
+                            }
+                        }
+                    }
+                }
+                // distinct keys so far
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, o);
+                if (lane == 0 && claims) atomicAdd(&s_m, claims);
+                claims = 0;
+                __syncthreads();
+                if (s_abort || s_m > kLimit) { aborted = true; break; }
+            }
+            if (!aborted) {                              // (the phantom alone: no round ran)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, o);
+                if (lane == 0 && claims) atomicAdd(&s_m, claims);
+                __syncthreads();
+                if (s_abort) aborted = true;
+            }
+            if (aborted) {
+                // occurrences of this pass are counted again by its two halves
+                Key<W> empty;
+                key_set_ones<W>(empty);
+                __syncthreads();
+                for (uint32_t i = tid; i < (uint32_t)TSLOTS; i += THREADS) { tk[i] = empty; tc[i] = 0; }
+                if (tid == 0) { s_m = 0; s_ones = 0; s_abort = 0; }
+                aborts_local++;
+                bits++;                                   // left half first
+                if (bits > 24) {
+                    if (tid == 0) atomicOr(&p.sc[SW_FAIL], 4ull);
+                    __syncthreads();
+                    break;
+                }
+                val <<= 1;
+                __syncthreads();
+                continue;
+            }
+            // ---- emit the pass: distinct (key, count) records appended to D, table cleared
+            const uint32_t m = s_m, ones = s_ones;
+            const uint32_t m_tot = m + (ones ? 1u : 0u);
+            if (tid == 0) {
+                s_base = m_tot ? atomicAdd(&p.sc[SW_D], (unsigned long long)m_tot) : 0ull;
+                s_off = 0;
+            }
+            __syncthreads();
+            const unsigned long long base = s_base;
+            if (base + m_tot > p.d_cap) {
+                if (tid == 0) atomicOr(&p.sc[SW_FAIL], 2ull);
+            }
+            Key<W> empty;
+            key_set_ones<W>(empty);
+            for (uint32_t i0 = 0; i0 < (uint32_t)TSLOTS; i0 += THREADS) {
+                const uint32_t i = i0 + tid;
+                const Key<W> k = tk[i];
+                const bool live = !key_all_ones<W>(k);
+                const uint32_t bal = __ballot_sync(0xffffffffu, live);
+                if (bal) {
+                    uint32_t b = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if ((int)lane == leader) b = atomicAdd(&s_off, (uint32_t)__popc(bal));
+                    b = __shfl_sync(0xffffffffu, b, leader);
+                    if (live) {
+                        const unsigned long long o = base + b + __popc(bal & lanemask_lt());
+                        if (o < p.d_cap) {
+                            st_key<W>(p.d_keys, o, k);
+                            p.d_counts[o] = tc[i];
+                        }
+                        atomicAdd(&s_hist[k.w[0] >> p.shift1], 1u);
+                        tk[i] = empty;
+                        tc[i] = 0;
+                    }
+                }
+            }
+            if (ones && tid == 0) {
+                const unsigned long long o = base + m;
+                if (o < p.d_cap) {
+                    st_key<W>(p.d_keys, o, empty);
+                    p.d_counts[o] = ones;
+                }
+                atomicAdd(&s_hist[p.nb1 - 1], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) { s_m = 0; s_ones = 0; }
+            // next pass: climb while this was a right half, then step to the right sibling
+            // (pass ids are prefixes of the pass hash, most significant bit first)
+            while (bits > 0 && (val & 1u)) { val >>= 1; bits--; }
+            if (bits == 0) { __syncthreads(); break; }
+            val |= 1u;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < (uint32_t)p.nb1; i += THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&p.hist1[i], c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) occ_local += __shfl_xor_sync(0xffffffffu, occ_local, o);
+    if (lane == 0 && occ_local) atomicAdd(&p.sc[SW_OCC], occ_local);
+    if (tid == 0 && aborts_local) atomicAdd(&p.sc[SW_ABORTS], (unsigned long long)aborts_local);
+}
+
+// ============================================================ S3: ordering the records
+// exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_t *start, int nb, uint32_t *s_warp) {
+    constexpr int PER = kNb1Max / THREADS > 0 ? kNb1Max / THREADS : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int b = tid * PER + i;
+        v[i] = b < nb ? cnt[b] : 0;
+        sum += v[i];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        const uint32_t t = s_warp[w];
+        if (w < warp) off += t;
+        total += t;
+    }
+    uint32_t run = off + incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int b = tid * PER + i;
+        if (b < nb) start[b] = run;
+        run += v[i];
+    }
+    __syncthreads();
+    return total;
+}
+
+// one block: level-1 bucket bases + cursors from the histogram S2 left, and the level-2 plan
+__global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restrict__ hist1, int b1, uint64_t d_cap,
+                                                       uint32_t sub_target, int sig_bits, uint32_t *__restrict__ base1,
+                                                       uint32_t *__restrict__ cursor1, SuperPlanDev *__restrict__ plan,
+                                                       const unsigned long long *__restrict__ sc) {
+    __shared__ uint32_t s_a[32];
+    const int nb1 = 1 << b1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = tid < nb1 ? hist1[tid] : 0;
+    uint32_t ia = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t xa = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += xa;
+    }
+    if (lane == 31) s_a[warp] = ia;
+    __syncthreads();
+    uint32_t oa = 0;
+    for (int w = 0; w < warp; w++) oa += s_a[w];
+    if (tid < nb1) {
+        base1[tid] = oa + ia - c;
+        cursor1[tid] = oa + ia - c;
+        if (tid == nb1 - 1) base1[nb1] = oa + ia;
+    }
+    if (tid == 0) {
+        unsigned long long nd = sc[SW_D];
+        if (nd > d_cap) nd = d_cap;
+        uint32_t b2 = 0;
+        while (b2 < 9 && b1 + (int)b2 < sig_bits && (nd >> (b1 + b2)) > sub_target) b2++;
+        plan->n_d = (uint32_t)nd;
+        plan->b2 = b2;
+        plan->shift2 = 64 - b1 - b2;
+        plan->n_sub = (uint32_t)nb1 << b2;
+        plan->prefix_bits = b1 + b2;
+    }
+}
+
+constexpr int kRsThreads = 256;
+template <int W> struct RsCfg { static constexpr int ITEMS = 16 / W, TILE = kRsThreads * ITEMS; };
+
+// Scatter of (key, count) records by a digit of the key, over flat tiles of the input.
+// LEVEL 1: digit = leading b1 bits, any bin may occur in a tile.
+// LEVEL 2: the input is grouped by the level-1 digit, so a tile's keys name (almost always) one
+// or two level-1 buckets: bins are relative to the first key's bucket, two buckets wide when the
+// tile straddles a boundary; a key further away is placed on its own.
+template <int W, int LEVEL>
+__global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t *__restrict__ in_keys,
+                                                                 const uint32_t *__restrict__ in_counts,
+                                                                 uint64_t *__restrict__ out_keys,
+                                                                 uint32_t *__restrict__ out_counts,
+                                                                 const SuperPlanDev *__restrict__ plan, int b1,
+                                                                 const unsigned long long *__restrict__ n_ptr, uint64_t cap,
+                                                                 uint32_t *__restrict__ g_cursor) {
+    constexpr int ITEMS = RsCfg<W>::ITEMS, TILE = RsCfg<W>::TILE;
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    Key<W> *stg_k = reinterpret_cast<Key<W> *>(rs_smem);                    // [TILE]
+    uint32_t *stg_c = reinterpret_cast<uint32_t *>(stg_k + TILE);           // [TILE]
+    uint32_t *cnt = stg_c + TILE, *start = cnt + kNb1Max, *gbase = start + kNb1Max;
+    __shared__ uint32_t s_warp[kRsThreads / 32];
+    uint32_t n;
+    if (LEVEL == 1) {
+        unsigned long long nn = *n_ptr;
+        n = (uint32_t)(nn > cap ? cap : nn);
+    } else {
+        n = plan->n_d;
+    }
+    const int b2 = LEVEL == 1 ? 0 : (int)plan->b2;
+    const int shift = LEVEL == 1 ? 64 - b1 : (int)plan->shift2;
+    const uint32_t nb2 = 1u << b2;
+    for (uint32_t begin = blockIdx.x * (uint32_t)TILE; begin < n; begin += gridDim.x * (uint32_t)TILE) {
+        const uint32_t end = begin + TILE < n ? begin + TILE : n;
+        Key<W> key[ITEMS];
+        uint32_t val[ITEMS];
+        uint16_t rank[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t idx = begin + i * kRsThreads + threadIdx.x;
+            if (idx < end) { key[i] = ld_key<W>(in_keys, idx); val[i] = in_counts[idx]; }
+            else { key[i].w[0] = 0; val[i] = 0; }
+        }
+        uint32_t p0 = 0, nb;
+        if (LEVEL == 1) {
+            nb = 1u << b1;
+        } else {
+            p0 = ((uint32_t)(in_keys[(size_t)begin * W] >> shift) >> b2) << b2;       // first sub-bucket of the first key's bucket
+            const uint32_t pl = (uint32_t)(in_keys[(size_t)(end - 1) * W] >> shift);
+            nb = (pl >> b2) == (p0 >> b2) ? nb2 : 2 * nb2;                            // 2 * nb2 <= 1024
+        }
+        for (uint32_t i = threadIdx.x; i < nb; i += kRsThreads) cnt[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t idx = begin + i * kRsThreads + threadIdx.x;
+            rank[i] = 0xffffu;
+            if (idx < end) {
+                const uint32_t pfx = (uint32_t)(key[i].w[0] >> shift);
+                const uint32_t rel = pfx - p0;
+                if (rel < nb) rank[i] = (uint16_t)atomicAdd(&cnt[rel], 1u);
+                else {
+                    const uint32_t o = atomicAdd(&g_cursor[pfx], 1u);
+                    st_key<W>(out_keys, o, key[i]);
+                    out_counts[o] = val[i];
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t total = block_scan_bins<kRsThreads>(cnt, start, (int)nb, s_warp);
+        // reserve the bins' ranges, stage the records while the atomics are in flight, then look at the answers
+        uint32_t reserved[kNb1Max / kRsThreads];
+#pragma unroll
+        for (int u = 0; u < kNb1Max / kRsThreads; u++) {
+            const uint32_t b = u * kRsThreads + threadIdx.x;
+            reserved[u] = 0;
+            if (b < nb) {
+                const uint32_t c = cnt[b];
+                if (c) reserved[u] = atomicAdd(&g_cursor[p0 + b], c);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++)
+            if (rank[i] != 0xffffu) {
+                const uint32_t o = start[(uint32_t)(key[i].w[0] >> shift) - p0] + rank[i];
+                stg_k[o] = key[i];
+                stg_c[o] = val[i];
+            }
+#pragma unroll
+        for (int u = 0; u < kNb1Max / kRsThreads; u++) {
+            const uint32_t b = u * kRsThreads + threadIdx.x;
+            if (b < nb) gbase[b] = reserved[u] - start[b];
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < total; i += kRsThreads) {
+            const Key<W> k = stg_k[i];
+            const uint32_t o = gbase[(uint32_t)(k.w[0] >> shift) - p0] + i;
+            st_key<W>(out_keys, o, k);
+            out_counts[o] = stg_c[i];
+        }
+        __syncthreads();
+    }
+}
+
+// Level-2 histogram of the level-1-grouped keys (flat chunks; counters of the chunk's first
+// bucket in shared memory, stragglers straight to the global counter).
+constexpr uint32_t kH2Chunk = 16384;
+template <int W>
+__global__ void __launch_bounds__(256) rec_hist2_kernel(const uint64_t *__restrict__ keys,
+                                                        const SuperPlanDev *__restrict__ plan,
+                                                        uint32_t *__restrict__ g_hist2) {
+    __shared__ uint32_t sh[kNb1Max];
+    const uint32_t n = plan->n_d;
+    const int b2 = (int)plan->b2, shift2 = (int)plan->shift2;
+    const uint32_t nb2 = 1u << b2, m2 = nb2 - 1;
+    for (uint32_t begin = blockIdx.x * kH2Chunk; begin < n; begin += gridDim.x * kH2Chunk) {
+        const uint32_t end = begin + kH2Chunk < n ? begin + kH2Chunk : n;
+        for (uint32_t i = threadIdx.x; i < nb2; i += 256) sh[i] = 0;
+        const uint32_t b0 = (uint32_t)(keys[(size_t)begin * W] >> shift2) >> b2;
+        __syncthreads();
+#pragma unroll 4
+        for (uint32_t i = begin + threadIdx.x; i < end; i += 256) {
+            const uint32_t pfx = (uint32_t)(keys[(size_t)i * W] >> shift2);
+            if ((pfx >> b2) == b0) atomicAdd(&sh[pfx & m2], 1u);
+            else atomicAdd(&g_hist2[pfx], 1u);
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nb2; i += 256) {
+            const uint32_t c = sh[i];
+            if (c) atomicAdd(&g_hist2[(size_t)b0 * nb2 + i], c);
+        }
+        __syncthreads();
+    }
+}
+
+// Exclusive scan over n entries -> base (n+1) and the mutable cursors. One CTA per tile of 4096;
+// a CTA sums the entries before its tile itself (a few MB out of L2 at most): no carried dependency.
+// n comes from the device plan (n_ptr) or, when n_ptr is NULL, from n_host.
+constexpr uint32_t kScanTile = 4096;
+__global__ void __launch_bounds__(1024) sw_scan_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ n_ptr,
+                                                       uint32_t n_host, uint32_t *__restrict__ base,
+                                                       uint32_t *__restrict__ cursor, unsigned long long *total_out) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t t0 = blockIdx.x * kScanTile;
+    if (t0 >= n) return;
+    uint32_t acc = 0;
+#pragma unroll 8
+    for (uint32_t i = tid; i < t0; i += 1024) acc += hist[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_w[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t c = 0;
+        for (int w = 0; w < 32; w++) c += s_w[w];
+        s_carry = c;
+    }
+    __syncthreads();
+    const uint32_t i0 = t0 + tid * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = i0 + u < n ? hist[i0 + u] : 0;
+    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();                        // s_w is reused
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = s_carry, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 32; w++) {
+        const uint32_t x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    uint32_t run = off + incl - sum;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (i0 + u < n) { base[i0 + u] = run; if (cursor) cursor[i0 + u] = run; }
+        run += v[u];
+    }
+    if (tid == 0 && t0 + kScanTile >= n) {       // the last tile closes the scan
+        base[n] = s_carry + tot;
+        if (total_out) *total_out = s_carry + tot;
+    }
+}
+
+__device__ __forceinline__ uint32_t pow2_ceil_u32(uint32_t x) { return x <= 1 ? 1u : 1u << (32 - __clz(x - 1)); }
+
+struct FinishParams {
+    const uint64_t *in_keys;
+    const uint32_t *in_counts;
+    const uint32_t *base2;          // [n_sub + 1]
+    const SuperPlanDev *plan;
+    uint64_t *out_keys;             // records of sub-bucket j at out[base2[j] ...)
+    uint32_t *out_counts;
+    uint32_t *m_out;                // DUP: records sub-bucket j kept
+    unsigned long long *sc;
+};
+
+// S3c: one CTA per sub-bucket (at most CAP records, all sharing their leading prefix_bits): a
+// counting sort on the next key bits into shared memory, an insertion sort inside each bin (a
+// bitonic network when a bin is crowded), then -- DUP only -- equal keys are folded (counts
+// added, uint32 wrap) and the survivors compacted. The records are written once, in key order.
+template <int W, int THREADS, int CAP, bool DUP>
+__global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
+    constexpr int NB3 = CAP;                                           // most counting-sort bins
+    extern __shared__ __align__(16) uint8_t fs_smem[];
+    Key<W> *ik = reinterpret_cast<Key<W> *>(fs_smem);                  // loaded      [CAP]
+    Key<W> *sk = ik + CAP;                                             // sorted      [CAP]
+    uint32_t *ic = reinterpret_cast<uint32_t *>(sk + CAP);             // [CAP]
+    uint32_t *scn = ic + CAP;                                          // [CAP]
+    uint32_t *c3 = scn + CAP;                                          // [NB3]
+    uint32_t *s3 = c3 + NB3;                                           // [NB3]
+    __shared__ uint32_t s_maxbin, s_cnt, s_j;
+    __shared__ uint32_t s_warp[THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_sub = p.plan->n_sub;
+    const int prefix_bits = (int)p.plan->prefix_bits;
+    unsigned long long folded_local = 0;
+
+    while (true) {
+        if (tid == 0) s_j = (uint32_t)atomicAdd(&p.sc[SW_TICKET2], 1ull);
+        __syncthreads();
+        const uint32_t j = s_j;
+        if (j >= n_sub) break;
+        const uint32_t b = p.base2[j], n = p.base2[j + 1] - b;
+        if (n == 0) {
+            if (DUP && tid == 0) p.m_out[j] = 0;
+            __syncthreads();
+            continue;
+        }
+        if (n > (uint32_t)CAP) {                     // does not fit: the caller re-counts this chunk another way
+            if (tid == 0) { atomicOr(&p.sc[SW_FAIL], 8ull); if (DUP) p.m_out[j] = 0; }
+            __syncthreads();
+            continue;
+        }
+        for (uint32_t i = tid; i < n; i += THREADS) { ik[i] = ld_key<W>(p.in_keys, b + i); ic[i] = p.in_counts[b + i]; }
+        uint32_t nb3 = pow2_ceil_u32(n);
+        nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)NB3 ? (uint32_t)NB3 : nb3);
+        int shift3 = 64 - prefix_bits - (31 - __clz(nb3));
+        if (shift3 < 0) shift3 = 0;
+        for (uint32_t i = tid; i < nb3; i += THREADS) c3[i] = 0;
+        if (tid == 0) { s_maxbin = 0; s_cnt = 0; }
+        __syncthreads();
+        constexpr int kPer = (CAP + THREADS - 1) / THREADS;
+        uint32_t rk[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const uint32_t i = u * THREADS + tid;
+            if (i < n) rk[u] = atomicAdd(&c3[(uint32_t)(ik[i].w[0] >> shift3) & (nb3 - 1)], 1u);
+        }
+        __syncthreads();
+        uint32_t mx = 0;
+        for (uint32_t i = tid; i < nb3; i += THREADS) mx = max(mx, c3[i]);
+        if (mx > 1) atomicMax(&s_maxbin, mx);
+        // exclusive scan of the nb3 bins (nb3 <= CAP, THREADS threads, nb3 / THREADS each)
+        {
+            constexpr int PER = NB3 / THREADS;
+            uint32_t v[PER];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const uint32_t bb = tid * PER + i;
+                v[i] = bb < nb3 ? c3[bb] : 0;
+                sum += v[i];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t off = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; w++) if ((uint32_t)w < warp) off += s_warp[w];
+            uint32_t run = off + incl - sum;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const uint32_t bb = tid * PER + i;
+                if (bb < nb3) s3[bb] = run;
+                run += v[i];
+            }
+            __syncthreads();
+        }
+        const uint32_t maxbin = s_maxbin;
+        Key<W> *rk_keys = sk;
+        uint32_t *rk_cnts = scn;
+        if (maxbin <= 24) {
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                const uint32_t i = u * THREADS + tid;
+                if (i < n) {
+                    const Key<W> k = ik[i];
+                    const uint32_t o = s3[(uint32_t)(k.w[0] >> shift3) & (nb3 - 1)] + rk[u];
+                    sk[o] = k;
+                    scn[o] = ic[i];
+                }
+            }
+            __syncthreads();
+            if (maxbin > 1) {
+                for (uint32_t bb = tid; bb < nb3; bb += THREADS) {
+                    const uint32_t cn = c3[bb];
+                    if (cn < 2) continue;
+                    const uint32_t s0 = s3[bb];
+                    for (uint32_t a = 1; a < cn; a++) {        // insertion sort of a handful of keys
+                        const Key<W> k = sk[s0 + a];
+                        const uint32_t c = scn[s0 + a];
+                        uint32_t q = a;
+                        while (q > 0 && key_lt<W>(k, sk[s0 + q - 1])) { sk[s0 + q] = sk[s0 + q - 1]; scn[s0 + q] = scn[s0 + q - 1]; q--; }
+                        sk[s0 + q] = k;
+                        scn[s0 + q] = c;
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            // crowded bins (keys sharing their next bits, or many copies of one key): bitonic network
+            // over the loaded arrays; pads are all-ones keys that sort behind a real all-ones key
+            rk_keys = ik;
+            rk_cnts = ic;
+            const uint32_t p2 = pow2_ceil_u32(n);
+            Key<W> pad;
+            key_set_ones<W>(pad);
+            for (uint32_t i = n + tid; i < p2; i += THREADS) { ik[i] = pad; ic[i] = 0; }
+            __syncthreads();
+            for (uint32_t size = 2; size <= p2; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t t = tid; t < (p2 >> 1); t += THREADS) {
+                        const uint32_t lo = 2 * t - (t & (stride - 1));
+                        const uint32_t hi = lo + stride;
+                        const bool up = (lo & size) == 0;
+                        const Key<W> a = ik[lo], bq = ik[hi];
+                        const uint32_t ca = ic[lo], cb = ic[hi];
+                        // order: key ascending, then count descending (real records before pads)
+                        const bool b_lt_a = key_lt<W>(bq, a) || (key_eq<W>(bq, a) && cb > ca);
+                        if (b_lt_a == up) {
+                            ik[lo] = bq; ik[hi] = a;
+                            ic[lo] = cb; ic[hi] = ca;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        if (!DUP) {
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                st_key<W>(p.out_keys, b + i, rk_keys[i]);
+                p.out_counts[b + i] = rk_cnts[i];
+            }
+        } else {
+            // fold: every record that equals its predecessor adds its count to the head of its group
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                if (i > 0 && key_eq<W>(rk_keys[i], rk_keys[i - 1])) {
+                    uint32_t hd = i - 1;
+                    while (hd > 0 && key_eq<W>(rk_keys[hd], rk_keys[hd - 1])) hd--;
+                    atomicAdd(&rk_cnts[hd], rk_cnts[i]);
+                }
+            }
+            __syncthreads();
+            // compaction of the heads, in order: warp ballots + running offset
+            for (uint32_t i0 = 0; i0 < n; i0 += THREADS) {
+                const uint32_t i = i0 + tid;
+                const bool head = i < n && (i == 0 || !key_eq<W>(rk_keys[i], rk_keys[i - 1]));
+                const uint32_t bal = __ballot_sync(0xffffffffu, head);
+                if (lane == 0) s_warp[warp] = __popc(bal);
+                __syncthreads();
+                uint32_t off = s_cnt;
+                for (uint32_t w = 0; w < warp; w++) off += s_warp[w];
+                if (head) {
+                    const uint32_t o = b + off + __popc(bal & lanemask_lt());
+                    st_key<W>(p.out_keys, o, rk_keys[i]);
+                    p.out_counts[o] = rk_cnts[i];
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t t = 0;
+                    for (int w = 0; w < THREADS / 32; w++) t += s_warp[w];
+                    s_cnt += t;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                p.m_out[j] = s_cnt;
+                folded_local += n - s_cnt;
+            }
+        }
+        __syncthreads();
+    }
+    if (DUP && tid == 0 && folded_local) atomicAdd(&p.sc[SW_FOLDED], folded_local);
+}
+
+// records of sub-bucket j: tmp[src[j] .. src[j] + m_j) -> out[off[j] ...); one warp per sub-bucket
+template <int W>
+__global__ void __launch_bounds__(256) sw_gather_kernel(const uint64_t *__restrict__ tmp_keys,
+                                                        const uint32_t *__restrict__ tmp_counts,
+                                                        const uint32_t *__restrict__ src,
+                                                        const uint32_t *__restrict__ off,
+                                                        const SuperPlanDev *__restrict__ plan,
+                                                        uint64_t *__restrict__ out_keys,
+                                                        uint32_t *__restrict__ out_counts) {
+    const uint32_t n_sub = plan->n_sub;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_sub; j += warps) {
+        const uint32_t o0 = off[j], m = off[j + 1] - o0;
+        const uint64_t s0 = src[j];
+        for (uint32_t i = lane; i < m; i += 32) {
+            st_key<W>(out_keys, o0 + i, ld_key<W>(tmp_keys, s0 + i));
+            out_counts[o0 + i] = tmp_counts[s0 + i];
+        }
+    }
+}
+
+inline uint64_t round512(uint64_t b) { return (b + 511) & ~511ull; }
+
+template <int W>
+struct FinishCfg { static constexpr int THREADS = 256, CAP = 2048; };
+
+}  // namespace
+
+// ------------------------------------------------------------------------ host
+bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out) {
+    if (k == 0 || k > 64 || L < k || L > 4096) return false;
+    SuperPlan pl{};
+    pl.W = (int)((k + 31) / 32);
+    pl.k = k;
+    pl.L = L;
+    const uint32_t mm = k % 32;
+    const bool masked = strict ? (mm != 0) : (mm >= 1 && mm <= 28);
+    pl.span = masked ? k : 32u * pl.W;
+    pl.last_mask = masked ? (~0ull << (64 - 2 * mm)) : ~0ull;
+    if (pl.span < 22) return false;
+    pl.m = 12;
+    pl.w = pl.span - pl.m + 1;
+    pl.nk = L - k + 1;
+    pl.nh = pl.nk + pl.w - 1;
+    pl.nh_stride = (pl.nh + 8) | 1u;                                   // odd stride: rows start in different banks
+    pl.seg_len = pl.w < (uint32_t)kSwMaxSeg ? pl.w : (uint32_t)kSwMaxSeg;
+    pl.segs_per_read = (pl.nk + pl.seg_len - 1) / pl.seg_len;
+    pl.seg_len = (pl.nk + pl.segs_per_read - 1) / pl.segs_per_read;    // even the segments out
+    pl.cmax = 32u * pl.W - 3;
+    if (max_windows == 0) max_windows = 1;
+    if (occ_per_bin == 0) occ_per_bin = 8192;
+    uint64_t nb = (max_windows + occ_per_bin - 1) / occ_per_bin;
+    if (nb < 8) nb = 8;
+    if (nb > (1ull << 24)) nb = 1ull << 24;
+    pl.n_bins = (uint32_t)nb;
+    // records per window: a new record whenever the minimizer changes (2 / (w + 1) of the windows for a
+    // random order), at every read start, and every cmax windows
+    const double rho = 2.0 / (pl.w + 1) + 1.2 / pl.nk + 1.0 / pl.cmax * 0.25;
+    const double est_total = (double)max_windows * rho;
+    const double per_bin = est_total / (double)pl.n_bins;
+    pl.bin_cap = (uint32_t)(per_bin * 2.0) + 64;          // minimizer weights make bins uneven (sd ~20% at the default size)
+    pl.bin_cap = (pl.bin_cap + 3) & ~3u;
+    pl.ovf_cap = (uint64_t)(est_total * 0.6) + 8192;
+    pl.ovf_slice = 4096;
+    pl.d_cap = max_windows < (1ull << 32) - 2 ? max_windows : (1ull << 32) - 2;
+    if (pl.d_cap < 1024) pl.d_cap = 1024;
+    // level 1: digits so that two levels reach sub-buckets of sub_target records even if every window is distinct
+    pl.sub_target = FinishCfg<1>::CAP * 7 / 10;
+    int B = 1;
+    while (B < 19 && (max_windows >> B) > pl.sub_target) B++;
+    pl.b1 = B - 9 < 4 ? (B < 4 ? B : 4) : B - 9;
+    if (pl.b1 > 10) pl.b1 = 10;
+    const int sig = pl.W == 1 ? (masked ? (int)(2 * mm) : 64) : 64;
+    if (pl.b1 > sig) pl.b1 = sig;
+    if (pl.b1 < 1) pl.b1 = 1;
+    // workspace
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { uint64_t r = o; o += round512(bytes); return r; };
+    const uint64_t rec_bytes = 16ull * pl.W;
+    pl.off_cursor = take((uint64_t)pl.n_bins * 4);
+    pl.off_hist1 = take((kNb1Max + 8) * 4);
+    pl.off_hist2 = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_base1 = take((kNb1Max + 8) * 4);
+    pl.off_cur1 = take((kNb1Max + 8) * 4);
+    pl.off_base2 = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_cur2 = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_mout = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_off = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_plan = take(sizeof(SuperPlanDev));
+    pl.off_bins = take((uint64_t)pl.n_bins * pl.bin_cap * rec_bytes);
+    pl.off_ovf = take(pl.ovf_cap * rec_bytes);
+    pl.off_dk = take(pl.d_cap * 8 * pl.W + 64);
+    pl.off_dc = take(pl.d_cap * 4 + 64);
+    pl.off_ek = take(pl.d_cap * 8 * pl.W + 64);
+    pl.off_ec = take(pl.d_cap * 4 + 64);
+    pl.ws_bytes = o;
+    *out = pl;
+    return true;
+}
+
+namespace {
+template <class T> T *at(void *ws, uint64_t off) { return reinterpret_cast<T *>(static_cast<uint8_t *>(ws) + off); }
+}  // namespace
+
+cudaError_t super_reset(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s) {
+    cudaError_t e;
+    // cursor, hist1, hist2 are contiguous at the start of the workspace
+    if ((e = cudaMemsetAsync(ws, 0, pl.off_base1, s)) != cudaSuccess) return e;
+    return cudaMemsetAsync(d_sc, 0, SW_COUNT * 8, s);
+}
+
+template <int W>
+static cudaError_t super_scatter_w(const SuperPlan &pl, const void *d_reads, uint64_t n_reads, bool strict, void *ws,
+                                   unsigned long long *d_sc, int n_sms, cudaStream_t s) {
+    static int tile_bytes = -1;                 // KC_SW_STAGE (development knob): bytes of reads per S1 tile
+    if (tile_bytes < 0) { const char *v = getenv("KC_SW_STAGE"); tile_bytes = v ? atoi(v) : 6400; }
+    SwScatterParams q{};
+    if (!extract_plan(d_reads, n_reads, pl.L, pl.k, strict, &d_sc[SW_INVALID], &q.ep, (uint32_t)tile_bytes))
+        return cudaErrorInvalidValue;
+    if (q.ep.n_tiles == 0) return cudaSuccess;
+    q.m = pl.m; q.w = pl.w; q.nh = pl.nh; q.nh_stride = pl.nh_stride;
+    q.seg_len = pl.seg_len; q.segs_per_read = pl.segs_per_read; q.cmax = pl.cmax;
+    q.h_off = (q.ep.smem_total + 15u) & ~15u;
+    q.bin_off = q.h_off + q.ep.tile_reads * pl.nh_stride * 4;
+    q.bits_off = q.bin_off + q.ep.tile_reads * pl.nk * 4;
+    const uint32_t smem = q.bits_off + (q.ep.tile_reads * pl.nk / 32 + 4) * 4;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    q.n_bins = pl.n_bins; q.bin_cap = pl.bin_cap; q.ovf_cap = pl.ovf_cap;
+    q.cursor = at<uint32_t>(ws, pl.off_cursor);
+    q.bins = at<uint8_t>(ws, pl.off_bins);
+    q.ovf = at<uint8_t>(ws, pl.off_ovf);
+    q.sc = d_sc;
+    auto kern = sw_scatter_kernel<W>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSwThreads, smem);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    uint32_t grid = (uint32_t)n_sms * per_sm;
+    if (grid > q.ep.n_tiles) grid = q.ep.n_tiles;
+    kern<<<grid, kSwThreads, smem, s>>>(q);
+    return cudaGetLastError();
+}
+
+// false when the shared-memory tile of S1 cannot hold even 16 reads of this length
+static bool super_scatter_fits(const SuperPlan &pl) {
+    ExtractParams ep;
+    if (!extract_plan(nullptr, 16, pl.L, pl.k, false, nullptr, &ep, 6400)) return false;
+    const uint64_t smem = ((ep.smem_total + 15u) & ~15u) + (uint64_t)ep.tile_reads * pl.nh_stride * 4 +
+                          (uint64_t)ep.tile_reads * pl.nk * 4 + (ep.tile_reads * pl.nk / 32 + 4) * 4;
+    return smem <= 200 * 1024;
+}
+
+cudaError_t super_scatter(const SuperPlan &pl, const void *d_reads, uint64_t n_reads, bool strict, void *ws,
+                          unsigned long long *d_sc, int n_sms, cudaStream_t s) {
+    if (pl.W == 1) return super_scatter_w<1>(pl, d_reads, n_reads, strict, ws, d_sc, n_sms, s);
+    if (pl.W == 2) return super_scatter_w<2>(pl, d_reads, n_reads, strict, ws, d_sc, n_sms, s);
+    return cudaErrorInvalidValue;
+}
+
+template <int W, int THREADS, int TSLOTS, int RPT = 2>
+static cudaError_t launch_count(const SwCountParams &cp, int n_sms, cudaStream_t s) {
+    const uint32_t smem = TSLOTS * (8 * W + 4) + THREADS * RPT * 16 * W + (THREADS * RPT + 8) * 4 + kNb1Max * 4;
+    auto kern = sw_count_kernel<W, THREADS, TSLOTS, RPT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    kern<<<(uint32_t)n_sms * per_sm, THREADS, smem, s>>>(cp);
+    return cudaGetLastError();
+}
+
+template <int W>
+static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                                 cudaStream_t s, cudaEvent_t *evs) {
+    cudaError_t e;
+    uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
+    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
+    uint32_t *hist1 = at<uint32_t>(ws, pl.off_hist1), *base1 = at<uint32_t>(ws, pl.off_base1),
+             *cur1 = at<uint32_t>(ws, pl.off_cur1), *hist2 = at<uint32_t>(ws, pl.off_hist2),
+             *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
+    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    // ---- S2
+    SwCountParams cp{};
+    cp.cursor = at<uint32_t>(ws, pl.off_cursor);
+    cp.bins = at<uint8_t>(ws, pl.off_bins);
+    cp.ovf = at<uint8_t>(ws, pl.off_ovf);
+    cp.n_bins = pl.n_bins; cp.bin_cap = pl.bin_cap; cp.ovf_slice = pl.ovf_slice; cp.ovf_cap = pl.ovf_cap;
+    cp.last_mask = pl.last_mask;
+    cp.d_keys = dk; cp.d_counts = dc; cp.d_cap = pl.d_cap;
+    cp.hist1 = hist1; cp.shift1 = 64 - pl.b1; cp.nb1 = 1 << pl.b1;
+    cp.add_phantom = add_phantom ? 1 : 0;
+    cp.sc = d_sc;
+    static int variant = -1;                    // KC_SW_COUNT (development knob): CTA / table shape of S2
+    if (variant < 0) { const char *v = getenv("KC_SW_COUNT"); variant = v ? atoi(v) : 0; }
+    if constexpr (W == 1) {
+        switch (variant) {
+            case 1: e = launch_count<1, 256, 2048, 2>(cp, n_sms, s); break;
+            case 2: e = launch_count<1, 512, 4096, 1>(cp, n_sms, s); break;
+            case 3: e = launch_count<1, 512, 8192, 1>(cp, n_sms, s); break;
+            case 4: e = launch_count<1, 128, 4096, 2>(cp, n_sms, s); break;
+            case 5: e = launch_count<1, 128, 2048, 2>(cp, n_sms, s); break;
+            case 6: e = launch_count<1, 256, 4096, 1>(cp, n_sms, s); break;
+            case 7: e = launch_count<1, 256, 4096, 4>(cp, n_sms, s); break;
+            default: e = launch_count<1, 256, 4096, 2>(cp, n_sms, s); break;
+        }
+    } else {
+        switch (variant) {
+            case 1: e = launch_count<2, 256, 2048, 1>(cp, n_sms, s); break;
+            case 2: e = launch_count<2, 256, 4096, 1>(cp, n_sms, s); break;
+            case 3: e = launch_count<2, 256, 4096, 2>(cp, n_sms, s); break;
+            default: e = launch_count<2, 512, 4096, 1>(cp, n_sms, s); break;
+        }
+    }
+    if (e != cudaSuccess) return e;
+    if (evs) cudaEventRecord(evs[0], s);
+    // ---- S3a: level-1 bases + device plan, scatter D -> E
+    const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
+    sw_plan_kernel<<<1, 1024, 0, s>>>(hist1, pl.b1, pl.d_cap, pl.sub_target, sig, base1, cur1, plan, d_sc);
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kNb1Max * 4;
+    {
+        auto k1 = rec_scatter_kernel<W, 1>;
+        auto k2 = rec_scatter_kernel<W, 2>;
+        if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kRsThreads, rs_smem);
+        if (per_sm < 1) per_sm = 1;
+        const uint32_t grid = (uint32_t)n_sms * per_sm;
+        k1<<<grid, kRsThreads, rs_smem, s>>>(dk, dc, ek, ec, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur1);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (evs) cudaEventRecord(evs[1], s);
+        // ---- level-2 histogram + scan (b2 == 0: one counter per level-1 bucket)
+        rec_hist2_kernel<W><<<(uint32_t)n_sms * 8, 256, 0, s>>>(ek, plan, hist2);
+        sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(hist2, &plan->n_sub, 0, base2, cur2, nullptr);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (evs) cudaEventRecord(evs[2], s);
+        // ---- S3b: scatter E -> D by the level-2 digit
+        k2<<<grid, kRsThreads, rs_smem, s>>>(ek, ec, dk, dc, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur2);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (evs) cudaEventRecord(evs[3], s);
+    }
+    return cudaSuccess;
+}
+
+cudaError_t super_count(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                        cudaStream_t s, cudaEvent_t *evs) {
+    if (pl.W == 1) return super_count_w<1>(pl, add_phantom, ws, d_sc, n_sms, s, evs);
+    if (pl.W == 2) return super_count_w<2>(pl, add_phantom, ws, d_sc, n_sms, s, evs);
+    return cudaErrorInvalidValue;
+}
+
+void super_tmp_buffers(const SuperPlan &pl, void *ws, uint64_t **tmp_keys, uint32_t **tmp_counts) {
+    *tmp_keys = at<uint64_t>(ws, pl.off_ek);
+    *tmp_counts = at<uint32_t>(ws, pl.off_ec);
+}
+
+template <int W, bool DUP>
+static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
+                                  uint32_t *out_counts, int n_sms, cudaStream_t s) {
+    constexpr int THREADS = FinishCfg<W>::THREADS, CAP = FinishCfg<W>::CAP;
+    FinishParams fp{};
+    fp.in_keys = at<uint64_t>(ws, pl.off_dk);
+    fp.in_counts = at<uint32_t>(ws, pl.off_dc);
+    fp.base2 = at<uint32_t>(ws, pl.off_base2);
+    fp.plan = at<SuperPlanDev>(ws, pl.off_plan);
+    fp.out_keys = out_keys;
+    fp.out_counts = out_counts;
+    fp.m_out = at<uint32_t>(ws, pl.off_mout);
+    fp.sc = d_sc;
+    const uint32_t smem = 2 * CAP * (8 * W + 4) + 2 * CAP * 4;
+    auto kern = rec_finish_kernel<W, THREADS, CAP, DUP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    kern<<<(uint32_t)n_sms * per_sm, THREADS, smem, s>>>(fp);
+    return cudaGetLastError();
+}
+
+cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
+                         uint32_t *out_counts, int n_sms, cudaStream_t s) {
+    if (pl.W == 1) return dup ? super_finish_w<1, true>(pl, ws, d_sc, out_keys, out_counts, n_sms, s)
+                              : super_finish_w<1, false>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    if (pl.W == 2) return dup ? super_finish_w<2, true>(pl, ws, d_sc, out_keys, out_counts, n_sms, s)
+                              : super_finish_w<2, false>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t super_fold_offsets(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s) {
+    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(
+        at<uint32_t>(ws, pl.off_mout), &plan->n_sub, 0, at<uint32_t>(ws, pl.off_off), nullptr, &d_sc[SW_OUT]);
+    return cudaGetLastError();
+}
+
+cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys, const uint32_t *tmp_counts,
+                         uint64_t *out_keys, uint32_t *out_counts, int n_sms, cudaStream_t s) {
+    const SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    const uint32_t *src = at<uint32_t>(ws, pl.off_base2), *off = at<uint32_t>(ws, pl.off_off);
+    if (pl.W == 1) sw_gather_kernel<1><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
+    else sw_gather_kernel<2><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
+    return cudaGetLastError();
+}
+
+bool super_supported(const SuperPlan &pl) { return super_scatter_fits(pl); }
+
+}  // namespace kc

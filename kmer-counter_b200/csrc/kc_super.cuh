@@ -1,0 +1,102 @@
+// kc_super.cuh -- plan and launchers of the super-window counting path (kc_super.cu).
+//
+// The path replaces extractKMers + the TBB accumulate + sortKmers + reduceKMers
+// (GPUHandler.cu:129-360, KMerCounter.cpp:61-82) for one chunk -- or for many chunks
+// accumulated into the same bins -- without ever writing a key per k-mer occurrence to
+// HBM:
+//
+//   S1  reads -> 2-bit "super-window" records.  Consecutive k-mer windows of a read whose
+//       minimizer (smallest hashed m-mer inside the window) falls into the same bin are
+//       packed into ONE 16W-byte record (first window + following bases + window count);
+//       a record is appended to its bin.  ~1.6 bytes per k-mer occurrence instead of 8W.
+//   S2  one CTA per bin: the records are expanded in shared memory and every window is
+//       inserted into a shared-memory open-addressing table (equal keys always share a bin,
+//       because the bin is a function of the key).  The distinct (key, count) records of the
+//       bin are appended to a dense array D.
+//   S3  D (U records, not N occurrences) is put into key order: two most-significant-digit
+//       scatter passes and a shared-memory sort per sub-bucket, written straight into the run.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kc_extract.cuh"
+
+namespace kc {
+
+// device scalars of one super-window pipeline (unsigned long long each)
+enum {
+    SW_INVALID = 0,     // k-mer slots without a k-mer
+    SW_OVF = 1,         // records appended to the overflow list (may exceed its capacity)
+    SW_D = 2,           // records appended to D (may exceed its capacity)
+    SW_FAIL = 3,        // bit 0: overflow list full, bit 1: D full, bit 2: a bin could not be split,
+                        // bit 3: a sub-bucket does not fit shared memory
+    SW_TICKET = 4,      // S2 work ticket
+    SW_WINDOWS = 5,     // windows packed into records by S1 (debug invariant: == slots - invalid)
+    SW_OCC = 6,         // occurrences counted by S2 (debug invariant)
+    SW_ABORTS = 7,      // bin passes S2 had to split
+    SW_FOLDED = 8,      // duplicate records folded by S3c
+    SW_OUT = 9,         // records in the run (DUP mode: after folding)
+    SW_RECORDS = 10,    // records S1 wrote (bins + overflow)
+    SW_TICKET2 = 11,    // S3c work ticket
+    SW_COUNT = 16
+};
+
+struct SuperPlanDev {           // level-2 plan, decided on the device once |D| is known
+    uint32_t n_d;               // records in D (clamped to capacity)
+    uint32_t b2, shift2, n_sub; // level-2 digit bits, key shift of the (b1+b2)-bit prefix, sub-buckets
+    uint32_t prefix_bits;
+    uint32_t pad[3];
+};
+
+struct SuperPlan {
+    int W;
+    uint32_t k, L, span;        // span = bases that make up a key (32W or k)
+    uint32_t m, w;              // minimizer length, m-mers per window (span - m + 1)
+    uint32_t nk, nh, nh_stride; // windows per read, m-mer positions per read (nk + w - 1), smem row stride
+    uint32_t seg_len, segs_per_read;
+    uint32_t cmax;              // most windows one record holds (32W - 3)
+    uint32_t n_bins, bin_cap;   // bins and records per bin
+    uint64_t ovf_cap;           // records of the shared overflow list
+    uint32_t ovf_slice;         // overflow records per S2 work unit
+    uint64_t d_cap;             // records D / the level buffers hold
+    int b1;                     // level-1 digit bits (nb1 = 1 << b1 <= 1024)
+    uint32_t sub_target;        // records per sub-bucket the level-2 plan aims for
+    uint64_t last_mask;
+    // workspace layout (bytes from the workspace base)
+    uint64_t off_cursor, off_bins, off_ovf, off_hist1, off_base1, off_cur1, off_hist2, off_base2, off_cur2,
+        off_mout, off_off, off_plan, off_dk, off_dc, off_ek, off_ec, ws_bytes;
+};
+
+constexpr uint32_t kSuperMaxSub = 1u << 20;
+
+// Plans a pipeline for up to max_windows k-mer slots (one chunk, or everything that will be
+// accumulated before the count). occ_per_bin = 0 -> default. Returns false for shapes the path
+// does not take (W > 2, span < 22, reads too long for the shared-memory tile).
+bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out);
+
+// zero cursors, histograms and scalars: once before the first super_scatter of a pipeline
+cudaError_t super_reset(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s);
+// S1: append the super-window records of (reads, n_reads) to the bins
+cudaError_t super_scatter(const SuperPlan &pl, const void *d_reads, uint64_t n_reads, bool strict, void *ws,
+                          unsigned long long *d_sc, int n_sms, cudaStream_t s);
+// S2 .. S3b: count the bins, place the distinct records into sub-buckets. evs (may be NULL):
+// events recorded after S2, S3a, H2, S3b.
+cudaError_t super_count(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                        cudaStream_t s, cudaEvent_t *evs);
+// S3c once the host knows |D| (= *d_sc[SW_D]) : sort every sub-bucket into (out_keys, out_counts).
+// dup == false: the records are distinct, the output is dense and final (n_d records).
+// dup == true : equal keys are folded; the output has gaps, m_out/off describe it; finish with super_gather.
+cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
+                         uint32_t *out_counts, int n_sms, cudaStream_t s);
+// DUP mode: after super_finish, offsets of the survivors (d_sc[SW_OUT] = records) ...
+cudaError_t super_fold_offsets(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s);
+// ... and the gather that closes the gaps
+cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys, const uint32_t *tmp_counts,
+                         uint64_t *out_keys, uint32_t *out_counts, int n_sms, cudaStream_t s);
+// false when S1's shared-memory tile cannot hold 16 reads of this length
+bool super_supported(const SuperPlan &pl);
+// where S3c's temporary output may live in DUP mode (the level-1 buffer is dead by then)
+void super_tmp_buffers(const SuperPlan &pl, void *ws, uint64_t **tmp_keys, uint32_t **tmp_counts);
+
+}  // namespace kc

@@ -11,7 +11,12 @@ STAGE_NAMES = {
     "sort": ["extract", "digit_histogram", "radix_scatter_passes", "run_length", "emit"],
     "hash": ["level1_histogram", "extract_scatter1", "level2_histogram", "scatter2", "smem_count_sort_write", "emit"],
     "hash_global": ["table_clear", "extract_insert", "compact_sort", "emit"],
+    "super": ["encode_minimizer_scatter", "smem_count_per_bin", "record_scatter1", "record_hist2", "record_scatter2",
+              "smem_sort_write"],
 }
+
+SW_SCALARS = ["invalid", "overflow_records", "d_records", "fail", "ticket", "windows", "occurrences", "aborts", "folded",
+              "out_records", "records", "ticket2"]
 
 
 class KcError(RuntimeError):
@@ -150,6 +155,12 @@ class Counter:
         d["stage_launches"] = [int(x) for x in st.stage_launches][:n]
         d["stage_names"] = (names + ["stage%d" % i for i in range(len(names), n)])[:n]
         return d
+
+    def debug_scalars(self) -> dict:
+        """Device scalars of the most recent chunk (super-window path: SW_* of kc_super.cuh)."""
+        out = (C.c_uint64 * 16)()
+        self._check(self._lib.kc_debug_scalars(self._ctx, out))
+        return {name: int(out[i]) for i, name in enumerate(SW_SCALARS)}
 
     def host_alloc(self, nbytes) -> np.ndarray:
         """Pinned host buffer as a uint8 array (freed with host_free)."""

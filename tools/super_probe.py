@@ -1,0 +1,120 @@
+"""GPU probe for the super-window path: parity cases against the oracle with the pipeline's
+device scalars printed, then a timed C2-shaped run. Development tool (gpurun), not a test."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+import kmer_counter_b200 as kc  # noqa: E402
+
+
+def diff(got, want, S):
+    g = np.frombuffer(got, dtype=np.uint8).reshape(-1, S) if len(got) % S == 0 else None
+    w = np.frombuffer(want, dtype=np.uint8).reshape(-1, S)
+    if g is None:
+        return "got %d bytes (not a multiple of %d)" % (len(got), S)
+    msg = "records got %d want %d" % (len(g), len(w))
+    n = min(len(g), len(w))
+    neq = np.nonzero((g[:n] != w[:n]).any(axis=1))[0]
+    if len(neq):
+        i = int(neq[0])
+        msg += "; first diff at %d: got %s want %s" % (i, g[i].tobytes().hex(), w[i].tobytes().hex())
+        gs = sum(int.from_bytes(r[-4:].tobytes(), "little") for r in g)
+        ws = sum(int.from_bytes(r[-4:].tobytes(), "little") for r in w)
+        msg += "; count sums got %d want %d" % (gs, ws)
+    return msg
+
+
+def case(R, L, k, G, e, n, seed=None, compat="ref", reads=None, **kw):
+    if reads is None:
+        reads = oracle.gen_reads(R, L, G, e, n, seed=seed if seed is not None else R + k)
+    if compat == "ref":
+        want = oracle.process_chunk(reads, L, k)
+    else:
+        want = oracle.naive_count(reads, L, k, strict=True)
+    with kc.Counter(k, L, method="super", compat=compat, n_slots=2, max_chunk_bytes=max(len(reads), 1 << 20), **kw) as c:
+        got = c.process_chunk(reads)
+        st = c.stats()
+        sc = c.debug_scalars()
+    ok = got == want
+    print("%s R=%d L=%d k=%d G=%d e=%g n=%g %s method=%s %s" % (
+        "ok  " if ok else "FAIL", len(reads) // L, L, k, G, e, n, kw or "", st["method_used"],
+        "" if ok else diff(got, want, 8 * ((k + 31) // 32) + 4)), flush=True)
+    if not ok or os.environ.get("VERBOSE"):
+        print("     scalars", sc, flush=True)
+    return ok
+
+
+def main():
+    ok = True
+    ok &= case(2000, 100, 31, 30000, 0.0, 0.0)
+    ok &= case(2000, 100, 31, 30000, 0.01, 0.002)
+    ok &= case(1500, 100, 32, 20000, 0.01, 0.001)
+    ok &= case(1500, 100, 28, 20000, 0.0, 0.001)
+    ok &= case(1500, 100, 29, 20000, 0.0, 0.001)
+    ok &= case(700, 70, 63, 5000, 0.001, 0.001)
+    ok &= case(700, 70, 60, 5000, 0.001, 0.001)
+    ok &= case(500, 41, 33, 0, 0.0, 0.01)
+    ok &= case(257, 33, 33, 0, 0.0, 0.0)
+    ok &= case(1000, 133, 31, 8000, 0.002, 0.0)
+    ok &= case(6000, 100, 31, 0, 0.0, 0.001, seed=77)                       # iid: all distinct
+    ok &= case(6000, 100, 31, 0, 0.0, 0.001, seed=77, table_slots=64)       # tiny bins
+    ok &= case(6000, 100, 31, 0, 0.0, 0.001, seed=77, table_slots=100000)   # bins beyond the table: split passes
+    ok &= case(2000, 100, 31, 30000, 0.01, 0.002, compat="strict")
+    L = 100
+    hot = oracle.gen_reads(3, L, 0, 0, 0, seed=5)
+    for reps, kk in ((4000, 31), (30000, 31), (30000, 63)):
+        reads = np.concatenate([np.tile(hot, reps), oracle.gen_reads(2000, L, 50000, 0.01, 0.001, seed=6)])
+        ok &= case(0, L, kk, 0, 0, 0, reads=reads)
+    reads = np.frombuffer((b"A" * 69) * 30 + (b"T" * 69) * 20 + (b"A" * 40 + b"N" + b"A" * 28) * 3, dtype=np.uint8)
+    ok &= case(0, 69, 31, 0, 0, 0, reads=reads)
+    ok &= case(0, 50, 31, 0, 0, 0, reads=np.frombuffer(b"N" * (50 * 40), dtype=np.uint8))
+    ok &= case(100000, 100, 31, 1000000, 0.0, 0.001, seed=1)                # C1
+    ok &= case(200000, 100, 63, 2000000, 0.001, 0.0, seed=3)
+    os.environ["KC_SW_FORCE_DUP"] = "1"
+    print("forced folding path:")
+    ok &= case(2000, 100, 31, 30000, 0.01, 0.002)
+    ok &= case(100000, 100, 31, 1000000, 0.0, 0.001, seed=1)
+    ok &= case(700, 70, 63, 5000, 0.001, 0.001)
+    print("ALL OK" if ok else "SOME FAILED", flush=True)
+
+    # timing, C2 shape
+    if len(sys.argv) > 1 and sys.argv[1] == "time":
+        import torch
+        from kmer_counter_b200 import synth
+        R, L, k = 10_000_000, 100, 31
+        dev = torch.device("cuda", 0)
+        d_reads = torch.empty(R * L + 256, dtype=torch.uint8, device=dev)
+        synth.synth_reads_device(d_reads.data_ptr(), R, L, 100_000_000, 1e-3, 0.0, 2)
+        torch.cuda.synchronize()
+        for method in ("super", "hash"):
+            with kc.Counter(k, L, method=method) as c:
+                for i in range(4):
+                    t0 = time.perf_counter()
+                    run = c.count_device(d_reads.data_ptr(), R * L)
+                    dt = time.perf_counter() - t0
+                    n = len(run)
+                    run.free()
+                st = c.stats()
+                print(method, "records", n, "wall ms %.2f" % (dt * 1e3), "ms_total %.2f" % st["ms_total"],
+                      dict(zip(st["stage_names"], [round(x, 3) for x in st["ms_stage"]])), flush=True)
+                if method == "super":
+                    print("   scalars", c.debug_scalars(), flush=True)
+        # digest check between the two methods on the full C2 input
+        import hashlib
+        digs = []
+        for method in ("super", "hash"):
+            with kc.Counter(k, L, method=method) as c:
+                run = c.count_device(d_reads.data_ptr(), R * L)
+                digs.append(hashlib.sha256(run.to_bytes()).hexdigest())
+                run.free()
+        print("C2 full-size super == hash:", digs[0] == digs[1], digs[0][:16], flush=True)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
