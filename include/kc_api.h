@@ -152,6 +152,53 @@ int  kc_wait(kc_ctx *ctx, uint32_t slot, kc_run **run);   /* caller owns *run (m
 /* Device-resident input (d_reads: device pointer, 16-byte aligned). */
 int  kc_count_device(kc_ctx *ctx, const void *d_reads, uint64_t n_bytes, kc_run **run);
 
+/* ---- accumulating mode: many chunks, one count ----
+ * The reference turns every chunk into a run file and merges the files (KMerCounter.cpp:51-89 +
+ * KMerFileMergeHandler). Here a chunk can instead be packed into 2-bit super-window records that
+ * are appended to minimizer bins resident in HBM (about 1.7 bytes per k-mer occurrence); the count
+ * happens once, over everything accumulated, in kc_accum_flush. The result is the same artefact as
+ * counting the chunks separately and merging their runs. Needs k <= 64 with windows of >= 22 bases.
+ *   kc_accum_begin(ctx, expected_reads)   plan + allocate for that many reads (at least one chunk);
+ *                                         more reads than planned are handled by counting what has
+ *                                         accumulated into a part first (parts are merged by the flush)
+ *   kc_accum_add_device / kc_accum_submit / kc_accum_submit_fastq
+ *                                         device-resident reads / the slot's pinned buffer / raw FASTQ
+ *                                         text (as kc_submit_fastq); asynchronous
+ *   kc_accum_wait(ctx, slot)              the slot's buffers may be refilled
+ *   kc_accum_flush(ctx, &run)             count -> sorted unique run; the bins are empty again */
+int  kc_accum_begin(kc_ctx *ctx, uint64_t expected_reads);
+int  kc_accum_add_device(kc_ctx *ctx, const void *d_reads, uint64_t n_bytes);
+int  kc_accum_submit(kc_ctx *ctx, uint32_t slot, uint64_t n_bytes);
+int  kc_accum_submit_fastq(kc_ctx *ctx, uint32_t slot, const void *host_text, uint64_t n_bytes,
+                           uint64_t *consumed, uint32_t *flags);
+int  kc_accum_wait(kc_ctx *ctx, uint32_t slot);
+int  kc_accum_flush(kc_ctx *ctx, kc_run **run);
+
+/* ---- multi-GPU: hash-partitioned by key range, one context per GPU ("rank") ----
+ * The reference has one implicit device. Here up to 8 contexts -- in one process
+ * (kc_xchg_run_all, the command line's gpus=N) or one process per GPU (handles exchanged through
+ * any host channel) -- each accumulate their share of the reads (kc_accum_add_device /
+ * kc_accum_submit after kc_xchg_begin), count it locally, and then exchange DISTINCT (key, count)
+ * records by key range: the ranges are cut from an all-gathered 1024-bin histogram so that every
+ * rank receives about the same number of records, and rank r ends with the sorted unique records
+ * of the r-th range -- the artefact is the concatenation in rank order. The exchange is fused into
+ * the placement kernel: its loads read the peers' grouped records over NVLink / NVSwitch.
+ * Order of calls on every rank, B = a barrier across ranks that the caller provides (stream-ordered
+ * is enough: an event wait or a tiny NCCL all-reduce on the context's stream):
+ *   kc_xchg_count_local -> all-gather of kc_xchg_hist's 1024 uint32 into its n_ranks x 1024 buffer
+ *   -> kc_xchg_group_local -> B -> kc_xchg_pull -> B -> kc_xchg_finish. */
+int  kc_xchg_begin(kc_ctx *ctx, uint32_t rank, uint32_t n_ranks, uint64_t expected_reads);
+int  kc_xchg_export(kc_ctx *ctx, void *handle64);                       /* CUDA IPC handle of this rank's workspace */
+int  kc_xchg_import(kc_ctx *ctx, uint32_t peer, const void *handle64);  /* a peer in another process               */
+int  kc_xchg_set_peer(kc_ctx *ctx, uint32_t peer, kc_ctx *peer_ctx);    /* a peer in this process                  */
+int  kc_xchg_count_local(kc_ctx *ctx);
+int  kc_xchg_hist(kc_ctx *ctx, void **d_hist, void **d_all_hist);
+int  kc_xchg_group_local(kc_ctx *ctx);
+int  kc_xchg_pull(kc_ctx *ctx);
+int  kc_xchg_finish(kc_ctx *ctx, kc_run **run);
+/* all ranks in this process: everything above, ordered by events; runs[r] = rank r's key range */
+int  kc_xchg_run_all(kc_ctx *const *ctxs, uint32_t n, kc_run **runs);
+
 /* ---- raw FASTQ chunks: replaces FASTQFileReader::readData (FASTQFileReader.cpp:49-89) ----
  * The text must start at a record boundary and be well formed (4 lines per record, the
  * line after the sequence starts with '+', every sequence read_len long); the parse runs

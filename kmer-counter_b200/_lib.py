@@ -54,6 +54,22 @@ SYMBOLS = {
     "kc_sync": (_i, [_vp]),
     "kc_stats_get": (_i, [_vp, C.POINTER(KcStats)]),
     "kc_debug_scalars": (_i, [_vp, _pu64]),
+    "kc_accum_begin": (_i, [_vp, _u64]),
+    "kc_accum_add_device": (_i, [_vp, _vp, _u64]),
+    "kc_accum_submit": (_i, [_vp, _u32, _u64]),
+    "kc_accum_submit_fastq": (_i, [_vp, _u32, _vp, _u64, _pu64, C.POINTER(C.c_uint32)]),
+    "kc_accum_wait": (_i, [_vp, _u32]),
+    "kc_accum_flush": (_i, [_vp, _pp]),
+    "kc_xchg_begin": (_i, [_vp, _u32, _u32, _u64]),
+    "kc_xchg_export": (_i, [_vp, _vp]),
+    "kc_xchg_import": (_i, [_vp, _u32, _vp]),
+    "kc_xchg_set_peer": (_i, [_vp, _u32, _vp]),
+    "kc_xchg_count_local": (_i, [_vp]),
+    "kc_xchg_hist": (_i, [_vp, _pp, _pp]),
+    "kc_xchg_group_local": (_i, [_vp]),
+    "kc_xchg_pull": (_i, [_vp]),
+    "kc_xchg_finish": (_i, [_vp, _pp]),
+    "kc_xchg_run_all": (_i, [_pp, _u32, _pp]),
     "kc_host_alloc": (_i, [_vp, _u64, _pp]),
     "kc_host_free": (_i, [_vp, _vp]),
     "kc_process_chunk": (_i, [_vp, _u32, _vp, _u64, _vp, _u64, _pu64]),

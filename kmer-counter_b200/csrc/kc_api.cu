@@ -88,6 +88,29 @@ struct kc_ctx {
     uint64_t copy_cap = 0;
     std::vector<Slot> slots;
     Pending direct;              // kc_count_device / kc_process_chunk without slots use this
+    // Accumulating mode (kc_accum_*): chunks are only packed into super-window records; one count at the end
+    struct Accum {
+        bool on = false;
+        SuperPlan pl{};
+        void *ws = nullptr;                  // plain cudaMalloc, owned
+        uint64_t ws_bytes = 0;
+        unsigned long long *d_sc = nullptr, *h_sc = nullptr;
+        uint64_t windows = 0, reads = 0;     // accumulated since the last reset
+        uint64_t max_windows = 0;            // what the plan was made for
+        uint64_t ovf_reserved = 0;           // overflow records that chunks queued so far may still produce
+        std::vector<kc_run *> parts;         // runs of earlier automatic flushes
+        cudaEvent_t ev[8] = {};
+        bool fresh = true;                   // bins are empty
+        // multi-GPU exchange (kc_xchg_*): this context is rank `rank` of `n_ranks`
+        bool xchg = false;
+        uint32_t rank = 0, n_ranks = 1;
+        void *peer_ws[8] = {};               // the ranks' workspaces as mapped into this device
+        bool peer_ipc[8] = {};               // opened with cudaIpcOpenMemHandle (to be closed)
+        uint32_t *d_all_hist = nullptr;      // n_ranks x 1024, filled by the caller's all-gather
+        float ms_scatter = 0;
+        uint64_t n_scatter = 0;
+    } acc;
+    std::recursive_mutex direct_mu;   // calls that take no slot (they share `direct`, its arena and `stream`) are serialised
     std::mutex mu;
     kc_stats stats{};
     unsigned long long last_scal[SC_COUNT] = {0};   // device scalars of the most recent chunk (kc_debug_scalars)
@@ -211,9 +234,20 @@ uint32_t pick_method(const kc_ctx *c) {
     return m;
 }
 
-// Queue extraction + counting of one chunk on stream s. Nothing is synchronised.
+int count_enqueue_impl(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, uint32_t method);
+
+// Queue extraction + counting of one chunk on stream s. Nothing is synchronised. A chunk that
+// could not be queued leaves the slot idle (not "in flight"): the next submit works, a wait says
+// KC_ERR_STATE.
 int count_enqueue(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, uint32_t method) {
+    const int rc = count_enqueue_impl(c, p, d_reads, n_bytes, s, method);
+    if (rc != KC_OK) pending_release(s, p);
+    return rc;
+}
+
+int count_enqueue_impl(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, uint32_t method) {
     KC_TRY(pending_init(c, p));
+    memset(p.h_scal, 0, SC_COUNT * 8);            // an empty chunk copies nothing back: no stale counters
     const uint32_t L = c->cfg.read_len, k = c->cfg.k;
     const int W = c->W;
     p.n_reads = n_bytes / L;
@@ -579,7 +613,12 @@ int count_finish_hash_global(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out
 
 int check_ctx(const kc_ctx *c) { return c ? KC_OK : KC_ERR_ARG; }
 
+void accum_free(kc_ctx *c);
+
 }  // namespace
+
+static int slot_upload_parse(kc_ctx *c, Slot &sl, const void *host_text, uint64_t n_bytes, uint64_t *n_reads,
+                             uint64_t *used, uint32_t *fl);
 
 // ---------------------------------------------------------------------- library
 extern "C" {
@@ -663,6 +702,7 @@ void kc_destroy(kc_ctx *c) {
     }
     pending_release(c->stream, c->direct);
     pending_destroy(c->direct);
+    accum_free(c);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->copy_buf) cudaFree(c->copy_buf);
@@ -710,9 +750,484 @@ int kc_host_free(kc_ctx *c, void *p) {
     return KC_OK;
 }
 
+}  // extern "C"
+
+// -------------------------------------------------------------------- accumulate
+namespace {
+
+void accum_free(kc_ctx *c) {
+    kc_ctx::Accum &a = c->acc;
+    for (int i = 0; i < 8; i++)
+        if (a.peer_ipc[i] && a.peer_ws[i]) cudaIpcCloseMemHandle(a.peer_ws[i]);
+    if (a.d_all_hist) cudaFree(a.d_all_hist);
+    if (a.ws) cudaFree(a.ws);
+    if (a.d_sc) cudaFree(a.d_sc);
+    if (a.h_sc) cudaFreeHost(a.h_sc);
+    for (auto &e : a.ev) if (e) cudaEventDestroy(e);
+    for (kc_run *r : a.parts) kc_run_free(c, r);
+    a = kc_ctx::Accum();
+}
+
+// Counts what the bins hold into one run (S2 .. S3c) and empties them. All slot streams are
+// drained first. An empty accumulator gives an empty run.
+int accum_finish(kc_ctx *c, bool force_dup, kc_run **out);
+
+int accum_count(kc_ctx *c, kc_run **out) {
+    kc_ctx::Accum &a = c->acc;
+    cudaStream_t s = c->stream;
+    *out = nullptr;
+    for (auto &sl : c->slots)
+        if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+    if (a.fresh) return make_run(c, s, 0, out);
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[0], s));
+    KC_CUDA_TRY(c, super_count(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s, &a.ev[1]));
+    return accum_finish(c, false, out);
+}
+
+// The sub-buckets are in place (S3b done or queued on the context's stream): sort them into a run
+// (folding equal keys if records may repeat), account, empty the bins.
+int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
+    kc_ctx::Accum &a = c->acc;
+    cudaStream_t s = c->stream;
+    *out = nullptr;
+    KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (a.h_sc[SW_FAIL])
+        return c->set_error(KC_ERR_CAPACITY, "accumulated input does not fit the plan (fail bits %llu): flush more often or "
+                            "raise the expected read count", (unsigned long long)a.h_sc[SW_FAIL]);
+    const uint64_t n_d = a.h_sc[SW_D];
+    const bool dup = force_dup || a.h_sc[SW_OVF] != 0;
+    kc_run *r = nullptr;
+    if (!dup) {
+        KC_TRY(make_run(c, s, n_d, &r));
+        if (n_d) KC_CUDA_TRY(c, super_finish(a.pl, false, a.ws, a.d_sc, r->d_keys, r->d_counts, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaEventRecord(a.ev[5], s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    } else {
+        uint64_t *tk = nullptr;
+        uint32_t *tc = nullptr;
+        super_tmp_buffers(a.pl, a.ws, &tk, &tc);
+        KC_CUDA_TRY(c, super_finish(a.pl, true, a.ws, a.d_sc, tk, tc, c->n_sms, s));
+        KC_CUDA_TRY(c, super_fold_offsets(a.pl, a.ws, a.d_sc, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (!a.h_sc[SW_FAIL]) {
+            KC_TRY(make_run(c, s, a.h_sc[SW_OUT], &r));
+            if (r->n) KC_CUDA_TRY(c, super_gather(a.pl, a.ws, tk, tc, r->d_keys, r->d_counts, c->n_sms, s));
+        }
+        KC_CUDA_TRY(c, cudaEventRecord(a.ev[5], s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    }
+    if (a.h_sc[SW_FAIL]) {
+        if (r) kc_run_free(c, r);
+        return c->set_error(KC_ERR_CAPACITY, "a key range of the accumulated input does not fit shared memory (fail bits %llu)",
+                            (unsigned long long)a.h_sc[SW_FAIL]);
+    }
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        kc_stats &st = c->stats;
+        memcpy(c->last_scal, a.h_sc, sizeof c->last_scal);
+        const uint64_t U = r->n, Kb = 8ull * c->W, ub = U * (Kb + 4), rec = a.h_sc[SW_RECORDS] * 16ull * c->W;
+        st.chunks++;
+        st.kmer_slots += a.windows;
+        st.kmers_valid += a.windows - a.h_sc[SW_INVALID];
+        st.reads += a.reads;
+        st.distinct_last = U;
+        st.method_used = KC_COUNT_SUPER;
+        st.launches += dup ? 11 : 9;
+        st.n_stages = 6;
+        for (int i = 0; i < 8; i++) { st.ms_stage[i] = 0; st.stage_bytes[i] = 0; st.stage_launches[i] = 0; }
+        st.ms_stage[0] = a.ms_scatter;                       // summed over the chunks' S1 launches
+        for (int i = 1; i < 6; i++) cudaEventElapsedTime(&st.ms_stage[i], a.ev[i - 1], a.ev[i]);
+        st.ms_total = 0;
+        for (int i = 0; i < 6; i++) st.ms_total += st.ms_stage[i];
+        st.stage_bytes[0] = a.reads * c->cfg.read_len + rec;   st.stage_launches[0] = (uint32_t)a.n_scatter;
+        st.stage_bytes[1] = rec + ub;                           st.stage_launches[1] = 1;
+        st.stage_bytes[2] = 2 * ub;                             st.stage_launches[2] = 1;
+        st.stage_bytes[3] = U * Kb;                             st.stage_launches[3] = 1;
+        st.stage_bytes[4] = 2 * ub;                             st.stage_launches[4] = 1;
+        st.stage_bytes[5] = 2 * ub;                             st.stage_launches[5] = 1;
+        int dom = 0;
+        for (int i = 1; i < 6; i++) if (st.ms_stage[i] > st.ms_stage[dom]) dom = i;
+        st.dominant_stage = (uint32_t)dom;
+        st.ms_dominant = st.ms_stage[dom];
+        st.dominant_bytes = st.stage_bytes[dom];
+        st.dominant_launches = st.stage_launches[dom] ? st.stage_launches[dom] : 1;
+        st.ms_extract = st.ms_stage[0];
+        st.ms_emit = st.ms_stage[5];
+        st.ms_count = st.ms_total - st.ms_extract - st.ms_emit;
+    }
+    // empty bins for whatever comes next
+    KC_CUDA_TRY(c, super_reset(a.pl, a.ws, a.d_sc, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    a.fresh = true;
+    a.windows = a.reads = 0;
+    a.ovf_reserved = 0;
+    a.ms_scatter = 0;
+    a.n_scatter = 0;
+    *out = r;
+    return KC_OK;
+}
+
+// Room check before a chunk of n_reads joins the bins: the chunk may need up to one record per
+// window in the overflow list (no read is ever dropped); if that or the plan's window budget is
+// not there, what has been accumulated is counted into a part first.
+int accum_make_room(kc_ctx *c, uint64_t n_reads) {
+    kc_ctx::Accum &a = c->acc;
+    const uint64_t nk = c->cfg.read_len - c->cfg.k + 1, w = n_reads * nk;
+    if (w > a.pl.ovf_cap || w > a.max_windows)
+        return c->set_error(KC_ERR_CAPACITY, "chunk of %llu reads exceeds what the accumulator was planned for", (unsigned long long)n_reads);
+    if (a.windows + w > a.max_windows || a.ovf_reserved + w > a.pl.ovf_cap) {
+        if (a.xchg) return c->set_error(KC_ERR_CAPACITY, "more reads than kc_xchg_begin planned for (%llu k-mer slots)", (unsigned long long)a.max_windows);
+        kc_run *part = nullptr;
+        KC_TRY(accum_count(c, &part));
+        a.parts.push_back(part);
+    }
+    return KC_OK;
+}
+
+// S1 of one chunk on stream s, timed
+int accum_scatter(kc_ctx *c, const void *d_reads, uint64_t n_reads, cudaStream_t s) {
+    kc_ctx::Accum &a = c->acc;
+    if (n_reads == 0) return KC_OK;
+    KC_CUDA_TRY(c, super_scatter(a.pl, d_reads, n_reads, c->strict, a.ws, a.d_sc, c->n_sms, s));
+    const uint64_t nk = c->cfg.read_len - c->cfg.k + 1;
+    a.fresh = false;
+    a.windows += n_reads * nk;
+    a.reads += n_reads;
+    // the overflow list only ever takes what the bins refuse; without looking at the device
+    // counters the host has to assume the worst for chunks still in flight
+    a.ovf_reserved += n_reads * nk;
+    a.n_scatter++;
+    return KC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kc_accum_begin(kc_ctx *c, uint64_t expected_reads) {
+    KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    cudaSetDevice(c->cfg.device);
+    if (!super_ok(c)) return c->set_error(KC_ERR_ARG, "accumulating mode needs k <= 64 with windows of >= 22 bases (k=%u)", c->cfg.k);
+    const uint64_t nk = c->cfg.read_len - c->cfg.k + 1;
+    uint64_t chunk_reads = c->cfg.max_chunk_bytes / c->cfg.read_len;
+    if (expected_reads < chunk_reads) expected_reads = chunk_reads;
+    if (expected_reads == 0) return c->set_error(KC_ERR_ARG, "kc_accum_begin: expected_reads and max_chunk_bytes are both 0");
+    uint64_t windows = expected_reads * nk;
+    if (windows > (1ull << 32) - 2) windows = (1ull << 32) - 2;     // record offsets are 32-bit: larger inputs flush in parts
+    kc_ctx::Accum &a = c->acc;
+    if (a.on && !a.fresh) return c->set_error(KC_ERR_STATE, "kc_accum_begin: reads are accumulated; flush first");
+    SuperPlan pl;
+    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, (uint32_t)c->cfg.table_slots, &pl))
+        return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", c->cfg.k, c->cfg.read_len);
+    // a chunk in flight may put every one of its windows into the overflow list
+    const uint64_t chunk_windows = (chunk_reads ? chunk_reads : expected_reads) * nk;
+    if (pl.ovf_cap < 2 * chunk_windows) {
+        SuperPlan p2 = pl;
+        // re-plan with the larger list: only the list and what follows it move
+        const uint64_t grow = (2 * chunk_windows - pl.ovf_cap) * 16ull * pl.W;
+        p2.ovf_cap = 2 * chunk_windows;
+        const uint64_t g512 = (grow + 511) & ~511ull;
+        p2.off_dk += g512; p2.off_dc += g512; p2.off_ek += g512; p2.off_ec += g512; p2.ws_bytes += g512;
+        pl = p2;
+    }
+    if (!a.d_sc) {
+        KC_CUDA_TRY(c, cudaMalloc((void **)&a.d_sc, SC_COUNT * 8));
+        KC_CUDA_TRY(c, cudaMallocHost((void **)&a.h_sc, SC_COUNT * 8));
+        for (auto &e : a.ev) KC_CUDA_TRY(c, cudaEventCreate(&e));
+    }
+    if (pl.ws_bytes > a.ws_bytes) {
+        KC_CUDA_TRY(c, cudaDeviceSynchronize());
+        if (a.ws) cudaFree(a.ws);
+        a.ws = nullptr;
+        a.ws_bytes = 0;
+        if (cudaMalloc(&a.ws, pl.ws_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return c->set_error(KC_ERR_NOMEM, "accumulator workspace of %llu bytes", (unsigned long long)pl.ws_bytes);
+        }
+        a.ws_bytes = pl.ws_bytes;
+    }
+    a.pl = pl;
+    a.max_windows = windows;
+    a.on = true;
+    a.fresh = true;
+    a.windows = a.reads = 0;
+    a.ovf_reserved = 0;
+    KC_CUDA_TRY(c, super_reset(a.pl, a.ws, a.d_sc, c->stream));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return KC_OK;
+}
+
+int kc_accum_add_device(kc_ctx *c, const void *d_reads, uint64_t n_bytes) {
+    KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    if (!c->acc.on) return c->set_error(KC_ERR_STATE, "kc_accum_begin first");
+    if (n_bytes && (!d_reads || (reinterpret_cast<uintptr_t>(d_reads) & 15)))
+        return c->set_error(KC_ERR_ARG, "d_reads must be a 16-byte aligned device pointer");
+    cudaSetDevice(c->cfg.device);
+    const uint32_t L = c->cfg.read_len;
+    const uint64_t n_reads = n_bytes / L;
+    // pieces the plan can take in one go (and whose worst-case overflow fits the list)
+    const uint64_t nk = L - c->cfg.k + 1;
+    uint64_t piece = std::min<uint64_t>(c->acc.pl.ovf_cap / 2, c->acc.max_windows) / nk;
+    piece -= piece % 16;
+    if (piece == 0) return c->set_error(KC_ERR_CAPACITY, "accumulator too small for any read");
+    for (uint64_t r0 = 0; r0 < n_reads; r0 += piece) {
+        const uint64_t nr = std::min(piece, n_reads - r0);
+        KC_TRY(accum_make_room(c, nr));
+        KC_TRY(accum_scatter(c, static_cast<const uint8_t *>(d_reads) + r0 * L, nr, c->stream));
+    }
+    return KC_OK;
+}
+
+int kc_accum_submit(kc_ctx *c, uint32_t slot, uint64_t n_bytes) {
+    KC_TRY(check_ctx(c));
+    if (slot >= c->slots.size() || !c->slots[slot].h_in) return c->set_error(KC_ERR_ARG, "slot %u not available", slot);
+    if (n_bytes > c->cfg.max_chunk_bytes) return c->set_error(KC_ERR_CAPACITY, "chunk of %llu bytes exceeds max_chunk_bytes", (unsigned long long)n_bytes);
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    if (!c->acc.on) return c->set_error(KC_ERR_STATE, "kc_accum_begin first");
+    cudaSetDevice(c->cfg.device);
+    Slot &sl = c->slots[slot];
+    const uint64_t n_reads = n_bytes / c->cfg.read_len;
+    KC_TRY(accum_make_room(c, n_reads));
+    sl.n_bytes = n_bytes;
+    if (n_bytes) KC_CUDA_TRY(c, cudaMemcpyAsync(sl.d_in, sl.h_in, n_bytes, cudaMemcpyHostToDevice, sl.stream));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.h2d_bytes += n_bytes;
+    }
+    return accum_scatter(c, sl.d_in, n_reads, sl.stream);
+}
+
+int kc_accum_submit_fastq(kc_ctx *c, uint32_t slot, const void *host_text, uint64_t n_bytes, uint64_t *consumed,
+                          uint32_t *flags) {
+    KC_TRY(check_ctx(c));
+    if (consumed) *consumed = 0;
+    if (flags) *flags = 0;
+    if (slot >= c->slots.size() || !c->slots[slot].d_in) return c->set_error(KC_ERR_ARG, "slot %u not available", slot);
+    if (n_bytes && !host_text) return c->set_error(KC_ERR_ARG, "null text");
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    if (!c->acc.on) return c->set_error(KC_ERR_STATE, "kc_accum_begin first");
+    cudaSetDevice(c->cfg.device);
+    Slot &sl = c->slots[slot];
+    uint64_t n_reads = 0, used = 0;
+    uint32_t fl = 0;
+    KC_TRY(slot_upload_parse(c, sl, host_text, n_bytes, &n_reads, &used, &fl));
+    if (flags) *flags = fl;
+    if (fl) return KC_OK;
+    if (consumed) *consumed = used;
+    KC_TRY(accum_make_room(c, n_reads));
+    sl.n_bytes = n_reads * c->cfg.read_len;
+    return accum_scatter(c, sl.d_in, n_reads, sl.stream);
+}
+
+int kc_accum_wait(kc_ctx *c, uint32_t slot) {
+    KC_TRY(check_ctx(c));
+    if (slot >= c->slots.size() || !c->slots[slot].stream) return c->set_error(KC_ERR_ARG, "slot %u not available", slot);
+    cudaSetDevice(c->cfg.device);
+    KC_CUDA_TRY(c, cudaStreamSynchronize(c->slots[slot].stream));
+    return KC_OK;
+}
+
+int kc_accum_flush(kc_ctx *c, kc_run **run) {
+    KC_TRY(check_ctx(c));
+    if (!run) return c->set_error(KC_ERR_ARG, "null run");
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    if (!c->acc.on) return c->set_error(KC_ERR_STATE, "kc_accum_begin first");
+    cudaSetDevice(c->cfg.device);
+    kc_ctx::Accum &a = c->acc;
+    kc_run *last = nullptr;
+    KC_TRY(accum_count(c, &last));
+    if (a.parts.empty()) { *run = last; return KC_OK; }
+    a.parts.push_back(last);
+    std::vector<kc_run *> parts;
+    parts.swap(a.parts);
+    const int rc = kc_merge_runs(c, parts.data(), (uint32_t)parts.size(), run);
+    for (kc_run *p : parts) kc_run_free(c, p);
+    return rc;
+}
+
+// ------------------------------------------------------------------- multi-GPU
+// One context per GPU ("rank"). Every rank accumulates its own reads (kc_accum_add_device /
+// kc_accum_submit), counts them locally, and the ranks then exchange DISTINCT (key, count)
+// records by key range: rank r ends with the sorted unique records of the r-th key range, the
+// artefact is the concatenation in rank order. The exchange is fused into the level-2 scatter
+// kernel, whose loads read the peers' HBM over NVLink / NVSwitch.
+int kc_xchg_begin(kc_ctx *c, uint32_t rank, uint32_t n_ranks, uint64_t expected_reads) {
+    KC_TRY(check_ctx(c));
+    if (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return c->set_error(KC_ERR_ARG, "kc_xchg_begin: rank %u of %u", rank, n_ranks);
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    KC_TRY(kc_accum_begin(c, expected_reads));
+    kc_ctx::Accum &a = c->acc;
+    if (a.pl.b1 != 10) return c->set_error(KC_ERR_ARG, "kc_xchg_begin: keys of k=%u have too few bits to exchange by range", c->cfg.k);
+    a.xchg = true;
+    a.rank = rank;
+    a.n_ranks = n_ranks;
+    a.peer_ws[rank] = a.ws;
+    if (!a.d_all_hist) KC_CUDA_TRY(c, cudaMalloc((void **)&a.d_all_hist, 8 * 1024 * 4));
+    return KC_OK;
+}
+
+int kc_xchg_export(kc_ctx *c, void *handle64) {
+    KC_TRY(check_ctx(c));
+    if (!handle64 || !c->acc.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    cudaSetDevice(c->cfg.device);
+    cudaIpcMemHandle_t h;
+    KC_CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->acc.ws));
+    memcpy(handle64, &h, 64);
+    return KC_OK;
+}
+
+int kc_xchg_import(kc_ctx *c, uint32_t peer, const void *handle64) {
+    KC_TRY(check_ctx(c));
+    kc_ctx::Accum &a = c->acc;
+    if (!handle64 || !a.xchg || peer >= a.n_ranks || peer == a.rank) return c->set_error(KC_ERR_ARG, "kc_xchg_import: bad peer");
+    cudaSetDevice(c->cfg.device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    if (a.peer_ipc[peer] && a.peer_ws[peer]) cudaIpcCloseMemHandle(a.peer_ws[peer]);
+    a.peer_ws[peer] = nullptr;
+    KC_CUDA_TRY(c, cudaIpcOpenMemHandle(&a.peer_ws[peer], h, cudaIpcMemLazyEnablePeerAccess));
+    a.peer_ipc[peer] = true;
+    return KC_OK;
+}
+
+int kc_xchg_set_peer(kc_ctx *c, uint32_t peer, kc_ctx *peer_ctx) {
+    KC_TRY(check_ctx(c));
+    kc_ctx::Accum &a = c->acc;
+    if (!peer_ctx || !a.xchg || !peer_ctx->acc.xchg || peer >= a.n_ranks)
+        return c->set_error(KC_ERR_ARG, "kc_xchg_set_peer: bad peer");
+    if (peer_ctx->acc.pl.ws_bytes != a.pl.ws_bytes) return c->set_error(KC_ERR_ARG, "kc_xchg_set_peer: the ranks were planned differently");
+    cudaSetDevice(c->cfg.device);
+    if (peer_ctx->cfg.device != c->cfg.device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_ctx->cfg.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return c->set_error(KC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_ctx->cfg.device, cudaGetErrorString(e));
+    }
+    a.peer_ws[peer] = peer_ctx->acc.ws;
+    a.peer_ipc[peer] = false;
+    return KC_OK;
+}
+
+int kc_xchg_count_local(kc_ctx *c) {
+    KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    kc_ctx::Accum &a = c->acc;
+    if (!a.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    cudaSetDevice(c->cfg.device);
+    cudaStream_t s = c->stream;
+    for (auto &sl : c->slots)
+        if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[0], s));
+    KC_CUDA_TRY(c, super_count_bins(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s));
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[1], s));
+    a.fresh = false;                          // (a rank without reads still takes part in the exchange)
+    return KC_OK;
+}
+
+int kc_xchg_hist(kc_ctx *c, void **d_hist, void **d_all_hist) {
+    KC_TRY(check_ctx(c));
+    if (!c->acc.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    if (d_hist) *d_hist = super_hist1(c->acc.pl, c->acc.ws);
+    if (d_all_hist) *d_all_hist = c->acc.d_all_hist;
+    return KC_OK;
+}
+
+int kc_xchg_group_local(kc_ctx *c) {
+    KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    kc_ctx::Accum &a = c->acc;
+    if (!a.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    cudaSetDevice(c->cfg.device);
+    KC_CUDA_TRY(c, super_x_local(a.pl, a.ws, a.d_sc, a.d_all_hist, a.rank, a.n_ranks, c->n_sms, c->stream));
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[2], c->stream));
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[3], c->stream));
+    return KC_OK;
+}
+
+int kc_xchg_pull(kc_ctx *c) {
+    KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    kc_ctx::Accum &a = c->acc;
+    if (!a.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    for (uint32_t i = 0; i < a.n_ranks; i++)
+        if (!a.peer_ws[i]) return c->set_error(KC_ERR_STATE, "kc_xchg_pull: rank %u's workspace is not mapped (kc_xchg_import / kc_xchg_set_peer)", i);
+    cudaSetDevice(c->cfg.device);
+    KC_CUDA_TRY(c, super_x_pull(a.pl, a.ws, a.d_sc, a.peer_ws, a.n_ranks, c->n_sms, c->stream));
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[4], c->stream));
+    return KC_OK;
+}
+
+int kc_xchg_finish(kc_ctx *c, kc_run **run) {
+    KC_TRY(check_ctx(c));
+    if (!run) return c->set_error(KC_ERR_ARG, "null run");
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    if (!c->acc.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    cudaSetDevice(c->cfg.device);
+    return accum_finish(c, true, run);
+}
+
+// All ranks in one process: counts what the n contexts have accumulated and leaves rank r's key
+// range in runs[r]. Cross-device ordering is by events; nothing waits inside a kernel, so the
+// contexts may also share a device (tests).
+int kc_xchg_run_all(kc_ctx *const *ctxs, uint32_t n, kc_run **runs) {
+    if (!ctxs || !runs || n == 0 || n > 8) return KC_ERR_ARG;
+    for (uint32_t r = 0; r < n; r++) {
+        if (!ctxs[r] || !ctxs[r]->acc.xchg || ctxs[r]->acc.n_ranks != n || ctxs[r]->acc.rank != r) return KC_ERR_ARG;
+        runs[r] = nullptr;
+    }
+    int rc = KC_OK;
+    std::vector<cudaEvent_t> ev(n);
+    for (uint32_t r = 0; r < n; r++) {
+        cudaSetDevice(ctxs[r]->cfg.device);
+        cudaEventCreateWithFlags(&ev[r], cudaEventDisableTiming);
+    }
+    // every stream waits for the events the other ranks recorded at their current position
+    auto barrier = [&]() {
+        for (uint32_t r = 0; r < n; r++) { cudaSetDevice(ctxs[r]->cfg.device); cudaEventRecord(ev[r], ctxs[r]->stream); }
+        for (uint32_t r = 0; r < n; r++) {
+            cudaSetDevice(ctxs[r]->cfg.device);
+            for (uint32_t q = 0; q < n; q++)
+                if (q != r) cudaStreamWaitEvent(ctxs[r]->stream, ev[q], 0);
+        }
+    };
+    for (uint32_t r = 0; r < n && rc == KC_OK; r++)
+        for (uint32_t q = 0; q < n && rc == KC_OK; q++)
+            if (q != r) rc = kc_xchg_set_peer(ctxs[r], q, ctxs[q]);
+    for (uint32_t r = 0; r < n && rc == KC_OK; r++) rc = kc_xchg_count_local(ctxs[r]);
+    if (rc == KC_OK) {
+        barrier();                                  // the histograms are complete
+        for (uint32_t r = 0; r < n; r++) {          // all-gather: rank r copies every rank's histogram
+            cudaSetDevice(ctxs[r]->cfg.device);
+            for (uint32_t q = 0; q < n; q++)
+                cudaMemcpyPeerAsync(ctxs[r]->acc.d_all_hist + q * 1024, ctxs[r]->cfg.device,
+                                    super_hist1(ctxs[q]->acc.pl, ctxs[q]->acc.ws), ctxs[q]->cfg.device, 1024 * 4,
+                                    ctxs[r]->stream);
+        }
+    }
+    for (uint32_t r = 0; r < n && rc == KC_OK; r++) rc = kc_xchg_group_local(ctxs[r]);
+    if (rc == KC_OK) barrier();                     // every rank's grouped array and sub-bucket counts are final
+    for (uint32_t r = 0; r < n && rc == KC_OK; r++) rc = kc_xchg_pull(ctxs[r]);
+    if (rc == KC_OK) barrier();                     // nobody reads a peer's grouped array any more
+    for (uint32_t r = 0; r < n && rc == KC_OK; r++) rc = kc_xchg_finish(ctxs[r], &runs[r]);
+    for (uint32_t r = 0; r < n; r++) { cudaSetDevice(ctxs[r]->cfg.device); cudaEventDestroy(ev[r]); }
+    if (rc != KC_OK)
+        for (uint32_t r = 0; r < n; r++)
+            if (runs[r]) { kc_run_free(ctxs[r], runs[r]); runs[r] = nullptr; }
+    return rc;
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // ------------------------------------------------------------------------ chunks
 int kc_count_device(kc_ctx *c, const void *d_reads, uint64_t n_bytes, kc_run **run) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!run) return c->set_error(KC_ERR_ARG, "null run");
     if (n_bytes && (!d_reads || (reinterpret_cast<uintptr_t>(d_reads) & 15)))
         return c->set_error(KC_ERR_ARG, "d_reads must be a 16-byte aligned device pointer");
@@ -767,9 +1282,36 @@ static int parse_fastq_impl(kc_ctx *c, Pending &ar, const void *d_text, uint64_t
     return KC_OK;
 }
 
+}  // extern "C"
+
+// host text -> the slot's device staging -> parsed into the slot's read buffer (sl.d_in)
+static int slot_upload_parse(kc_ctx *c, Slot &sl, const void *host_text, uint64_t n_bytes, uint64_t *n_reads,
+                             uint64_t *used, uint32_t *fl) {
+    if (n_bytes + 64 > sl.text_cap) {                    // device staging for the raw text, grown on demand
+        KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+        if (sl.d_text) cudaFree(sl.d_text);
+        sl.d_text = nullptr;
+        sl.text_cap = 0;
+        const uint64_t want = n_bytes + n_bytes / 8 + 4096;
+        if (cudaMalloc(&sl.d_text, want) != cudaSuccess) {
+            cudaGetLastError();
+            return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes for FASTQ text failed", (unsigned long long)want);
+        }
+        sl.text_cap = want;
+    }
+    if (n_bytes) KC_CUDA_TRY(c, cudaMemcpyAsync(sl.d_text, host_text, n_bytes, cudaMemcpyHostToDevice, sl.stream));
+    KC_TRY(parse_fastq_impl(c, sl.pend, sl.d_text, n_bytes, sl.d_in, c->cfg.max_chunk_bytes, sl.stream, n_reads, used, fl));
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stats.h2d_bytes += n_bytes;
+    return KC_OK;
+}
+
+extern "C" {
+
 int kc_parse_fastq_device(kc_ctx *c, const void *d_text, uint64_t n_bytes, void *d_reads, uint64_t reads_cap_bytes,
                           uint64_t *n_reads, uint64_t *consumed, uint32_t *flags) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if ((n_bytes && (!d_text || !d_reads))) return c->set_error(KC_ERR_ARG, "null argument");
     if (c->direct.active) return c->set_error(KC_ERR_STATE, "a chunk is in flight on this context");
     cudaSetDevice(c->cfg.device);
@@ -786,26 +1328,9 @@ int kc_submit_fastq(kc_ctx *c, uint32_t slot, const void *host_text, uint64_t n_
     Slot &sl = c->slots[slot];
     if (sl.pend.active) return c->set_error(KC_ERR_STATE, "slot %u already has a chunk in flight", slot);
     cudaSetDevice(c->cfg.device);
-    if (n_bytes + 64 > sl.text_cap) {                    // device staging for the raw text, grown on demand
-        KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
-        if (sl.d_text) cudaFree(sl.d_text);
-        sl.d_text = nullptr;
-        sl.text_cap = 0;
-        const uint64_t want = n_bytes + n_bytes / 8 + 4096;
-        if (cudaMalloc(&sl.d_text, want) != cudaSuccess) {
-            cudaGetLastError();
-            return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes for FASTQ text failed", (unsigned long long)want);
-        }
-        sl.text_cap = want;
-    }
-    if (n_bytes) KC_CUDA_TRY(c, cudaMemcpyAsync(sl.d_text, host_text, n_bytes, cudaMemcpyHostToDevice, sl.stream));
     uint64_t n_reads = 0, used = 0;
     uint32_t fl = 0;
-    KC_TRY(parse_fastq_impl(c, sl.pend, sl.d_text, n_bytes, sl.d_in, c->cfg.max_chunk_bytes, sl.stream, &n_reads, &used, &fl));
-    {
-        std::lock_guard<std::mutex> g(c->mu);
-        c->stats.h2d_bytes += n_bytes;
-    }
+    KC_TRY(slot_upload_parse(c, sl, host_text, n_bytes, &n_reads, &used, &fl));
     if (flags) *flags = fl;
     if (fl) return KC_OK;                                // not the shape the device parser handles: nothing submitted
     if (consumed) *consumed = used;
@@ -962,6 +1487,7 @@ int kc_merge_parts(kc_ctx *c, uint32_t n_src, const void *const *d_keys, const v
                    const void *const *d_offsets, const uint64_t *n_records, uint32_t n_sub, uint32_t prefix_bits,
                    kc_run **out) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!out || n_src == 0 || n_src > 8 || !d_keys || !d_counts || !d_offsets || !n_records || n_sub == 0)
         return c->set_error(KC_ERR_ARG, "kc_merge_parts: bad argument");
     if (c->W != 1) return c->set_error(KC_ERR_ARG, "kc_merge_parts: 64-bit keys only");
@@ -1064,6 +1590,7 @@ int kc_run_copy_records(kc_ctx *c, const kc_run *r, void *dst, uint64_t cap, uin
 
 int kc_run_from_device(kc_ctx *c, const void *d_keys, const void *d_counts, uint64_t n, kc_run **out) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!out || (n && (!d_keys || !d_counts))) return c->set_error(KC_ERR_ARG, "null argument");
     cudaSetDevice(c->cfg.device);
     kc_run *r = nullptr;
@@ -1078,6 +1605,7 @@ int kc_run_from_device(kc_ctx *c, const void *d_keys, const void *d_counts, uint
 
 int kc_run_upload(kc_ctx *c, const void *records, uint64_t n_bytes, kc_run **out) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!out || (n_bytes && !records)) return c->set_error(KC_ERR_ARG, "null argument");
     const uint64_t n = n_bytes / c->S;
     if (n >= (1ull << 32)) return c->set_error(KC_ERR_CAPACITY, "run too long for one upload");
@@ -1086,21 +1614,31 @@ int kc_run_upload(kc_ctx *c, const void *records, uint64_t n_bytes, kc_run **out
     if (n == 0) return make_run(c, s, 0, out);
     void *d_rec = nullptr, *ws = nullptr;
     kc_run *raw = nullptr, *folded = nullptr;
-    KC_TRY(dev_alloc(c, s, n * c->S, &d_rec));
-    KC_CUDA_TRY(c, cudaMemcpyAsync(d_rec, records, n * c->S, cudaMemcpyHostToDevice, s));
-    KC_TRY(make_run(c, s, n, &raw));
-    KC_TRY(make_run(c, s, n, &folded));
-    KC_CUDA_TRY(c, unpack_records(d_rec, n, c->W, raw->d_keys, raw->d_counts, s));
-    const uint64_t ws_bytes = ((rle_workspace_bytes(n) + 255) & ~255ull) + (n + 1) * 4 + 256;
-    KC_TRY(dev_alloc(c, s, ws_bytes, &ws));
     unsigned long long *d_num = nullptr;
-    KC_TRY(dev_alloc(c, s, 8, (void **)&d_num));
-    int launches = 1;
-    KC_CUDA_TRY(c, fold_sorted_pairs(raw->d_keys, raw->d_counts, n, c->W, folded->d_keys, folded->d_counts, d_num,
-                                     ws, s, &launches));
     unsigned long long U = 0;
-    KC_CUDA_TRY(c, cudaMemcpyAsync(&U, d_num, 8, cudaMemcpyDeviceToHost, s));
-    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    int launches = 1;
+    auto body = [&]() -> int {
+        KC_TRY(dev_alloc(c, s, n * c->S, &d_rec));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(d_rec, records, n * c->S, cudaMemcpyHostToDevice, s));
+        KC_TRY(make_run(c, s, n, &raw));
+        KC_TRY(make_run(c, s, n, &folded));
+        KC_CUDA_TRY(c, unpack_records(d_rec, n, c->W, raw->d_keys, raw->d_counts, s));
+        const uint64_t ws_bytes = ((rle_workspace_bytes(n) + 255) & ~255ull) + (n + 1) * 4 + 256;
+        KC_TRY(dev_alloc(c, s, ws_bytes, &ws));
+        KC_TRY(dev_alloc(c, s, 8, (void **)&d_num));
+        KC_CUDA_TRY(c, fold_sorted_pairs(raw->d_keys, raw->d_counts, n, c->W, folded->d_keys, folded->d_counts, d_num,
+                                         ws, s, &launches));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(&U, d_num, 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        return KC_OK;
+    };
+    const int brc = body();
+    if (brc != KC_OK) {                                  // nothing allocated so far outlives a failed upload
+        dev_free(s, d_rec); dev_free(s, ws); dev_free(s, d_num);
+        if (raw) kc_run_free(c, raw);
+        if (folded) kc_run_free(c, folded);
+        return brc;
+    }
     folded->n = U;
     dev_free(s, d_rec); dev_free(s, ws); dev_free(s, d_num);
     kc_run_free(c, raw);
@@ -1138,6 +1676,7 @@ int kc_run_write(kc_ctx *c, const kc_run *r, const char *path, int append) {
 
 int kc_run_split(kc_ctx *c, const kc_run *r, const uint64_t *splitters, uint32_t n_splitters, uint64_t *offsets) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!r || !offsets || (n_splitters && !splitters)) return c->set_error(KC_ERR_ARG, "null argument");
     const uint64_t n = r->n - r->skip;
     offsets[0] = 0;
@@ -1162,6 +1701,7 @@ int kc_run_split(kc_ctx *c, const kc_run *r, const uint64_t *splitters, uint32_t
 // ------------------------------------------------------------------------- merge
 int kc_merge_runs(kc_ctx *c, kc_run *const *runs, uint32_t n, kc_run **out) {
     KC_TRY(check_ctx(c));
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!out || (n && !runs)) return c->set_error(KC_ERR_ARG, "null argument");
     cudaSetDevice(c->cfg.device);
     cudaStream_t s = c->stream;

@@ -49,6 +49,19 @@ __host__ __device__ __forceinline__ bool key_is_zero(const Key<W> &a) {
 }
 
 // ------------------------------------------------------------- small utils
+// SMs of the current device (grids of grid-stride kernels are a multiple of it)
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
 __host__ __device__ __forceinline__ uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

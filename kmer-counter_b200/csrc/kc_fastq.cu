@@ -172,7 +172,7 @@ cudaError_t fastq_parse(const void *d_text, uint64_t n_bytes, uint32_t L, void *
     scan_u32_kernel<<<1, 1024, 0, s>>>(tile_counts, tiles, tile_base);
     const uint32_t nl_cap = (uint32_t)(n_bytes / 2 + 1024);
     nl_write_kernel<<<tiles, kFqThreads, 0, s>>>(text, n_bytes, tile_base, nl_pos, nl_cap);
-    fastq_pack_kernel<<<148 * 8, 256, 0, s>>>(text, nl_pos, tile_base + tiles, nl_cap, L, max_reads,
+    fastq_pack_kernel<<<(uint32_t)sm_count() * 8, 256, 0, s>>>(text, nl_pos, tile_base + tiles, nl_cap, L, max_reads,
                                               static_cast<uint8_t *>(d_reads), d_out);
     if (n_launches) *n_launches += 4;
     return cudaGetLastError();

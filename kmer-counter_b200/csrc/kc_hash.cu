@@ -110,7 +110,7 @@ uint64_t hash_table_bytes(uint64_t capacity) { return capacity * 16 + 64; }
 cudaError_t hash_clear(HashTable t, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(t.side, 0, 32, s);
     if (e != cudaSuccess) return e;
-    hash_fill_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<ulonglong2 *>(t.slots), t.capacity);
+    hash_fill_kernel<<<(uint32_t)sm_count() * 8, 256, 0, s>>>(reinterpret_cast<ulonglong2 *>(t.slots), t.capacity);
     return cudaGetLastError();
 }
 
@@ -139,7 +139,7 @@ cudaError_t hash_compact(HashTable t, uint64_t *out_keys, uint32_t *out_counts, 
                          cudaStream_t s, int *n_launches) {
     cudaError_t e = cudaMemsetAsync(d_num, 0, 8, s);
     if (e != cudaSuccess) return e;
-    hash_compact_kernel<<<148 * 8, 256, 0, s>>>(t, out_keys, out_counts, d_num);
+    hash_compact_kernel<<<(uint32_t)sm_count() * 8, 256, 0, s>>>(t, out_keys, out_counts, d_num);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

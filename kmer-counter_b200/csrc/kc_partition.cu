@@ -854,8 +854,8 @@ cudaError_t partition_gather(int W, uint64_t n_slots, int sig_bits, int target_s
     uint32_t *base2 = hist2 + pl.n_sub + 8;
     uint32_t *off = base2 + pl.n_sub + 8;
     uint32_t *tmp_start = off + pl.n_sub + 8 + pl.n_sub + 8;
-    if (W == 1) gather_kernel<1><<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
-    else gather_kernel<2><<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
+    if (W == 1) gather_kernel<1><<<(uint32_t)sm_count() * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
+    else gather_kernel<2><<<(uint32_t)sm_count() * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, pl.n_sub, out_keys, out_counts);
     return cudaGetLastError();
 }
 
@@ -914,7 +914,7 @@ cudaError_t merge_parts_gather(uint32_t n_sub, const uint64_t *tmp_keys, const u
     uint32_t *m_out = reinterpret_cast<uint32_t *>(ws);
     uint32_t *off = m_out + n_sub + 8;
     uint32_t *tmp_start = off + n_sub + 8;
-    gather_kernel<1><<<148 * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, n_sub, out_keys, out_counts);
+    gather_kernel<1><<<(uint32_t)sm_count() * 8, 256, 0, s>>>(tmp_keys, tmp_counts, tmp_start, off, n_sub, out_keys, out_counts);
     if (out_offsets) {
         cudaError_t e = cudaMemcpyAsync(out_offsets, off, (size_t)(n_sub + 1) * 4, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;

@@ -166,7 +166,8 @@ __global__ void lower_bound_kernel(const uint64_t *__restrict__ keys, uint64_t n
     out[t] = lo;
 }
 
-inline uint32_t grid_for(uint64_t n, int threads, uint32_t cap = 148 * 16) {
+inline uint32_t grid_for(uint64_t n, int threads, uint32_t cap = 0) {
+    if (cap == 0) cap = (uint32_t)sm_count() * 16;
     uint64_t g = div_up(n ? n : 1, (uint64_t)threads);
     return (uint32_t)(g < cap ? g : cap);
 }

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kSwThreads) sw_scatter_kernel(SwScatterParams 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.bar_off);
     uint32_t *hh = reinterpret_cast<uint32_t *>(smem + q.h_off);
     uint32_t *bid = reinterpret_cast<uint32_t *>(smem + q.bin_off);
-    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + q.bits_off);
+    uint32_t *seg_st = reinterpret_cast<uint32_t *>(smem + q.bits_off);       // [tile_reads * segs_per_read]
+    uint32_t *seg_bd = seg_st + p.tile_reads * q.segs_per_read;
     __shared__ uint32_t s_nstart;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
@@ -139,82 +140,99 @@ __global__ void __launch_bounds__(kSwThreads) sw_scatter_kernel(SwScatterParams 
         __syncthreads();
 
         // ---- C: minimum over the w m-mers of each window -> bin of the window. A thread takes a
-        // segment of s <= min(18, w) consecutive windows: they all contain m-mers [s-1, w) of the
-        // segment (the core); window i adds a suffix of [i, s-1) and a prefix of [w, w+i).
+        // segment of s <= 17 consecutive windows plus, as a look-behind, the window before them.
+        // All of those windows contain the m-mers [s'-1, w) counted from the first one (the core);
+        // window i adds a suffix of [i, s'-1) and a prefix of [w, w+i). With the bins in registers
+        // the thread also finds where runs of equal bins start inside its segment: bit i of
+        // seg_st = window i starts a run, bit i of seg_bd = it starts one or holds no k-mer.
         const uint32_t n_seg = nreads * q.segs_per_read;
         for (uint32_t sg = tid; sg < n_seg; sg += kSwThreads) {
             const uint32_t r = sg / q.segs_per_read;
             const uint32_t p0 = (sg - r * q.segs_per_read) * q.seg_len;
-            if (p0 >= p.nk) continue;
+            if (p0 >= p.nk) { seg_st[sg] = 0; seg_bd[sg] = 0; continue; }
             const uint32_t s = min(q.seg_len, p.nk - p0);
-            const uint32_t *g = hh + r * q.nh_stride + p0;
+            const uint32_t lb = p0 > 0 ? 1u : 0u;                  // look-behind window
+            const uint32_t se = s + lb;                            // windows whose bin this thread derives
+            const uint32_t *g = hh + r * q.nh_stride + p0 - lb;
             uint32_t S[kSwMaxSeg];
             S[kSwMaxSeg - 1] = 0xffffffffu;
 #pragma unroll
             for (int i = kSwMaxSeg - 2; i >= 0; i--) {
-                const uint32_t v = (uint32_t)i + 1 < s ? g[i] : 0xffffffffu;
+                const uint32_t v = (uint32_t)i + 1 < se ? g[i] : 0xffffffffu;
                 S[i] = min(v, S[i + 1]);
             }
             uint32_t core = 0xffffffffu;
-            for (uint32_t t = s - 1; t < q.w; t++) core = min(core, g[t]);
+            for (uint32_t t = se - 1; t < q.w; t++) core = min(core, g[t]);
             uint32_t pm = 0xffffffffu;
             const bool check = flag[r] != 0;
-            uint32_t *brow = bid + r * p.nk + p0;
+            uint32_t *brow = bid + r * p.nk + p0 - lb;
+            uint32_t prev = kNoBin, stm = 0, bdm = 0;
 #pragma unroll
             for (uint32_t i = 0; i < (uint32_t)kSwMaxSeg; i++) {
-                if (i < s) {
+                if (i < se) {
                     const uint32_t mn = min(min(S[i], core), pm);
-                    const bool valid = check ? kmer_window_valid(bad4 + r * p.nb4, p0 + i, p.k) : true;
-                    if (!valid) invalid_local++;
-                    brow[i] = valid ? bin_of_min(mn, q.n_bins) : kNoBin;
-                    if (i + 1 < s) pm = min(pm, g[q.w + i]);
+                    const bool valid = check ? kmer_window_valid(bad4 + r * p.nb4, p0 - lb + i, p.k) : true;
+                    const uint32_t b = valid ? bin_of_min(mn, q.n_bins) : kNoBin;
+                    if (i >= lb) {                                 // an owned window
+                        if (!valid) invalid_local++;
+                        brow[i] = b;
+                        const uint32_t st = (valid && b != prev) ? 1u : 0u;
+                        stm |= st << (i - lb);
+                        bdm |= (st | (valid ? 0u : 1u)) << (i - lb);
+                    }
+                    prev = b;
+                    if (i + 1 < se) pm = min(pm, g[q.w + i]);
                 }
             }
+            seg_st[sg] = stm;
+            seg_bd[sg] = bdm;
         }
         __syncthreads();
 
         // ---- D: a run of equal bins becomes records of at most cmax windows: 64W bases from the
         // run's first base (the first key and the bases that follow it), the window count in the
         // low byte of the last word.
-        // D1: boundary bitmask over the tile's windows (a run start, or a slot without a k-mer) and
-        // a compact list of the run starts; window indices are flat (bid rows are nk long).
-        const uint32_t total = nreads * p.nk;
-        const uint32_t n_words = (total + 31) >> 5;
-        uint32_t *list = hh;                            // the m-mer hashes are dead: tile_reads * nh_stride >= total words
-        for (uint32_t base = (tid >> 5) << 5; base < n_words * 32; base += kSwThreads) {
-            const uint32_t sidx = base + lane;
-            bool st = false, bd = true;                 // past the tile: a boundary that closes the last run
-            if (sidx < total) {
-                uint32_t r = p.nk == 1 ? sidx : __umulhi(sidx, p.nk_magic);
-                if (r * p.nk > sidx) r--;
-                const uint32_t b = bid[sidx];
-                st = b != kNoBin && (sidx == r * p.nk || bid[sidx - 1] != b);
-                bd = st || b == kNoBin;
+        // D1: compact list of the run starts, entry = segment << 5 | window inside the segment
+        // (the m-mer hashes are dead: the list lives in their place).
+        uint32_t *list = hh;
+        for (uint32_t base = 0; base < n_seg; base += kSwThreads) {
+            const uint32_t sg = base + tid;
+            uint32_t stm = sg < n_seg ? seg_st[sg] : 0u;
+            const uint32_t cnt = __popc(stm);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
             }
-            const uint32_t bm = __ballot_sync(0xffffffffu, bd), sm = __ballot_sync(0xffffffffu, st);
             uint32_t off = 0;
-            if (lane == 0) {
-                bits[base >> 5] = bm;
-                if (sm) off = atomicAdd(&s_nstart, (uint32_t)__popc(sm));
+            if (lane == 31 && incl) off = atomicAdd(&s_nstart, incl);
+            off = __shfl_sync(0xffffffffu, off, 31) + incl - cnt;
+            while (stm) {
+                const uint32_t i = __ffs(stm) - 1;
+                stm &= stm - 1;
+                list[off++] = (sg << 5) | i;
             }
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (st) list[off + __popc(sm & lanemask_lt())] = sidx;
         }
-        if (tid == 0) bits[n_words] = 0xffffffffu;
         __syncthreads();
-        // D2: one thread per run. The bin's cursor is bumped first; the record is assembled while
-        // that atomic is in flight.
+        // D2: one thread per run. The run ends at the next boundary bit (this segment's or a later
+        // one's of the same read) or at the end of the read. The bin's cursor is bumped first; the
+        // record is assembled while that atomic is in flight.
         const uint32_t n_start = s_nstart;
         for (uint32_t en = tid; en < n_start; en += kSwThreads) {
-            const uint32_t sidx = list[en];
-            uint32_t wd = sidx >> 5;
-            uint32_t mk = bits[wd] & ~(0xffffffffu >> (31 - (sidx & 31u)));      // boundaries after sidx in its word
-            while (mk == 0) mk = bits[++wd];
-            const uint32_t len = wd * 32 + (uint32_t)__ffs(mk) - 1 - sidx;
-            uint32_t r = p.nk == 1 ? sidx : __umulhi(sidx, p.nk_magic);
-            if (r * p.nk > sidx) r--;
-            const uint32_t pos = sidx - r * p.nk;
-            const uint32_t b = bid[sidx];
+            const uint32_t ent = list[en];
+            const uint32_t sg = ent >> 5, wi0 = ent & 31u;
+            const uint32_t r = sg / q.segs_per_read, si = sg - r * q.segs_per_read;
+            const uint32_t pos = si * q.seg_len + wi0;
+            uint32_t end = p.nk;
+            {
+                uint32_t mk = seg_bd[sg] & ~(0xffffffffu >> (31 - wi0));          // boundaries after this window
+                uint32_t sj = si;
+                while (mk == 0 && ++sj < q.segs_per_read) mk = seg_bd[r * q.segs_per_read + sj];
+                if (mk) end = min(p.nk, sj * q.seg_len + (uint32_t)__ffs(mk) - 1);
+            }
+            const uint32_t len = end - pos;
+            const uint32_t b = bid[r * p.nk + pos];
             const uint64_t *e = enc + r * enc_row;
             for (uint32_t q0 = 0; q0 < len; q0 += q.cmax) {
                 const uint32_t idx = atomicAdd(&q.cursor[b], 1u);
@@ -338,7 +356,9 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
     ulonglong2 *recs = reinterpret_cast<ulonglong2 *>(tk + TSLOTS);         // [RB * W]
     uint32_t *tc = reinterpret_cast<uint32_t *>(recs + RB * W);             // [TSLOTS]
     uint32_t *pre = tc + TSLOTS;                                            // [RB + 8]
-    uint32_t *s_hist = pre + RB + 8;                                        // [nb1]
+    uint32_t *s_hist = pre + RB + 8;                                        // [kNb1Max]
+    constexpr int kQueue = 128;                                             // collided keys a warp parks before it drains them
+    Key<W> *queue = reinterpret_cast<Key<W> *>(s_hist + kNb1Max);           // [THREADS / 32][kQueue]
     __shared__ uint32_t s_unit, s_m, s_ones, s_abort, s_off;
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_warp[THREADS / 32];
@@ -475,19 +495,22 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                 const uint32_t tot = csum;
                 // this thread's share of the tot windows: [f0, f1)
                 const uint32_t per = (tot + THREADS - 1) / THREADS;
-                const uint32_t f0 = tid * per, f1 = min(f0 + per, tot);
-                if (f0 < f1) {
-                    uint32_t lo = 0, hi = nr;                      // last record whose first window is <= f0
-                    while (hi - lo > 1) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (pre[mid] <= f0) lo = mid; else hi = mid;
-                    }
-                    uint32_t ri = lo;                              // next record to open
+                const uint32_t f0 = min(tid * per, tot), f1 = min(f0 + per, tot);
+                {
                     uint32_t rem = f1 - f0;                        // windows this lane still has to fetch
                     occ_local += rem;
+                    uint32_t ri = 0;                               // next record to open
                     uint64_t rw[2 * W];
-                    uint32_t in_rec;                               // windows left in the open record
-                    {   // open the first record at window j
+#pragma unroll
+                    for (int t = 0; t < 2 * W; t++) rw[t] = 0;
+                    uint32_t in_rec = 0;                           // windows left in the open record
+                    if (rem) {   // open the first record at window j
+                        uint32_t lo = 0, hi = nr;                  // last record whose first window is <= f0
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (pre[mid] <= f0) lo = mid; else hi = mid;
+                        }
+                        ri = lo;
                         const uint32_t j = f0 - pre[lo];
 #pragma unroll
                         for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
@@ -509,55 +532,86 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                         in_rec = min(rem, cnt - j);
                         ri++;
                     }
-                    Key<W> key;
-                    uint32_t h = 0, probes = 0;
-                    bool need = true, active = true;
+                    // Pass 1: every lane gives each of its keys ONE probe at its home slot (no loop, so
+                    // no lane waits for another's probe sequence). A key whose home slot holds a
+                    // different key goes to the warp's queue; the queue is drained with the usual
+                    // linear probing whenever it fills up, and after the last key.
+                    Key<W> *wq = queue + warp * kQueue;
+                    uint32_t qn = 0;                               // keys queued (uniform across the warp)
+                    auto drain = [&]() {
+                        __syncwarp();
+                        for (uint32_t en = lane; en < qn; en += 32) {
+                            const Key<W> k = wq[en];
+                            uint32_t h = key_hash<W>(k) >> hshift;
+                            bool done = false;
 #pragma unroll 1
-                    while (active) {
-                        if (need) {                                // fetch this lane's next window
-                            if (rem == 0) {
-                                active = false;
+                            for (uint32_t probes = 0; probes < 64u && !done; probes++) {
+                                Key<W> cur = tk[h];
+                                if (key_any_word_ones<W>(cur)) {
+                                    cur = slot_claim(&tk[h], k);
+                                    if (key_all_ones<W>(cur)) { claims++; done = true; }
+                                }
+                                if (done || key_eq<W>(cur, k)) { atomicAdd(&tc[h], 1u); done = true; }
+                                else h = (h + 1) & (TSLOTS - 1);
+                            }
+                            if (!done) s_abort = 1;                // table (nearly) full: the pass is abandoned
+                        }
+                        __syncwarp();
+                        qn = 0;
+                    };
+#pragma unroll 1
+                    for (uint32_t it = 0; it < per; it++) {
+                        bool act = rem != 0;
+                        Key<W> key;
+                        uint32_t h = 0;
+                        if (act) {
+                            if (in_rec == 0) {
+#pragma unroll
+                                for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
+                                in_rec = min(rem, (uint32_t)(rw[2 * W - 1] & 0xffull));
+                                ri++;
+                            }
+#pragma unroll
+                            for (int t = 0; t < W; t++) key.w[t] = rw[t];
+                            key.w[W - 1] &= p.last_mask;
+                            in_rec--;
+                            rem--;
+#pragma unroll
+                            for (int t = 0; t < 2 * W - 1; t++) rw[t] = (rw[t] << 2) | (rw[t + 1] >> 62);
+                            rw[2 * W - 1] <<= 2;
+                            if (key_all_ones<W>(key)) {            // the table's empty marker: counted on the side
+                                if (in_pass(0x9E3779B1u)) atomicAdd(&s_ones, 1u);
+                                act = false;
                             } else {
-                                if (in_rec == 0) {
-#pragma unroll
-                                    for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
-                                    in_rec = min(rem, (uint32_t)(rw[2 * W - 1] & 0xffull));
-                                    ri++;
-                                }
-#pragma unroll
-                                for (int t = 0; t < W; t++) key.w[t] = rw[t];
-                                key.w[W - 1] &= p.last_mask;
-                                in_rec--;
-                                rem--;
-#pragma unroll
-                                for (int t = 0; t < 2 * W - 1; t++) rw[t] = (rw[t] << 2) | (rw[t + 1] >> 62);
-                                rw[2 * W - 1] <<= 2;
-                                if (key_all_ones<W>(key)) {        // the table's empty marker: counted on the side
-                                    if (in_pass(0x9E3779B1u)) atomicAdd(&s_ones, 1u);
-                                } else {
-                                    const uint32_t hv = key_hash<W>(key);
-                                    if (in_pass(hv)) { h = hv >> hshift; probes = 0; need = false; }
-                                }
+                                const uint32_t hv = key_hash<W>(key);
+                                h = hv >> hshift;
+                                act = in_pass(hv);
                             }
                         }
-                        if (!need) {                               // one probe
+                        bool coll = false;
+                        if (act) {
                             Key<W> cur = tk[h];
-                            bool done = key_eq<W>(cur, key);
+                            bool hit;
                             // a slot that looks (even partly: a 128-bit read may tear) empty is settled by the CAS
-                            if (!done && key_any_word_ones<W>(cur)) {
+                            if (key_any_word_ones<W>(cur)) {
                                 cur = slot_claim(&tk[h], key);
-                                if (key_all_ones<W>(cur)) { claims++; done = true; }
-                                else done = key_eq<W>(cur, key);
-                            }
-                            if (done) {
-                                atomicAdd(&tc[h], 1u);
-                                need = true;
+                                hit = key_all_ones<W>(cur);
+                                if (hit) claims++;
+                                else hit = key_eq<W>(cur, key);
                             } else {
-                                h = (h + 1) & (TSLOTS - 1);
-                                if (++probes >= 64u) { s_abort = 1; need = true; }   // table (nearly) full: the pass is abandoned
+                                hit = key_eq<W>(cur, key);
                             }
+                            if (hit) atomicAdd(&tc[h], 1u);
+                            coll = !hit;
+                        }
+                        const uint32_t cm = __ballot_sync(0xffffffffu, coll);
+                        if (cm) {
+                            if (coll) wq[qn + __popc(cm & lanemask_lt())] = key;
+                            qn += __popc(cm);
+                            if (qn > (uint32_t)kQueue - 32u) drain();
                         }
                     }
+                    if (qn) drain();
                 }
                 // distinct keys so far
 #pragma unroll
@@ -697,15 +751,28 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_
     return total;
 }
 
-// one block: level-1 bucket bases + cursors from the histogram S2 left, and the level-2 plan
-__global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restrict__ hist1, int b1, uint64_t d_cap,
+// One block. S2 left a histogram of the records' leading b1_max bits; the plan picks the two
+// digit widths from the number of records actually there -- B = b1 + b2 bits so that a sub-bucket
+// holds about sub_target records, level 1 as narrow as level 2's limit of 9 bits allows (long
+// runs per bin in the unordered first scatter) -- folds the histogram to b1 bits and scans it.
+__global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restrict__ hist1, int b1_max, uint64_t d_cap,
                                                        uint32_t sub_target, int sig_bits, uint32_t *__restrict__ base1,
                                                        uint32_t *__restrict__ cursor1, SuperPlanDev *__restrict__ plan,
                                                        const unsigned long long *__restrict__ sc) {
     __shared__ uint32_t s_a[32];
-    const int nb1 = 1 << b1;
+    unsigned long long nd = sc[SW_D];
+    if (nd > d_cap) nd = d_cap;
+    int B = 1;
+    while (B < b1_max + 9 && B < sig_bits && (nd >> B) > sub_target) B++;
+    int b1 = B - 9 > (B < 16 ? B / 2 : 8) ? B - 9 : (B < 16 ? B / 2 : 8);
+    if (b1 > b1_max) b1 = b1_max;
+    if (b1 < 1) b1 = 1;
+    const int b2 = B - b1 > 0 ? B - b1 : 0;
+    const int nb1 = 1 << b1, group = 1 << (b1_max - b1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t c = tid < nb1 ? hist1[tid] : 0;
+    uint32_t c = 0;
+    if (tid < nb1)
+        for (int j = 0; j < group; j++) c += hist1[tid * group + j];
     uint32_t ia = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -722,15 +789,130 @@ __global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restric
         if (tid == nb1 - 1) base1[nb1] = oa + ia;
     }
     if (tid == 0) {
-        unsigned long long nd = sc[SW_D];
-        if (nd > d_cap) nd = d_cap;
-        uint32_t b2 = 0;
-        while (b2 < 9 && b1 + (int)b2 < sig_bits && (nd >> (b1 + b2)) > sub_target) b2++;
         plan->n_d = (uint32_t)nd;
-        plan->b2 = b2;
+        plan->b1 = (uint32_t)b1;
+        plan->b2 = (uint32_t)b2;
         plan->shift2 = 64 - b1 - b2;
         plan->n_sub = (uint32_t)nb1 << b2;
         plan->prefix_bits = b1 + b2;
+        plan->sub0 = 0;
+    }
+}
+
+// ------------------------------------------------------------- multi-GPU exchange
+// Every rank has counted its own reads (S2) and holds the histogram of its records' leading
+// kXB1 bits; the histograms of all ranks were all-gathered. One block derives, identically on
+// every rank: the owner of each level-1 bucket (contiguous bucket ranges with about equal record
+// totals: rank o owns keys whose leading bits lie in [lo[o], lo[o+1])) and the level-2 digit width
+// (from the global total, so that every rank cuts the same sub-buckets); and for this rank: its own
+// level-1 bases (the local scatter), where its key range starts and ends inside every source's
+// grouped array, and the plan of its part of the key space.
+constexpr int kXB1 = 10;
+struct XDev {
+    uint32_t lo[16];                 // bucket range of owner o: [lo[o], lo[o + 1])
+    uint32_t src_range[8][2];        // records of this rank's key range inside source s's grouped array
+    uint32_t n_recv, pad[3];
+};
+
+__global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict__ all_hist, uint32_t rank, uint32_t P,
+                                                      uint64_t d_cap, uint32_t sub_target, int sig_bits,
+                                                      uint32_t *__restrict__ base1, uint32_t *__restrict__ cursor1,
+                                                      SuperPlanDev *__restrict__ plan, XDev *__restrict__ x,
+                                                      unsigned long long *__restrict__ sc) {
+    constexpr int NB = 1 << kXB1;
+    __shared__ unsigned long long s_scan[32];
+    __shared__ uint32_t s_lo[17];
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // block-wide inclusive scan of 64-bit values (1024 threads)
+    auto block_incl = [&](unsigned long long v) -> unsigned long long {
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        unsigned long long off = 0;
+        for (int w = 0; w < warp; w++) off += s_scan[w];
+        return off + incl;
+    };
+    unsigned long long tot = 0;
+    for (uint32_t s2 = 0; s2 < P; s2++) tot += all_hist[s2 * NB + tid];
+    const unsigned long long cum = block_incl(tot);
+    if (tid == NB - 1) s_total = cum;
+    if (tid <= 16) s_lo[tid] = NB;
+    __syncthreads();
+    const unsigned long long total = s_total;
+    // owner of bucket tid: where the middle of the bucket falls in P equal shares of the total
+    uint32_t owner = 0;
+    if (total) owner = (uint32_t)(((cum - tot) + tot / 2) * P / total);
+    if (owner >= P) owner = P - 1;
+    atomicMin(&s_lo[owner], (uint32_t)tid);
+    __syncthreads();
+    if (tid == 0) {                                   // owners without a bucket start where the next one does
+        s_lo[P] = NB;
+        for (int o = (int)P - 1; o >= 0; o--)
+            if (s_lo[o] > s_lo[o + 1]) s_lo[o] = s_lo[o + 1];
+        s_lo[0] = 0;
+        for (uint32_t o = 0; o <= P; o++) x->lo[o] = s_lo[o];
+    }
+    __syncthreads();
+    const uint32_t my_lo = s_lo[rank], my_hi = s_lo[rank + 1];
+    // this rank's key range inside every source's grouped array
+    unsigned long long n_recv = 0;
+    for (uint32_t s2 = 0; s2 < P; s2++) {
+        const unsigned long long incl = block_incl(all_hist[s2 * NB + tid]);
+        __shared__ unsigned long long s_b, s_e;
+        if (tid == 0) { s_b = 0; s_e = 0; }
+        __syncthreads();
+        if (my_lo > 0 && tid == (int)my_lo - 1) s_b = incl;
+        if (my_hi > 0 && tid == (int)my_hi - 1) s_e = incl;
+        __syncthreads();
+        if (tid == 0) { x->src_range[s2][0] = (uint32_t)s_b; x->src_range[s2][1] = (uint32_t)s_e; }
+        n_recv += s_e - s_b;
+        __syncthreads();
+    }
+    // own level-1 bases: the local scatter groups this rank's records by the kXB1-bit digit
+    {
+        const uint32_t c = all_hist[rank * NB + tid];
+        const unsigned long long incl = block_incl(c);
+        base1[tid] = (uint32_t)(incl - c);
+        cursor1[tid] = (uint32_t)(incl - c);
+        if (tid == NB - 1) base1[NB] = (uint32_t)incl;
+    }
+    if (tid == 0) {
+        unsigned long long nd = sc[SW_D];
+        if (nd > d_cap) nd = d_cap;
+        int b2 = 0;
+        while (b2 < 9 && kXB1 + b2 < sig_bits && (total >> (kXB1 + b2)) > sub_target) b2++;
+        plan->n_d = (uint32_t)nd;
+        plan->b1 = kXB1;
+        plan->b2 = (uint32_t)b2;
+        plan->shift2 = 64 - kXB1 - b2;
+        plan->n_sub = (my_hi - my_lo) << b2;
+        plan->sub0 = my_lo << b2;
+        plan->prefix_bits = kXB1 + b2;
+        x->n_recv = (uint32_t)(n_recv > 0xffffffffull ? 0xffffffffull : n_recv);
+        if (n_recv > d_cap) atomicOr(&sc[SW_FAIL], 16ull);       // this rank's share does not fit its buffers
+    }
+}
+
+// level-2 counters of this rank's sub-buckets = sum over the sources' own histograms (peer loads)
+struct XPeers {
+    const uint64_t *keys[8];
+    const uint32_t *counts[8];
+    const uint32_t *hist2[8];
+};
+__global__ void __launch_bounds__(256) x_merge_hist_kernel(XPeers peers, uint32_t P, const SuperPlanDev *__restrict__ plan,
+                                                           uint32_t *__restrict__ out) {
+    const uint32_t n = plan->n_sub, sub0 = plan->sub0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        uint32_t c = 0;
+        for (uint32_t s2 = 0; s2 < P; s2++) c += peers.hist2[s2][sub0 + j];
+        out[j] = c;
     }
 }
 
@@ -749,24 +931,30 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
                                                                  uint32_t *__restrict__ out_counts,
                                                                  const SuperPlanDev *__restrict__ plan, int b1,
                                                                  const unsigned long long *__restrict__ n_ptr, uint64_t cap,
-                                                                 uint32_t *__restrict__ g_cursor) {
+                                                                 uint32_t *__restrict__ g_cursor,
+                                                                 const uint32_t *__restrict__ range) {
     constexpr int ITEMS = RsCfg<W>::ITEMS, TILE = RsCfg<W>::TILE;
     extern __shared__ __align__(16) uint8_t rs_smem[];
     Key<W> *stg_k = reinterpret_cast<Key<W> *>(rs_smem);                    // [TILE]
     uint32_t *stg_c = reinterpret_cast<uint32_t *>(stg_k + TILE);           // [TILE]
     uint32_t *cnt = stg_c + TILE, *start = cnt + kNb1Max, *gbase = start + kNb1Max;
     __shared__ uint32_t s_warp[kRsThreads / 32];
-    uint32_t n;
+    uint32_t n, first = 0;
     if (LEVEL == 1) {
         unsigned long long nn = *n_ptr;
         n = (uint32_t)(nn > cap ? cap : nn);
+    } else if (range) {                          // a slice of a (peer's) grouped array: records [range[0], range[1])
+        first = range[0];
+        n = range[1];
     } else {
         n = plan->n_d;
     }
     const int b2 = LEVEL == 1 ? 0 : (int)plan->b2;
+    if (LEVEL == 1) b1 = (int)plan->b1;
     const int shift = LEVEL == 1 ? 64 - b1 : (int)plan->shift2;
     const uint32_t nb2 = 1u << b2;
-    for (uint32_t begin = blockIdx.x * (uint32_t)TILE; begin < n; begin += gridDim.x * (uint32_t)TILE) {
+    const uint32_t sub0 = LEVEL == 1 ? 0u : plan->sub0;     // cursors are indexed relative to this rank's first sub-bucket
+    for (uint32_t begin = first + blockIdx.x * (uint32_t)TILE; begin < n; begin += gridDim.x * (uint32_t)TILE) {
         const uint32_t end = begin + TILE < n ? begin + TILE : n;
         Key<W> key[ITEMS];
         uint32_t val[ITEMS];
@@ -796,7 +984,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
                 const uint32_t rel = pfx - p0;
                 if (rel < nb) rank[i] = (uint16_t)atomicAdd(&cnt[rel], 1u);
                 else {
-                    const uint32_t o = atomicAdd(&g_cursor[pfx], 1u);
+                    const uint32_t o = atomicAdd(&g_cursor[pfx - sub0], 1u);
                     st_key<W>(out_keys, o, key[i]);
                     out_counts[o] = val[i];
                 }
@@ -812,7 +1000,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
             reserved[u] = 0;
             if (b < nb) {
                 const uint32_t c = cnt[b];
-                if (c) reserved[u] = atomicAdd(&g_cursor[p0 + b], c);
+                if (c) reserved[u] = atomicAdd(&g_cursor[p0 - sub0 + b], c);
             }
         }
 #pragma unroll
@@ -945,25 +1133,31 @@ struct FinishParams {
 // counting sort on the next key bits into shared memory, an insertion sort inside each bin (a
 // bitonic network when a bin is crowded), then -- DUP only -- equal keys are folded (counts
 // added, uint32 wrap) and the survivors compacted. The records are written once, in key order.
+// Every loop runs over the sub-bucket's own size, not over CAP.
 template <int W, int THREADS, int CAP, bool DUP>
 __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
-    constexpr int NB3 = CAP;                                           // most counting-sort bins
     extern __shared__ __align__(16) uint8_t fs_smem[];
     Key<W> *ik = reinterpret_cast<Key<W> *>(fs_smem);                  // loaded      [CAP]
     Key<W> *sk = ik + CAP;                                             // sorted      [CAP]
     uint32_t *ic = reinterpret_cast<uint32_t *>(sk + CAP);             // [CAP]
     uint32_t *scn = ic + CAP;                                          // [CAP]
-    uint32_t *c3 = scn + CAP;                                          // [NB3]
-    uint32_t *s3 = c3 + NB3;                                           // [NB3]
+    uint32_t *c3 = scn + CAP;                                          // counting-sort bins [CAP]
+    uint32_t *s3 = c3 + CAP;                                           // their starts       [CAP]
+    uint16_t *rks = reinterpret_cast<uint16_t *>(s3 + CAP);            // rank of record i inside its bin [CAP]
     __shared__ uint32_t s_maxbin, s_cnt, s_j;
     __shared__ uint32_t s_warp[THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_sub = p.plan->n_sub;
     const int prefix_bits = (int)p.plan->prefix_bits;
     unsigned long long folded_local = 0;
+    uint32_t next_ticket = 0;
+    if (tid == 0) next_ticket = (uint32_t)atomicAdd(&p.sc[SW_TICKET2], 1ull);
 
     while (true) {
-        if (tid == 0) s_j = (uint32_t)atomicAdd(&p.sc[SW_TICKET2], 1ull);
+        if (tid == 0) {
+            s_j = next_ticket;
+            if (next_ticket < n_sub) next_ticket = (uint32_t)atomicAdd(&p.sc[SW_TICKET2], 1ull);
+        }
         __syncthreads();
         const uint32_t j = s_j;
         if (j >= n_sub) break;
@@ -980,34 +1174,23 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
         }
         for (uint32_t i = tid; i < n; i += THREADS) { ik[i] = ld_key<W>(p.in_keys, b + i); ic[i] = p.in_counts[b + i]; }
         uint32_t nb3 = pow2_ceil_u32(n);
-        nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)NB3 ? (uint32_t)NB3 : nb3);
+        nb3 = nb3 < 64 ? 64 : nb3;                                     // <= CAP
         int shift3 = 64 - prefix_bits - (31 - __clz(nb3));
         if (shift3 < 0) shift3 = 0;
         for (uint32_t i = tid; i < nb3; i += THREADS) c3[i] = 0;
         if (tid == 0) { s_maxbin = 0; s_cnt = 0; }
         __syncthreads();
-        constexpr int kPer = (CAP + THREADS - 1) / THREADS;
-        uint32_t rk[kPer];
-#pragma unroll
-        for (int u = 0; u < kPer; u++) {
-            const uint32_t i = u * THREADS + tid;
-            if (i < n) rk[u] = atomicAdd(&c3[(uint32_t)(ik[i].w[0] >> shift3) & (nb3 - 1)], 1u);
-        }
+        for (uint32_t i = tid; i < n; i += THREADS)
+            rks[i] = (uint16_t)atomicAdd(&c3[(uint32_t)(ik[i].w[0] >> shift3) & (nb3 - 1)], 1u);
         __syncthreads();
-        uint32_t mx = 0;
-        for (uint32_t i = tid; i < nb3; i += THREADS) mx = max(mx, c3[i]);
-        if (mx > 1) atomicMax(&s_maxbin, mx);
-        // exclusive scan of the nb3 bins (nb3 <= CAP, THREADS threads, nb3 / THREADS each)
+        // exclusive scan of the nb3 bins: thread t owns bins [t * per3, (t + 1) * per3)
         {
-            constexpr int PER = NB3 / THREADS;
-            uint32_t v[PER];
-            uint32_t sum = 0;
-#pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const uint32_t bb = tid * PER + i;
-                v[i] = bb < nb3 ? c3[bb] : 0;
-                sum += v[i];
-            }
+            const uint32_t per3 = nb3 >= (uint32_t)THREADS ? nb3 / THREADS : 1u;
+            const uint32_t b0 = tid * per3;
+            uint32_t sum = 0, mx = 0;
+            if (b0 < nb3)
+                for (uint32_t q = 0; q < per3; q++) { const uint32_t v = c3[b0 + q]; sum += v; mx = max(mx, v); }
+            if (mx > 1) atomicMax(&s_maxbin, mx);
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1020,27 +1203,19 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
 #pragma unroll
             for (int w = 0; w < THREADS / 32; w++) if ((uint32_t)w < warp) off += s_warp[w];
             uint32_t run = off + incl - sum;
-#pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const uint32_t bb = tid * PER + i;
-                if (bb < nb3) s3[bb] = run;
-                run += v[i];
-            }
+            if (b0 < nb3)
+                for (uint32_t q = 0; q < per3; q++) { s3[b0 + q] = run; run += c3[b0 + q]; }
             __syncthreads();
         }
         const uint32_t maxbin = s_maxbin;
         Key<W> *rk_keys = sk;
         uint32_t *rk_cnts = scn;
         if (maxbin <= 24) {
-#pragma unroll
-            for (int u = 0; u < kPer; u++) {
-                const uint32_t i = u * THREADS + tid;
-                if (i < n) {
-                    const Key<W> k = ik[i];
-                    const uint32_t o = s3[(uint32_t)(k.w[0] >> shift3) & (nb3 - 1)] + rk[u];
-                    sk[o] = k;
-                    scn[o] = ic[i];
-                }
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const Key<W> k = ik[i];
+                const uint32_t o = s3[(uint32_t)(k.w[0] >> shift3) & (nb3 - 1)] + rks[i];
+                sk[o] = k;
+                scn[o] = ic[i];
             }
             __syncthreads();
             if (maxbin > 1) {
@@ -1181,7 +1356,7 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.nk = L - k + 1;
     pl.nh = pl.nk + pl.w - 1;
     pl.nh_stride = (pl.nh + 8) | 1u;                                   // odd stride: rows start in different banks
-    pl.seg_len = pl.w < (uint32_t)kSwMaxSeg ? pl.w : (uint32_t)kSwMaxSeg;
+    pl.seg_len = pl.w - 1 < (uint32_t)kSwMaxSeg - 1 ? pl.w - 1 : (uint32_t)kSwMaxSeg - 1;   // + the look-behind window
     pl.segs_per_read = (pl.nk + pl.seg_len - 1) / pl.seg_len;
     pl.seg_len = (pl.nk + pl.segs_per_read - 1) / pl.segs_per_read;    // even the segments out
     pl.cmax = 32u * pl.W - 3;
@@ -1202,15 +1377,10 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.ovf_slice = 4096;
     pl.d_cap = max_windows < (1ull << 32) - 2 ? max_windows : (1ull << 32) - 2;
     if (pl.d_cap < 1024) pl.d_cap = 1024;
-    // level 1: digits so that two levels reach sub-buckets of sub_target records even if every window is distinct
+    // S2 keeps a histogram of the leading b1 bits; the device plan picks the digits from it
     pl.sub_target = FinishCfg<1>::CAP * 7 / 10;
-    int B = 1;
-    while (B < 19 && (max_windows >> B) > pl.sub_target) B++;
-    pl.b1 = B - 9 < 4 ? (B < 4 ? B : 4) : B - 9;
-    if (pl.b1 > 10) pl.b1 = 10;
     const int sig = pl.W == 1 ? (masked ? (int)(2 * mm) : 64) : 64;
-    if (pl.b1 > sig) pl.b1 = sig;
-    if (pl.b1 < 1) pl.b1 = 1;
+    pl.b1 = sig < 10 ? sig : 10;
     // workspace
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) { uint64_t r = o; o += round512(bytes); return r; };
@@ -1225,6 +1395,8 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.off_mout = take((uint64_t)(kSuperMaxSub + 8) * 4);
     pl.off_off = take((uint64_t)(kSuperMaxSub + 8) * 4);
     pl.off_plan = take(sizeof(SuperPlanDev));
+    pl.off_x = take(sizeof(XDev));
+    pl.off_h2m = take((uint64_t)(kSuperMaxSub + 8) * 4);
     pl.off_bins = take((uint64_t)pl.n_bins * pl.bin_cap * rec_bytes);
     pl.off_ovf = take(pl.ovf_cap * rec_bytes);
     pl.off_dk = take(pl.d_cap * 8 * pl.W + 64);
@@ -1261,7 +1433,7 @@ static cudaError_t super_scatter_w(const SuperPlan &pl, const void *d_reads, uin
     q.h_off = (q.ep.smem_total + 15u) & ~15u;
     q.bin_off = q.h_off + q.ep.tile_reads * pl.nh_stride * 4;
     q.bits_off = q.bin_off + q.ep.tile_reads * pl.nk * 4;
-    const uint32_t smem = q.bits_off + (q.ep.tile_reads * pl.nk / 32 + 4) * 4;
+    const uint32_t smem = q.bits_off + 2 * q.ep.tile_reads * pl.segs_per_read * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     q.n_bins = pl.n_bins; q.bin_cap = pl.bin_cap; q.ovf_cap = pl.ovf_cap;
     q.cursor = at<uint32_t>(ws, pl.off_cursor);
@@ -1285,7 +1457,7 @@ static bool super_scatter_fits(const SuperPlan &pl) {
     ExtractParams ep;
     if (!extract_plan(nullptr, 16, pl.L, pl.k, false, nullptr, &ep, 6400)) return false;
     const uint64_t smem = ((ep.smem_total + 15u) & ~15u) + (uint64_t)ep.tile_reads * pl.nh_stride * 4 +
-                          (uint64_t)ep.tile_reads * pl.nk * 4 + (ep.tile_reads * pl.nk / 32 + 4) * 4;
+                          (uint64_t)ep.tile_reads * pl.nk * 4 + 2ull * ep.tile_reads * pl.segs_per_read * 4;
     return smem <= 200 * 1024;
 }
 
@@ -1298,7 +1470,8 @@ cudaError_t super_scatter(const SuperPlan &pl, const void *d_reads, uint64_t n_r
 
 template <int W, int THREADS, int TSLOTS, int RPT = 2>
 static cudaError_t launch_count(const SwCountParams &cp, int n_sms, cudaStream_t s) {
-    const uint32_t smem = TSLOTS * (8 * W + 4) + THREADS * RPT * 16 * W + (THREADS * RPT + 8) * 4 + kNb1Max * 4;
+    const uint32_t smem = TSLOTS * (8 * W + 4) + THREADS * RPT * 16 * W + (THREADS * RPT + 8) * 4 + kNb1Max * 4 +
+                          (THREADS / 32) * 128 * 8 * W;
     auto kern = sw_count_kernel<W, THREADS, TSLOTS, RPT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1310,24 +1483,17 @@ static cudaError_t launch_count(const SwCountParams &cp, int n_sms, cudaStream_t
 }
 
 template <int W>
-static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
-                                 cudaStream_t s, cudaEvent_t *evs) {
+static cudaError_t super_count_bins_w(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                                      cudaStream_t s) {
     cudaError_t e;
-    uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
-    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
-    uint32_t *hist1 = at<uint32_t>(ws, pl.off_hist1), *base1 = at<uint32_t>(ws, pl.off_base1),
-             *cur1 = at<uint32_t>(ws, pl.off_cur1), *hist2 = at<uint32_t>(ws, pl.off_hist2),
-             *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
-    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
-    // ---- S2
     SwCountParams cp{};
     cp.cursor = at<uint32_t>(ws, pl.off_cursor);
     cp.bins = at<uint8_t>(ws, pl.off_bins);
     cp.ovf = at<uint8_t>(ws, pl.off_ovf);
     cp.n_bins = pl.n_bins; cp.bin_cap = pl.bin_cap; cp.ovf_slice = pl.ovf_slice; cp.ovf_cap = pl.ovf_cap;
     cp.last_mask = pl.last_mask;
-    cp.d_keys = dk; cp.d_counts = dc; cp.d_cap = pl.d_cap;
-    cp.hist1 = hist1; cp.shift1 = 64 - pl.b1; cp.nb1 = 1 << pl.b1;
+    cp.d_keys = at<uint64_t>(ws, pl.off_dk); cp.d_counts = at<uint32_t>(ws, pl.off_dc); cp.d_cap = pl.d_cap;
+    cp.hist1 = at<uint32_t>(ws, pl.off_hist1); cp.shift1 = 64 - pl.b1; cp.nb1 = 1 << pl.b1;
     cp.add_phantom = add_phantom ? 1 : 0;
     cp.sc = d_sc;
     static int variant = -1;                    // KC_SW_COUNT (development knob): CTA / table shape of S2
@@ -1341,6 +1507,8 @@ static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws
             case 5: e = launch_count<1, 128, 2048, 2>(cp, n_sms, s); break;
             case 6: e = launch_count<1, 256, 4096, 1>(cp, n_sms, s); break;
             case 7: e = launch_count<1, 256, 4096, 4>(cp, n_sms, s); break;
+            case 8: e = launch_count<1, 512, 4096, 2>(cp, n_sms, s); break;
+            case 9: e = launch_count<1, 384, 4096, 2>(cp, n_sms, s); break;
             default: e = launch_count<1, 256, 4096, 2>(cp, n_sms, s); break;
         }
     } else {
@@ -1351,7 +1519,28 @@ static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws
             default: e = launch_count<2, 512, 4096, 1>(cp, n_sms, s); break;
         }
     }
-    if (e != cudaSuccess) return e;
+    return e;
+}
+
+cudaError_t super_count_bins(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                             cudaStream_t s) {
+    if (pl.W == 1) return super_count_bins_w<1>(pl, add_phantom, ws, d_sc, n_sms, s);
+    if (pl.W == 2) return super_count_bins_w<2>(pl, add_phantom, ws, d_sc, n_sms, s);
+    return cudaErrorInvalidValue;
+}
+
+template <int W>
+static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                                 cudaStream_t s, cudaEvent_t *evs) {
+    cudaError_t e;
+    uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
+    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
+    uint32_t *hist1 = at<uint32_t>(ws, pl.off_hist1), *base1 = at<uint32_t>(ws, pl.off_base1),
+             *cur1 = at<uint32_t>(ws, pl.off_cur1), *hist2 = at<uint32_t>(ws, pl.off_hist2),
+             *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
+    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    // ---- S2
+    if ((e = super_count_bins_w<W>(pl, add_phantom, ws, d_sc, n_sms, s)) != cudaSuccess) return e;
     if (evs) cudaEventRecord(evs[0], s);
     // ---- S3a: level-1 bases + device plan, scatter D -> E
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
@@ -1366,7 +1555,7 @@ static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kRsThreads, rs_smem);
         if (per_sm < 1) per_sm = 1;
         const uint32_t grid = (uint32_t)n_sms * per_sm;
-        k1<<<grid, kRsThreads, rs_smem, s>>>(dk, dc, ek, ec, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur1);
+        k1<<<grid, kRsThreads, rs_smem, s>>>(dk, dc, ek, ec, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur1, nullptr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (evs) cudaEventRecord(evs[1], s);
         // ---- level-2 histogram + scan (b2 == 0: one counter per level-1 bucket)
@@ -1375,7 +1564,7 @@ static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (evs) cudaEventRecord(evs[2], s);
         // ---- S3b: scatter E -> D by the level-2 digit
-        k2<<<grid, kRsThreads, rs_smem, s>>>(ek, ec, dk, dc, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur2);
+        k2<<<grid, kRsThreads, rs_smem, s>>>(ek, ec, dk, dc, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur2, nullptr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (evs) cudaEventRecord(evs[3], s);
     }
@@ -1407,7 +1596,7 @@ static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long l
     fp.out_counts = out_counts;
     fp.m_out = at<uint32_t>(ws, pl.off_mout);
     fp.sc = d_sc;
-    const uint32_t smem = 2 * CAP * (8 * W + 4) + 2 * CAP * 4;
+    const uint32_t smem = 2 * CAP * (8 * W + 4) + 2 * CAP * 4 + CAP * 2;
     auto kern = rec_finish_kernel<W, THREADS, CAP, DUP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1444,5 +1633,78 @@ cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys
 }
 
 bool super_supported(const SuperPlan &pl) { return super_scatter_fits(pl); }
+
+// ---- multi-GPU exchange (see x_plan_kernel). Every rank's workspace has the same layout, so a
+// peer's buffers are found from its workspace base.
+template <int W>
+static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
+                                   uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s) {
+    cudaError_t e;
+    uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
+    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
+    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
+    x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, pl.d_cap, pl.sub_target, sig, at<uint32_t>(ws, pl.off_base1),
+                                     at<uint32_t>(ws, pl.off_cur1), plan, at<XDev>(ws, pl.off_x), d_sc);
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kNb1Max * 4;
+    auto k1 = rec_scatter_kernel<W, 1>;
+    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kRsThreads, rs_smem);
+    if (per_sm < 1) per_sm = 1;
+    k1<<<(uint32_t)n_sms * per_sm, kRsThreads, rs_smem, s>>>(dk, dc, ek, ec, plan, pl.b1, &d_sc[SW_D], pl.d_cap,
+                                                            at<uint32_t>(ws, pl.off_cur1), nullptr);
+    rec_hist2_kernel<W><<<(uint32_t)n_sms * 8, 256, 0, s>>>(ek, plan, at<uint32_t>(ws, pl.off_hist2));
+    return cudaGetLastError();
+}
+
+cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
+                          uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s) {
+    if (pl.b1 != kXB1 || n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return cudaErrorInvalidValue;
+    if (pl.W == 1) return super_x_local_w<1>(pl, ws, d_sc, d_all_hist, rank, n_ranks, n_sms, s);
+    if (pl.W == 2) return super_x_local_w<2>(pl, ws, d_sc, d_all_hist, rank, n_ranks, n_sms, s);
+    return cudaErrorInvalidValue;
+}
+
+template <int W>
+static cudaError_t super_x_pull_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws,
+                                  uint32_t n_ranks, int n_sms, cudaStream_t s) {
+    cudaError_t e;
+    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    XDev *x = at<XDev>(ws, pl.off_x);
+    XPeers peers{};
+    for (uint32_t i = 0; i < n_ranks; i++) {
+        peers.keys[i] = at<uint64_t>(peer_ws[i], pl.off_ek);
+        peers.counts[i] = at<uint32_t>(peer_ws[i], pl.off_ec);
+        peers.hist2[i] = at<uint32_t>(peer_ws[i], pl.off_hist2);
+    }
+    uint32_t *h2m = at<uint32_t>(ws, pl.off_h2m), *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
+    x_merge_hist_kernel<<<(uint32_t)n_sms * 4, 256, 0, s>>>(peers, n_ranks, plan, h2m);
+    sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(h2m, &plan->n_sub, 0, base2, cur2, nullptr);
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kNb1Max * 4;
+    auto k2 = rec_scatter_kernel<W, 2>;
+    if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, kRsThreads, rs_smem);
+    if (per_sm < 1) per_sm = 1;
+    // the level-2 scatter reads this rank's key range straight out of every source's grouped array:
+    // the exchange happens inside the kernel's loads (NVLink / NVSwitch for the peers)
+    for (uint32_t i = 0; i < n_ranks; i++)
+        k2<<<(uint32_t)n_sms * per_sm, kRsThreads, rs_smem, s>>>(peers.keys[i], peers.counts[i], at<uint64_t>(ws, pl.off_dk),
+                                                                at<uint32_t>(ws, pl.off_dc), plan, pl.b1, &d_sc[SW_D],
+                                                                pl.d_cap, cur2, &x->src_range[i][0]);
+    return cudaGetLastError();
+}
+
+cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t n_ranks,
+                         int n_sms, cudaStream_t s) {
+    if (n_ranks == 0 || n_ranks > 8) return cudaErrorInvalidValue;
+    if (pl.W == 1) return super_x_pull_w<1>(pl, ws, d_sc, peer_ws, n_ranks, n_sms, s);
+    if (pl.W == 2) return super_x_pull_w<2>(pl, ws, d_sc, peer_ws, n_ranks, n_sms, s);
+    return cudaErrorInvalidValue;
+}
+
+uint32_t *super_hist1(const SuperPlan &pl, void *ws) { return at<uint32_t>(ws, pl.off_hist1); }
+const void *super_x_info(const SuperPlan &pl, void *ws) { return at<XDev>(ws, pl.off_x); }
 
 }  // namespace kc

@@ -46,7 +46,9 @@ struct SuperPlanDev {           // level-2 plan, decided on the device once |D| 
     uint32_t n_d;               // records in D (clamped to capacity)
     uint32_t b2, shift2, n_sub; // level-2 digit bits, key shift of the (b1+b2)-bit prefix, sub-buckets
     uint32_t prefix_bits;
-    uint32_t pad[3];
+    uint32_t b1;                // level-1 digit bits actually used (<= SuperPlan::b1)
+    uint32_t sub0;              // first (absolute) sub-bucket of this rank's key range; 0 on one GPU
+    uint32_t pad[1];
 };
 
 struct SuperPlan {
@@ -60,12 +62,12 @@ struct SuperPlan {
     uint64_t ovf_cap;           // records of the shared overflow list
     uint32_t ovf_slice;         // overflow records per S2 work unit
     uint64_t d_cap;             // records D / the level buffers hold
-    int b1;                     // level-1 digit bits (nb1 = 1 << b1 <= 1024)
+    int b1;                     // bits of the histogram S2 keeps (most level-1 digit bits; 1 << b1 <= 1024)
     uint32_t sub_target;        // records per sub-bucket the level-2 plan aims for
     uint64_t last_mask;
     // workspace layout (bytes from the workspace base)
     uint64_t off_cursor, off_bins, off_ovf, off_hist1, off_base1, off_cur1, off_hist2, off_base2, off_cur2,
-        off_mout, off_off, off_plan, off_dk, off_dc, off_ek, off_ec, ws_bytes;
+        off_mout, off_off, off_plan, off_x, off_h2m, off_dk, off_dc, off_ek, off_ec, ws_bytes;
 };
 
 constexpr uint32_t kSuperMaxSub = 1u << 20;
@@ -94,6 +96,19 @@ cudaError_t super_fold_offsets(const SuperPlan &pl, void *ws, unsigned long long
 // ... and the gather that closes the gaps
 cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys, const uint32_t *tmp_counts,
                          uint64_t *out_keys, uint32_t *out_counts, int n_sms, cudaStream_t s);
+// S2 only: count the bins into the dense array D (+ histogram of the records' leading b1 bits)
+cudaError_t super_count_bins(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
+                             cudaStream_t s);
+// ---- multi-GPU (one context per rank, every rank planned alike): after super_count_bins and an
+// all-gather of the ranks' histograms (super_hist1: 1024 uint32 each) ...
+uint32_t *super_hist1(const SuperPlan &pl, void *ws);
+// ... the rank groups its own records by their leading 10 bits and counts the global sub-buckets,
+cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
+                          uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s);
+// ... and, once every rank has done that, pulls its key range out of every rank's grouped array
+// (peer_ws[i] = rank i's workspace as mapped here) into sub-buckets. Then super_finish(dup = true).
+cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t n_ranks,
+                         int n_sms, cudaStream_t s);
 // false when S1's shared-memory tile cannot hold 16 reads of this length
 bool super_supported(const SuperPlan &pl);
 // where S3c's temporary output may live in DUP mode (the level-1 buffer is dead by then)

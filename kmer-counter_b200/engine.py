@@ -19,6 +19,19 @@ SW_SCALARS = ["invalid", "overflow_records", "d_records", "fail", "ticket", "win
               "out_records", "records", "ticket2"]
 
 
+def xchg_run_all(counters):
+    """All ranks in this process (kc_xchg_run_all): what the counters accumulated -> [run of rank r's key range]."""
+    lib = counters[0]._lib
+    n = len(counters)
+    ctxs = (C.c_void_p * n)(*[c._ctx for c in counters])
+    runs = (C.c_void_p * n)()
+    rc = lib.kc_xchg_run_all(ctxs, n, runs)
+    if rc != 0:
+        msgs = [(lib.kc_last_error(c._ctx) or b"").decode() for c in counters]
+        raise KcError(rc, "; ".join(m for m in msgs if m))
+    return [Run(c, C.c_void_p(runs[i])) for i, c in enumerate(counters)]
+
+
 class KcError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("kc error %d: %s" % (code, msg))
@@ -155,6 +168,59 @@ class Counter:
         d["stage_launches"] = [int(x) for x in st.stage_launches][:n]
         d["stage_names"] = (names + ["stage%d" % i for i in range(len(names), n)])[:n]
         return d
+
+    # -- accumulating mode: many chunks, one count (kc_accum_*)
+    def accum_begin(self, expected_reads=0):
+        self._check(self._lib.kc_accum_begin(self._ctx, expected_reads))
+
+    def accum_add_device(self, d_ptr, n_bytes):
+        self._check(self._lib.kc_accum_add_device(self._ctx, d_ptr, n_bytes))
+
+    def accum_submit(self, slot, n_bytes):
+        self._check(self._lib.kc_accum_submit(self._ctx, slot, n_bytes))
+
+    def accum_wait(self, slot):
+        self._check(self._lib.kc_accum_wait(self._ctx, slot))
+
+    def accum_flush(self) -> "Run":
+        h = C.c_void_p()
+        self._check(self._lib.kc_accum_flush(self._ctx, C.byref(h)))
+        return Run(self, h)
+
+    # -- multi-GPU exchange (kc_xchg_*): this counter is one rank
+    def xchg_begin(self, rank, n_ranks, expected_reads=0):
+        self._check(self._lib.kc_xchg_begin(self._ctx, rank, n_ranks, expected_reads))
+
+    def xchg_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.kc_xchg_export(self._ctx, buf))
+        return buf.raw
+
+    def xchg_import(self, peer, handle: bytes):
+        self._check(self._lib.kc_xchg_import(self._ctx, peer, C.create_string_buffer(handle, 64)))
+
+    def xchg_set_peer(self, peer, other: "Counter"):
+        self._check(self._lib.kc_xchg_set_peer(self._ctx, peer, other._ctx))
+
+    def xchg_count_local(self):
+        self._check(self._lib.kc_xchg_count_local(self._ctx))
+
+    def xchg_hist(self):
+        """(device pointer of this rank's 1024-bin histogram, of the n_ranks x 1024 gather buffer)"""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.kc_xchg_hist(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def xchg_group_local(self):
+        self._check(self._lib.kc_xchg_group_local(self._ctx))
+
+    def xchg_pull(self):
+        self._check(self._lib.kc_xchg_pull(self._ctx))
+
+    def xchg_finish(self) -> "Run":
+        h = C.c_void_p()
+        self._check(self._lib.kc_xchg_finish(self._ctx, C.byref(h)))
+        return Run(self, h)
 
     def debug_scalars(self) -> dict:
         """Device scalars of the most recent chunk (super-window path: SW_* of kc_super.cuh)."""

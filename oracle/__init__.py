@@ -208,6 +208,10 @@ def ref():
         r.ref_count_packed.restype = C.c_int64
         r.ref_count_packed.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32,
                                        C.c_char_p, C.c_char_p]
+        if hasattr(r, "ref_count_packed_ex"):
+            r.ref_count_packed_ex.restype = C.c_int64
+            r.ref_count_packed_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32,
+                                              C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
         r.ref_read_fastq_dir.restype = C.c_int64
         r.ref_read_fastq_dir.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         r.ref_free.argtypes = [C.c_void_p]
@@ -233,6 +237,16 @@ def ref_count_packed(reads, L, k, chunk_reads, threads, tmp_dir, out_path) -> in
     a = _as_u8(reads)
     return ref().ref_count_packed(a.ctypes.data, a.size, L, k, chunk_reads, threads, tmp_dir.encode(),
                                   out_path.encode())
+
+
+def ref_count_packed_ex(reads, L, k, chunk_reads, threads, fan_in, merge_threads, tmp_dir, out_path) -> dict:
+    """Pipeline B with per-stage seconds and the reference's merge policy (fan-in, merger threads)."""
+    a = _as_u8(reads)
+    t = (C.c_double * 6)()
+    runs = ref().ref_count_packed_ex(a.ctypes.data, a.size, L, k, chunk_reads, threads, fan_in, merge_threads,
+                                     tmp_dir.encode(), out_path.encode(), t)
+    return {"runs": int(runs), "encode_extract_thread_s": t[0], "sort_thread_s": t[1], "reduce_dump_thread_s": t[2],
+            "chunk_phase_wall_s": t[3], "merge_wall_s": t[4], "threads_busy": int(t[5])}
 
 
 def ref_read_fastq_dir(path, chunk_size=1 << 30):

@@ -65,6 +65,101 @@ def test_chunk_matches_oracle_hash(kc, R, L, k, G, e, n, method):
     assert got == want
 
 
+SUPER_CASES = [c for c in CASES if 22 <= c[2] <= 64]
+
+
+@pytest.mark.parametrize("R,L,k,G,e,n", SUPER_CASES)
+def test_chunk_matches_oracle_super(kc, R, L, k, G, e, n):
+    """The super-window path (minimizer-binned 2-bit records, per-bin shared-memory count, MSD
+    placement of the distinct records), also with its folding variant forced."""
+    reads = oracle.gen_reads(R, L, G, e, n, seed=R + k)
+    want = oracle.process_chunk(reads, L, k)
+    for force_dup in ("0", "1"):
+        os.environ["KC_SW_FORCE_DUP"] = force_dup
+        try:
+            with _counter(kc, k, L, method="super") as c:
+                got = c.process_chunk(reads)
+                assert c.stats()["method_used"] == "super"
+                sc = c.debug_scalars()
+        finally:
+            os.environ["KC_SW_FORCE_DUP"] = "0"
+        assert got == want, (force_dup, sc)
+        assert sc["windows"] == R * (L - k + 1) - sc["invalid"]          # S1 packed every k-mer into a record
+
+
+def test_auto_picks_super_where_it_applies(kc):
+    reads = oracle.gen_reads(500, 100, 9000, 0.01, 0.002, seed=3)
+    for k, want_method in ((31, "super"), (63, "super"), (22, "super"), (21, "hash"), (5, "sort"), (96, "sort")):
+        with _counter(kc, k, 100, method="auto") as c:
+            assert c.process_chunk(reads) == oracle.process_chunk(reads, 100, k)
+            assert c.stats()["method_used"] == want_method, k
+
+
+@pytest.mark.parametrize("occ", [64, 1000, 100000])
+def test_super_bin_sizes_and_split_passes(kc, occ):
+    """table_slots = k-mer occurrences per minimizer bin: tiny bins, and bins whose distinct keys
+    exceed the shared-memory table (counted in 2, 4, ... passes). The artefact must not depend on it."""
+    for k in (31, 63):
+        reads = np.concatenate([oracle.gen_reads(6000, 100, 0, 0.0, 0.001, seed=77),          # iid: all distinct
+                                np.tile(oracle.gen_reads(2, 100, 0, 0, 0, seed=79), 500),      # heavy hitters
+                                np.frombuffer((b"T" * 100) * 7 + (b"A" * 100) * 5, dtype=np.uint8)])
+        want = oracle.process_chunk(reads, 100, k)
+        with _counter(kc, k, 100, method="super", table_slots=occ, cap=1 << 26) as c:
+            assert c.process_chunk(reads) == want, k
+            assert c.stats()["method_used"] == "super"
+
+
+def test_super_heavy_hitters_overflow_list(kc):
+    """Tens of thousands of copies of a few reads overflow their minimizer bins: the surplus goes to
+    the shared overflow list, is counted in slices, and the duplicates are folded after the sort."""
+    L = 100
+    hot = oracle.gen_reads(3, L, 0, 0, 0, seed=5)
+    for reps, kk in ((4000, 31), (30000, 31), (30000, 63)):
+        reads = np.concatenate([np.tile(hot, reps), oracle.gen_reads(2000, L, 50000, 0.01, 0.001, seed=6)])
+        want = oracle.process_chunk(reads, L, kk)
+        with _counter(kc, kk, L, method="super", cap=1 << 26) as c:
+            assert c.process_chunk(reads) == want, (reps, kk)
+            st, sc = c.stats(), c.debug_scalars()
+        if st["method_used"] == "super":
+            assert sc["overflow_records"] > 0 and sc["folded"] > 0, (reps, kk, sc)
+
+
+def test_super_accumulate_many_chunks_one_count(kc):
+    """kc_accum_*: chunks are only packed into super-window records; one count at the end gives the
+    artefact of counting the chunks separately and merging (KMerFileMerger). Also with a plan that
+    is too small, so that parts are counted early and merged by the flush."""
+    import torch
+    for (R, L, k, G, e, n, expected, chunk_reads) in [
+            (30000, 100, 31, 200000, 0.01, 0.002, 30000, 7000),
+            (30000, 100, 31, 200000, 0.01, 0.002, 7000, 7000),
+            (20000, 100, 63, 100000, 0.001, 0.001, 20000, 4096),
+            (5000, 70, 28, 0, 0.0, 0.01, 0, 1000)]:
+        reads = oracle.gen_reads(R, L, G, e, n, seed=R + k + 1)
+        want = oracle.count(reads, L, k)
+        for how in ("slots", "device"):
+            with kc.Counter(k, L, method="super", n_slots=2, max_chunk_bytes=chunk_reads * L) as c:
+                c.accum_begin(expected)
+                if how == "slots":
+                    sl, busy = 0, [False, False]
+                    for r0 in range(0, R, chunk_reads):
+                        part = reads[r0 * L:(r0 + chunk_reads) * L]
+                        if busy[sl]:
+                            c.accum_wait(sl)
+                        c.slot_buffer(sl)[:len(part)] = part
+                        c.accum_submit(sl, len(part))
+                        busy[sl] = True
+                        sl ^= 1
+                else:
+                    d = torch.from_numpy(reads.copy()).cuda()
+                    c.accum_add_device(d.data_ptr(), len(reads))
+                run = c.accum_flush()
+                assert run.to_bytes() == want, (how, R, k, expected)
+                run.free()
+                run = c.accum_flush()                              # nothing accumulated: an empty run
+                assert len(run) == 0
+                run.free()
+
+
 @pytest.mark.parametrize("target", [16, 300, 4000])
 def test_partitioned_hash_128bit_keys_bucket_sizes_and_rounds(kc, target):
     R, L, k = 4000, 100, 63
@@ -120,7 +215,7 @@ def test_all_invalid_reads_give_only_the_phantom(kc):
     reads = np.frombuffer(b"N" * (L * 40), dtype=np.uint8)
     want = oracle.process_chunk(reads, L, k)
     assert want == bytes(12)                                      # key 0, count 0
-    for method in ("sort", "hash", "hash_global"):
+    for method in ("sort", "hash", "hash_global", "super"):
         with _counter(kc, k, L, method=method) as c:
             assert c.process_chunk(reads) == want
 
@@ -129,7 +224,7 @@ def test_poly_a_and_poly_t(kc):
     L, k = 64 + 5, 31
     reads = np.frombuffer((b"A" * L) * 30 + (b"T" * L) * 20 + (b"A" * 40 + b"N" + b"A" * (L - 41)) * 3, dtype=np.uint8)
     want = oracle.process_chunk(reads, L, k)
-    for method in ("sort", "hash", "hash_global"):
+    for method in ("sort", "hash", "hash_global", "super"):
         with _counter(kc, k, L, method=method) as c:
             assert c.process_chunk(reads) == want
 
@@ -159,7 +254,7 @@ def test_random_shapes_and_hostile_alphabet(kc):
             reads = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=R * L)].copy()
             reads[rng.integers(0, R * L, size=max(1, R * L // 40))] = rng.choice(alphabet, size=max(1, R * L // 40))
         want = oracle.process_chunk(reads, L, k)
-        for method in (("sort", "hash") if k <= 64 else ("sort",)):
+        for method in (("sort", "hash", "super") if k <= 64 else ("sort",)):       # super falls back where it does not apply
             with _counter(kc, k, L, method=method) as c:
                 assert c.process_chunk(reads) == want, (L, k, R, method)
         done += 1
@@ -169,7 +264,7 @@ def test_strict_mode_matches_naive_model(kc):
     for (R, L, k) in [(800, 100, 31), (500, 80, 63), (500, 60, 28)]:
         reads = oracle.gen_reads(R, L, 9000, 0.005, 0.003, seed=k)
         want = oracle.naive_count(reads, L, k, strict=True)
-        for method in (("sort", "hash", "hash_global") if k <= 32 else ("sort", "hash")):
+        for method in (("sort", "hash", "hash_global", "super") if k <= 32 else ("sort", "hash", "super")):
             with _counter(kc, k, L, compat="strict", method=method) as c:
                 assert c.process_chunk(reads) == want, (k, method)
 
@@ -254,7 +349,7 @@ def test_config1_full_size(kc):
     R, L, k = 100_000, 100, 31
     reads = oracle.gen_reads(R, L, 1_000_000, 0.0, 1e-3, seed=1)
     want = oracle.count(reads, L, k, chunk_reads=89364, threads=4)
-    for method in ("sort", "hash", "hash_global"):
+    for method in ("sort", "hash", "hash_global", "super"):
         with _counter(kc, k, L, method=method) as c:
             got = c.process_chunk(reads)
         assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest(), method
@@ -354,7 +449,7 @@ def test_full_size_properties_config2(kc):
     synth.synth_reads_device(d.data_ptr(), R, L, 100_000_000, 1e-3, 0.0, seed=2)
     torch.cuda.synchronize()
     digests = {}
-    for method in ("hash", "sort"):
+    for method in ("super", "hash", "sort"):
         with kc.Counter(k, L, method=method) as c:
             run = c.count_device(d.data_ptr(), R * L)
             kptr, cptr, n = run.device_arrays()
@@ -366,14 +461,14 @@ def test_full_size_properties_config2(kc):
             assert bool((kk[1:] > kk[:-1]).all()), "keys not strictly ascending"
             assert int(counts_t.to(torch.int64).sum()) == R * (L - k + 1)
             digests[method] = (n, int(ku.sum()), int((ku * counts_t.to(torch.int64)).sum()))
-            if method == "hash":
+            if method in ("hash", "super"):
                 pre = 200_000
                 r2 = c.count_device(d.data_ptr(), pre * L)
                 host = d[: pre * L].cpu().numpy()
                 assert r2.to_bytes() == oracle.count(host, L, k, threads=8)
                 r2.free()
             run.free()
-    assert digests["hash"] == digests["sort"]
+    assert digests["hash"] == digests["sort"] == digests["super"]
 
 
 def test_fastq_parse_on_device(kc):

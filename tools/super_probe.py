@@ -49,6 +49,48 @@ def case(R, L, k, G, e, n, seed=None, compat="ref", reads=None, **kw):
     return ok
 
 
+def accum_cases():
+    """accumulating mode: chunks through the pinned slots / device buffers, one count"""
+    import torch
+    ok = True
+    for (R, L, k, G, e, n, expected, chunk_reads) in [
+            (30000, 100, 31, 200000, 0.01, 0.002, 30000, 7000),     # fits the plan: one count
+            (30000, 100, 31, 200000, 0.01, 0.002, 7000, 7000),      # planned too small: parts + merge
+            (20000, 100, 63, 100000, 0.001, 0.001, 20000, 4096),
+            (5000, 70, 28, 0, 0.0, 0.01, 0, 1000)]:
+        reads = oracle.gen_reads(R, L, G, e, n, seed=R + k + 1)
+        want = oracle.count(reads, L, k)
+        for how in ("slots", "device"):
+            with kc.Counter(k, L, method="super", n_slots=2, max_chunk_bytes=chunk_reads * L) as c:
+                c.accum_begin(expected)
+                if how == "slots":
+                    sl = 0
+                    busy = [False, False]
+                    for r0 in range(0, R, chunk_reads):
+                        part = reads[r0 * L:(r0 + chunk_reads) * L]
+                        if busy[sl]:
+                            c.accum_wait(sl)
+                        c.slot_buffer(sl)[:len(part)] = part
+                        c.accum_submit(sl, len(part))
+                        busy[sl] = True
+                        sl ^= 1
+                else:
+                    d = torch.from_numpy(reads.copy()).cuda()
+                    c.accum_add_device(d.data_ptr(), len(reads))
+                run = c.accum_flush()
+                got = run.to_bytes()
+                run.free()
+                sc = c.debug_scalars()
+            good = got == want
+            ok &= good
+            print("%s accum %s R=%d L=%d k=%d expected=%d chunk=%d %s" % (
+                "ok  " if good else "FAIL", how, R, L, k, expected, chunk_reads,
+                "" if good else diff(got, want, 8 * ((k + 31) // 32) + 4)), flush=True)
+            if not good:
+                print("     scalars", sc, flush=True)
+    return ok
+
+
 def main():
     ok = True
     ok &= case(2000, 100, 31, 30000, 0.0, 0.0)
@@ -80,6 +122,8 @@ def main():
     ok &= case(2000, 100, 31, 30000, 0.01, 0.002)
     ok &= case(100000, 100, 31, 1000000, 0.0, 0.001, seed=1)
     ok &= case(700, 70, 63, 5000, 0.001, 0.001)
+    os.environ["KC_SW_FORCE_DUP"] = "0"
+    ok &= accum_cases()
     print("ALL OK" if ok else "SOME FAILED", flush=True)
 
     # timing, C2 shape
