@@ -907,8 +907,16 @@ int accum_scatter(kc_ctx *c, const void *d_reads, uint64_t n_reads, cudaStream_t
 
 extern "C" {
 
+static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange);
+
 int kc_accum_begin(kc_ctx *c, uint64_t expected_reads) {
     KC_TRY(check_ctx(c));
+    return accum_begin_impl(c, expected_reads, false);
+}
+
+// exchange: the record buffers also take what the peers send, which is this rank's share of the
+// key space only on average (ranges are cut at 1/1024 of the key space): a quarter more room
+static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange) {
     std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     cudaSetDevice(c->cfg.device);
     if (!super_ok(c)) return c->set_error(KC_ERR_ARG, "accumulating mode needs k <= 64 with windows of >= 22 bases (k=%u)", c->cfg.k);
@@ -921,7 +929,7 @@ int kc_accum_begin(kc_ctx *c, uint64_t expected_reads) {
     kc_ctx::Accum &a = c->acc;
     if (a.on && !a.fresh) return c->set_error(KC_ERR_STATE, "kc_accum_begin: reads are accumulated; flush first");
     SuperPlan pl;
-    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, (uint32_t)c->cfg.table_slots, &pl))
+    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, (uint32_t)c->cfg.table_slots, &pl, exchange ? 0.25 : 0.0))
         return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", c->cfg.k, c->cfg.read_len);
     // a chunk in flight may put every one of its windows into the overflow list
     const uint64_t chunk_windows = (chunk_reads ? chunk_reads : expected_reads) * nk;
@@ -1060,7 +1068,7 @@ int kc_xchg_begin(kc_ctx *c, uint32_t rank, uint32_t n_ranks, uint64_t expected_
     KC_TRY(check_ctx(c));
     if (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return c->set_error(KC_ERR_ARG, "kc_xchg_begin: rank %u of %u", rank, n_ranks);
     std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
-    KC_TRY(kc_accum_begin(c, expected_reads));
+    KC_TRY(accum_begin_impl(c, expected_reads, true));
     kc_ctx::Accum &a = c->acc;
     if (a.pl.b1 != 10) return c->set_error(KC_ERR_ARG, "kc_xchg_begin: keys of k=%u have too few bits to exchange by range", c->cfg.k);
     a.xchg = true;

@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t bin_of_min(uint32_t mn, uint32_t n_bins) {
 // ===================================================================== S1: scatter
 struct SwScatterParams {
     ExtractParams ep;
-    uint32_t m, w, nh, nh_stride, seg_len, segs_per_read, cmax;
+    uint32_t m, w, nh, nh_stride, seg_len, segs_per_read, cmax, span;
     uint32_t h_off, bin_off, bits_off;  // shared-memory offsets: m-mer hashes, window bins, boundary bitmask
     uint32_t n_bins, bin_cap;
     uint64_t ovf_cap;
@@ -244,6 +244,15 @@ __global__ void __launch_bounds__(kSwThreads) sw_scatter_kernel(SwScatterParams 
                 uint64_t rec[2 * W];
 #pragma unroll
                 for (int t = 0; t < 2 * W; t++) rec[t] = sh ? ((ew[t] << sh) | (ew[t + 1] >> (64 - sh))) : ew[t];
+                // bases behind the last window are whatever follows in the read: zeroed, so that the same
+                // run of the same locus gives the same record in every read (S2 counts equal records once)
+                const uint32_t nbases = q.span + c - 1;
+#pragma unroll
+                for (int t = 0; t < 2 * W; t++) {
+                    const int keep = (int)nbases - 32 * t;
+                    if (keep <= 0) rec[t] = 0;
+                    else if (keep < 32) rec[t] &= ~0ull << (64 - 2 * keep);
+                }
                 rec[2 * W - 1] = (rec[2 * W - 1] & ~0xffull) | c;
                 ulonglong2 *dst = nullptr;
                 if (idx < q.bin_cap) {
@@ -357,8 +366,15 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
     uint32_t *tc = reinterpret_cast<uint32_t *>(recs + RB * W);             // [TSLOTS]
     uint32_t *pre = tc + TSLOTS;                                            // [RB + 8]
     uint32_t *s_hist = pre + RB + 8;                                        // [kNb1Max]
-    constexpr int kQueue = 128;                                             // collided keys a warp parks before it drains them
+    constexpr int kQueue = 64;                                              // collided keys a warp parks before it drains them
     Key<W> *queue = reinterpret_cast<Key<W> *>(s_hist + kNb1Max);           // [THREADS / 32][kQueue]
+    uint32_t *queue_m = reinterpret_cast<uint32_t *>(queue + (THREADS / 32) * kQueue);   // their weights
+    // record-level table (DEDUP): equal records of a round are counted once, with a multiplicity
+    constexpr bool DEDUP = (W == 1);
+    constexpr int RT = DEDUP ? 2 * RB : 1;
+    ulonglong2 *rt_keys = reinterpret_cast<ulonglong2 *>(queue_m + (THREADS / 32) * kQueue);   // [RT]
+    uint32_t *rt_mult = reinterpret_cast<uint32_t *>(rt_keys + RT);         // [RT]
+    uint32_t *rec_mult = rt_mult + RT;                                      // [RB] weight of staged record i (0: a duplicate)
     __shared__ uint32_t s_unit, s_m, s_ones, s_abort, s_off;
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_warp[THREADS / 32];
@@ -458,6 +474,50 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                         c[u2] = (uint32_t)(pf[u2][W - 1].y & 0xffull);
                     }
                 }
+                // equal records of the round (the same run of the same locus, seen by several reads) are
+                // counted once: the first copy claims a slot of the record table and carries the
+                // multiplicity, the others drop out (0 windows)
+                uint32_t rslot[RPT];
+                if constexpr (DEDUP) {
+                    for (uint32_t i = tid; i < (uint32_t)RT; i += THREADS) { rt_keys[i] = make_ulonglong2(~0ull, ~0ull); rt_mult[i] = 0; }
+                    __syncthreads();
+#pragma unroll
+                    for (int u2 = 0; u2 < RPT; u2++) {
+                        rslot[u2] = 0xffffffffu;
+                        const uint32_t i = u2 * THREADS + tid;
+                        if (i < nr) {
+                            const ulonglong2 rec = pf[u2][0];
+                            uint32_t h = ((uint32_t)rec.x ^ (uint32_t)(rec.x >> 32) * 0x85EBCA6Bu ^ (uint32_t)(rec.y >> 8) * 0xC2B2AE35u ^
+                                          (uint32_t)(rec.y >> 40)) * 0x9E3779B1u >> (32 - ILog2<(uint32_t)RT>::v);
+                            while (true) {                       // the table holds twice the records of a round: never full
+                                ulonglong2 cur = rt_keys[h];
+                                if (cur.x == ~0ull || cur.y == ~0ull) {        // looks empty (a record is never all ones): settled by the CAS
+                                    const uint32_t a = smem_u32(&rt_keys[h]);
+                                    asm volatile(
+                                        "{\n"
+                                        ".reg .b128 c, n, o;\n"
+                                        "mov.b128 c, {%3, %3};\n"
+                                        "mov.b128 n, {%4, %5};\n"
+                                        "atom.shared.cas.b128 o, [%2], c, n;\n"
+                                        "mov.b128 {%0, %1}, o;\n"
+                                        "}\n"
+                                        : "=l"(cur.x), "=l"(cur.y)
+                                        : "r"(a), "l"(~0ull), "l"(rec.x), "l"(rec.y)
+                                        : "memory");
+                                    if (cur.x == ~0ull && cur.y == ~0ull) { rslot[u2] = h; atomicAdd(&rt_mult[h], 1u); break; }
+                                }
+                                if (cur.x == rec.x && cur.y == rec.y) { atomicAdd(&rt_mult[h], 1u); c[u2] = 0; break; }
+                                h = (h + 1) & (RT - 1);
+                            }
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int u2 = 0; u2 < RPT; u2++) {
+                        const uint32_t i = u2 * THREADS + tid;
+                        if (i < nr) rec_mult[i] = rslot[u2] != 0xffffffffu ? rt_mult[rslot[u2]] : 0u;
+                    }
+                }
                 // prefetch the next round
 #pragma unroll
                 for (int u2 = 0; u2 < RPT; u2++) {
@@ -504,14 +564,16 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
 #pragma unroll
                     for (int t = 0; t < 2 * W; t++) rw[t] = 0;
                     uint32_t in_rec = 0;                           // windows left in the open record
+                    uint32_t wgt = 1;                              // how many equal records the open one stands for
                     if (rem) {   // open the first record at window j
                         uint32_t lo = 0, hi = nr;                  // last record whose first window is <= f0
                         while (hi - lo > 1) {
                             const uint32_t mid = (lo + hi) >> 1;
                             if (pre[mid] <= f0) lo = mid; else hi = mid;
                         }
-                        ri = lo;
+                        ri = lo;                                   // (a record with windows: duplicates have none)
                         const uint32_t j = f0 - pre[lo];
+                        if constexpr (DEDUP) wgt = rec_mult[ri];
 #pragma unroll
                         for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
                         const uint32_t cnt = (uint32_t)(rw[2 * W - 1] & 0xffull);
@@ -537,11 +599,13 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                     // different key goes to the warp's queue; the queue is drained with the usual
                     // linear probing whenever it fills up, and after the last key.
                     Key<W> *wq = queue + warp * kQueue;
+                    uint32_t *wqm = queue_m + warp * kQueue;
                     uint32_t qn = 0;                               // keys queued (uniform across the warp)
                     auto drain = [&]() {
                         __syncwarp();
                         for (uint32_t en = lane; en < qn; en += 32) {
                             const Key<W> k = wq[en];
+                            const uint32_t kw = wqm[en];
                             uint32_t h = key_hash<W>(k) >> hshift;
                             bool done = false;
 #pragma unroll 1
@@ -551,7 +615,7 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                                     cur = slot_claim(&tk[h], k);
                                     if (key_all_ones<W>(cur)) { claims++; done = true; }
                                 }
-                                if (done || key_eq<W>(cur, k)) { atomicAdd(&tc[h], 1u); done = true; }
+                                if (done || key_eq<W>(cur, k)) { atomicAdd(&tc[h], kw); done = true; }
                                 else h = (h + 1) & (TSLOTS - 1);
                             }
                             if (!done) s_abort = 1;                // table (nearly) full: the pass is abandoned
@@ -566,6 +630,7 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                         uint32_t h = 0;
                         if (act) {
                             if (in_rec == 0) {
+                                if constexpr (DEDUP) { while ((wgt = rec_mult[ri]) == 0) ri++; }   // duplicates carry no windows
 #pragma unroll
                                 for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
                                 in_rec = min(rem, (uint32_t)(rw[2 * W - 1] & 0xffull));
@@ -580,7 +645,7 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                             for (int t = 0; t < 2 * W - 1; t++) rw[t] = (rw[t] << 2) | (rw[t + 1] >> 62);
                             rw[2 * W - 1] <<= 2;
                             if (key_all_ones<W>(key)) {            // the table's empty marker: counted on the side
-                                if (in_pass(0x9E3779B1u)) atomicAdd(&s_ones, 1u);
+                                if (in_pass(0x9E3779B1u)) atomicAdd(&s_ones, wgt);
                                 act = false;
                             } else {
                                 const uint32_t hv = key_hash<W>(key);
@@ -588,25 +653,26 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                                 act = in_pass(hv);
                             }
                         }
-                        bool coll = false;
-                        if (act) {
-                            Key<W> cur = tk[h];
-                            bool hit;
-                            // a slot that looks (even partly: a 128-bit read may tear) empty is settled by the CAS
-                            if (key_any_word_ones<W>(cur)) {
-                                cur = slot_claim(&tk[h], key);
-                                hit = key_all_ones<W>(cur);
-                                if (hit) claims++;
-                                else hit = key_eq<W>(cur, key);
-                            } else {
-                                hit = key_eq<W>(cur, key);
-                            }
-                            if (hit) atomicAdd(&tc[h], 1u);
-                            coll = !hit;
+                        // one probe, written so that the common path (the slot holds this key) stays
+                        // converged: only the lanes that see an empty slot branch off to claim it
+                        Key<W> cur = tk[h];                        // (inactive lanes read slot 0: harmless)
+                        const bool looks_empty = key_any_word_ones<W>(cur);   // even partly: a 128-bit read may tear
+                        bool hit = !looks_empty && key_eq<W>(cur, key);
+                        if (act && looks_empty) {
+                            cur = slot_claim(&tk[h], key);
+                            const bool claimed = key_all_ones<W>(cur);
+                            claims += claimed ? 1u : 0u;
+                            hit = claimed || key_eq<W>(cur, key);
                         }
+                        if (act && hit) atomicAdd(&tc[h], wgt);
+                        const bool coll = act && !hit;
                         const uint32_t cm = __ballot_sync(0xffffffffu, coll);
                         if (cm) {
-                            if (coll) wq[qn + __popc(cm & lanemask_lt())] = key;
+                            if (coll) {
+                                const uint32_t qi = qn + __popc(cm & lanemask_lt());
+                                wq[qi] = key;
+                                wqm[qi] = wgt;
+                            }
                             qn += __popc(cm);
                             if (qn > (uint32_t)kQueue - 32u) drain();
                         }
@@ -1129,21 +1195,23 @@ struct FinishParams {
     unsigned long long *sc;
 };
 
-// S3c: one CTA per sub-bucket (at most CAP records, all sharing their leading prefix_bits): a
-// counting sort on the next key bits into shared memory, an insertion sort inside each bin (a
-// bitonic network when a bin is crowded), then -- DUP only -- equal keys are folded (counts
-// added, uint32 wrap) and the survivors compacted. The records are written once, in key order.
-// Every loop runs over the sub-bucket's own size, not over CAP.
+// S3c: one CTA per sub-bucket (at most CAP records, all sharing their leading prefix_bits). The
+// records go from global memory into registers, are grouped by a counting sort on the next key
+// bits (about two bins per record) in shared memory, and every record then finds its final place
+// by comparing itself with the few records of its own bin -- no serial insertion sort, every lane
+// busy. A bitonic network takes over when some bin is crowded (keys sharing their next bits, many
+// copies of one key). DUP: equal keys are folded (counts added, uint32 wrap), survivors compacted.
+// The records are written once, in key order.
 template <int W, int THREADS, int CAP, bool DUP>
 __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
+    constexpr int kPer = CAP / THREADS;
     extern __shared__ __align__(16) uint8_t fs_smem[];
-    Key<W> *ik = reinterpret_cast<Key<W> *>(fs_smem);                  // loaded      [CAP]
-    Key<W> *sk = ik + CAP;                                             // sorted      [CAP]
-    uint32_t *ic = reinterpret_cast<uint32_t *>(sk + CAP);             // [CAP]
-    uint32_t *scn = ic + CAP;                                          // [CAP]
-    uint32_t *c3 = scn + CAP;                                          // counting-sort bins [CAP]
+    Key<W> *sk = reinterpret_cast<Key<W> *>(fs_smem);                  // grouped by bin [CAP]
+    Key<W> *fk = sk + (DUP ? CAP : 0);                                 // DUP: in final order [CAP]
+    uint32_t *scn = reinterpret_cast<uint32_t *>(fk + CAP);            // [CAP]
+    uint32_t *fc = scn + (DUP ? CAP : 0);                              // DUP [CAP]
+    uint32_t *c3 = fc + CAP;                                           // counting-sort bins [CAP]
     uint32_t *s3 = c3 + CAP;                                           // their starts       [CAP]
-    uint16_t *rks = reinterpret_cast<uint16_t *>(s3 + CAP);            // rank of record i inside its bin [CAP]
     __shared__ uint32_t s_maxbin, s_cnt, s_j;
     __shared__ uint32_t s_warp[THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1172,16 +1240,28 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             __syncthreads();
             continue;
         }
-        for (uint32_t i = tid; i < n; i += THREADS) { ik[i] = ld_key<W>(p.in_keys, b + i); ic[i] = p.in_counts[b + i]; }
-        uint32_t nb3 = pow2_ceil_u32(n);
-        nb3 = nb3 < 64 ? 64 : nb3;                                     // <= CAP
+        // the loads are issued first; their latency overlaps the clearing of the bins
+        Key<W> rk[kPer];
+        uint32_t rc[kPer], rr[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const uint32_t i = u * THREADS + tid;
+            if (u * THREADS >= n) break;
+            if (i < n) { rk[u] = ld_key<W>(p.in_keys, b + i); rc[u] = p.in_counts[b + i]; }
+        }
+        uint32_t nb3 = 2 * pow2_ceil_u32(n);
+        nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)CAP ? (uint32_t)CAP : nb3);
         int shift3 = 64 - prefix_bits - (31 - __clz(nb3));
         if (shift3 < 0) shift3 = 0;
         for (uint32_t i = tid; i < nb3; i += THREADS) c3[i] = 0;
         if (tid == 0) { s_maxbin = 0; s_cnt = 0; }
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += THREADS)
-            rks[i] = (uint16_t)atomicAdd(&c3[(uint32_t)(ik[i].w[0] >> shift3) & (nb3 - 1)], 1u);
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const uint32_t i = u * THREADS + tid;
+            if (u * THREADS >= n) break;
+            if (i < n) rr[u] = atomicAdd(&c3[(uint32_t)(rk[u].w[0] >> shift3) & (nb3 - 1)], 1u);
+        }
         __syncthreads();
         // exclusive scan of the nb3 bins: thread t owns bins [t * per3, (t + 1) * per3)
         {
@@ -1190,7 +1270,7 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             uint32_t sum = 0, mx = 0;
             if (b0 < nb3)
                 for (uint32_t q = 0; q < per3; q++) { const uint32_t v = c3[b0 + q]; sum += v; mx = max(mx, v); }
-            if (mx > 1) atomicMax(&s_maxbin, mx);
+            if (mx > 2) atomicMax(&s_maxbin, mx);
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1208,41 +1288,47 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             __syncthreads();
         }
         const uint32_t maxbin = s_maxbin;
-        Key<W> *rk_keys = sk;
-        uint32_t *rk_cnts = scn;
-        if (maxbin <= 24) {
-            for (uint32_t i = tid; i < n; i += THREADS) {
-                const Key<W> k = ik[i];
-                const uint32_t o = s3[(uint32_t)(k.w[0] >> shift3) & (nb3 - 1)] + rks[i];
-                sk[o] = k;
-                scn[o] = ic[i];
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const uint32_t i = u * THREADS + tid;
+            if (u * THREADS >= n) break;
+            if (i < n) {
+                const uint32_t o = s3[(uint32_t)(rk[u].w[0] >> shift3) & (nb3 - 1)] + rr[u];
+                sk[o] = rk[u];
+                scn[o] = rc[u];
             }
-            __syncthreads();
-            if (maxbin > 1) {
-                for (uint32_t bb = tid; bb < nb3; bb += THREADS) {
-                    const uint32_t cn = c3[bb];
-                    if (cn < 2) continue;
-                    const uint32_t s0 = s3[bb];
-                    for (uint32_t a = 1; a < cn; a++) {        // insertion sort of a handful of keys
-                        const Key<W> k = sk[s0 + a];
-                        const uint32_t c = scn[s0 + a];
-                        uint32_t q = a;
-                        while (q > 0 && key_lt<W>(k, sk[s0 + q - 1])) { sk[s0 + q] = sk[s0 + q - 1]; scn[s0 + q] = scn[s0 + q - 1]; q--; }
-                        sk[s0 + q] = k;
-                        scn[s0 + q] = c;
-                    }
+        }
+        __syncthreads();
+        const Key<W> *srt_k = fk;           // DUP: where the sorted sequence ends up in shared memory
+        uint32_t *srt_c = fc;
+        if (maxbin <= 32) {
+            // position inside the bin = records of the bin that sort before this one
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const Key<W> k = sk[i];
+                const uint32_t d = (uint32_t)(k.w[0] >> shift3) & (nb3 - 1);
+                const uint32_t s0 = s3[d], cn = c3[d];
+                uint32_t less = 0;
+                for (uint32_t q = 0; q < cn; q++) {
+                    const Key<W> o = sk[s0 + q];
+                    less += (key_lt<W>(o, k) || (DUP && s0 + q < i && key_eq<W>(o, k))) ? 1u : 0u;
                 }
-                __syncthreads();
+                if (!DUP) {
+                    st_key<W>(p.out_keys, b + s0 + less, k);
+                    p.out_counts[b + s0 + less] = scn[i];
+                } else {
+                    fk[s0 + less] = k;
+                    fc[s0 + less] = scn[i];
+                }
             }
         } else {
-            // crowded bins (keys sharing their next bits, or many copies of one key): bitonic network
-            // over the loaded arrays; pads are all-ones keys that sort behind a real all-ones key
-            rk_keys = ik;
-            rk_cnts = ic;
+            // crowded bins: bitonic network over the grouped arrays; pads are all-ones keys that
+            // sort behind a real all-ones key
+            srt_k = sk;
+            srt_c = scn;
             const uint32_t p2 = pow2_ceil_u32(n);
             Key<W> pad;
             key_set_ones<W>(pad);
-            for (uint32_t i = n + tid; i < p2; i += THREADS) { ik[i] = pad; ic[i] = 0; }
+            for (uint32_t i = n + tid; i < p2; i += THREADS) { sk[i] = pad; scn[i] = 0; }
             __syncthreads();
             for (uint32_t size = 2; size <= p2; size <<= 1) {
                 for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -1250,38 +1336,40 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
                         const uint32_t lo = 2 * t - (t & (stride - 1));
                         const uint32_t hi = lo + stride;
                         const bool up = (lo & size) == 0;
-                        const Key<W> a = ik[lo], bq = ik[hi];
-                        const uint32_t ca = ic[lo], cb = ic[hi];
+                        const Key<W> a = sk[lo], bq = sk[hi];
+                        const uint32_t ca = scn[lo], cb = scn[hi];
                         // order: key ascending, then count descending (real records before pads)
                         const bool b_lt_a = key_lt<W>(bq, a) || (key_eq<W>(bq, a) && cb > ca);
                         if (b_lt_a == up) {
-                            ik[lo] = bq; ik[hi] = a;
-                            ic[lo] = cb; ic[hi] = ca;
+                            sk[lo] = bq; sk[hi] = a;
+                            scn[lo] = cb; scn[hi] = ca;
                         }
                     }
                     __syncthreads();
                 }
             }
-        }
-        if (!DUP) {
-            for (uint32_t i = tid; i < n; i += THREADS) {
-                st_key<W>(p.out_keys, b + i, rk_keys[i]);
-                p.out_counts[b + i] = rk_cnts[i];
+            if (!DUP) {
+                for (uint32_t i = tid; i < n; i += THREADS) {
+                    st_key<W>(p.out_keys, b + i, sk[i]);
+                    p.out_counts[b + i] = scn[i];
+                }
             }
-        } else {
+        }
+        if (DUP) {
+            __syncthreads();
             // fold: every record that equals its predecessor adds its count to the head of its group
             for (uint32_t i = tid; i < n; i += THREADS) {
-                if (i > 0 && key_eq<W>(rk_keys[i], rk_keys[i - 1])) {
+                if (i > 0 && key_eq<W>(srt_k[i], srt_k[i - 1])) {
                     uint32_t hd = i - 1;
-                    while (hd > 0 && key_eq<W>(rk_keys[hd], rk_keys[hd - 1])) hd--;
-                    atomicAdd(&rk_cnts[hd], rk_cnts[i]);
+                    while (hd > 0 && key_eq<W>(srt_k[hd], srt_k[hd - 1])) hd--;
+                    atomicAdd(&srt_c[hd], srt_c[i]);
                 }
             }
             __syncthreads();
             // compaction of the heads, in order: warp ballots + running offset
             for (uint32_t i0 = 0; i0 < n; i0 += THREADS) {
                 const uint32_t i = i0 + tid;
-                const bool head = i < n && (i == 0 || !key_eq<W>(rk_keys[i], rk_keys[i - 1]));
+                const bool head = i < n && (i == 0 || !key_eq<W>(srt_k[i], srt_k[i - 1]));
                 const uint32_t bal = __ballot_sync(0xffffffffu, head);
                 if (lane == 0) s_warp[warp] = __popc(bal);
                 __syncthreads();
@@ -1289,8 +1377,8 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
                 for (uint32_t w = 0; w < warp; w++) off += s_warp[w];
                 if (head) {
                     const uint32_t o = b + off + __popc(bal & lanemask_lt());
-                    st_key<W>(p.out_keys, o, rk_keys[i]);
-                    p.out_counts[o] = rk_cnts[i];
+                    st_key<W>(p.out_keys, o, srt_k[i]);
+                    p.out_counts[o] = srt_c[i];
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -1340,7 +1428,8 @@ struct FinishCfg { static constexpr int THREADS = 256, CAP = 2048; };
 }  // namespace
 
 // ------------------------------------------------------------------------ host
-bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out) {
+bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
+                double record_headroom) {
     if (k == 0 || k > 64 || L < k || L > 4096) return false;
     SuperPlan pl{};
     pl.W = (int)((k + 31) / 32);
@@ -1375,7 +1464,8 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.bin_cap = (pl.bin_cap + 3) & ~3u;
     pl.ovf_cap = (uint64_t)(est_total * 0.6) + 8192;
     pl.ovf_slice = 4096;
-    pl.d_cap = max_windows < (1ull << 32) - 2 ? max_windows : (1ull << 32) - 2;
+    pl.d_cap = max_windows + (uint64_t)((double)max_windows * record_headroom) + (record_headroom > 0 ? 8192 : 0);
+    if (pl.d_cap > (1ull << 32) - 2) pl.d_cap = (1ull << 32) - 2;
     if (pl.d_cap < 1024) pl.d_cap = 1024;
     // S2 keeps a histogram of the leading b1 bits; the device plan picks the digits from it
     pl.sub_target = FinishCfg<1>::CAP * 7 / 10;
@@ -1423,13 +1513,13 @@ template <int W>
 static cudaError_t super_scatter_w(const SuperPlan &pl, const void *d_reads, uint64_t n_reads, bool strict, void *ws,
                                    unsigned long long *d_sc, int n_sms, cudaStream_t s) {
     static int tile_bytes = -1;                 // KC_SW_STAGE (development knob): bytes of reads per S1 tile
-    if (tile_bytes < 0) { const char *v = getenv("KC_SW_STAGE"); tile_bytes = v ? atoi(v) : 6400; }
+    if (tile_bytes < 0) { const char *v = getenv("KC_SW_STAGE"); tile_bytes = v ? atoi(v) : 4800; }   // 3200: 3.82 ms, 4800: 3.60, 6400: 4.0, 9600: 4.28 at C2
     SwScatterParams q{};
     if (!extract_plan(d_reads, n_reads, pl.L, pl.k, strict, &d_sc[SW_INVALID], &q.ep, (uint32_t)tile_bytes))
         return cudaErrorInvalidValue;
     if (q.ep.n_tiles == 0) return cudaSuccess;
     q.m = pl.m; q.w = pl.w; q.nh = pl.nh; q.nh_stride = pl.nh_stride;
-    q.seg_len = pl.seg_len; q.segs_per_read = pl.segs_per_read; q.cmax = pl.cmax;
+    q.seg_len = pl.seg_len; q.segs_per_read = pl.segs_per_read; q.cmax = pl.cmax; q.span = pl.span;
     q.h_off = (q.ep.smem_total + 15u) & ~15u;
     q.bin_off = q.h_off + q.ep.tile_reads * pl.nh_stride * 4;
     q.bits_off = q.bin_off + q.ep.tile_reads * pl.nk * 4;
@@ -1470,8 +1560,9 @@ cudaError_t super_scatter(const SuperPlan &pl, const void *d_reads, uint64_t n_r
 
 template <int W, int THREADS, int TSLOTS, int RPT = 2>
 static cudaError_t launch_count(const SwCountParams &cp, int n_sms, cudaStream_t s) {
-    const uint32_t smem = TSLOTS * (8 * W + 4) + THREADS * RPT * 16 * W + (THREADS * RPT + 8) * 4 + kNb1Max * 4 +
-                          (THREADS / 32) * 128 * 8 * W;
+    const uint32_t RB = THREADS * RPT, RT = W == 1 ? 2 * RB : 1;
+    const uint32_t smem = TSLOTS * (8 * W + 4) + RB * 16 * W + (RB + 8) * 4 + kNb1Max * 4 +
+                          (THREADS / 32) * 64 * (8 * W + 4) + RT * 20 + RB * 4 + 64;
     auto kern = sw_count_kernel<W, THREADS, TSLOTS, RPT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1509,7 +1600,8 @@ static cudaError_t super_count_bins_w(const SuperPlan &pl, bool add_phantom, voi
             case 7: e = launch_count<1, 256, 4096, 4>(cp, n_sms, s); break;
             case 8: e = launch_count<1, 512, 4096, 2>(cp, n_sms, s); break;
             case 9: e = launch_count<1, 384, 4096, 2>(cp, n_sms, s); break;
-            default: e = launch_count<1, 256, 4096, 2>(cp, n_sms, s); break;
+            case 10: e = launch_count<1, 256, 4096, 2>(cp, n_sms, s); break;
+            default: e = launch_count<1, 512, 4096, 1>(cp, n_sms, s); break;
         }
     } else {
         switch (variant) {
@@ -1596,7 +1688,7 @@ static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long l
     fp.out_counts = out_counts;
     fp.m_out = at<uint32_t>(ws, pl.off_mout);
     fp.sc = d_sc;
-    const uint32_t smem = 2 * CAP * (8 * W + 4) + 2 * CAP * 4 + CAP * 2;
+    const uint32_t smem = (DUP ? 2 : 1) * CAP * (8 * W + 4) + 2 * CAP * 4;
     auto kern = rec_finish_kernel<W, THREADS, CAP, DUP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -75,7 +75,8 @@ constexpr uint32_t kSuperMaxSub = 1u << 20;
 // Plans a pipeline for up to max_windows k-mer slots (one chunk, or everything that will be
 // accumulated before the count). occ_per_bin = 0 -> default. Returns false for shapes the path
 // does not take (W > 2, span < 22, reads too long for the shared-memory tile).
-bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out);
+bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
+                double record_headroom = 0.0);
 
 // zero cursors, histograms and scalars: once before the first super_scatter of a pipeline
 cudaError_t super_reset(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s);

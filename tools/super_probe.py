@@ -91,6 +91,41 @@ def accum_cases():
     return ok
 
 
+def xchg_cases():
+    """multi-GPU exchange with all ranks as contexts of this process on device 0 (kc_xchg_run_all)"""
+    import torch
+    from kmer_counter_b200 import engine
+    ok = True
+    for (P, R, L, k, G, e, n) in [(2, 20000, 100, 31, 100000, 0.01, 0.002), (4, 30000, 100, 31, 50000, 0.01, 0.001),
+                                  (8, 40000, 100, 31, 0, 0.0, 0.0), (3, 9000, 100, 63, 40000, 0.001, 0.001),
+                                  (8, 800, 100, 31, 3000, 0.0, 0.01), (4, 12000, 70, 28, 30000, 0.01, 0.001)]:
+        reads = oracle.gen_reads(R, L, G, e, n, seed=P * 1000 + k)
+        want = oracle.count(reads, L, k)
+        per = (R + P - 1) // P
+        cs = [kc.Counter(k, L, method="super") for _ in range(P)]
+        try:
+            bufs = []
+            for r, c in enumerate(cs):
+                c.xchg_begin(r, P, per)
+                part = reads[r * per * L:(r + 1) * per * L]
+                d = torch.from_numpy(part.copy()).cuda() if len(part) else torch.empty(16, dtype=torch.uint8, device="cuda")
+                bufs.append(d)
+                c.accum_add_device(d.data_ptr(), len(part))
+            runs = engine.xchg_run_all(cs)
+            got = b"".join(r.to_bytes() for r in runs)
+            sizes = [len(r) for r in runs]
+            for r in runs:
+                r.free()
+        finally:
+            for c in cs:
+                c.close()
+        good = got == want
+        ok &= good
+        print("%s xchg P=%d R=%d L=%d k=%d sizes=%s %s" % ("ok  " if good else "FAIL", P, R, L, k, sizes,
+              "" if good else diff(got, want, 8 * ((k + 31) // 32) + 4)), flush=True)
+    return ok
+
+
 def main():
     ok = True
     ok &= case(2000, 100, 31, 30000, 0.0, 0.0)
@@ -124,6 +159,7 @@ def main():
     ok &= case(700, 70, 63, 5000, 0.001, 0.001)
     os.environ["KC_SW_FORCE_DUP"] = "0"
     ok &= accum_cases()
+    ok &= xchg_cases()
     print("ALL OK" if ok else "SOME FAILED", flush=True)
 
     # timing, C2 shape
