@@ -366,12 +366,12 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
     uint32_t *tc = reinterpret_cast<uint32_t *>(recs + RB * W);             // [TSLOTS]
     uint32_t *pre = tc + TSLOTS;                                            // [RB + 8]
     uint32_t *s_hist = pre + RB + 8;                                        // [kNb1Max]
-    constexpr int kQueue = 64;                                              // collided keys a warp parks before it drains them
+    constexpr int kQueue = RPT > 1 ? 64 : 96;                               // collided keys a warp parks before it drains them
     Key<W> *queue = reinterpret_cast<Key<W> *>(s_hist + kNb1Max);           // [THREADS / 32][kQueue]
     uint32_t *queue_m = reinterpret_cast<uint32_t *>(queue + (THREADS / 32) * kQueue);   // their weights
     // record-level table (DEDUP): equal records of a round are counted once, with a multiplicity
     constexpr bool DEDUP = (W == 1);
-    constexpr int RT = DEDUP ? 2 * RB : 1;
+    constexpr int RT = DEDUP ? (RPT > 1 ? RB : 2 * RB) : 1;               // (whole-bin rounds: records are ~40% distinct)
     ulonglong2 *rt_keys = reinterpret_cast<ulonglong2 *>(queue_m + (THREADS / 32) * kQueue);   // [RT]
     uint32_t *rt_mult = reinterpret_cast<uint32_t *>(rt_keys + RT);         // [RT]
     uint32_t *rec_mult = rt_mult + RT;                                      // [RB] weight of staged record i (0: a duplicate)
@@ -433,18 +433,22 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                 for (int i = 0; i < W; i++) zero.w[i] = 0;
                 const uint32_t hv = key_hash<W>(zero);
                 if (in_pass(hv)) {
-                    uint32_t h = hv >> hshift;
+                    uint32_t hb = hv >> (hshift + 1);
+                    bool done = false;
 #pragma unroll 1
-                    for (uint32_t probes = 0; probes < 64u; probes++) {
-                        Key<W> cur = tk[h];
-                        if (key_any_word_ones<W>(cur)) {
-                            cur = slot_claim(&tk[h], zero);
-                            if (key_all_ones<W>(cur)) { claims++; break; }
+                    for (uint32_t probes = 0; probes < 64u && !done; probes++) {
+#pragma unroll 1
+                        for (uint32_t sl = 0; sl < 2 && !done; sl++) {
+                            Key<W> cur = tk[2 * hb + sl];
+                            if (key_any_word_ones<W>(cur)) {
+                                cur = slot_claim(&tk[2 * hb + sl], zero);
+                                if (key_all_ones<W>(cur)) { claims++; done = true; }
+                            }
+                            if (key_eq<W>(cur, zero)) done = true;
                         }
-                        if (key_eq<W>(cur, zero)) break;
-                        h = (h + 1) & (TSLOTS - 1);
-                        if (probes == 63u) s_abort = 1;
+                        hb = (hb + 1) & (TSLOTS / 2 - 1);
                     }
+                    if (!done) s_abort = 1;
                 }
             }
             bool aborted = false;
@@ -460,25 +464,19 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
             }
             for (uint32_t r0 = 0; r0 < n_rec; r0 += RB) {
                 const uint32_t nr = min((uint32_t)RB, n_rec - r0);
-                // stage the records, exclusive scan of their window counts
-                uint32_t c[RPT];
-                uint32_t csum = 0;
-                // records were fetched with a stride of THREADS (coalesced); their place in the round keeps that order
+                // The round's records sit in registers (fetched with a stride of THREADS: coalesced).
+                // Equal records of the round (the same run of the same locus, seen by several reads) are
+                // counted once: the first copy claims a slot of the record table and carries the
+                // multiplicity, the others drop out.
+                uint32_t c[RPT], wt[RPT];
 #pragma unroll
                 for (int u2 = 0; u2 < RPT; u2++) {
                     const uint32_t i = u2 * THREADS + tid;
-                    c[u2] = 0;
-                    if (i < nr) {
-#pragma unroll
-                        for (int t = 0; t < W; t++) recs[i * W + t] = pf[u2][t];
-                        c[u2] = (uint32_t)(pf[u2][W - 1].y & 0xffull);
-                    }
+                    c[u2] = i < nr ? (uint32_t)(pf[u2][W - 1].y & 0xffull) : 0u;
+                    wt[u2] = i < nr ? 1u : 0u;
                 }
-                // equal records of the round (the same run of the same locus, seen by several reads) are
-                // counted once: the first copy claims a slot of the record table and carries the
-                // multiplicity, the others drop out (0 windows)
-                uint32_t rslot[RPT];
                 if constexpr (DEDUP) {
+                    uint32_t rslot[RPT];
                     for (uint32_t i = tid; i < (uint32_t)RT; i += THREADS) { rt_keys[i] = make_ulonglong2(~0ull, ~0ull); rt_mult[i] = 0; }
                     __syncthreads();
 #pragma unroll
@@ -506,33 +504,23 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                                         : "memory");
                                     if (cur.x == ~0ull && cur.y == ~0ull) { rslot[u2] = h; atomicAdd(&rt_mult[h], 1u); break; }
                                 }
-                                if (cur.x == rec.x && cur.y == rec.y) { atomicAdd(&rt_mult[h], 1u); c[u2] = 0; break; }
+                                if (cur.x == rec.x && cur.y == rec.y) { atomicAdd(&rt_mult[h], 1u); break; }
                                 h = (h + 1) & (RT - 1);
                             }
                         }
                     }
                     __syncthreads();
 #pragma unroll
-                    for (int u2 = 0; u2 < RPT; u2++) {
-                        const uint32_t i = u2 * THREADS + tid;
-                        if (i < nr) rec_mult[i] = rslot[u2] != 0xffffffffu ? rt_mult[rslot[u2]] : 0u;
-                    }
+                    for (int u2 = 0; u2 < RPT; u2++) wt[u2] = rslot[u2] != 0xffffffffu ? rt_mult[rslot[u2]] : 0u;
                 }
-                // prefetch the next round
-#pragma unroll
-                for (int u2 = 0; u2 < RPT; u2++) {
-                    const uint32_t i = r0 + RB + u2 * THREADS + tid;
-                    if (i < n_rec) {
-#pragma unroll
-                        for (int t = 0; t < W; t++) pf[u2][t] = src[(uint64_t)i * W + t];
-                    }
-                }
-                // exclusive scan over the round in record order i = u2 * THREADS + tid: scan each stripe
-                // u2 across the CTA, stripes one after the other
+                // One scan gives every surviving record its place in the compacted round (high half)
+                // and the index of its first window in the flattened window sequence (low half: a round
+                // has fewer than 65536 windows). Record order i = u2 * THREADS + tid, stripe after stripe.
                 uint32_t stripe_base = 0;
 #pragma unroll
                 for (int u2 = 0; u2 < RPT; u2++) {
-                    uint32_t incl = c[u2];
+                    const uint32_t v = wt[u2] ? ((1u << 16) | c[u2]) : 0u;
+                    uint32_t incl = v;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -547,12 +535,27 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                         if ((uint32_t)wq < warp) woff += t;
                         tot += t;
                     }
-                    pre[u2 * THREADS + tid] = stripe_base + woff + incl - c[u2];
+                    const uint32_t excl = stripe_base + woff + incl - v;
+                    if (wt[u2]) {
+                        const uint32_t ci = excl >> 16;
+#pragma unroll
+                        for (int t = 0; t < W; t++) recs[ci * W + t] = pf[u2][t];
+                        pre[ci] = excl & 0xffffu;
+                        rec_mult[ci] = wt[u2];
+                    }
                     stripe_base += tot;
-                    csum = stripe_base;
                     __syncthreads();
                 }
-                const uint32_t tot = csum;
+                const uint32_t n_live = stripe_base >> 16, tot = stripe_base & 0xffffu;
+                // prefetch the next round
+#pragma unroll
+                for (int u2 = 0; u2 < RPT; u2++) {
+                    const uint32_t i = r0 + RB + u2 * THREADS + tid;
+                    if (i < n_rec) {
+#pragma unroll
+                        for (int t = 0; t < W; t++) pf[u2][t] = src[(uint64_t)i * W + t];
+                    }
+                }
                 // this thread's share of the tot windows: [f0, f1)
                 const uint32_t per = (tot + THREADS - 1) / THREADS;
                 const uint32_t f0 = min(tid * per, tot), f1 = min(f0 + per, tot);
@@ -566,14 +569,14 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                     uint32_t in_rec = 0;                           // windows left in the open record
                     uint32_t wgt = 1;                              // how many equal records the open one stands for
                     if (rem) {   // open the first record at window j
-                        uint32_t lo = 0, hi = nr;                  // last record whose first window is <= f0
+                        uint32_t lo = 0, hi = n_live;              // last record whose first window is <= f0
                         while (hi - lo > 1) {
                             const uint32_t mid = (lo + hi) >> 1;
                             if (pre[mid] <= f0) lo = mid; else hi = mid;
                         }
-                        ri = lo;                                   // (a record with windows: duplicates have none)
+                        ri = lo;
                         const uint32_t j = f0 - pre[lo];
-                        if constexpr (DEDUP) wgt = rec_mult[ri];
+                        wgt = rec_mult[ri];
 #pragma unroll
                         for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
                         const uint32_t cnt = (uint32_t)(rw[2 * W - 1] & 0xffull);
@@ -594,29 +597,55 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                         in_rec = min(rem, cnt - j);
                         ri++;
                     }
-                    // Pass 1: every lane gives each of its keys ONE probe at its home slot (no loop, so
-                    // no lane waits for another's probe sequence). A key whose home slot holds a
-                    // different key goes to the warp's queue; the queue is drained with the usual
-                    // linear probing whenever it fills up, and after the last key.
+                    // Pass 1: every lane gives each of its keys ONE probe at its home bucket (two
+                    // adjacent slots, one 16-byte load for 64-bit keys) -- no loop, so no lane waits for
+                    // another's probe sequence. A key whose bucket is taken by two other keys goes to
+                    // the warp's queue; the queue is drained with the usual bucket-by-bucket probing
+                    // whenever it fills up, and after the last key.
                     Key<W> *wq = queue + warp * kQueue;
                     uint32_t *wqm = queue_m + warp * kQueue;
                     uint32_t qn = 0;                               // keys queued (uniform across the warp)
+                    // found or placed in bucket hb (count += kw): true; both slots hold other keys: false
+                    auto try_bucket = [&](uint32_t hb, const Key<W> &key, uint32_t kw, bool act) -> bool {
+                        Key<W> k0, k1;
+                        if constexpr (W == 1) {
+                            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(tk + 2 * hb);
+                            k0.w[0] = v.x; k1.w[0] = v.y;
+                        } else {
+                            k0 = tk[2 * hb]; k1 = tk[2 * hb + 1];
+                        }
+                        // a slot that looks (even partly: a 128-bit read may tear) empty is settled by a CAS
+                        const bool e0 = key_any_word_ones<W>(k0), e1 = key_any_word_ones<W>(k1);
+                        const bool h1 = !e1 && key_eq<W>(k1, key);
+                        bool hit = h1 || (!e0 && key_eq<W>(k0, key));
+                        uint32_t slot = 2 * hb + (h1 ? 1u : 0u);
+                        if (act && !hit && (e0 || e1)) {           // only these lanes branch off
+                            slot = 2 * hb + (e0 ? 0u : 1u);
+                            Key<W> old = slot_claim(&tk[slot], key);
+                            bool claimed = key_all_ones<W>(old);
+                            hit = claimed || key_eq<W>(old, key);
+                            if (!hit && e0 && e1) {                // slot 0 went to another key; slot 1 looked empty too
+                                slot = 2 * hb + 1;
+                                old = slot_claim(&tk[slot], key);
+                                claimed = key_all_ones<W>(old);
+                                hit = claimed || key_eq<W>(old, key);
+                            }
+                            claims += claimed ? 1u : 0u;
+                        }
+                        if (act && hit) atomicAdd(&tc[slot], kw);
+                        return hit;
+                    };
                     auto drain = [&]() {
                         __syncwarp();
                         for (uint32_t en = lane; en < qn; en += 32) {
                             const Key<W> k = wq[en];
                             const uint32_t kw = wqm[en];
-                            uint32_t h = key_hash<W>(k) >> hshift;
+                            uint32_t hb = key_hash<W>(k) >> (hshift + 1);
                             bool done = false;
 #pragma unroll 1
                             for (uint32_t probes = 0; probes < 64u && !done; probes++) {
-                                Key<W> cur = tk[h];
-                                if (key_any_word_ones<W>(cur)) {
-                                    cur = slot_claim(&tk[h], k);
-                                    if (key_all_ones<W>(cur)) { claims++; done = true; }
-                                }
-                                if (done || key_eq<W>(cur, k)) { atomicAdd(&tc[h], kw); done = true; }
-                                else h = (h + 1) & (TSLOTS - 1);
+                                done = try_bucket(hb, k, kw, true);
+                                hb = (hb + 1) & (TSLOTS / 2 - 1);
                             }
                             if (!done) s_abort = 1;                // table (nearly) full: the pass is abandoned
                         }
@@ -627,10 +656,12 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                     for (uint32_t it = 0; it < per; it++) {
                         bool act = rem != 0;
                         Key<W> key;
-                        uint32_t h = 0;
+#pragma unroll
+                        for (int t = 0; t < W; t++) key.w[t] = 0;
+                        uint32_t hb = 0;
                         if (act) {
                             if (in_rec == 0) {
-                                if constexpr (DEDUP) { while ((wgt = rec_mult[ri]) == 0) ri++; }   // duplicates carry no windows
+                                wgt = rec_mult[ri];
 #pragma unroll
                                 for (int t = 0; t < W; t++) { const ulonglong2 v = recs[ri * W + t]; rw[2 * t] = v.x; rw[2 * t + 1] = v.y; }
                                 in_rec = min(rem, (uint32_t)(rw[2 * W - 1] & 0xffull));
@@ -649,22 +680,11 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                                 act = false;
                             } else {
                                 const uint32_t hv = key_hash<W>(key);
-                                h = hv >> hshift;
+                                hb = hv >> (hshift + 1);
                                 act = in_pass(hv);
                             }
                         }
-                        // one probe, written so that the common path (the slot holds this key) stays
-                        // converged: only the lanes that see an empty slot branch off to claim it
-                        Key<W> cur = tk[h];                        // (inactive lanes read slot 0: harmless)
-                        const bool looks_empty = key_any_word_ones<W>(cur);   // even partly: a 128-bit read may tear
-                        bool hit = !looks_empty && key_eq<W>(cur, key);
-                        if (act && looks_empty) {
-                            cur = slot_claim(&tk[h], key);
-                            const bool claimed = key_all_ones<W>(cur);
-                            claims += claimed ? 1u : 0u;
-                            hit = claimed || key_eq<W>(cur, key);
-                        }
-                        if (act && hit) atomicAdd(&tc[h], wgt);
+                        const bool hit = try_bucket(hb, key, wgt, act);       // (inactive lanes read bucket 0: harmless)
                         const bool coll = act && !hit;
                         const uint32_t cm = __ballot_sync(0xffffffffu, coll);
                         if (cm) {
@@ -1560,9 +1580,9 @@ cudaError_t super_scatter(const SuperPlan &pl, const void *d_reads, uint64_t n_r
 
 template <int W, int THREADS, int TSLOTS, int RPT = 2>
 static cudaError_t launch_count(const SwCountParams &cp, int n_sms, cudaStream_t s) {
-    const uint32_t RB = THREADS * RPT, RT = W == 1 ? 2 * RB : 1;
+    const uint32_t RB = THREADS * RPT, RT = W == 1 ? (RPT > 1 ? RB : 2 * RB) : 1;
     const uint32_t smem = TSLOTS * (8 * W + 4) + RB * 16 * W + (RB + 8) * 4 + kNb1Max * 4 +
-                          (THREADS / 32) * 64 * (8 * W + 4) + RT * 20 + RB * 4 + 64;
+                          (THREADS / 32) * (RPT > 1 ? 64 : 96) * (8 * W + 4) + RT * 20 + RB * 4 + 64;
     auto kern = sw_count_kernel<W, THREADS, TSLOTS, RPT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
