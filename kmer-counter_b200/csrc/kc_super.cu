@@ -1618,10 +1618,10 @@ static cudaError_t super_count_bins_w(const SuperPlan &pl, bool add_phantom, voi
             case 5: e = launch_count<1, 128, 2048, 2>(cp, n_sms, s); break;
             case 6: e = launch_count<1, 256, 4096, 1>(cp, n_sms, s); break;
             case 7: e = launch_count<1, 256, 4096, 4>(cp, n_sms, s); break;
-            case 8: e = launch_count<1, 512, 4096, 2>(cp, n_sms, s); break;
+            case 8: e = launch_count<1, 512, 4096, 1>(cp, n_sms, s); break;
             case 9: e = launch_count<1, 384, 4096, 2>(cp, n_sms, s); break;
             case 10: e = launch_count<1, 256, 4096, 2>(cp, n_sms, s); break;
-            default: e = launch_count<1, 512, 4096, 1>(cp, n_sms, s); break;
+            default: e = launch_count<1, 512, 4096, 2>(cp, n_sms, s); break;   // whole bins per round: 5.06 ms at C2 (RPT 1: 6.06)
         }
     } else {
         switch (variant) {
