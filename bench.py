@@ -3,24 +3,28 @@
 
     python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...   (the reference's CPU path)
+    python bench.py --config c3|c4|c5 ...                     (the other BASELINE configurations)
 
-A step is one pass of the whole counting path over one batch of synthetic reads of
-BASELINE.json configs[1]'s shape (10M x 100 bp, k=31; per GPU when N > 1 -- weak
-scaling): extract -> count -> sorted key-unique run [-> exchange -> merge].
+A step is one pass of the whole counting path over one batch of synthetic reads:
+reads -> super-window records -> per-bin count -> distinct records in key order
+[-> exchange over NVLink for N > 1] -> sorted key-unique run.
   value : whole-job k-mers/s with the reads already resident in HBM
   e2e   : the same through the host-buffer API: pinned host reads -> H2D -> count ->
           packed records D2H into pinned host memory, every step
-  roofline      : dominant kernel (radix scatter pass / hash insert), algorithmic bytes per
-                  launch over its device time (CUDA events inside libkc_b200 on the stream
-                  the kernels run on), against MEASURED_PEAKS.json's HBM copy bandwidth
+  parity: before anything is timed, a prefix of every rank's reads goes through the SAME path
+          that is timed and is compared with the CPU oracle (bit-exact, sha256); a mismatch
+          fails the run
+  roofline      : dominant kernel of the step; algorithmic bytes over its device time (CUDA
+                  events inside libkc_b200 on the stream the kernels run on), against
+                  MEASURED_PEAKS.json's HBM copy bandwidth
   path_roofline : SURVEY.md 8(d)'s whole-path figure B_alg = B_in + N*(Kb+8) + U*S over step time
-  cpu_baseline  : oracle/_ref (the reference's own sources) on a bounded sample, host cores
+  cpu_baseline  : oracle/_ref (the reference's own sources) on bounded samples, host cores
 One JSON line on stdout (rank 0).
 """
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import tempfile
 import threading
@@ -32,6 +36,22 @@ if ROOT not in sys.path:
 
 METRIC = "k-mers counted/s at k=31"
 UNIT = "kmers/s"
+REF_CHUNK = 89364           # reads per chunk at the reference's defaults (KMerCounter.cpp:193-212)
+
+# BASELINE.json configs[0..4] (SURVEY.md 8(d) "Synthetic inputs"); reads are per GPU
+CONFIGS = {
+    "c1": dict(reads=100_000, k=31, genome=1_000_000, sub_rate=0.0, n_rate=1e-3, seed=1, zipf_loci=0, runs=1,
+               name="configs[0]: synthetic 100k x 100 bp reads, k=31"),
+    "c2": dict(reads=10_000_000, k=31, genome=100_000_000, sub_rate=1e-3, n_rate=0.0, seed=2, zipf_loci=0, runs=1,
+               name="configs[1]: synthetic 10M x 100 bp reads (1 Gbase, 10x of a 100 Mbase genome), k=31"),
+    "c3": dict(reads=200_000_000, k=63, genome=1_000_000_000, sub_rate=1e-3, n_rate=0.0, seed=3, zipf_loci=0, runs=1,
+               name="configs[2]: synthetic 200M x 100 bp reads (20 Gbase, 20x of a 1 Gbase genome), k=63 (128-bit keys)"),
+    "c4": dict(reads=125_000_000, k=31, genome=3_330_000_000, sub_rate=1e-3, n_rate=0.0, seed=4, zipf_loci=0, runs=1,
+               name="configs[3]: 125M x 100 bp reads per GPU of a 3.33 Gbase genome (100 Gbase = 30x at 8 GPUs), k=31"),
+    "c5": dict(reads=125_000_000, k=31, genome=3_330_000_000, sub_rate=1e-3, n_rate=0.0, seed=5, zipf_loci=1_000_000, runs=16,
+               name="configs[4]: 125M x 100 bp reads per GPU, half of them at 1M Zipf-distributed hot loci, counted "
+                    "in 16 runs per GPU that are merged on the GPU (merge path), k=31"),
+}
 
 
 def parse_args():
@@ -40,40 +60,55 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (configs[1]: 10M)")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="default: c2 (per GPU, scaled out for N > 1)")
+    ap.add_argument("--reads", type=int, default=None, help="reads per GPU (overrides the config)")
     ap.add_argument("--read-len", type=int, default=100)
-    ap.add_argument("--k", type=int, default=31)
-    ap.add_argument("--genome", type=int, default=100_000_000)
-    ap.add_argument("--sub-rate", type=float, default=1e-3)
-    ap.add_argument("--n-rate", type=float, default=0.0)
-    ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--zipf-loci", type=int, default=0)
-    ap.add_argument("--method", default="auto", choices=["auto", "sort", "hash"])
-    ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--genome", type=int, default=None)
+    ap.add_argument("--sub-rate", type=float, default=None)
+    ap.add_argument("--n-rate", type=float, default=None)
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--zipf-loci", type=int, default=None)
+    ap.add_argument("--runs", type=int, default=None, help="count every GPU's reads in this many runs and merge them")
+    ap.add_argument("--method", default="auto", choices=["auto", "sort", "hash", "super"])
+    ap.add_argument("--parity-reads", type=int, default=200_000, help="reads per rank of the in-run parity check (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--check", action="store_true", help="verify a prefix against the oracle before timing")
-    ap.add_argument("--target", type=int, default=0, help="keys per sub-bucket the partition plan aims for (0 = library default)")
-    return ap.parse_args()
+    ap.add_argument("--occ", type=int, default=0, help="k-mer occurrences per minimizer bin (0 = library default)")
+    a = ap.parse_args()
+    cfg = dict(CONFIGS[a.config or "c2"])
+    for key in ("reads", "k", "genome", "sub_rate", "n_rate", "seed", "zipf_loci", "runs"):
+        v = getattr(a, key)
+        if v is not None:
+            cfg[key] = v
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg["scaled_out"] = False
+    if a.config is None and world > 1 and a.genome is None:
+        # weak scaling of configs[1]: the job is N x 10M reads of a genome N times as long (10x coverage of
+        # the whole job, as in configs[1]); rank r counts reads [r*R, (r+1)*R) of it
+        cfg["genome"] *= world
+        cfg["scaled_out"] = True
+        cfg["name"] = ("configs[1] scaled out: %d x 10M x 100 bp reads of a %d Mbase genome (10x), 10M reads per GPU, k=31"
+                       % (world, cfg["genome"] // 1_000_000))
+    a.cfg = cfg
+    return a
 
 
 E2E_SLOTS = 2           # pinned input slots of the end-to-end pipeline (chunks whose H2D / kernels are in flight)
 
 
-def workload(a):
-    return {"workload": "configs[1]: synthetic 10M x 100 bp reads, k=31, one B200" if a.gpus == 1 and a.reads == 10_000_000
-            else "configs[1] shape per GPU (weak scaling)" if a.reads == 10_000_000 else "custom",
-            "reads_per_gpu": a.reads, "read_len": a.read_len, "k": a.k, "genome_len": a.genome,
-            "sub_rate": a.sub_rate, "n_rate": a.n_rate, "seed": a.seed, "zipf_loci": a.zipf_loci,
-            "kmers_per_step_per_gpu": a.reads * (a.read_len - a.k + 1),
-            "l2_policy": "inputs larger than L2 (1 GB of reads, 5.6 GB of keys per step vs 126 MB L2)"}
+def workload(a, world, mode=None):
+    c = a.cfg
+    L = a.read_len
+    return {"workload": c["name"], "reads_per_gpu": c["reads"], "read_len": L, "k": c["k"], "genome_len": c["genome"],
+            "sub_rate": c["sub_rate"], "n_rate": c["n_rate"], "seed": c["seed"], "zipf_loci": c["zipf_loci"],
+            "runs_per_gpu": c["runs"], "kmers_per_step_per_gpu": c["reads"] * (L - c["k"] + 1), "mode": mode,
+            "l2_policy": "inputs larger than L2 (%.1f GB of reads per GPU per step vs 126 MB L2)" % (c["reads"] * L / 1e9)}
 
 
 def bind_near_gpu(index):
     """Run this process on the CPUs next to GPU `index` (NVML's ideal affinity) before anything is
-    allocated: the pinned buffers of the end-to-end path then live in that NUMA node's memory, which is
-    what the GPU's PCIe link reaches without crossing the socket interconnect. Returns the CPU count
-    bound to, or None when NVML has no answer (KC_NO_BIND=1 skips it)."""
+    allocated. Returns the CPU count bound to, or None (KC_NO_BIND=1 skips it)."""
     if os.environ.get("KC_NO_BIND") == "1":
         return None
     try:
@@ -87,12 +122,12 @@ def bind_near_gpu(index):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML every 20 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled through NVML every 5 ms while the timed region runs."""
 
     def __init__(self, index):
         self.index, self.sm, self.mx, self.reasons, self.stop, self.th = index, [], 0, set(), threading.Event(), None
         self.nv = self.h = None
-        try:                                        # NVML is initialised before the timed region starts
+        try:
             import pynvml as nv
             nv.nvmlInit()
             self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
@@ -101,7 +136,7 @@ class ClockSampler:
                           "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                           "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                           "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        except Exception as e:                      # no NVML: report that instead of inventing numbers
+        except Exception as e:
             self.reasons.add("nvml_unavailable: %s" % type(e).__name__)
 
     def _sample(self):
@@ -124,7 +159,7 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
-        self._sample()                              # one sample is taken while the last step is still in flight
+        self._sample()
         self.stop.set()
         self.th.join(timeout=5)
 
@@ -142,327 +177,384 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-# --------------------------------------------------------------- reference arm
+# --------------------------------------------------------- the reference's CPU path
+def _ref_row(oracle, reads, L, k, threads, fan_in, merge_threads, tmp_root):
+    """One timed run of the reference's Pipeline B (oracle/_ref) -> row with per-stage seconds."""
+    n_reads = len(reads) // L
+    kmers = n_reads * (L - k + 1)
+    t0 = time.perf_counter()
+    if oracle.ref_available() and hasattr(oracle.ref(), "ref_count_packed_ex"):
+        with tempfile.TemporaryDirectory(dir=tmp_root) as d:
+            st = oracle.ref_count_packed_ex(reads, L, k, REF_CHUNK, threads, fan_in, merge_threads, d, os.path.join(d, "out.bin"))
+        kind = "reference"
+    else:
+        oracle.count(reads, L, k, REF_CHUNK, threads=threads)
+        st, kind = {}, "port"
+    dt = time.perf_counter() - t0
+    row = {"threads": threads, "merge_threads": merge_threads, "merge_fan_in": fan_in, "reads": n_reads, "kmers": kmers,
+           "seconds": dt, "value": kmers / dt, "unit": UNIT, "kind": kind}
+    row.update({"stage_seconds": {kx: round(v, 4) for kx, v in st.items() if kx.endswith("_s")},
+                "runs": st.get("runs"), "threads_busy": st.get("threads_busy")})
+    return row
+
+
+def _read_stage_seconds(oracle, n_reads, L, c, tmp_root):
+    """The reference's reader (FASTQFileReader / InputFileHandler) on the same sample written as a FASTQ file."""
+    if not oracle.ref_available():
+        return None
+    try:
+        fq = oracle.gen_fastq(n_reads, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"])
+        with tempfile.TemporaryDirectory(dir=tmp_root) as d:
+            with open(os.path.join(d, "sample.fastq"), "wb") as f:
+                f.write(fq)
+            t0 = time.perf_counter()
+            oracle.ref_read_fastq_dir(d)
+            return time.perf_counter() - t0
+    except Exception:
+        return None
+
+
+def cpu_rows(a, budget_reads=None):
+    """(i) 1 thread, (ii) 8 chunk workers (the reference's 8 GPUStream threads,
+    KMerCounter.cpp:117) + noOfMergeThreads=2 mergers with fan-in 2, on bounded samples of the workload."""
+    import oracle
+    c, L = a.cfg, a.read_len
+    cores = os.cpu_count() or 1
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    n8 = min(c["reads"], budget_reads or 8 * REF_CHUNK)
+    n1 = min(c["reads"], 2 * REF_CHUNK)
+    gen = lambda n: oracle.gen_reads(n, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], zipf_loci=c["zipf_loci"])
+    rows = []
+    reads8 = gen(n8)
+    rows.append(_ref_row(oracle, reads8[: n1 * L], L, c["k"], 1, 2, 1, tmp_root))
+    rows.append(_ref_row(oracle, reads8, L, c["k"], min(8, cores), 2, 2, tmp_root))
+    rd = _read_stage_seconds(oracle, n1, L, c, tmp_root)
+    if rd is not None:
+        rows[0]["stage_seconds"]["read_fastq_s"] = round(rd, 4)
+    return rows, cores
+
+
+def cpu_baseline(a):
+    rows, cores = cpu_rows(a)
+    best = max(rows, key=lambda r: r["value"])
+    return {"value": best["value"], "unit": UNIT, "cores": best["threads"], "host_cores": cores, "kind": best["kind"],
+            "sample": "first %d reads (%d k-mers) of the workload in chunks of %d reads (the reference's default), %d chunk-worker "
+                      "threads busy, KMerFileMerger with fan-in %d on %d merger threads; rows: 1 thread and 8+2 threads"
+                      % (best["reads"], best["kmers"], REF_CHUNK, best.get("threads_busy") or best["threads"],
+                         best["merge_fan_in"], best["merge_threads"]),
+            "rows": rows}
+
+
 def run_reference(a, rank):
     """The reference's own CPU implementation of the path (oracle/_ref: its sources compiled in
-    place) on the host cores, on a bounded sample of this arm's workload."""
+    place) on the host cores; each step a bounded sample of this arm's workload."""
     if rank != 0:
         return
-    import numpy as np
     import oracle
+    c, L = a.cfg, a.read_len
     cores = os.cpu_count() or 1
-    L, k = a.read_len, a.k
-    sample = min(a.reads, a.cpu_sample_reads)
-    kind = "reference" if oracle.ref_available() else "port"
-    reads = oracle.gen_reads(sample, L, a.genome, a.sub_rate, a.n_rate, seed=a.seed, zipf_loci=a.zipf_loci)
     tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
-
-    def one_step():
-        t0 = time.perf_counter()
-        if kind == "reference":
-            with tempfile.TemporaryDirectory(dir=tmp_root) as d:
-                oracle.ref_count_packed(reads, L, k, 89364, cores, d, os.path.join(d, "out.bin"))
-        else:
-            oracle.count(reads, L, k, 89364, threads=cores)
-        return time.perf_counter() - t0
-
+    # ~40k reads/s on 8 threads: size the per-step sample so that K + 1 steps stay within ~150 s
+    per_step = int(150.0 / (max(a.steps, 1) + 1) * 40_000)
+    sample = max(2 * REF_CHUNK, min(8 * REF_CHUNK, per_step, c["reads"]))
+    sample = min(sample, c["reads"])
+    reads = oracle.gen_reads(sample, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], zipf_loci=c["zipf_loci"])
+    threads = min(8, cores)
+    rows = []
     for _ in range(min(a.warmup, 1)):
-        one_step()
-    times = [one_step() for _ in range(max(a.steps, 1))]
-    dt = sum(times) / len(times)
-    kmers = sample * (L - k + 1)
+        _ref_row(oracle, reads, L, c["k"], threads, 2, 2, tmp_root)
+    for _ in range(max(a.steps, 1)):
+        rows.append(_ref_row(oracle, reads, L, c["k"], threads, 2, 2, tmp_root))
+    dt = sum(r["seconds"] for r in rows) / len(rows)
+    kmers = sample * (L - c["k"] + 1)
     val = kmers / dt
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "impl": "reference", "config": workload(a),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "%d reads (%d k-mers) of the workload per step; runs through FileDump files in %s, "
-                                       "8-thread chunk workers like KMerCounter.cpp:117, single KMerFileMerger" %
-                                       (sample, kmers, tmp_root or "tmp")},
+            "dtype": "u64" if c["k"] <= 32 else "u128", "data": "synthetic", "impl": "reference",
+            "config": workload(a, max(a.gpus, 1), "reference CPU path"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": rows[-1]["kind"],
+                             "sample": "%d reads (%d k-mers) of the workload per step, chunks of %d reads through FileDump run files in %s, "
+                                       "%d chunk-worker threads (%s busy), KMerFileMerger fan-in 2 on 2 merger threads"
+                                       % (sample, kmers, REF_CHUNK, tmp_root or "tmp", threads, rows[-1].get("threads_busy")),
+                             "stage_seconds_last_step": rows[-1]["stage_seconds"]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(a):
-    import oracle
-    cores = os.cpu_count() or 1
-    L, k = a.read_len, a.k
-    sample = min(a.reads, a.cpu_sample_reads)
-    kind = "reference" if oracle.ref_available() else "port"
-    reads = oracle.gen_reads(sample, L, a.genome, a.sub_rate, a.n_rate, seed=a.seed, zipf_loci=a.zipf_loci)
-    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    t0 = time.perf_counter()
-    if kind == "reference":
-        with tempfile.TemporaryDirectory(dir=tmp_root) as d:
-            oracle.ref_count_packed(reads, L, k, 89364, cores, d, os.path.join(d, "out.bin"))
-    else:
-        oracle.count(reads, L, k, 89364, threads=cores)
-    dt = time.perf_counter() - t0
-    kmers = sample * (L - k + 1)
-    return {"value": kmers / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
-            "sample": "first %d reads (%d k-mers) of the workload, chunks of 89,364 reads (the reference's default), "
-                      "%d chunk-worker threads, one serial KMerFileMerger" % (sample, kmers, cores)}
-
-
 # ------------------------------------------------------------------- our arm
-def run_ours(a, rank, world, local_rank):
+class Job:
+    """One rank's share of the workload and the path it is counted through."""
+
+    def __init__(self, a, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        import kmer_counter_b200 as kc
+        from kmer_counter_b200 import multigpu
+        self.torch, self.dist, self.kc, self.multigpu = torch, dist, kc, multigpu
+        self.a, self.c, self.rank, self.world = a, a.cfg, rank, world
+        c = a.cfg
+        self.L, self.k, self.R = a.read_len, c["k"], c["reads"]
+        self.nk = self.L - self.k + 1
+        self.n_bytes = self.R * self.L
+        self.dev = torch.device("cuda", local_rank)
+        self.stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        torch.cuda.set_stream(self.stream)
+        windows = self.R * self.nk
+        self.runs = max(1, c["runs"])
+        if world > 1:
+            self.mode = "exchange"
+        elif self.runs > 1 or windows > (1 << 30) - 1:
+            self.mode = "accumulate"
+        else:
+            self.mode = "chunk"
+        self.e2e = not a.no_e2e and self.runs == 1 and windows <= (1 << 30) - 1
+        per_run = (self.R + self.runs - 1) // self.runs
+        # distinct keys a flush may see: the genome's k-mers + ~k per sequencing error (bounded by the windows)
+        est_u = min(per_run * self.nk, c["genome"] + int(per_run * self.L * c["sub_rate"] * self.k * 1.2) + (1 << 20)) if c["genome"] else 0
+        self.counter = kc.Counter(self.k, self.L, device=local_rank, method=a.method, n_slots=E2E_SLOTS,
+                                  max_chunk_bytes=self.n_bytes if self.e2e else 0, table_slots=a.occ,
+                                  stream=self.stream.cuda_stream,
+                                  distinct_hint=est_u if self.mode != "chunk" and per_run * self.nk > (1 << 31) else 0)
+        self.exchange = None
+        if self.mode == "exchange":
+            self.exchange = multigpu.Exchange(self.counter, self.dev, per_run)
+        elif self.mode == "accumulate":
+            self.counter.accum_begin(per_run)
+        self.per_run = per_run
+        self.d_reads = None
+
+    def make_reads(self):
+        from kmer_counter_b200 import synth
+        c = self.c
+        self.d_reads = self.torch.empty(self.n_bytes + 256, dtype=self.torch.uint8, device=self.dev)
+        synth.synth_reads_device(self.d_reads.data_ptr(), self.R, self.L, c["genome"], c["sub_rate"], c["n_rate"], c["seed"],
+                                 first_read=self.rank * self.R, zipf_loci=c["zipf_loci"], stream=self.stream.cuda_stream)
+        self.stream.synchronize()
+
+    def count(self, ptr, n_reads):
+        """n_reads device-resident reads at ptr through the timed path -> Run of this rank's records."""
+        c, L = self.counter, self.L
+        if self.mode == "chunk":
+            return c.count_device(ptr, n_reads * L)
+        # `runs` pieces of about equal size (whole multiples of 16 reads: device pieces stay 16-byte aligned),
+        # each counted into its own run; the runs are then merged on the GPU (merge path = KMerFileMerger)
+        runs = self.runs if n_reads >= 16 * self.runs else 1
+        per = (n_reads // runs) // 16 * 16 if runs > 1 else n_reads
+        parts = []
+        for i in range(runs):
+            r0 = i * per
+            nr = per if i + 1 < runs else n_reads - r0
+            c.accum_add_device(ptr + r0 * L, nr * L)
+            parts.append(self.exchange.finish() if self.exchange is not None else c.accum_flush())
+            if self.exchange is not None and runs > 1 and i == 0:
+                c.xchg_fix_ranges(True)              # every run of this count is cut at the first run's key ranges
+        if self.exchange is not None and runs > 1:
+            c.xchg_fix_ranges(False)
+        if len(parts) == 1:
+            return parts[0]
+        merged = c.merge(parts)
+        for p in parts:
+            p.free()
+        return merged
+
+    def step(self):
+        run = self.count(self.d_reads.data_ptr(), self.R)
+        n = len(run)
+        run.free()
+        return n
+
+
+def parity_check(job, a):
+    """A prefix of every rank's reads through the path that is timed, against the CPU oracle."""
     import numpy as np
+    import oracle
+    torch, dist = job.torch, job.dist
+    pre = min(job.R, a.parity_reads)
+    if pre <= 0:
+        return {"checked": False}
+    c, L, k = job.c, job.L, job.k
+    run = job.count(job.d_reads.data_ptr(), pre)
+    got = run.to_bytes()
+    run.free()
+    S = job.counter.record_size
+    mine = {"n": len(got) // S, "sha": hashlib.sha256(got).hexdigest()}
+    if job.world > 1:
+        lo, _, _ = job.counter.xchg_info(job.world)
+        mine["lo"] = lo
+        everyone = [None] * job.world
+        dist.all_gather_object(everyone, mine)
+    else:
+        everyone = [mine]
+    ok, detail = True, None
+    if job.rank == 0:
+        host = job.d_reads[: pre * L].cpu().numpy()
+        gen = oracle.gen_reads(pre, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], zipf_loci=c["zipf_loci"])
+        assert bytes(host) == bytes(gen), "device generator != host generator"
+        shards = [gen] + [oracle.gen_reads(pre, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], zipf_loci=c["zipf_loci"],
+                                           first_read=r * job.R) for r in range(1, job.world)]
+        want = oracle.count(np.concatenate(shards), L, k, chunk_reads=REF_CHUNK, threads=os.cpu_count() or 1)
+        if job.world == 1:
+            ok = hashlib.sha256(want).hexdigest() == mine["sha"]
+        else:
+            # rank r holds the keys whose leading 10 bits lie in [lo[r], lo[r+1]): cut the oracle's artefact there
+            keys, _ = oracle.records_to_arrays(want, k)
+            b = (keys[:, 0] >> np.uint64(54)).astype(np.int64)
+            lo = everyone[0]["lo"]
+            cuts = [int(np.searchsorted(b, x, side="left")) for x in lo]
+            for r, e in enumerate(everyone):
+                piece = want[cuts[r] * S: cuts[r + 1] * S]
+                if e["lo"] != lo or e["n"] != cuts[r + 1] - cuts[r] or hashlib.sha256(piece).hexdigest() != e["sha"]:
+                    ok, detail = False, "rank %d: %d records, oracle has %d in its key range" % (r, e["n"], cuts[r + 1] - cuts[r])
+                    break
+        res = {"checked": True, "ok": ok, "reads_per_rank": pre, "ranks": job.world, "records": sum(e["n"] for e in everyone),
+               "sha256": hashlib.sha256(want).hexdigest(), "oracle": "oracle.count (C restatement pinned to oracle/_ref)",
+               "path": job.mode}
+        if detail:
+            res["detail"] = detail
+    else:
+        res = None
+    if job.world > 1:
+        box = [res]
+        dist.broadcast_object_list(box, src=0)
+        res = box[0]
+    if not res["ok"]:
+        if job.rank == 0:
+            sys.stderr.write("bench.py: PARITY FAILED: %s\n" % json.dumps(res))
+        sys.exit(3)
+    return res
+
+
+def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    import kmer_counter_b200 as kc
-    from kmer_counter_b200 import multigpu, synth
 
     numa = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    L, k, R = a.read_len, a.k, a.reads
-    nk = L - k + 1
-    n_bytes = R * L
-    # high priority: the combine step and the record read-back of chunk i are queued while the
-    # kernels of chunks i+1, i+2 occupy the SMs on the (default-priority) slot streams
-    stream = torch.cuda.Stream(device=dev, priority=-1)
-    torch.cuda.set_stream(stream)
-    counter = kc.Counter(k, L, device=local_rank, method=a.method, n_slots=E2E_SLOTS, max_chunk_bytes=0 if a.no_e2e else n_bytes, table_slots=a.target,
-                         stream=stream.cuda_stream)
-    d_reads = torch.empty(n_bytes + 256, dtype=torch.uint8, device=dev)
-    synth.synth_reads_device(d_reads.data_ptr(), R, L, a.genome, a.sub_rate, a.n_rate, a.seed,
-                             first_read=rank * R, zipf_loci=a.zipf_loci, stream=stream.cuda_stream)
-    stream.synchronize()
+    job = Job(a, rank, world, local_rank)
+    counter, stream = job.counter, job.stream
+    L, k, R, nk, n_bytes = job.L, job.k, job.R, job.nk, job.n_bytes
+    job.make_reads()
 
-    if a.check and rank == 0:
-        import oracle
-        pre = min(R, 200_000)
-        host = d_reads[: pre * L].cpu().numpy()
-        assert bytes(host) == bytes(oracle.gen_reads(pre, L, a.genome, a.sub_rate, a.n_rate, seed=a.seed,
-                                                     zipf_loci=a.zipf_loci)), "device generator != host generator"
-        want = oracle.count(host, L, k, threads=os.cpu_count() or 1)
-        r = counter.count_device(d_reads.data_ptr(), pre * L)
-        assert r.to_bytes() == want, "prefix parity failed"
-        r.free()
-        sys.stderr.write("check: %d-read prefix bit-exact against the oracle\n" % pre)
+    parity = parity_check(job, a)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    peer = None
-    if world > 1 and os.environ.get("KC_NO_PEER") != "1":
-        try:            # exchange fused into the combine kernel over NVLink peer memory
-            peer = multigpu.PeerCombine(counter, dev, max_records=int(R * nk * 0.45))
-        except Exception as e:
-            sys.stderr.write("peer-memory exchange unavailable (%s): using NCCL\n" % e)
-            peer = None
-
-    def step():
-        if world > 1:
-            run = multigpu.count_shard(counter, d_reads.data_ptr(), n_bytes, dev, peer=peer)
-        else:
-            run = counter.count_device(d_reads.data_ptr(), n_bytes)
-        n = len(run)
-        run.free()
-        return n
-
     for _ in range(a.warmup):
-        step()
+        job.step()
     barrier()
     st0 = counter.stats()
-    dom_ms, dom_bytes, dom_launch, tot_ms = 0.0, 0, 0, 0.0
+    acc = {"dom_ms": 0.0, "dom_bytes": 0, "dom_launch": 0, "tot_ms": 0.0, "stage_ms": None}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         ev0.record(stream)
         t0 = time.perf_counter()
         distinct = 0
         for _ in range(a.steps):
-            distinct = step()
+            distinct = job.step()
             s = counter.stats()
-            dom_ms += s["ms_dominant"]; dom_bytes += s["dominant_bytes"]; dom_launch += s["dominant_launches"]
-            tot_ms += s["ms_total"]
+            acc["dom_ms"] += s["ms_dominant"]; acc["dom_bytes"] += s["dominant_bytes"]; acc["dom_launch"] += s["dominant_launches"]
+            acc["tot_ms"] += s["ms_total"]
         ev1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     st1 = counter.stats()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, float(distinct)], dtype=torch.float64, device=dev)
+    tsum = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / a.steps
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t[0].item()) / a.steps
+    distinct_total = int(tsum[1].item()) if world > 1 else distinct
     kmers_step = R * nk * world
     value = kmers_step / (ms_per_step * 1e-3)
     method_used = st1["method_used"]
     launches = st1["launches"] - st0["launches"]
+    nvlink = None
+    if world > 1:
+        _, recv, remote = counter.xchg_info(world)
+        # bytes this rank pulled from its peers in the last step: super-window records of its bins + its key range's records
+        rec_bytes = 16 * counter.words
+        sc = counter.debug_scalars()
+        pulled_rec = sc["records"] * (world - 1) // world * rec_bytes      # this rank's bins hold 1/P of every rank's records
+        pulled_d = remote * (8 * counter.words + 4)
+        x = torch.tensor([float(pulled_rec + pulled_d)], dtype=torch.float64, device=dev)
+        dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        nvlink = {"bytes_in_per_step_per_gpu": int(x.item()), "super_window_records_bytes": int(pulled_rec),
+                  "distinct_records_bytes": int(pulled_d),
+                  "achieved_gbs_over_step": x.item() / (ms_per_step * 1e-3) / 1e9, "peak": 900, "measured_peer_copy": 770,
+                  "note": "both exchanges are the load side of the consuming kernels (peer loads over NVLink/NVSwitch), "
+                          "spread over the step: the rate is bytes over the whole step time, not a link saturation figure"}
 
     # ---- end to end through the host-buffer API (pinned in, pinned out)
     e2e = None
-    if not a.no_e2e:
-        host_reads = d_reads[:n_bytes].cpu().numpy()
-        for sl in range(E2E_SLOTS):                         # every pinned input slot holds the step's reads
-            counter.slot_buffer(sl)[:n_bytes] = host_reads
-        out_cap = (distinct + 1024) * counter.record_size if world == 1 else (R * nk // 2) * counter.record_size
-        pinned_out = counter.host_alloc(out_cap)
-        d2h = 0
-        e2e_parts = {"h2d_count": 0.0, "exchange_merge": 0.0, "records_d2h": 0.0}
-
-        def finish(sl):
-            """wait for the slot's chunk, [exchange + combine], records D2H into pinned memory"""
-            t_a = time.perf_counter()
-            run = counter.wait(sl)
-            t_b = time.perf_counter()
-            if world > 1:
-                merged = peer.combine(run) if peer is not None else None
-                run = merged if merged is not None else multigpu.exchange_and_combine(counter, run, dev)
-            t_c = time.perf_counter()
-            nb = run.copy_into(pinned_out.ctypes.data, out_cap)
-            run.free()
-            t_d = time.perf_counter()
-            e2e_parts["h2d_count"] += t_b - t_a; e2e_parts["exchange_merge"] += t_c - t_b; e2e_parts["records_d2h"] += t_d - t_c
-            return nb
-
-        # (1) one step at a time: the latency of a single chunk, with its parts
-        for _ in range(2):
-            counter.submit(0, n_bytes); finish(0)
-        for kx in e2e_parts:
-            e2e_parts[kx] = 0.0
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            counter.submit(0, n_bytes); d2h = finish(0)
-        barrier()
-        single_ms = (time.perf_counter() - t0) / a.steps * 1e3
-        parts = {kx: v / a.steps * 1e3 for kx, v in e2e_parts.items()}
-        # (2) the reported number: the same K steps pipelined over the pinned slots, which is how the
-        # API is meant to be driven (kc_submit / kc_wait from the producer, the records read back by a
-        # consumer thread): H2D of step i, the kernels of step i-1 and the records D2H of step i-2
-        # overlap (two copy engines + SMs). Every step still moves all its bytes both ways.
-        import queue
-        todo, res = queue.Queue(maxsize=1), {"nb": 0, "err": None}
-
-        trace = [] if os.environ.get("KC_E2E_TRACE") == "1" and rank == 0 else None   # (what, start ms, ms) per call
-
-        def timed(what, fn, *args):
-            if trace is None:
-                return fn(*args)
-            t_s = time.perf_counter()
-            out = fn(*args)
-            trace.append((what, t_s * 1e3, (time.perf_counter() - t_s) * 1e3))
-            return out
-
-        def reader():
-            while True:
-                run = todo.get()
-                if run is None:
-                    return
-                try:
-                    res["nb"] = timed("copy", run.copy_into, pinned_out.ctypes.data, out_cap)
-                    run.free()
-                except Exception as e:                       # surfaced after the join
-                    res["err"] = e
-
-        def combine(run):
-            merged = peer.combine(run) if peer is not None else None
-            return merged if merged is not None else multigpu.exchange_and_combine(counter, run, dev)
-
-        def emit(run):
-            """[exchange + combine of a finished chunk], then hand its records to the reader"""
-            if world > 1:
-                run = timed("combine", combine, run)
-            timed("put", todo.put, run)
-
-        def pipelined(n_steps):
-            # Steady state of iteration i: H2D of chunk i is in flight, chunk i-1 is being counted, chunk
-            # i-2 is combined with the peers' parts as soon as i-1's kernels have drained (so the combine
-            # runs in the shadow of i's H2D instead of fighting i-1's kernels for SMs), and the reader
-            # thread copies the records of chunk i-3 to the host.
-            th = threading.Thread(target=reader, daemon=True)
-            th.start()
-            held = None                                     # counted, not yet combined
-            for i in range(n_steps + 1):
-                if i < n_steps:
-                    timed("submit%d" % (i % E2E_SLOTS), counter.submit, i % E2E_SLOTS, n_bytes)
-                if i >= 1:
-                    sl = (i - 1) % E2E_SLOTS
-                    run = timed("wait%d" % sl, counter.wait, sl)
-                    if world == 1:                          # nothing to combine: straight to the reader
-                        emit(run)
-                        continue
-                    if held is not None:
-                        emit(held)
-                    held = run
-            if held is not None:
-                emit(held)
-            todo.put(None)
-            th.join()
-            if res["err"] is not None:
-                raise res["err"]
-
-        pipelined(max(a.warmup, 2 * E2E_SLOTS))             # untimed: every slot's arena and the run pool reach their steady size
-        barrier()
-        t0 = time.perf_counter()
-        if trace is not None:
-            del trace[:]
-        pipelined(a.steps)
-        d2h = res["nb"]
-        barrier()
-        if trace:
-            t_first = min(t for _, t, _ in trace)
-            for what, t_s, dur in sorted(trace, key=lambda x: x[1]):
-                sys.stderr.write("e2e-trace %8.1f  %-9s %7.2f\n" % (t_s - t_first, what, dur))
-        e2e_dt = (time.perf_counter() - t0) / a.steps
-        t = torch.tensor([e2e_dt, single_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt, single_ms = float(t[0].item()), float(t[1].item())
-        e2e = {"value": kmers_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_dt * 1e3,
-               "timing": "wall clock around K steps pipelined over %d pinned slots (kc_submit/kc_wait, records read back "
-                         "by a consumer thread), sync on both sides, max over ranks; every step copies its reads H2D "
-                         "and its records D2H" % E2E_SLOTS,
-               "single_step_ms": single_ms, "single_step_value": kmers_step / (single_ms * 1e-3),
-               "single_step_parts_ms_rank0": parts, "cpus_bound_near_gpu": numa}
-        counter.host_free(pinned_out)
+    if job.e2e:
+        e2e = run_e2e(job, a, distinct, kmers_step, barrier, numa)
 
     clocks = clk.summary()
     peak, peak_src = measured_peak_gbs()
     if rank == 0:
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        dom_name = st1["stage_names"][st1["dominant_stage"]] if st1["stage_names"] else "none"
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this
-        # workload (bytes per launch), if there is one for this method and size
+        dom_ms, dom_bytes, dom_launch, tot_ms = acc["dom_ms"], acc["dom_bytes"], acc["dom_launch"], acc["tot_ms"]
+        names = st1["stage_names"]
+        dom_name = names[st1["dominant_stage"]] if names else "none"
+        Kb, S = 8 * counter.words, counter.record_size
+        U = distinct_total // world if world > 1 else distinct
+        N = R * nk
+        # SURVEY 8(d): per occurrence one key-sized read + a 4-byte count read and write of its table slot.
+        # The kernel that does those N table updates is the per-bin count (it keeps the table in shared
+        # memory); its share of B_alg is N*(Kb+8). Its own HBM input/output is reported beside it.
+        survey_bytes = N * (Kb + 8) * a.steps if dom_name == "smem_count_per_bin" else dom_bytes
+        achieved = survey_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        io_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
-            ent = tj.get("%s/%s/%d" % (method_used, dom_name, R))
+            ent = tj.get("%s/%s/k%d/R%d/G%d/z%d" % (method_used, dom_name, k, R, a.cfg["genome"], a.cfg["zipf_loci"]))
             if ent:
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             pass
-        Kb, S = 8 * counter.words, counter.record_size
-        b_alg = R * L + R * nk * (Kb + 8) + distinct * S
-        path_ach = b_alg / (tot_ms / a.steps * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+        b_alg = R * L + N * (Kb + 8) + U * S
+        path_ms = ms_per_step if world > 1 else (tot_ms / a.steps if tot_ms > 0 else ms_per_step)
+        path_ach = b_alg / (path_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": dict(workload(a), method=method_used,
-                                                                     exchange=None if world == 1 else
-                                                                     "peer memory: combine kernel loads the parts from the peers' HBM over NVLink (CUDA IPC)"
-                                                                     if peer is not None else "NCCL grouped send/recv, then combine"),
+            "dtype": "u64" if k <= 32 else "u128", "data": "synthetic",
+            "config": dict(workload(a, world, job.mode), method=method_used,
+                           exchange=None if world == 1 else
+                           "fused into the consuming kernels: the per-bin count loads every rank's super-window records of its bins, "
+                           "the level-2 placement loads its key range of every rank's distinct records (peer memory over NVLink, CUDA IPC)"),
+            "parity": parity,
             "bases_per_s": R * L * world / (ms_per_step * 1e-3),
-            "distinct_per_gpu": distinct,
+            "distinct_per_gpu": U,
             "roofline": {"bound": "hbm", "kernel": dom_name,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "definition": "SURVEY 8(d) algorithmic bytes of the kernel's work: N*(Kb+8) for the per-bin count "
+                                       "(one key read + count read/write per k-mer occurrence; the table lives in shared memory), "
+                                       "the stage's HBM input+output for any other kernel",
+                         "hbm_io_achieved": io_achieved, "hbm_io_frac": io_achieved / peak if peak else None,
+                         "hbm_io_bytes_per_launch": dom_bytes / max(dom_launch, 1),
                          "peak_source": peak_src + " HBM copy bandwidth (MEASURED_PEAKS.json)",
-                         "bytes_per_launch": dom_bytes / max(dom_launch, 1), "launches_per_step": dom_launch / a.steps,
+                         "bytes_per_launch": survey_bytes / max(dom_launch, 1), "launches_per_step": dom_launch / a.steps,
                          "ms_per_launch": dom_ms / max(dom_launch, 1),
                          "share_of_step": dom_ms / tot_ms if tot_ms else None, "traffic": traffic,
                          "traffic_source": traffic_src},
             "path_roofline": {"bound": "hbm", "b_alg_bytes": b_alg, "achieved": path_ach, "peak": peak, "unit": "GB/s",
-                              "frac": path_ach / peak if peak else None,
-                              "definition": "SURVEY 8(d): B_in + N*(Kb+8) + U*S over the local counting time"},
-            "stages_last_step": {n: round(m, 4) for n, m in zip(st1["stage_names"], st1["ms_stage"])},
+                              "frac": path_ach / peak if peak else None, "ms": path_ms,
+                              "definition": "SURVEY 8(d): B_in + N*(Kb+8) + U*S per GPU over the step time (device time of the "
+                                            "counting path on one GPU; the whole step, exchange included, for N > 1)"},
+            "stages_last_step": {n: round(m, 4) for n, m in zip(names, st1["ms_stage"])},
+            "stage_hbm_io_bytes_last_step": {n: int(b) for n, b in zip(names, st1["stage_bytes"])},
+            "nvlink": nvlink,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_ms_per_step": wall / a.steps * 1e3,
         }
@@ -473,6 +565,109 @@ def run_ours(a, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_e2e(job, a, distinct, kmers_step, barrier, numa):
+    """K steps through the host-buffer API: pinned reads -> H2D -> count -> records D2H into pinned memory."""
+    import queue
+    torch, dist = job.torch, job.dist
+    counter, world, rank, dev = job.counter, job.world, job.rank, job.dev
+    n_bytes, R, nk = job.n_bytes, job.R, job.nk
+    host_reads = job.d_reads[:n_bytes].cpu().numpy()
+    for sl in range(E2E_SLOTS):                         # every pinned input slot holds the step's reads
+        counter.slot_buffer(sl)[:n_bytes] = host_reads
+    out_cap = (distinct + distinct // 4 + 4096) * counter.record_size
+    pinned_out = counter.host_alloc(out_cap)
+    parts = {"h2d_count": 0.0, "records_d2h": 0.0}
+
+    if world == 1:
+        def one(sl):
+            t_a = time.perf_counter()
+            counter.submit(sl, n_bytes)
+            run = counter.wait(sl)
+            t_b = time.perf_counter()
+            nb = run.copy_into(pinned_out.ctypes.data, out_cap)
+            run.free()
+            parts["h2d_count"] += t_b - t_a
+            parts["records_d2h"] += time.perf_counter() - t_b
+            return nb
+    else:
+        def one(sl):
+            t_a = time.perf_counter()
+            counter.accum_submit(sl, n_bytes)
+            run = job.exchange.finish()
+            t_b = time.perf_counter()
+            nb = run.copy_into(pinned_out.ctypes.data, out_cap)
+            run.free()
+            parts["h2d_count"] += t_b - t_a
+            parts["records_d2h"] += time.perf_counter() - t_b
+            return nb
+
+    # (1) one step at a time: the latency of a single chunk, with its parts
+    for _ in range(2):
+        one(0)
+    for kx in parts:
+        parts[kx] = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(a.steps):
+        d2h = one(0)
+    barrier()
+    single_ms = (time.perf_counter() - t0) / a.steps * 1e3
+    parts_ms = {kx: v / a.steps * 1e3 for kx, v in parts.items()}
+    e2e_dt = single_ms * 1e-3
+    timing = "wall clock around K steps, one at a time (kc_accum_submit -> exchange -> kc_run_copy_records), sync on both sides, max over ranks"
+    if world == 1:
+        # (2) the reported number: the same K steps pipelined over the pinned slots, which is how the API is
+        # meant to be driven (kc_submit / kc_wait from the producer, the records read back by a consumer
+        # thread): H2D of step i, the kernels of step i-1 and the records D2H of step i-2 overlap.
+        todo, res = queue.Queue(maxsize=1), {"nb": 0, "err": None}
+
+        def reader():
+            while True:
+                run = todo.get()
+                if run is None:
+                    return
+                try:
+                    res["nb"] = run.copy_into(pinned_out.ctypes.data, out_cap)
+                    run.free()
+                except Exception as e:
+                    res["err"] = e
+
+        def pipelined(n_steps):
+            th = threading.Thread(target=reader, daemon=True)
+            th.start()
+            for i in range(n_steps + 1):
+                if i < n_steps:
+                    counter.submit(i % E2E_SLOTS, n_bytes)
+                if i >= 1:
+                    todo.put(counter.wait((i - 1) % E2E_SLOTS))
+            todo.put(None)
+            th.join()
+            if res["err"] is not None:
+                raise res["err"]
+
+        pipelined(max(a.warmup, 2 * E2E_SLOTS))
+        barrier()
+        t0 = time.perf_counter()
+        pipelined(a.steps)
+        d2h = res["nb"]
+        barrier()
+        e2e_dt = (time.perf_counter() - t0) / a.steps
+        timing = ("wall clock around K steps pipelined over %d pinned slots (kc_submit/kc_wait, records read back by a consumer "
+                  "thread), sync on both sides; every step copies its reads H2D and its records D2H" % E2E_SLOTS)
+    t = torch.tensor([e2e_dt, single_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_dt, single_ms = float(t[0].item()), float(t[1].item())
+    out = {"value": kmers_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_dt * 1e3, "timing": timing,
+           "pcie_gbs": {"h2d": n_bytes / e2e_dt / 1e9, "d2h": d2h / e2e_dt / 1e9},
+           "single_step_ms": single_ms, "single_step_value": kmers_step / (single_ms * 1e-3),
+           "single_step_parts_ms_rank0": parts_ms, "cpus_bound_near_gpu": numa}
+    counter.host_free(pinned_out)
+    return out
 
 
 def main():

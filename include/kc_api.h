@@ -80,6 +80,8 @@ typedef struct kc_config {
                                   KC_COUNT_HASH: k-mer occurrences per sub-bucket; KC_COUNT_SUPER:
                                   k-mer occurrences per minimizer bin                      */
     void    *stream;           /* cudaStream_t to run on, NULL = a stream owned by the ctx */
+    uint64_t distinct_hint;    /* accumulating mode: distinct keys expected per flush (sizes the
+                                  record buffers); 0 = as many as there are k-mers (always fits) */
 } kc_config;
 
 typedef struct kc_stats {
@@ -178,15 +180,21 @@ int  kc_accum_flush(kc_ctx *ctx, kc_run **run);
  * The reference has one implicit device. Here up to 8 contexts -- in one process
  * (kc_xchg_run_all, the command line's gpus=N) or one process per GPU (handles exchanged through
  * any host channel) -- each accumulate their share of the reads (kc_accum_add_device /
- * kc_accum_submit after kc_xchg_begin), count it locally, and then exchange DISTINCT (key, count)
- * records by key range: the ranges are cut from an all-gathered 1024-bin histogram so that every
- * rank receives about the same number of records, and rank r ends with the sorted unique records
- * of the r-th range -- the artefact is the concatenation in rank order. The exchange is fused into
- * the placement kernel: its loads read the peers' grouped records over NVLink / NVSwitch.
- * Order of calls on every rank, B = a barrier across ranks that the caller provides (stream-ordered
- * is enough: an event wait or a tiny NCCL all-reduce on the context's stream):
- *   kc_xchg_count_local -> all-gather of kc_xchg_hist's 1024 uint32 into its n_ranks x 1024 buffer
- *   -> kc_xchg_group_local -> B -> kc_xchg_pull -> B -> kc_xchg_finish. */
+ * kc_accum_submit after kc_xchg_begin) as super-window records in its own minimizer bins. Two
+ * exchanges follow, both fused into the kernel that consumes the data (its loads read the peers'
+ * HBM over NVLink / NVSwitch; there is no send/receive step and no staging copy):
+ *   1. bins are hash-partitioned: rank r counts bins [r*B/P, (r+1)*B/P) and reads what EVERY rank
+ *      put into them (about 1.7 bytes per k-mer occurrence cross the links, not 8), so its distinct
+ *      (key, count) records are distinct across the whole job;
+ *   2. the key space is cut into P contiguous ranges of about equal record totals (from an
+ *      all-gathered 1024-bin histogram), every rank groups its records by their leading bits, and
+ *      rank r pulls range r out of all ranks' grouped arrays while placing it into sub-buckets.
+ * Rank r ends with the sorted unique records of the r-th key range: the artefact is the
+ * concatenation in rank order. Order of calls on every rank, B = a barrier across ranks that the
+ * caller provides (stream-ordered is enough: an event wait or a tiny NCCL all-reduce on the
+ * context's stream):
+ *   [accumulate] -> B -> kc_xchg_count_local -> all-gather of kc_xchg_hist's 1024 uint32 into its
+ *   n_ranks x 1024 buffer -> kc_xchg_group_local -> B -> kc_xchg_pull -> B -> kc_xchg_finish. */
 int  kc_xchg_begin(kc_ctx *ctx, uint32_t rank, uint32_t n_ranks, uint64_t expected_reads);
 int  kc_xchg_export(kc_ctx *ctx, void *handle64);                       /* CUDA IPC handle of this rank's workspace */
 int  kc_xchg_import(kc_ctx *ctx, uint32_t peer, const void *handle64);  /* a peer in another process               */
@@ -196,6 +204,12 @@ int  kc_xchg_hist(kc_ctx *ctx, void **d_hist, void **d_all_hist);
 int  kc_xchg_group_local(kc_ctx *ctx);
 int  kc_xchg_pull(kc_ctx *ctx);
 int  kc_xchg_finish(kc_ctx *ctx, kc_run **run);
+/* on != 0: the following exchanges cut the key space where the previous one did (instead of
+ * balancing anew), so that a rank's runs of several exchanges cover one key range and can be merged */
+int  kc_xchg_fix_ranges(kc_ctx *ctx, int on);
+/* the last exchange: lo[0..n_ranks] = bucket boundaries of the owners' key ranges (of 1024: the
+ * leading 10 key bits), records this rank pulled in all, and how many of them came from peers */
+int  kc_xchg_info(kc_ctx *ctx, uint32_t *lo, uint64_t *recv_records, uint64_t *remote_records);
 /* all ranks in this process: everything above, ordered by events; runs[r] = rank r's key range */
 int  kc_xchg_run_all(kc_ctx *const *ctxs, uint32_t n, kc_run **runs);
 

@@ -24,6 +24,7 @@ class KcConfig(C.Structure):
         ("struct_size", C.c_uint32), ("k", C.c_uint32), ("read_len", C.c_uint32), ("device", C.c_int32),
         ("flags", C.c_uint32), ("method", C.c_uint32), ("n_slots", C.c_uint32), ("reserved0", C.c_uint32),
         ("max_chunk_bytes", C.c_uint64), ("table_slots", C.c_uint64), ("stream", C.c_void_p),
+        ("distinct_hint", C.c_uint64),
     ]
 
 
@@ -69,6 +70,8 @@ SYMBOLS = {
     "kc_xchg_group_local": (_i, [_vp]),
     "kc_xchg_pull": (_i, [_vp]),
     "kc_xchg_finish": (_i, [_vp, _pp]),
+    "kc_xchg_fix_ranges": (_i, [_vp, _i]),
+    "kc_xchg_info": (_i, [_vp, C.POINTER(C.c_uint32), _pu64, _pu64]),
     "kc_xchg_run_all": (_i, [_pp, _u32, _pp]),
     "kc_host_alloc": (_i, [_vp, _u64, _pp]),
     "kc_host_free": (_i, [_vp, _vp]),

@@ -107,6 +107,8 @@ struct kc_ctx {
         void *peer_ws[8] = {};               // the ranks' workspaces as mapped into this device
         bool peer_ipc[8] = {};               // opened with cudaIpcOpenMemHandle (to be closed)
         uint32_t *d_all_hist = nullptr;      // n_ranks x 1024, filled by the caller's all-gather
+        SuperXInfo x_info{};                 // the last exchange's plan (kc_xchg_info)
+        bool keep_ranges = false;            // kc_xchg_fix_ranges
         float ms_scatter = 0;
         uint64_t n_scatter = 0;
     } acc;
@@ -761,7 +763,6 @@ void accum_free(kc_ctx *c) {
         if (a.peer_ipc[i] && a.peer_ws[i]) cudaIpcCloseMemHandle(a.peer_ws[i]);
     if (a.d_all_hist) cudaFree(a.d_all_hist);
     if (a.ws) cudaFree(a.ws);
-    if (a.d_sc) cudaFree(a.d_sc);
     if (a.h_sc) cudaFreeHost(a.h_sc);
     for (auto &e : a.ev) if (e) cudaEventDestroy(e);
     for (kc_run *r : a.parts) kc_run_free(c, r);
@@ -878,8 +879,19 @@ int accum_make_room(kc_ctx *c, uint64_t n_reads) {
     const uint64_t nk = c->cfg.read_len - c->cfg.k + 1, w = n_reads * nk;
     if (w > a.pl.ovf_cap || w > a.max_windows)
         return c->set_error(KC_ERR_CAPACITY, "chunk of %llu reads exceeds what the accumulator was planned for", (unsigned long long)n_reads);
+    if (a.ovf_reserved + w > a.pl.ovf_cap) {
+        // the reservations are worst cases (every window of a chunk in flight overflowing): look at
+        // what the list really holds once the chunks queued so far are through
+        KC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        for (auto &sl : c->slots)
+            if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+        unsigned long long used = 0;
+        KC_CUDA_TRY(c, cudaMemcpy(&used, a.d_sc + SW_OVF, 8, cudaMemcpyDeviceToHost));
+        a.ovf_reserved = used;
+    }
     if (a.windows + w > a.max_windows || a.ovf_reserved + w > a.pl.ovf_cap) {
-        if (a.xchg) return c->set_error(KC_ERR_CAPACITY, "more reads than kc_xchg_begin planned for (%llu k-mer slots)", (unsigned long long)a.max_windows);
+        if (a.xchg) return c->set_error(KC_ERR_CAPACITY, "more reads than kc_xchg_begin planned for (%llu k-mer slots, overflow list %llu of %llu)",
+                                        (unsigned long long)a.max_windows, (unsigned long long)a.ovf_reserved, (unsigned long long)a.pl.ovf_cap);
         kc_run *part = nullptr;
         KC_TRY(accum_count(c, &part));
         a.parts.push_back(part);
@@ -924,15 +936,16 @@ static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange) {
     uint64_t chunk_reads = c->cfg.max_chunk_bytes / c->cfg.read_len;
     if (expected_reads < chunk_reads) expected_reads = chunk_reads;
     if (expected_reads == 0) return c->set_error(KC_ERR_ARG, "kc_accum_begin: expected_reads and max_chunk_bytes are both 0");
-    uint64_t windows = expected_reads * nk;
-    if (windows > (1ull << 32) - 2) windows = (1ull << 32) - 2;     // record offsets are 32-bit: larger inputs flush in parts
+    const uint64_t windows = expected_reads * nk;     // (record offsets are 32-bit: at most 2^32 - 2 DISTINCT keys per flush)
     kc_ctx::Accum &a = c->acc;
     if (a.on && !a.fresh) return c->set_error(KC_ERR_STATE, "kc_accum_begin: reads are accumulated; flush first");
     SuperPlan pl;
-    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, (uint32_t)c->cfg.table_slots, &pl, exchange ? 0.25 : 0.0))
+    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, (uint32_t)c->cfg.table_slots, &pl, exchange ? 0.25 : 0.0,
+                    c->cfg.distinct_hint))
         return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", c->cfg.k, c->cfg.read_len);
-    // a chunk in flight may put every one of its windows into the overflow list
-    const uint64_t chunk_windows = (chunk_reads ? chunk_reads : expected_reads) * nk;
+    // a chunk submitted through a slot may put every one of its windows into the overflow list
+    // (device-resident input is cut into pieces that fit the list as planned)
+    const uint64_t chunk_windows = chunk_reads * nk;
     if (pl.ovf_cap < 2 * chunk_windows) {
         SuperPlan p2 = pl;
         // re-plan with the larger list: only the list and what follows it move
@@ -942,8 +955,7 @@ static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange) {
         p2.off_dk += g512; p2.off_dc += g512; p2.off_ek += g512; p2.off_ec += g512; p2.ws_bytes += g512;
         pl = p2;
     }
-    if (!a.d_sc) {
-        KC_CUDA_TRY(c, cudaMalloc((void **)&a.d_sc, SC_COUNT * 8));
+    if (!a.h_sc) {
         KC_CUDA_TRY(c, cudaMallocHost((void **)&a.h_sc, SC_COUNT * 8));
         for (auto &e : a.ev) KC_CUDA_TRY(c, cudaEventCreate(&e));
     }
@@ -959,6 +971,7 @@ static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange) {
         a.ws_bytes = pl.ws_bytes;
     }
     a.pl = pl;
+    a.d_sc = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(a.ws) + pl.off_sc);   // (peers read the scalars too)
     a.max_windows = windows;
     a.on = true;
     a.fresh = true;
@@ -1129,8 +1142,10 @@ int kc_xchg_count_local(kc_ctx *c) {
     cudaStream_t s = c->stream;
     for (auto &sl : c->slots)
         if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
+    for (uint32_t i = 0; i < a.n_ranks; i++)
+        if (!a.peer_ws[i]) return c->set_error(KC_ERR_STATE, "kc_xchg_count_local: rank %u's workspace is not mapped (kc_xchg_import / kc_xchg_set_peer)", i);
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[0], s));
-    KC_CUDA_TRY(c, super_count_bins(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s));
+    KC_CUDA_TRY(c, super_count_bins(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s, a.peer_ws, a.rank, a.n_ranks));
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[1], s));
     a.fresh = false;                          // (a rank without reads still takes part in the exchange)
     return KC_OK;
@@ -1150,7 +1165,7 @@ int kc_xchg_group_local(kc_ctx *c) {
     kc_ctx::Accum &a = c->acc;
     if (!a.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
     cudaSetDevice(c->cfg.device);
-    KC_CUDA_TRY(c, super_x_local(a.pl, a.ws, a.d_sc, a.d_all_hist, a.rank, a.n_ranks, c->n_sms, c->stream));
+    KC_CUDA_TRY(c, super_x_local(a.pl, a.ws, a.d_sc, a.d_all_hist, a.rank, a.n_ranks, a.keep_ranges, c->n_sms, c->stream));
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[2], c->stream));
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[3], c->stream));
     return KC_OK;
@@ -1175,7 +1190,32 @@ int kc_xchg_finish(kc_ctx *c, kc_run **run) {
     std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     if (!c->acc.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
     cudaSetDevice(c->cfg.device);
-    return accum_finish(c, true, run);
+    KC_CUDA_TRY(c, cudaMemcpyAsync(&c->acc.x_info, super_x_info(c->acc.pl, c->acc.ws), sizeof(SuperXInfo),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    return accum_finish(c, true, run);        // (synchronises the stream)
+}
+
+int kc_xchg_fix_ranges(kc_ctx *c, int on) {
+    KC_TRY(check_ctx(c));
+    if (!c->acc.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    c->acc.keep_ranges = on != 0;
+    return KC_OK;
+}
+
+int kc_xchg_info(kc_ctx *c, uint32_t *lo, uint64_t *recv_records, uint64_t *remote_records) {
+    KC_TRY(check_ctx(c));
+    const kc_ctx::Accum &a = c->acc;
+    if (!a.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
+    if (lo) for (uint32_t i = 0; i <= a.n_ranks; i++) lo[i] = a.x_info.lo[i];
+    uint64_t all = 0, remote = 0;
+    for (uint32_t s2 = 0; s2 < a.n_ranks; s2++) {
+        const uint64_t n = a.x_info.src_range[s2][1] - a.x_info.src_range[s2][0];
+        all += n;
+        if (s2 != a.rank) remote += n;
+    }
+    if (recv_records) *recv_records = all;
+    if (remote_records) *remote_records = remote;
+    return KC_OK;
 }
 
 // All ranks in one process: counts what the n contexts have accumulated and leaves rank r's key
@@ -1205,6 +1245,7 @@ int kc_xchg_run_all(kc_ctx *const *ctxs, uint32_t n, kc_run **runs) {
     for (uint32_t r = 0; r < n && rc == KC_OK; r++)
         for (uint32_t q = 0; q < n && rc == KC_OK; q++)
             if (q != r) rc = kc_xchg_set_peer(ctxs[r], q, ctxs[q]);
+    if (rc == KC_OK) barrier();                     // every rank's bins are complete
     for (uint32_t r = 0; r < n && rc == KC_OK; r++) rc = kc_xchg_count_local(ctxs[r]);
     if (rc == KC_OK) {
         barrier();                                  // the histograms are complete

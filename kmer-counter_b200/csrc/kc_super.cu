@@ -16,7 +16,8 @@ namespace {
 constexpr uint32_t kNoBin = 0xffffffffu;
 constexpr int kSwThreads = 256;
 constexpr int kSwMaxSeg = 18;           // windows one thread derives minimizers for
-constexpr int kNb1Max = 1024;
+constexpr int kNb1Max = 1024;           // level-1 bins / histogram bins S2 keeps
+constexpr int kRsBins = 2048;           // bins a record-scatter tile handles (level 2: two buckets x 1024)
 
 // ---------------------------------------------------------------- minimizer -> bin
 // Order of m-mers = order of a 32-bit bijective hash of their 2-bit codes (no ties between
@@ -334,8 +335,15 @@ template <int W> __device__ __forceinline__ uint32_t key_hash(const Key<W> &k) {
 __device__ __forceinline__ uint32_t pass_hash(uint32_t h) { return (h ^ (h >> 15)) * 0x2C1B3C6Du; }
 
 struct SwCountParams {
-    const uint32_t *cursor;
-    const uint8_t *bins, *ovf;
+    // bins [bin_begin, bin_begin + n_bins) are counted here; the records of a bin are what every
+    // source put there (one source on one GPU; with several GPUs the peers' bins are read in place,
+    // over NVLink -- the exchange of super-window records is the load side of this kernel)
+    uint32_t n_src;
+    const uint32_t *src_cursor[8];
+    const uint8_t *src_bins[8];
+    const unsigned long long *src_sc[8];
+    uint32_t bin_begin;
+    const uint8_t *ovf;
     uint32_t n_bins, bin_cap, ovf_slice;
     uint64_t ovf_cap;
     uint64_t last_mask;
@@ -408,19 +416,42 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
         __syncthreads();
         const uint32_t u = s_unit;
         if (u >= n_units) break;
-        const ulonglong2 *src;
-        uint32_t n_rec;
+        const ulonglong2 *src = nullptr;             // overflow slice: one contiguous piece
+        uint32_t n_rec = 0;
+        uint32_t spre[9];                            // bin: records of sources 0..s-1 come before source s's
+        const uint64_t bin_off = (uint64_t)(p.bin_begin + u) * p.bin_cap * W;
         if (u < p.n_bins) {
-            const uint32_t c = p.cursor[u];
-            n_rec = c < p.bin_cap ? c : p.bin_cap;
-            src = reinterpret_cast<const ulonglong2 *>(p.bins) + (uint64_t)u * p.bin_cap * W;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                spre[q] = n_rec;
+                if ((uint32_t)q < p.n_src) {
+                    const uint32_t c = p.src_cursor[q][p.bin_begin + u];
+                    n_rec += c < p.bin_cap ? c : p.bin_cap;
+                }
+            }
+            spre[8] = n_rec;
         } else {
             const uint64_t o0 = (uint64_t)(u - p.n_bins) * p.ovf_slice;
             n_rec = (uint32_t)min((unsigned long long)p.ovf_slice, n_ovf - o0);
             src = reinterpret_cast<const ulonglong2 *>(p.ovf) + o0 * W;
         }
-        // key 0 joins with count += 0 whenever a slot held no k-mer: its bin is bin 0
-        const bool phantom = u == 0 && p.add_phantom && p.sc[SW_INVALID] != 0;
+        // where record i of the unit lives
+        auto rec_at = [&](uint32_t i) -> const ulonglong2 * {
+            if (src) return src + (uint64_t)i * W;
+            uint32_t off = i;
+            const uint8_t *base = p.src_bins[0];
+#pragma unroll
+            for (int q = 1; q < 8; q++)
+                if ((uint32_t)q < p.n_src && i >= spre[q]) { off = i - spre[q]; base = p.src_bins[q]; }
+            return reinterpret_cast<const ulonglong2 *>(base) + bin_off + (uint64_t)off * W;
+        };
+        // key 0 joins with count += 0 whenever a slot held no k-mer on any rank: its bin is bin 0
+        bool phantom = false;
+        if (u == 0 && p.bin_begin == 0 && p.add_phantom) {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if ((uint32_t)q < p.n_src && p.src_sc[q][SW_INVALID] != 0) phantom = true;
+        }
         if (n_rec == 0 && !phantom) { __syncthreads(); continue; }
 
         uint32_t bits = 0, val = 0;
@@ -458,8 +489,9 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
             for (int u2 = 0; u2 < RPT; u2++) {
                 const uint32_t i = u2 * THREADS + tid;
                 if (i < n_rec) {
+                    const ulonglong2 *rp = rec_at(i);
 #pragma unroll
-                    for (int t = 0; t < W; t++) pf[u2][t] = src[(uint64_t)i * W + t];
+                    for (int t = 0; t < W; t++) pf[u2][t] = rp[t];
                 }
             }
             for (uint32_t r0 = 0; r0 < n_rec; r0 += RB) {
@@ -552,8 +584,9 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                 for (int u2 = 0; u2 < RPT; u2++) {
                     const uint32_t i = r0 + RB + u2 * THREADS + tid;
                     if (i < n_rec) {
+                        const ulonglong2 *rp = rec_at(i);
 #pragma unroll
-                        for (int t = 0; t < W; t++) pf[u2][t] = src[(uint64_t)i * W + t];
+                        for (int t = 0; t < W; t++) pf[u2][t] = rp[t];
                     }
                 }
                 // this thread's share of the tot windows: [f0, f1)
@@ -801,7 +834,7 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
 template <int THREADS>
 __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_t *start, int nb, uint32_t *s_warp) {
-    constexpr int PER = kNb1Max / THREADS > 0 ? kNb1Max / THREADS : 1;
+    constexpr int PER = kRsBins / THREADS > 0 ? kRsBins / THREADS : 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t v[PER];
     uint32_t sum = 0;
@@ -849,8 +882,8 @@ __global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restric
     unsigned long long nd = sc[SW_D];
     if (nd > d_cap) nd = d_cap;
     int B = 1;
-    while (B < b1_max + 9 && B < sig_bits && (nd >> B) > sub_target) B++;
-    int b1 = B - 9 > (B < 16 ? B / 2 : 8) ? B - 9 : (B < 16 ? B / 2 : 8);
+    while (B < b1_max + 10 && B < sig_bits && (nd >> B) > sub_target) B++;
+    int b1 = B - 9 > (B < 16 ? B / 2 : 8) ? B - 9 : (B < 16 ? B / 2 : 8);       // (level 2 takes a 10th bit only when level 1 is at its 10)
     if (b1 > b1_max) b1 = b1_max;
     if (b1 < 1) b1 = 1;
     const int b2 = B - b1 > 0 ? B - b1 : 0;
@@ -894,14 +927,10 @@ __global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restric
 // level-1 bases (the local scatter), where its key range starts and ends inside every source's
 // grouped array, and the plan of its part of the key space.
 constexpr int kXB1 = 10;
-struct XDev {
-    uint32_t lo[16];                 // bucket range of owner o: [lo[o], lo[o + 1])
-    uint32_t src_range[8][2];        // records of this rank's key range inside source s's grouped array
-    uint32_t n_recv, pad[3];
-};
+typedef SuperXInfo XDev;
 
 __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict__ all_hist, uint32_t rank, uint32_t P,
-                                                      uint64_t d_cap, uint32_t sub_target, int sig_bits,
+                                                      int keep_ranges, uint64_t d_cap, uint32_t sub_target, int sig_bits,
                                                       uint32_t *__restrict__ base1, uint32_t *__restrict__ cursor1,
                                                       SuperPlanDev *__restrict__ plan, XDev *__restrict__ x,
                                                       unsigned long long *__restrict__ sc) {
@@ -943,6 +972,8 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         for (int o = (int)P - 1; o >= 0; o--)
             if (s_lo[o] > s_lo[o + 1]) s_lo[o] = s_lo[o + 1];
         s_lo[0] = 0;
+        if (keep_ranges)                              // the ranges of the previous exchange (runs that will be merged)
+            for (uint32_t o = 0; o <= P; o++) s_lo[o] = x->lo[o];
         for (uint32_t o = 0; o <= P; o++) x->lo[o] = s_lo[o];
     }
     __syncthreads();
@@ -973,7 +1004,7 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         unsigned long long nd = sc[SW_D];
         if (nd > d_cap) nd = d_cap;
         int b2 = 0;
-        while (b2 < 9 && kXB1 + b2 < sig_bits && (total >> (kXB1 + b2)) > sub_target) b2++;
+        while (b2 < 10 && kXB1 + b2 < sig_bits && (total >> (kXB1 + b2)) > sub_target) b2++;
         plan->n_d = (uint32_t)nd;
         plan->b1 = kXB1;
         plan->b2 = (uint32_t)b2;
@@ -1023,7 +1054,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
     extern __shared__ __align__(16) uint8_t rs_smem[];
     Key<W> *stg_k = reinterpret_cast<Key<W> *>(rs_smem);                    // [TILE]
     uint32_t *stg_c = reinterpret_cast<uint32_t *>(stg_k + TILE);           // [TILE]
-    uint32_t *cnt = stg_c + TILE, *start = cnt + kNb1Max, *gbase = start + kNb1Max;
+    uint32_t *cnt = stg_c + TILE, *start = cnt + kRsBins, *gbase = start + kRsBins;
     __shared__ uint32_t s_warp[kRsThreads / 32];
     uint32_t n, first = 0;
     if (LEVEL == 1) {
@@ -1057,7 +1088,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
         } else {
             p0 = ((uint32_t)(in_keys[(size_t)begin * W] >> shift) >> b2) << b2;       // first sub-bucket of the first key's bucket
             const uint32_t pl = (uint32_t)(in_keys[(size_t)(end - 1) * W] >> shift);
-            nb = (pl >> b2) == (p0 >> b2) ? nb2 : 2 * nb2;                            // 2 * nb2 <= 1024
+            nb = (pl >> b2) == (p0 >> b2) ? nb2 : 2 * nb2;                            // 2 * nb2 <= kRsBins
         }
         for (uint32_t i = threadIdx.x; i < nb; i += kRsThreads) cnt[i] = 0;
         __syncthreads();
@@ -1079,9 +1110,9 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
         __syncthreads();
         const uint32_t total = block_scan_bins<kRsThreads>(cnt, start, (int)nb, s_warp);
         // reserve the bins' ranges, stage the records while the atomics are in flight, then look at the answers
-        uint32_t reserved[kNb1Max / kRsThreads];
+        uint32_t reserved[kRsBins / kRsThreads];
 #pragma unroll
-        for (int u = 0; u < kNb1Max / kRsThreads; u++) {
+        for (int u = 0; u < kRsBins / kRsThreads; u++) {
             const uint32_t b = u * kRsThreads + threadIdx.x;
             reserved[u] = 0;
             if (b < nb) {
@@ -1097,7 +1128,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
                 stg_c[o] = val[i];
             }
 #pragma unroll
-        for (int u = 0; u < kNb1Max / kRsThreads; u++) {
+        for (int u = 0; u < kRsBins / kRsThreads; u++) {
             const uint32_t b = u * kRsThreads + threadIdx.x;
             if (b < nb) gbase[b] = reserved[u] - start[b];
         }
@@ -1442,14 +1473,13 @@ __global__ void __launch_bounds__(256) sw_gather_kernel(const uint64_t *__restri
 
 inline uint64_t round512(uint64_t b) { return (b + 511) & ~511ull; }
 
-template <int W>
-struct FinishCfg { static constexpr int THREADS = 256, CAP = 2048; };
+constexpr int kFinCapSmall = 2048, kFinCapLarge = 4096;     // records a sub-bucket may hold (S3c variants)
 
 }  // namespace
 
 // ------------------------------------------------------------------------ host
 bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
-                double record_headroom) {
+                double record_headroom, uint64_t distinct_hint) {
     if (k == 0 || k > 64 || L < k || L > 4096) return false;
     SuperPlan pl{};
     pl.W = (int)((k + 31) / 32);
@@ -1482,13 +1512,19 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     const double per_bin = est_total / (double)pl.n_bins;
     pl.bin_cap = (uint32_t)(per_bin * 2.0) + 64;          // minimizer weights make bins uneven (sd ~20% at the default size)
     pl.bin_cap = (pl.bin_cap + 3) & ~3u;
+    // (also what bounds the pieces device-resident input is accumulated in: 1/32 of the plan's windows each)
     pl.ovf_cap = (uint64_t)(est_total * 0.6) + 8192;
+    if (pl.ovf_cap < max_windows / 16) pl.ovf_cap = max_windows / 16;
     pl.ovf_slice = 4096;
-    pl.d_cap = max_windows + (uint64_t)((double)max_windows * record_headroom) + (record_headroom > 0 ? 8192 : 0);
+    // records the dense / grouped arrays hold: every k-mer distinct unless the caller knows better
+    const uint64_t d_base = distinct_hint && distinct_hint < max_windows ? distinct_hint + distinct_hint / 8 + 4096 : max_windows;
+    pl.d_cap = d_base + (uint64_t)((double)d_base * record_headroom) + (record_headroom > 0 ? 8192 : 0);
     if (pl.d_cap > (1ull << 32) - 2) pl.d_cap = (1ull << 32) - 2;
     if (pl.d_cap < 1024) pl.d_cap = 1024;
     // S2 keeps a histogram of the leading b1 bits; the device plan picks the digits from it
-    pl.sub_target = FinishCfg<1>::CAP * 7 / 10;
+    // sub-buckets of 2048 records unless the 2^20 sub-buckets two levels can cut would be too few
+    pl.fin_cap = pl.d_cap > (uint64_t)kSuperMaxSub * (kFinCapSmall * 7 / 10) ? kFinCapLarge : kFinCapSmall;
+    pl.sub_target = pl.fin_cap * 7 / 10;
     const int sig = pl.W == 1 ? (masked ? (int)(2 * mm) : 64) : 64;
     pl.b1 = sig < 10 ? sig : 10;
     // workspace
@@ -1506,6 +1542,7 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.off_off = take((uint64_t)(kSuperMaxSub + 8) * 4);
     pl.off_plan = take(sizeof(SuperPlanDev));
     pl.off_x = take(sizeof(XDev));
+    pl.off_sc = take(SW_COUNT * 8);
     pl.off_h2m = take((uint64_t)(kSuperMaxSub + 8) * 4);
     pl.off_bins = take((uint64_t)pl.n_bins * pl.bin_cap * rec_bytes);
     pl.off_ovf = take(pl.ovf_cap * rec_bytes);
@@ -1595,13 +1632,23 @@ static cudaError_t launch_count(const SwCountParams &cp, int n_sms, cudaStream_t
 
 template <int W>
 static cudaError_t super_count_bins_w(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
-                                      cudaStream_t s) {
+                                      cudaStream_t s, void *const *peer_ws = nullptr, uint32_t rank = 0,
+                                      uint32_t n_ranks = 1) {
     cudaError_t e;
     SwCountParams cp{};
-    cp.cursor = at<uint32_t>(ws, pl.off_cursor);
-    cp.bins = at<uint8_t>(ws, pl.off_bins);
+    const uint32_t n_src = peer_ws ? n_ranks : 1u;
+    cp.n_src = n_src;
+    for (uint32_t i = 0; i < n_src; i++) {
+        void *w = peer_ws ? peer_ws[i] : ws;
+        cp.src_cursor[i] = at<uint32_t>(w, pl.off_cursor);
+        cp.src_bins[i] = at<uint8_t>(w, pl.off_bins);
+        cp.src_sc[i] = peer_ws ? at<unsigned long long>(w, pl.off_sc) : d_sc;
+    }
+    // rank r counts the bins [r * n_bins / P, (r + 1) * n_bins / P): bins are hash values, so the split is even
+    cp.bin_begin = peer_ws ? (uint32_t)((uint64_t)pl.n_bins * rank / n_ranks) : 0u;
+    cp.n_bins = peer_ws ? (uint32_t)((uint64_t)pl.n_bins * (rank + 1) / n_ranks) - cp.bin_begin : pl.n_bins;
     cp.ovf = at<uint8_t>(ws, pl.off_ovf);
-    cp.n_bins = pl.n_bins; cp.bin_cap = pl.bin_cap; cp.ovf_slice = pl.ovf_slice; cp.ovf_cap = pl.ovf_cap;
+    cp.bin_cap = pl.bin_cap; cp.ovf_slice = pl.ovf_slice; cp.ovf_cap = pl.ovf_cap;
     cp.last_mask = pl.last_mask;
     cp.d_keys = at<uint64_t>(ws, pl.off_dk); cp.d_counts = at<uint32_t>(ws, pl.off_dc); cp.d_cap = pl.d_cap;
     cp.hist1 = at<uint32_t>(ws, pl.off_hist1); cp.shift1 = 64 - pl.b1; cp.nb1 = 1 << pl.b1;
@@ -1635,9 +1682,10 @@ static cudaError_t super_count_bins_w(const SuperPlan &pl, bool add_phantom, voi
 }
 
 cudaError_t super_count_bins(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
-                             cudaStream_t s) {
-    if (pl.W == 1) return super_count_bins_w<1>(pl, add_phantom, ws, d_sc, n_sms, s);
-    if (pl.W == 2) return super_count_bins_w<2>(pl, add_phantom, ws, d_sc, n_sms, s);
+                             cudaStream_t s, void *const *peer_ws, uint32_t rank, uint32_t n_ranks) {
+    if (peer_ws && (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks)) return cudaErrorInvalidValue;
+    if (pl.W == 1) return super_count_bins_w<1>(pl, add_phantom, ws, d_sc, n_sms, s, peer_ws, rank, n_ranks);
+    if (pl.W == 2) return super_count_bins_w<2>(pl, add_phantom, ws, d_sc, n_sms, s, peer_ws, rank, n_ranks);
     return cudaErrorInvalidValue;
 }
 
@@ -1657,7 +1705,7 @@ static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws
     // ---- S3a: level-1 bases + device plan, scatter D -> E
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
     sw_plan_kernel<<<1, 1024, 0, s>>>(hist1, pl.b1, pl.d_cap, pl.sub_target, sig, base1, cur1, plan, d_sc);
-    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kNb1Max * 4;
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
     {
         auto k1 = rec_scatter_kernel<W, 1>;
         auto k2 = rec_scatter_kernel<W, 2>;
@@ -1695,10 +1743,9 @@ void super_tmp_buffers(const SuperPlan &pl, void *ws, uint64_t **tmp_keys, uint3
     *tmp_counts = at<uint32_t>(ws, pl.off_ec);
 }
 
-template <int W, bool DUP>
+template <int W, bool DUP, int THREADS, int CAP>
 static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
                                   uint32_t *out_counts, int n_sms, cudaStream_t s) {
-    constexpr int THREADS = FinishCfg<W>::THREADS, CAP = FinishCfg<W>::CAP;
     FinishParams fp{};
     fp.in_keys = at<uint64_t>(ws, pl.off_dk);
     fp.in_counts = at<uint32_t>(ws, pl.off_dc);
@@ -1719,12 +1766,20 @@ static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long l
     return cudaGetLastError();
 }
 
+template <int W>
+static cudaError_t super_finish_d(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
+                                  uint32_t *out_counts, int n_sms, cudaStream_t s) {
+    if (pl.fin_cap == kFinCapLarge)
+        return dup ? super_finish_w<W, true, 512, kFinCapLarge>(pl, ws, d_sc, out_keys, out_counts, n_sms, s)
+                   : super_finish_w<W, false, 512, kFinCapLarge>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    return dup ? super_finish_w<W, true, 256, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s)
+               : super_finish_w<W, false, 256, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+}
+
 cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
                          uint32_t *out_counts, int n_sms, cudaStream_t s) {
-    if (pl.W == 1) return dup ? super_finish_w<1, true>(pl, ws, d_sc, out_keys, out_counts, n_sms, s)
-                              : super_finish_w<1, false>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
-    if (pl.W == 2) return dup ? super_finish_w<2, true>(pl, ws, d_sc, out_keys, out_counts, n_sms, s)
-                              : super_finish_w<2, false>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    if (pl.W == 1) return super_finish_d<1>(pl, dup, ws, d_sc, out_keys, out_counts, n_sms, s);
+    if (pl.W == 2) return super_finish_d<2>(pl, dup, ws, d_sc, out_keys, out_counts, n_sms, s);
     return cudaErrorInvalidValue;
 }
 
@@ -1750,15 +1805,15 @@ bool super_supported(const SuperPlan &pl) { return super_scatter_fits(pl); }
 // peer's buffers are found from its workspace base.
 template <int W>
 static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
-                                   uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s) {
+                                   uint32_t rank, uint32_t n_ranks, bool keep_ranges, int n_sms, cudaStream_t s) {
     cudaError_t e;
     uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
     uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
     SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
-    x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, pl.d_cap, pl.sub_target, sig, at<uint32_t>(ws, pl.off_base1),
+    x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, keep_ranges ? 1 : 0, pl.d_cap, pl.sub_target, sig, at<uint32_t>(ws, pl.off_base1),
                                      at<uint32_t>(ws, pl.off_cur1), plan, at<XDev>(ws, pl.off_x), d_sc);
-    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kNb1Max * 4;
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
     auto k1 = rec_scatter_kernel<W, 1>;
     if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
     int per_sm = 1;
@@ -1771,10 +1826,10 @@ static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long 
 }
 
 cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
-                          uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s) {
+                          uint32_t rank, uint32_t n_ranks, bool keep_ranges, int n_sms, cudaStream_t s) {
     if (pl.b1 != kXB1 || n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return cudaErrorInvalidValue;
-    if (pl.W == 1) return super_x_local_w<1>(pl, ws, d_sc, d_all_hist, rank, n_ranks, n_sms, s);
-    if (pl.W == 2) return super_x_local_w<2>(pl, ws, d_sc, d_all_hist, rank, n_ranks, n_sms, s);
+    if (pl.W == 1) return super_x_local_w<1>(pl, ws, d_sc, d_all_hist, rank, n_ranks, keep_ranges, n_sms, s);
+    if (pl.W == 2) return super_x_local_w<2>(pl, ws, d_sc, d_all_hist, rank, n_ranks, keep_ranges, n_sms, s);
     return cudaErrorInvalidValue;
 }
 
@@ -1793,7 +1848,7 @@ static cudaError_t super_x_pull_w(const SuperPlan &pl, void *ws, unsigned long l
     uint32_t *h2m = at<uint32_t>(ws, pl.off_h2m), *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
     x_merge_hist_kernel<<<(uint32_t)n_sms * 4, 256, 0, s>>>(peers, n_ranks, plan, h2m);
     sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(h2m, &plan->n_sub, 0, base2, cur2, nullptr);
-    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kNb1Max * 4;
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
     auto k2 = rec_scatter_kernel<W, 2>;
     if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
     int per_sm = 1;
@@ -1817,6 +1872,6 @@ cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc
 }
 
 uint32_t *super_hist1(const SuperPlan &pl, void *ws) { return at<uint32_t>(ws, pl.off_hist1); }
-const void *super_x_info(const SuperPlan &pl, void *ws) { return at<XDev>(ws, pl.off_x); }
+const SuperXInfo *super_x_info(const SuperPlan &pl, void *ws) { return at<XDev>(ws, pl.off_x); }
 
 }  // namespace kc

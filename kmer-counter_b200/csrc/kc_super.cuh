@@ -51,6 +51,12 @@ struct SuperPlanDev {           // level-2 plan, decided on the device once |D| 
     uint32_t pad[1];
 };
 
+struct SuperXInfo {             // multi-GPU exchange: what the device plan decided (kc_xchg_info)
+    uint32_t lo[16];            // rank o owns the keys whose leading 10 bits lie in [lo[o], lo[o + 1])
+    uint32_t src_range[8][2];   // records of this rank's key range inside rank s's grouped array
+    uint32_t n_recv, pad[3];    // records this rank pulls (its own included)
+};
+
 struct SuperPlan {
     int W;
     uint32_t k, L, span;        // span = bases that make up a key (32W or k)
@@ -64,10 +70,11 @@ struct SuperPlan {
     uint64_t d_cap;             // records D / the level buffers hold
     int b1;                     // bits of the histogram S2 keeps (most level-1 digit bits; 1 << b1 <= 1024)
     uint32_t sub_target;        // records per sub-bucket the level-2 plan aims for
+    int fin_cap;                // records a sub-bucket may hold (the S3c variant: 2048 or 4096)
     uint64_t last_mask;
     // workspace layout (bytes from the workspace base)
     uint64_t off_cursor, off_bins, off_ovf, off_hist1, off_base1, off_cur1, off_hist2, off_base2, off_cur2,
-        off_mout, off_off, off_plan, off_x, off_h2m, off_dk, off_dc, off_ek, off_ec, ws_bytes;
+        off_mout, off_off, off_plan, off_x, off_sc, off_h2m, off_dk, off_dc, off_ek, off_ec, ws_bytes;
 };
 
 constexpr uint32_t kSuperMaxSub = 1u << 20;
@@ -76,7 +83,7 @@ constexpr uint32_t kSuperMaxSub = 1u << 20;
 // accumulated before the count). occ_per_bin = 0 -> default. Returns false for shapes the path
 // does not take (W > 2, span < 22, reads too long for the shared-memory tile).
 bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
-                double record_headroom = 0.0);
+                double record_headroom = 0.0, uint64_t distinct_hint = 0);
 
 // zero cursors, histograms and scalars: once before the first super_scatter of a pipeline
 cudaError_t super_reset(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s);
@@ -97,15 +104,20 @@ cudaError_t super_fold_offsets(const SuperPlan &pl, void *ws, unsigned long long
 // ... and the gather that closes the gaps
 cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys, const uint32_t *tmp_counts,
                          uint64_t *out_keys, uint32_t *out_counts, int n_sms, cudaStream_t s);
-// S2 only: count the bins into the dense array D (+ histogram of the records' leading b1 bits)
+// S2 only: count the bins into the dense array D (+ histogram of the records' leading b1 bits).
+// With peer_ws (multi-GPU: the ranks' workspaces as mapped here, scalars at off_sc) this rank counts
+// its share of the bins and reads what every rank put into them -- the exchange of super-window
+// records happens in the kernel's loads.
 cudaError_t super_count_bins(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
-                             cudaStream_t s);
+                             cudaStream_t s, void *const *peer_ws = nullptr, uint32_t rank = 0, uint32_t n_ranks = 1);
 // ---- multi-GPU (one context per rank, every rank planned alike): after super_count_bins and an
 // all-gather of the ranks' histograms (super_hist1: 1024 uint32 each) ...
 uint32_t *super_hist1(const SuperPlan &pl, void *ws);
+const SuperXInfo *super_x_info(const SuperPlan &pl, void *ws);      // device pointer
 // ... the rank groups its own records by their leading 10 bits and counts the global sub-buckets,
+// (keep_ranges: cut at the key ranges of the previous exchange instead of balancing anew)
 cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
-                          uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s);
+                          uint32_t rank, uint32_t n_ranks, bool keep_ranges, int n_sms, cudaStream_t s);
 // ... and, once every rank has done that, pulls its key range out of every rank's grouped array
 // (peer_ws[i] = rank i's workspace as mapped here) into sub-buckets. Then super_finish(dup = true).
 cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t n_ranks,

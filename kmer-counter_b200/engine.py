@@ -112,7 +112,7 @@ class Counter:
     """One kc_ctx: the replacement for PrepareGPU's GPUStream array (GPUHandler.cu:479-509)."""
 
     def __init__(self, k, read_len, device=0, method="auto", compat="ref", n_slots=2, max_chunk_bytes=0,
-                 table_slots=0, stream=None):
+                 table_slots=0, stream=None, distinct_hint=0):
         self._lib = _lib.load()
         cfg = KcConfig()
         cfg.struct_size = C.sizeof(KcConfig)
@@ -121,6 +121,7 @@ class Counter:
         cfg.method = METHODS[method] if isinstance(method, str) else int(method)
         cfg.n_slots, cfg.max_chunk_bytes, cfg.table_slots = n_slots, max_chunk_bytes, table_slots
         cfg.stream = stream
+        cfg.distinct_hint = distinct_hint
         ctx = C.c_void_p()
         rc = self._lib.kc_create(C.byref(cfg), C.byref(ctx))
         if rc != 0:
@@ -221,6 +222,16 @@ class Counter:
         h = C.c_void_p()
         self._check(self._lib.kc_xchg_finish(self._ctx, C.byref(h)))
         return Run(self, h)
+
+    def xchg_fix_ranges(self, on=True):
+        self._check(self._lib.kc_xchg_fix_ranges(self._ctx, 1 if on else 0))
+
+    def xchg_info(self, n_ranks):
+        """(bucket boundaries lo[0..n_ranks], records pulled, records pulled from peers) of the last exchange"""
+        lo = (C.c_uint32 * 17)()
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.kc_xchg_info(self._ctx, lo, C.byref(a), C.byref(b)))
+        return [int(lo[i]) for i in range(n_ranks + 1)], a.value, b.value
 
     def debug_scalars(self) -> dict:
         """Device scalars of the most recent chunk (super-window path: SW_* of kc_super.cuh)."""

@@ -1,17 +1,102 @@
 """Multi-GPU counting: one process per GPU, key-range ownership, one exchange step.
 
-The reference has no multi-device path (SURVEY.md 2.2 row C*); this is the one place
-the path shards.  Each rank counts its own shard of reads into a
-sorted key-unique run FIRST (local pre-aggregation: a key crosses NVLink once per
-rank, with its count, instead of once per occurrence), cuts the run at the owners'
-key-range splitters (contiguous slices, no partition kernel needed), exchanges the
-slices with one all-to-all-v over NCCL, and merges the P slices it received with the
-merge-path kernel.  Rank r then holds the final records of key range r; the global
-artefact is the concatenation of the ranks' runs in rank order.
+The reference has no multi-device path (SURVEY.md 2.2 row C*); this is the one place the
+path shards.  Each rank packs its own reads into super-window records and
+counts them locally FIRST (a key crosses NVLink once per rank, with its count, instead of once
+per occurrence).  The ranks then all-gather a 1024-bin histogram of their records' leading
+bits, cut the key space into P contiguous ranges of about equal record totals, and every rank
+pulls the records of its range out of all ranks' grouped arrays -- the pull is the load side of
+the level-2 placement kernel (kc_xchg_pull), so the transfer over NVLink / NVSwitch happens
+inside the kernel that consumes it.  Rank r ends with the sorted unique records of key range r;
+the artefact is the concatenation in rank order.
 
-torch.distributed is plumbing only: it moves bytes between ranks.
+torch.distributed is plumbing only: the tiny all-gather and two stream-ordered barriers.
+The NCCL all-to-all-v of run slices below (exchange_and_combine) is kept for keys the
+super-window path does not take (k > 64).
 """
 import numpy as np
+
+XCHG_BINS = 1024            # histogram bins = leading 10 key bits (kXB1 in kc_super.cu)
+
+
+def plan_owner_ranges(all_hist, world):
+    """Host model of the device plan (x_plan_kernel): all_hist[s][b] = records of rank s whose
+    leading 10 key bits are b.  Bucket b belongs to the rank in whose equal share of the total
+    the middle of the bucket falls; returns lo[0..world]: rank o owns buckets [lo[o], lo[o+1])."""
+    h = np.asarray(all_hist, dtype=np.uint64).reshape(world, XCHG_BINS)
+    tot = h.sum(axis=0)
+    total = int(tot.sum())
+    lo = [XCHG_BINS] * (world + 1)
+    cum = 0
+    for b in range(XCHG_BINS):
+        t = int(tot[b])
+        owner = min(world - 1, (cum + t // 2) * world // total) if total else 0
+        lo[owner] = min(lo[owner], b)
+        cum += t
+    for o in range(world - 1, -1, -1):
+        lo[o] = min(lo[o], lo[o + 1])
+    lo[0] = 0
+    return lo
+
+
+class Exchange:
+    """kc_xchg_* driven by torch.distributed (one process per GPU).
+
+    The counter's stream must be torch's current stream: the all-gather and the barriers are
+    ordered against the kernels by stream order alone, the host never waits inside a step."""
+
+    def __init__(self, counter, device, expected_reads, group=None):
+        import torch
+        import torch.distributed as dist
+        self.c, self.dev, self.group = counter, device, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        counter.xchg_begin(self.rank, self.world, expected_reads)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, counter.xchg_export(), group=group)
+        for r, h in enumerate(everyone):
+            if r != self.rank:
+                counter.xchg_import(r, h)           # the peer's workspace, mapped into this process (CUDA IPC)
+        hp, ap = counter.xchg_hist()
+        self.hist = torch.as_tensor(_CudaView(hp, (XCHG_BINS,), "<i4"), device=device)
+        self.all_hist = torch.as_tensor(_CudaView(ap, (self.world * XCHG_BINS,), "<i4"), device=device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def barrier(self):
+        """Stream-ordered: a one-element all-reduce queued behind this rank's kernels."""
+        import torch.distributed as dist
+        dist.all_reduce(self.flag, group=self.group)
+
+    def add_device(self, d_ptr, n_bytes):
+        self.c.accum_add_device(d_ptr, n_bytes)
+
+    def finish(self):
+        """Everything accumulated on all ranks -> this rank's key range as a Run. Collective."""
+        import torch.distributed as dist
+        c = self.c
+        self.barrier()                              # every rank's bins are complete
+        c.xchg_count_local()                        # (reads the peers' bins over NVLink)
+        dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
+        c.xchg_group_local()
+        self.barrier()                              # every rank's grouped records and counters are final
+        c.xchg_pull()
+        self.barrier()                              # nobody reads a peer's grouped records any more
+        return c.xchg_finish()
+
+
+def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, exchange=None):
+    """This rank's share of the distributed count: returns the Run of this rank's key range.
+    Collective. With an Exchange (k <= 64) the records are pulled over NVLink inside the placement
+    kernel; without one, run slices travel by an NCCL all-to-all-v and are merged (merge path)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if exchange is not None and world > 1:
+        exchange.add_device(d_reads_ptr, n_bytes)
+        return exchange.finish()
+    local = counter.count_device(d_reads_ptr, n_bytes)
+    if world == 1:
+        return local
+    return exchange_and_combine(counter, local, device, group)
 
 
 # ------------------------------------------------------------------ ownership
@@ -121,93 +206,13 @@ def run_as_tensors(run, device):
     return keys, counts
 
 
-def count_shard(counter, d_reads_ptr, n_bytes, device, group=None, splitters=None, peer=None):
-    """This rank's share of the distributed count.  Returns the Run holding the final
-    records of this rank's key range.  Collective: every rank of `group` must call it.
-
-    Runs of the partitioned hash path carry their partition structure (n_sub equal key ranges
-    with record offsets); when all ranks agree on it, rank r owns ranges [r*n_sub/P, (r+1)*n_sub/P),
-    receives each peer's records and offsets for them, and combines the P parts range by range in
-    shared-memory tables (kc_merge_parts): one pass whose cost does not grow with P.  Otherwise
-    (sort path, k > 32) slices are cut at key splitters and merged by the merge-path tree."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if peer is not None and world > 1:
-        peer.place()                                # count straight into the staging buffer the peers read
-    local = counter.count_device(d_reads_ptr, n_bytes)
-    if world == 1:
-        return local
-    if peer is not None:
-        merged = peer.combine(local)                # the exchange happens inside the combine kernel
-        if merged is not None:
-            return merged
-    return exchange_and_combine(counter, local, device, group, splitters)
-
-
 def exchange_and_combine(counter, local, device, group=None, splitters=None):
     """Second half of count_shard: `local` is this rank's run; returns the run of this rank's
     key range. Frees `local`."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    off_ptr, n_sub, pbits = local.parts()
-    plan = torch.tensor([n_sub, pbits], dtype=torch.int64, device=device)
-    plans = [torch.empty_like(plan) for _ in range(world)]
-    dist.all_gather(plans, plan, group=group)
-    agreed = counter.words == 1 and n_sub >= world and n_sub % world == 0 and all(bool((q == plan).all()) for q in plans)
     keys_t, counts_t = run_as_tensors(local, device)
-    if agreed:
-        per = n_sub // world
-        off_t = torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=device)
-        # offsets of every owner's ranges, relative to the start of its slice; the last entry of a
-        # row is the slice length, so this one small all-to-all also tells the receiver the sizes
-        rel = (off_t.unfold(0, per + 1, per) - off_t[0:n_sub:per].unsqueeze(1)).contiguous()
-        recv_rel = torch.empty_like(rel)
-        nccl = dist.get_backend(group) == "nccl"
-        if nccl:
-            dist.all_to_all_single(recv_rel, rel, group=group)
-        else:
-            _p2p_all_to_all(recv_rel, rel, [1] * world, [1] * world, group)
-        send = rel[:, per].tolist()
-        sizes = recv_rel[:, per].tolist()
-        starts = off_t[0:n_sub:per].tolist()
-        rk = torch.empty((sum(sizes), 1), dtype=keys_t.dtype, device=device)
-        rc = torch.empty((sum(sizes),), dtype=counts_t.dtype, device=device)
-        if nccl:
-            # keys and counts of all peers in ONE grouped launch
-            rank = dist.get_rank(group)
-            ops, pos = [], 0
-            for p in range(world):
-                peer = dist.get_global_rank(group, p) if group else p
-                a, b = starts[p], starts[p] + send[p]
-                if p == rank:
-                    rk[pos:pos + sizes[p]].copy_(keys_t[a:b])
-                    rc[pos:pos + sizes[p]].copy_(counts_t[a:b])
-                else:
-                    if send[p]:
-                        ops.append(dist.P2POp(dist.isend, keys_t[a:b], peer, group))
-                        ops.append(dist.P2POp(dist.isend, counts_t[a:b], peer, group))
-                    if sizes[p]:
-                        ops.append(dist.P2POp(dist.irecv, rk[pos:pos + sizes[p]], peer, group))
-                        ops.append(dist.P2POp(dist.irecv, rc[pos:pos + sizes[p]], peer, group))
-                pos += sizes[p]
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-        else:
-            bounds = [starts[p] for p in range(world)] + [starts[-1] + send[-1]]
-            _p2p_all_to_all(rk, keys_t, sizes, [bounds[p + 1] - bounds[p] for p in range(world)], group)
-            _p2p_all_to_all(rc, counts_t, sizes, [bounds[p + 1] - bounds[p] for p in range(world)], group)
-        torch.cuda.current_stream().synchronize()
-        local.free()
-        kp, cp, op, pos = [], [], [], 0
-        for src, sz in enumerate(sizes):
-            kp.append(rk.data_ptr() + pos * 8 if sz else 0)
-            cp.append(rc.data_ptr() + pos * 4 if sz else 0)
-            op.append(recv_rel[src].data_ptr())
-            pos += sz
-        return counter.merge_parts(kp, cp, op, sizes, per, pbits)
     if splitters is None:
         splitters = range_splitters(world, counter.words)
     off = local.split(splitters)
@@ -223,131 +228,3 @@ def exchange_and_combine(counter, local, device, group=None, splitters=None):
     for p in parts:
         p.free()
     return merged
-
-
-# ------------------------------------------------ exchange fused into the combine kernel (peer memory)
-class PeerCombine:
-    """The all-to-all fused into the combine kernel over NVLink peer memory.
-
-    Every rank keeps its run (keys, counts, range offsets) in a staging buffer whose CUDA IPC
-    handle its peers have opened once.  A step is then: count locally -> copy the run into the
-    staging buffer -> barrier -> kc_merge_parts reads, for every key range this rank owns, the
-    P parts straight out of the peers' staging buffers (P2P loads through NVSwitch) while it
-    combines them in shared memory -> barrier.  No exchange kernel, no receive buffer: the
-    transfer happens inside the kernel that consumes it.  Needs partition-structured runs
-    (64-bit keys); exchange_and_combine() over NCCL is the general path."""
-
-    def __init__(self, counter, device, max_records, n_sub_max=1 << 20, group=None):
-        import torch
-        import torch.distributed as dist
-        self.c, self.dev, self.group = counter, device, group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.cap, self.n_sub_max = int(max_records), int(n_sub_max)
-        self.loc_offs = None
-        self._readers_pending = False
-        # one allocation: keys u64[cap] | counts u32[cap] | range offsets u32[n_sub_max + 1]
-        self._o_counts = 8 * self.cap
-        self._o_offs = (12 * self.cap + 255) // 256 * 256
-        self.base, handle = counter.peer_alloc(self._o_offs + 4 * (self.n_sub_max + 1))
-        self.keys = torch.as_tensor(_CudaView(self.base, (self.cap,), "<i8"), device=device)
-        self.counts = torch.as_tensor(_CudaView(self.base + self._o_counts, (self.cap,), "<i4"), device=device)
-        self.offs = torch.as_tensor(_CudaView(self.base + self._o_offs, (self.n_sub_max + 1,), "<i4"), device=device)
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, handle, group=group)
-        # per rank: base pointer of its staging buffer as mapped into this process
-        self.peer_base, err = [], None
-        for r, h in enumerate(everyone):
-            try:
-                self.peer_base.append(self.base if r == self.rank else counter.peer_open(h))
-            except Exception as e:                      # no peer access to that GPU
-                err = e
-                break
-        # all ranks or none: a rank that cannot map a peer makes everybody fall back together
-        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
-            for r, p in enumerate(self.peer_base):
-                if r != self.rank:
-                    counter.peer_close(p)
-            dist.barrier(group=group)
-            self.keys = self.counts = self.offs = None
-            counter.peer_free(self.base)
-            self.base = None
-            raise RuntimeError("peer staging buffers cannot be mapped on every rank: %s" % (err or "a peer failed"))
-
-    def close(self):
-        import torch.distributed as dist
-        if self.base is None:
-            return
-        dist.barrier(group=self.group)                  # nobody is still reading
-        for r, p in enumerate(self.peer_base):
-            if r != self.rank:
-                self.c.peer_close(p)
-        dist.barrier(group=self.group)                  # every mapping is gone before the memory is
-        self.keys = self.counts = self.offs = None
-        self.c.peer_free(self.base)
-        self.base = None
-
-    def _settle(self):
-        """Peers may still be reading this rank's staging buffer for the previous step: wait for them
-        before it is written again. Deferred to here so that it overlaps the local count."""
-        import torch.distributed as dist
-        if self._readers_pending:
-            dist.barrier(group=self.group)
-            self._readers_pending = False
-
-    def place(self):
-        """Have the next run of the partitioned path written straight into the staging buffer
-        (kc_place_next_run): saves the copy. Call right before the count whose run goes to combine()."""
-        self._settle()
-        self.c.place_next_run(self.base, self.base + self._o_counts, self.base + self._o_offs, self.cap, self.n_sub_max + 1)
-
-    def combine(self, local):
-        """`local`: this rank's run (freed here). Returns the run of this rank's key range, or None
-        if the runs have no common partition structure (caller falls back to NCCL)."""
-        import torch
-        import torch.distributed as dist
-        off_ptr, n_sub, pbits = local.parts()
-        kptr, cptr, n = local.device_arrays()
-        P = self.world
-        usable = self.c.words == 1 and n_sub >= P and n_sub % P == 0 and n_sub <= self.n_sub_max and n <= self.cap
-        per = n_sub // P if usable else 1
-        placed = usable and kptr == self.base               # the count already wrote it here (place())
-        if usable and not placed:
-            self._settle()
-            keys_t, counts_t = run_as_tensors(local, self.dev)
-            self.keys[:n].copy_(keys_t[:, 0])
-            self.counts[:n].copy_(counts_t)
-            self.offs[:n_sub + 1].copy_(torch.as_tensor(_CudaView(off_ptr, (n_sub + 1,), "<i4"), device=self.dev))
-        # One small all-gather: plan, size, and the record boundaries of the owners' ranges. It is
-        # queued behind the copies above on this stream, so a peer that has received this rank's
-        # entry knows that its staging buffer is complete: no separate barrier.
-        info = torch.zeros(4 + P + 1, dtype=torch.int64, device=self.dev)
-        info[0], info[1], info[2], info[3] = n_sub, pbits, n, int(usable)
-        if usable:
-            info[4:] = self.offs[:n_sub + 1:per].to(torch.int64)
-        infos = [torch.empty_like(info) for _ in range(P)]
-        dist.all_gather(infos, info, group=self.group)
-        infos = [t.tolist() for t in infos]
-        if not all(i[3] == 1 and i[0] == n_sub and i[1] == pbits for i in infos):
-            return None                                 # (a placed run is still a valid run for the NCCL exchange)
-        local.free()
-        kp = list(self.peer_base)                       # absolute offsets index the peer's whole array
-        cp = [b + self._o_counts for b in self.peer_base]
-        # The range offsets are read twice per range and part: bring this rank's slice of every
-        # peer's offsets over once (per + 1 integers each) instead of paying a link round trip per read.
-        if self.loc_offs is None or self.loc_offs.shape[1] < per + 1:
-            self.loc_offs = torch.empty((P, per + 1), dtype=torch.int32, device=self.dev)
-        op = []
-        for r, b in enumerate(self.peer_base):
-            src = b + self._o_offs + 4 * self.rank * per
-            if r == self.rank:
-                op.append(src)
-            else:
-                self.loc_offs[r, :per + 1].copy_(torch.as_tensor(_CudaView(src, (per + 1,), "<i4"), device=self.dev))
-                op.append(self.loc_offs[r].data_ptr())
-        torch.cuda.current_stream().synchronize()
-        sizes = [i[4 + self.rank + 1] - i[4 + self.rank] for i in infos]    # records this rank reads from each peer
-        merged = self.c.merge_parts(kp, cp, op, sizes, per, pbits)
-        self._readers_pending = True                    # settled (barrier) before the staging buffer is written again
-        return merged
