@@ -38,8 +38,9 @@ def test_pure_functions():
 
 def test_config_struct_layout_matches_header():
     import kmer_counter_b200 as kc
-    assert C.sizeof(kc._lib.KcConfig) == 56
+    assert C.sizeof(kc._lib.KcConfig) == 64                      # grew by distinct_hint (struct_size keeps old callers working)
     assert kc._lib.KcConfig.max_chunk_bytes.offset == 32 and kc._lib.KcConfig.stream.offset == 48
+    assert kc._lib.KcConfig.distinct_hint.offset == 56
     assert kc._lib.KcStats.ms_stage.offset % 4 == 0
 
 
