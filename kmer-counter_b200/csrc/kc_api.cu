@@ -111,6 +111,7 @@ struct kc_ctx {
         bool keep_ranges = false;            // kc_xchg_fix_ranges
         float ms_scatter = 0;
         uint64_t n_scatter = 0;
+        std::vector<cudaEvent_t> sc_ev;      // begin/end event pairs of the S1 launches since the last flush
     } acc;
     std::recursive_mutex direct_mu;   // calls that take no slot (they share `direct`, its arena and `stream`) are serialised
     std::mutex mu;
@@ -765,6 +766,7 @@ void accum_free(kc_ctx *c) {
     if (a.ws) cudaFree(a.ws);
     if (a.h_sc) cudaFreeHost(a.h_sc);
     for (auto &e : a.ev) if (e) cudaEventDestroy(e);
+    for (auto &e : a.sc_ev) if (e) cudaEventDestroy(e);
     for (kc_run *r : a.parts) kc_run_free(c, r);
     a = kc_ctx::Accum();
 }
@@ -796,8 +798,12 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
     if (a.h_sc[SW_FAIL])
         return c->set_error(KC_ERR_CAPACITY, "accumulated input does not fit the plan (fail bits %llu): flush more often or "
                             "raise the expected read count", (unsigned long long)a.h_sc[SW_FAIL]);
-    const uint64_t n_d = a.h_sc[SW_D];
-    const bool dup = force_dup || a.h_sc[SW_OVF] != 0;
+    // exchange: this rank's records are the sub-buckets it pulled (n_recv), and they can only repeat if
+    // some rank used its overflow list (those records are counted where they are, not by the bin's owner)
+    const uint64_t n_d = a.xchg ? a.x_info.n_recv : a.h_sc[SW_D];
+    static int env_dup = -1;
+    if (env_dup < 0) { const char *v = getenv("KC_SW_FORCE_DUP"); env_dup = (v && v[0] == '1') ? 1 : 0; }
+    const bool dup = env_dup || (a.xchg ? (force_dup && a.x_info.any_ovf != 0) : (force_dup || a.h_sc[SW_OVF] != 0));
     kc_run *r = nullptr;
     if (!dup) {
         KC_TRY(make_run(c, s, n_d, &r));
@@ -839,7 +845,13 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
         st.launches += dup ? 11 : 9;
         st.n_stages = 6;
         for (int i = 0; i < 8; i++) { st.ms_stage[i] = 0; st.stage_bytes[i] = 0; st.stage_launches[i] = 0; }
-        st.ms_stage[0] = a.ms_scatter;                       // summed over the chunks' S1 launches
+        a.ms_scatter = 0;                                    // summed over the chunks' S1 launches (all complete by now)
+        for (uint64_t i = 0; i < a.n_scatter; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, a.sc_ev[2 * i], a.sc_ev[2 * i + 1]) == cudaSuccess) a.ms_scatter += ms;
+        }
+        cudaGetLastError();
+        st.ms_stage[0] = a.ms_scatter;
         for (int i = 1; i < 6; i++) cudaEventElapsedTime(&st.ms_stage[i], a.ev[i - 1], a.ev[i]);
         st.ms_total = 0;
         for (int i = 0; i < 6; i++) st.ms_total += st.ms_stage[i];
@@ -877,21 +889,10 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
 int accum_make_room(kc_ctx *c, uint64_t n_reads) {
     kc_ctx::Accum &a = c->acc;
     const uint64_t nk = c->cfg.read_len - c->cfg.k + 1, w = n_reads * nk;
-    if (w > a.pl.ovf_cap || w > a.max_windows)
+    if (w > a.max_windows)
         return c->set_error(KC_ERR_CAPACITY, "chunk of %llu reads exceeds what the accumulator was planned for", (unsigned long long)n_reads);
-    if (a.ovf_reserved + w > a.pl.ovf_cap) {
-        // the reservations are worst cases (every window of a chunk in flight overflowing): look at
-        // what the list really holds once the chunks queued so far are through
-        KC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        for (auto &sl : c->slots)
-            if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
-        unsigned long long used = 0;
-        KC_CUDA_TRY(c, cudaMemcpy(&used, a.d_sc + SW_OVF, 8, cudaMemcpyDeviceToHost));
-        a.ovf_reserved = used;
-    }
-    if (a.windows + w > a.max_windows || a.ovf_reserved + w > a.pl.ovf_cap) {
-        if (a.xchg) return c->set_error(KC_ERR_CAPACITY, "more reads than kc_xchg_begin planned for (%llu k-mer slots, overflow list %llu of %llu)",
-                                        (unsigned long long)a.max_windows, (unsigned long long)a.ovf_reserved, (unsigned long long)a.pl.ovf_cap);
+    if (a.windows + w > a.max_windows) {
+        if (a.xchg) return c->set_error(KC_ERR_CAPACITY, "more reads than kc_xchg_begin planned for (%llu k-mer slots)", (unsigned long long)a.max_windows);
         kc_run *part = nullptr;
         KC_TRY(accum_count(c, &part));
         a.parts.push_back(part);
@@ -903,14 +904,18 @@ int accum_make_room(kc_ctx *c, uint64_t n_reads) {
 int accum_scatter(kc_ctx *c, const void *d_reads, uint64_t n_reads, cudaStream_t s) {
     kc_ctx::Accum &a = c->acc;
     if (n_reads == 0) return KC_OK;
+    while (a.sc_ev.size() < 2 * (a.n_scatter + 1)) {
+        cudaEvent_t e = nullptr;
+        KC_CUDA_TRY(c, cudaEventCreate(&e));
+        a.sc_ev.push_back(e);
+    }
+    KC_CUDA_TRY(c, cudaEventRecord(a.sc_ev[2 * a.n_scatter], s));
     KC_CUDA_TRY(c, super_scatter(a.pl, d_reads, n_reads, c->strict, a.ws, a.d_sc, c->n_sms, s));
+    KC_CUDA_TRY(c, cudaEventRecord(a.sc_ev[2 * a.n_scatter + 1], s));
     const uint64_t nk = c->cfg.read_len - c->cfg.k + 1;
     a.fresh = false;
     a.windows += n_reads * nk;
     a.reads += n_reads;
-    // the overflow list only ever takes what the bins refuse; without looking at the device
-    // counters the host has to assume the worst for chunks still in flight
-    a.ovf_reserved += n_reads * nk;
     a.n_scatter++;
     return KC_OK;
 }
@@ -919,7 +924,7 @@ int accum_scatter(kc_ctx *c, const void *d_reads, uint64_t n_reads, cudaStream_t
 
 extern "C" {
 
-static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange);
+static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange, uint32_t n_ranks = 1);
 
 int kc_accum_begin(kc_ctx *c, uint64_t expected_reads) {
     KC_TRY(check_ctx(c));
@@ -928,7 +933,7 @@ int kc_accum_begin(kc_ctx *c, uint64_t expected_reads) {
 
 // exchange: the record buffers also take what the peers send, which is this rank's share of the
 // key space only on average (ranges are cut at 1/1024 of the key space): a quarter more room
-static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange) {
+static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange, uint32_t n_ranks) {
     std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
     cudaSetDevice(c->cfg.device);
     if (!super_ok(c)) return c->set_error(KC_ERR_ARG, "accumulating mode needs k <= 64 with windows of >= 22 bases (k=%u)", c->cfg.k);
@@ -940,21 +945,11 @@ static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange) {
     kc_ctx::Accum &a = c->acc;
     if (a.on && !a.fresh) return c->set_error(KC_ERR_STATE, "kc_accum_begin: reads are accumulated; flush first");
     SuperPlan pl;
-    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, (uint32_t)c->cfg.table_slots, &pl, exchange ? 0.25 : 0.0,
-                    c->cfg.distinct_hint))
+    // exchange: a bin collects what ALL ranks put into it, so each rank plans bins 1/n_ranks the size
+    uint32_t occ = (uint32_t)c->cfg.table_slots;
+    if (exchange && n_ranks > 1) occ = (occ ? occ : 8192u) / n_ranks;
+    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, occ, &pl, exchange ? 0.25 : 0.0, c->cfg.distinct_hint))
         return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", c->cfg.k, c->cfg.read_len);
-    // a chunk submitted through a slot may put every one of its windows into the overflow list
-    // (device-resident input is cut into pieces that fit the list as planned)
-    const uint64_t chunk_windows = chunk_reads * nk;
-    if (pl.ovf_cap < 2 * chunk_windows) {
-        SuperPlan p2 = pl;
-        // re-plan with the larger list: only the list and what follows it move
-        const uint64_t grow = (2 * chunk_windows - pl.ovf_cap) * 16ull * pl.W;
-        p2.ovf_cap = 2 * chunk_windows;
-        const uint64_t g512 = (grow + 511) & ~511ull;
-        p2.off_dk += g512; p2.off_dc += g512; p2.off_ek += g512; p2.off_ec += g512; p2.ws_bytes += g512;
-        pl = p2;
-    }
     if (!a.h_sc) {
         KC_CUDA_TRY(c, cudaMallocHost((void **)&a.h_sc, SC_COUNT * 8));
         for (auto &e : a.ev) KC_CUDA_TRY(c, cudaEventCreate(&e));
@@ -993,7 +988,7 @@ int kc_accum_add_device(kc_ctx *c, const void *d_reads, uint64_t n_bytes) {
     const uint64_t n_reads = n_bytes / L;
     // pieces the plan can take in one go (and whose worst-case overflow fits the list)
     const uint64_t nk = L - c->cfg.k + 1;
-    uint64_t piece = std::min<uint64_t>(c->acc.pl.ovf_cap / 2, c->acc.max_windows) / nk;
+    uint64_t piece = std::min<uint64_t>(1ull << 30, c->acc.max_windows) / nk;
     piece -= piece % 16;
     if (piece == 0) return c->set_error(KC_ERR_CAPACITY, "accumulator too small for any read");
     for (uint64_t r0 = 0; r0 < n_reads; r0 += piece) {
@@ -1081,7 +1076,7 @@ int kc_xchg_begin(kc_ctx *c, uint32_t rank, uint32_t n_ranks, uint64_t expected_
     KC_TRY(check_ctx(c));
     if (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return c->set_error(KC_ERR_ARG, "kc_xchg_begin: rank %u of %u", rank, n_ranks);
     std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
-    KC_TRY(accum_begin_impl(c, expected_reads, true));
+    KC_TRY(accum_begin_impl(c, expected_reads, true, n_ranks));
     kc_ctx::Accum &a = c->acc;
     if (a.pl.b1 != 10) return c->set_error(KC_ERR_ARG, "kc_xchg_begin: keys of k=%u have too few bits to exchange by range", c->cfg.k);
     a.xchg = true;
@@ -1165,7 +1160,7 @@ int kc_xchg_group_local(kc_ctx *c) {
     kc_ctx::Accum &a = c->acc;
     if (!a.xchg) return c->set_error(KC_ERR_STATE, "kc_xchg_begin first");
     cudaSetDevice(c->cfg.device);
-    KC_CUDA_TRY(c, super_x_local(a.pl, a.ws, a.d_sc, a.d_all_hist, a.rank, a.n_ranks, a.keep_ranges, c->n_sms, c->stream));
+    KC_CUDA_TRY(c, super_x_local(a.pl, a.ws, a.d_sc, a.d_all_hist, a.rank, a.n_ranks, a.keep_ranges, a.peer_ws, c->n_sms, c->stream));
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[2], c->stream));
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[3], c->stream));
     return KC_OK;

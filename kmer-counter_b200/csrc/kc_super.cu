@@ -403,48 +403,79 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
     const uint32_t n_units = p.n_bins + n_ovf_units;
     unsigned long long occ_local = 0;
     uint32_t aborts_local = 0;
-    // thread 0 draws the ticket of the NEXT unit while the current one is counted
-    uint32_t next_ticket = 0;
-    if (tid == 0) next_ticket = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
+    // Work units are drawn from an atomic ticket two units ahead, so that a CTA knows its next unit
+    // while it counts the current one: the next unit's record counts and its first round of
+    // records are fetched in the shadow of the current unit's inserts (with several GPUs those
+    // are loads from a peer's HBM, several microseconds each). Unit descriptors live in shared
+    // memory, double-buffered: [0..7] records of sources 0..s-1 come before source s's, [8] records.
+    __shared__ uint32_t s_desc[2][10];
+    __shared__ uint32_t s_next;
+    __shared__ const uint8_t *s_bins[8];
+    if (tid < 8) s_bins[tid] = tid < p.n_src ? p.src_bins[tid] : p.src_bins[0];
+    auto setup = [&](uint32_t u, uint32_t buf) {         // warp 0
+        if (warp != 0) return;
+        uint32_t c = 0;
+        if (u < p.n_bins && lane < p.n_src) {
+            c = p.src_cursor[lane][p.bin_begin + u];
+            c = c < p.bin_cap ? c : p.bin_cap;
+        }
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane < 8) s_desc[buf][lane] = incl - c;
+        if (lane == 7) {
+            uint32_t n = incl;
+            if (u >= p.n_bins) {
+                n = 0;
+                if (u < n_units) n = (uint32_t)min((unsigned long long)p.ovf_slice, n_ovf - (uint64_t)(u - p.n_bins) * p.ovf_slice);
+            }
+            s_desc[buf][8] = n;
+        }
+    };
+    // where record i of unit u (descriptor in buffer buf) lives
+    auto rec_of = [&](uint32_t u, uint32_t buf, uint32_t i) -> const ulonglong2 * {
+        if (u >= p.n_bins)
+            return reinterpret_cast<const ulonglong2 *>(p.ovf) + ((uint64_t)(u - p.n_bins) * p.ovf_slice + i) * W;
+        uint32_t off = i, q_src = 0;
+        for (uint32_t q = 1; q < p.n_src; q++)
+            if (i >= s_desc[buf][q]) { off = i - s_desc[buf][q]; q_src = q; }
+        return reinterpret_cast<const ulonglong2 *>(s_bins[q_src]) + ((uint64_t)(p.bin_begin + u) * p.bin_cap + off) * W;
+    };
+    uint32_t t_c = 0;                                // thread 0: the ticket after the next one (its atomic is in flight for a whole unit)
+    if (tid == 0) {
+        const uint32_t t_a = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
+        const uint32_t t_b = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
+        s_unit = t_a;
+        s_next = t_b;
+        t_c = t_b < n_units ? (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull) : t_b;
+    }
     __syncthreads();
+    setup(s_unit, 0);
+    uint32_t par = 0;                                // descriptor buffer of the current unit
+    uint32_t pf_id = 0xffffffffu;                    // unit whose first round sits in pf[]
+    ulonglong2 pf[RPT][W];
+    bool first_iter = true;
 
     while (true) {
-        if (tid == 0) {
-            s_unit = next_ticket;
-            if (next_ticket < n_units) next_ticket = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
-        }
-        __syncthreads();
-        const uint32_t u = s_unit;
-        if (u >= n_units) break;
-        const ulonglong2 *src = nullptr;             // overflow slice: one contiguous piece
-        uint32_t n_rec = 0;
-        uint32_t spre[9];                            // bin: records of sources 0..s-1 come before source s's
-        const uint64_t bin_off = (uint64_t)(p.bin_begin + u) * p.bin_cap * W;
-        if (u < p.n_bins) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                spre[q] = n_rec;
-                if ((uint32_t)q < p.n_src) {
-                    const uint32_t c = p.src_cursor[q][p.bin_begin + u];
-                    n_rec += c < p.bin_cap ? c : p.bin_cap;
-                }
+        if (!first_iter) {
+            // (the previous unit ended with a barrier) hand over to the next unit
+            if (tid == 0) {
+                s_unit = s_next;
+                s_next = t_c;
+                if (t_c < n_units) t_c = (uint32_t)atomicAdd(&p.sc[SW_TICKET], 1ull);
             }
-            spre[8] = n_rec;
-        } else {
-            const uint64_t o0 = (uint64_t)(u - p.n_bins) * p.ovf_slice;
-            n_rec = (uint32_t)min((unsigned long long)p.ovf_slice, n_ovf - o0);
-            src = reinterpret_cast<const ulonglong2 *>(p.ovf) + o0 * W;
+            par ^= 1;
         }
-        // where record i of the unit lives
-        auto rec_at = [&](uint32_t i) -> const ulonglong2 * {
-            if (src) return src + (uint64_t)i * W;
-            uint32_t off = i;
-            const uint8_t *base = p.src_bins[0];
-#pragma unroll
-            for (int q = 1; q < 8; q++)
-                if ((uint32_t)q < p.n_src && i >= spre[q]) { off = i - spre[q]; base = p.src_bins[q]; }
-            return reinterpret_cast<const ulonglong2 *>(base) + bin_off + (uint64_t)off * W;
-        };
+        first_iter = false;
+        __syncthreads();
+        const uint32_t u = s_unit, un = s_next;
+        if (u >= n_units) break;
+        setup(un, par ^ 1);                          // (consumed after later barriers)
+        const uint32_t n_rec = s_desc[par][8];
+        auto rec_at = [&](uint32_t i) -> const ulonglong2 * { return rec_of(u, par, i); };
         // key 0 joins with count += 0 whenever a slot held no k-mer on any rank: its bin is bin 0
         bool phantom = false;
         if (u == 0 && p.bin_begin == 0 && p.add_phantom) {
@@ -483,17 +514,19 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
                 }
             }
             bool aborted = false;
-            // the first round's records travel while the pass is set up
-            ulonglong2 pf[RPT][W];
+            // the first round's records: prefetched while the previous unit was counted, or fetched now
+            if (pf_id != u) {
 #pragma unroll
-            for (int u2 = 0; u2 < RPT; u2++) {
-                const uint32_t i = u2 * THREADS + tid;
-                if (i < n_rec) {
-                    const ulonglong2 *rp = rec_at(i);
+                for (int u2 = 0; u2 < RPT; u2++) {
+                    const uint32_t i = u2 * THREADS + tid;
+                    if (i < n_rec) {
+                        const ulonglong2 *rp = rec_at(i);
 #pragma unroll
-                    for (int t = 0; t < W; t++) pf[u2][t] = rp[t];
+                        for (int t = 0; t < W; t++) pf[u2][t] = rp[t];
+                    }
                 }
             }
+            pf_id = 0xffffffffu;
             for (uint32_t r0 = 0; r0 < n_rec; r0 += RB) {
                 const uint32_t nr = min((uint32_t)RB, n_rec - r0);
                 // The round's records sit in registers (fetched with a stride of THREADS: coalesced).
@@ -588,6 +621,19 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
 #pragma unroll
                         for (int t = 0; t < W; t++) pf[u2][t] = rp[t];
                     }
+                }
+                if (r0 + RB >= n_rec && bits == 0 && un < n_units) {     // last round of the unit's first pass: the next unit's first round
+                    const uint32_t n_next = s_desc[par ^ 1][8];
+#pragma unroll
+                    for (int u2 = 0; u2 < RPT; u2++) {
+                        const uint32_t i = u2 * THREADS + tid;
+                        if (i < n_next) {
+                            const ulonglong2 *rp = rec_of(un, par ^ 1, i);
+#pragma unroll
+                            for (int t = 0; t < W; t++) pf[u2][t] = rp[t];
+                        }
+                    }
+                    pf_id = un;
                 }
                 // this thread's share of the tot windows: [f0, f1)
                 const uint32_t per = (tot + THREADS - 1) / THREADS;
@@ -926,18 +972,20 @@ __global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restric
 // (from the global total, so that every rank cuts the same sub-buckets); and for this rank: its own
 // level-1 bases (the local scatter), where its key range starts and ends inside every source's
 // grouped array, and the plan of its part of the key space.
-constexpr int kXB1 = 10;
+constexpr int kXB1 = 10;                // bits of the histogram the ranks exchange
 typedef SuperXInfo XDev;
+struct XScalars { const unsigned long long *sc[8]; };
 
 __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict__ all_hist, uint32_t rank, uint32_t P,
                                                       int keep_ranges, uint64_t d_cap, uint32_t sub_target, int sig_bits,
                                                       uint32_t *__restrict__ base1, uint32_t *__restrict__ cursor1,
                                                       SuperPlanDev *__restrict__ plan, XDev *__restrict__ x,
-                                                      unsigned long long *__restrict__ sc) {
+                                                      unsigned long long *__restrict__ sc, XScalars peers) {
     constexpr int NB = 1 << kXB1;
     __shared__ unsigned long long s_scan[32];
     __shared__ uint32_t s_lo[17];
-    __shared__ unsigned long long s_total;
+    __shared__ unsigned long long s_total, s_b, s_e;
+    __shared__ int s_b1, s_b2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // block-wide inclusive scan of 64-bit values (1024 threads)
     auto block_incl = [&](unsigned long long v) -> unsigned long long {
@@ -961,11 +1009,32 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
     if (tid <= 16) s_lo[tid] = NB;
     __syncthreads();
     const unsigned long long total = s_total;
-    // owner of bucket tid: where the middle of the bucket falls in P equal shares of the total
+    if (tid == 0) {
+        // digit widths from the job's record total: B bits so that a sub-bucket holds about sub_target
+        // records, level 1 as narrow as level 2's limit of 10 bits allows but not below 8 (the key
+        // ranges of up to 8 ranks are cut at level-1 buckets)
+        int B = 8;
+        while (B < kXB1 + 10 && B < sig_bits && (total >> B) > sub_target) B++;
+        int b1 = B - 10 > 8 ? B - 10 : 8;
+        if (b1 > kXB1 || keep_ranges) b1 = kXB1;     // kept ranges may have been cut at any histogram bin
+        if (b1 > sig_bits) b1 = sig_bits;
+        s_b1 = b1;
+        s_b2 = B - b1 > 0 ? B - b1 : 0;
+    }
+    __syncthreads();
+    const int b1 = s_b1, b2 = s_b2, fold = kXB1 - b1;          // 2^fold histogram bins per level-1 bucket
+    // owner of histogram bin tid = owner of its level-1 bucket: where the middle of the BUCKET falls in
+    // P equal shares of the total (all bins of a bucket get the same owner)
+    const uint32_t bk0 = ((uint32_t)tid >> fold) << fold;      // first bin of this bin's bucket
+    __shared__ unsigned long long s_cum[NB + 1];
+    s_cum[tid + 1] = cum;
+    if (tid == 0) s_cum[0] = 0;
+    __syncthreads();
+    const unsigned long long bk_lo = s_cum[bk0], bk_hi = s_cum[bk0 + (1u << fold)];
     uint32_t owner = 0;
-    if (total) owner = (uint32_t)(((cum - tot) + tot / 2) * P / total);
+    if (total) owner = (uint32_t)((bk_lo + (bk_hi - bk_lo) / 2) * P / total);
     if (owner >= P) owner = P - 1;
-    atomicMin(&s_lo[owner], (uint32_t)tid);
+    atomicMin(&s_lo[owner], bk0);
     __syncthreads();
     if (tid == 0) {                                   // owners without a bucket start where the next one does
         s_lo[P] = NB;
@@ -977,12 +1046,11 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         for (uint32_t o = 0; o <= P; o++) x->lo[o] = s_lo[o];
     }
     __syncthreads();
-    const uint32_t my_lo = s_lo[rank], my_hi = s_lo[rank + 1];
+    const uint32_t my_lo = s_lo[rank], my_hi = s_lo[rank + 1];      // in histogram bins (multiples of 2^fold unless kept)
     // this rank's key range inside every source's grouped array
     unsigned long long n_recv = 0;
     for (uint32_t s2 = 0; s2 < P; s2++) {
         const unsigned long long incl = block_incl(all_hist[s2 * NB + tid]);
-        __shared__ unsigned long long s_b, s_e;
         if (tid == 0) { s_b = 0; s_e = 0; }
         __syncthreads();
         if (my_lo > 0 && tid == (int)my_lo - 1) s_b = incl;
@@ -992,27 +1060,35 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         n_recv += s_e - s_b;
         __syncthreads();
     }
-    // own level-1 bases: the local scatter groups this rank's records by the kXB1-bit digit
+    // own level-1 bases: the local scatter groups this rank's records by their leading b1 bits
     {
-        const uint32_t c = all_hist[rank * NB + tid];
+        const uint32_t nb1 = 1u << b1;
+        uint32_t c = 0;
+        if ((uint32_t)tid < nb1)
+            for (int j = 0; j < (1 << fold); j++) c += all_hist[rank * NB + ((uint32_t)tid << fold) + j];
         const unsigned long long incl = block_incl(c);
-        base1[tid] = (uint32_t)(incl - c);
-        cursor1[tid] = (uint32_t)(incl - c);
-        if (tid == NB - 1) base1[NB] = (uint32_t)incl;
+        if ((uint32_t)tid < nb1) {
+            base1[tid] = (uint32_t)(incl - c);
+            cursor1[tid] = (uint32_t)(incl - c);
+            if ((uint32_t)tid == nb1 - 1) base1[nb1] = (uint32_t)incl;
+        }
     }
     if (tid == 0) {
         unsigned long long nd = sc[SW_D];
         if (nd > d_cap) nd = d_cap;
-        int b2 = 0;
-        while (b2 < 10 && kXB1 + b2 < sig_bits && (total >> (kXB1 + b2)) > sub_target) b2++;
+        uint32_t any_ovf = 0;
+        for (uint32_t s2 = 0; s2 < P; s2++)
+            if (peers.sc[s2][SW_OVF] != 0) any_ovf = 1;
         plan->n_d = (uint32_t)nd;
-        plan->b1 = kXB1;
+        plan->b1 = (uint32_t)b1;
         plan->b2 = (uint32_t)b2;
-        plan->shift2 = 64 - kXB1 - b2;
-        plan->n_sub = (my_hi - my_lo) << b2;
-        plan->sub0 = my_lo << b2;
-        plan->prefix_bits = kXB1 + b2;
+        plan->shift2 = 64 - b1 - b2;
+        // this rank's sub-buckets: the (b1+b2)-bit prefixes inside its key range
+        plan->sub0 = (my_lo >> fold) << b2;
+        plan->n_sub = (((my_hi + (1u << fold) - 1) >> fold) << b2) - plan->sub0;
+        plan->prefix_bits = b1 + b2;
         x->n_recv = (uint32_t)(n_recv > 0xffffffffull ? 0xffffffffull : n_recv);
+        x->any_ovf = any_ovf;
         if (n_recv > d_cap) atomicOr(&sc[SW_FAIL], 16ull);       // this rank's share does not fit its buffers
     }
 }
@@ -1805,14 +1881,17 @@ bool super_supported(const SuperPlan &pl) { return super_scatter_fits(pl); }
 // peer's buffers are found from its workspace base.
 template <int W>
 static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
-                                   uint32_t rank, uint32_t n_ranks, bool keep_ranges, int n_sms, cudaStream_t s) {
+                                   uint32_t rank, uint32_t n_ranks, bool keep_ranges, void *const *peer_ws, int n_sms,
+                                   cudaStream_t s) {
     cudaError_t e;
     uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
     uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
     SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
+    XScalars xs{};
+    for (uint32_t i = 0; i < n_ranks; i++) xs.sc[i] = peer_ws ? at<unsigned long long>(peer_ws[i], pl.off_sc) : d_sc;
     x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, keep_ranges ? 1 : 0, pl.d_cap, pl.sub_target, sig, at<uint32_t>(ws, pl.off_base1),
-                                     at<uint32_t>(ws, pl.off_cur1), plan, at<XDev>(ws, pl.off_x), d_sc);
+                                     at<uint32_t>(ws, pl.off_cur1), plan, at<XDev>(ws, pl.off_x), d_sc, xs);
     const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
     auto k1 = rec_scatter_kernel<W, 1>;
     if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
@@ -1826,10 +1905,10 @@ static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long 
 }
 
 cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
-                          uint32_t rank, uint32_t n_ranks, bool keep_ranges, int n_sms, cudaStream_t s) {
+                          uint32_t rank, uint32_t n_ranks, bool keep_ranges, void *const *peer_ws, int n_sms, cudaStream_t s) {
     if (pl.b1 != kXB1 || n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return cudaErrorInvalidValue;
-    if (pl.W == 1) return super_x_local_w<1>(pl, ws, d_sc, d_all_hist, rank, n_ranks, keep_ranges, n_sms, s);
-    if (pl.W == 2) return super_x_local_w<2>(pl, ws, d_sc, d_all_hist, rank, n_ranks, keep_ranges, n_sms, s);
+    if (pl.W == 1) return super_x_local_w<1>(pl, ws, d_sc, d_all_hist, rank, n_ranks, keep_ranges, peer_ws, n_sms, s);
+    if (pl.W == 2) return super_x_local_w<2>(pl, ws, d_sc, d_all_hist, rank, n_ranks, keep_ranges, peer_ws, n_sms, s);
     return cudaErrorInvalidValue;
 }
 

@@ -54,7 +54,9 @@ struct SuperPlanDev {           // level-2 plan, decided on the device once |D| 
 struct SuperXInfo {             // multi-GPU exchange: what the device plan decided (kc_xchg_info)
     uint32_t lo[16];            // rank o owns the keys whose leading 10 bits lie in [lo[o], lo[o + 1])
     uint32_t src_range[8][2];   // records of this rank's key range inside rank s's grouped array
-    uint32_t n_recv, pad[3];    // records this rank pulls (its own included)
+    uint32_t n_recv;            // records this rank pulls (its own included)
+    uint32_t any_ovf;           // some rank's overflow list is in use: records may repeat across ranks
+    uint32_t pad[2];
 };
 
 struct SuperPlan {
@@ -117,7 +119,7 @@ const SuperXInfo *super_x_info(const SuperPlan &pl, void *ws);      // device po
 // ... the rank groups its own records by their leading 10 bits and counts the global sub-buckets,
 // (keep_ranges: cut at the key ranges of the previous exchange instead of balancing anew)
 cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_sc, const uint32_t *d_all_hist,
-                          uint32_t rank, uint32_t n_ranks, bool keep_ranges, int n_sms, cudaStream_t s);
+                          uint32_t rank, uint32_t n_ranks, bool keep_ranges, void *const *peer_ws, int n_sms, cudaStream_t s);
 // ... and, once every rank has done that, pulls its key range out of every rank's grouped array
 // (peer_ws[i] = rank i's workspace as mapped here) into sub-buckets. Then super_finish(dup = true).
 cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t n_ranks,
