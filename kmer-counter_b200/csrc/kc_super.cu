@@ -4,6 +4,7 @@
 // (GPUHandler.cu:129-233, 8.4x the input), the host hash accumulate (KMerCounter.cpp:61-82)
 // and sortKmers + reduceKMers (GPUHandler.cu:300-360). Key semantics are those of
 // kc_extract.cuh: the key of window p is the 2-bit codes of s[p .. p+span).
+#include <math.h>
 #include <stdlib.h>
 
 #include "kc_internal.h"
@@ -1586,7 +1587,9 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     const double rho = 2.0 / (pl.w + 1) + 1.2 / pl.nk + 1.0 / pl.cmax * 0.25;
     const double est_total = (double)max_windows * rho;
     const double per_bin = est_total / (double)pl.n_bins;
-    pl.bin_cap = (uint32_t)(per_bin * 2.0) + 64;          // minimizer weights make bins uneven (sd ~20% at the default size)
+    // minimizer weights make bins uneven: sd ~20% of the mean at 8192 occurrences per bin, growing as
+    // bins shrink (fewer minimizers each). Five sigma of room, so that only skewed input overflows.
+    pl.bin_cap = (uint32_t)(per_bin * (1.0 + 90.0 / sqrt((double)occ_per_bin))) + 64;
     pl.bin_cap = (pl.bin_cap + 3) & ~3u;
     // (also what bounds the pieces device-resident input is accumulated in: 1/32 of the plan's windows each)
     pl.ovf_cap = (uint64_t)(est_total * 0.6) + 8192;

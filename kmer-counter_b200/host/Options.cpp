@@ -26,9 +26,14 @@ Options Options::parse(int argc, char **argv) {
         else if (take(argv[i], "device=", &v)) o.device = atoi(v);
         else if (take(argv[i], "keepRuns=", &v)) o.keepRuns = atoi(v) != 0;
         else if (take(argv[i], "parser=", &v)) o.parser = v;
+        else if (take(argv[i], "gpus=", &v)) o.gpus = atoi(v);
+        else if (take(argv[i], "mode=", &v)) o.mode = v;
+        else if (take(argv[i], "expectedReads=", &v)) o.expectedReads = strtoll(v, nullptr, 10);
         else if (take(argv[i], "runBudget=", &v)) o.runBudget = strtoll(v, nullptr, 10);
     }
     if (o.noOfMergersAtOnce < 2) o.noOfMergersAtOnce = 2;
+    if (o.gpus < 1) o.gpus = 1;
+    if (o.gpus > 8) o.gpus = 8;
     return o;
 }
 

@@ -20,6 +20,13 @@ struct Options {
     bool keepRuns = false;                    // keepRuns=1: also write every chunk's run to tempFileLocation/<id>
     int64_t runBudget = 0;                    // runBudget=BYTES: a merged run larger than this is spilled to pinned host
                                               // memory and the final merge runs out of core, range by range (0 = never)
+    int gpus = 1;                             // gpus=N: N contexts on devices device .. device+N-1; reads are dealt to them
+                                              // chunk by chunk, super-window records and distinct records are exchanged
+                                              // over NVLink inside the counting kernels (kc_xchg_*)
+    std::string mode = "auto";                // mode=auto|accumulate|runs: accumulate = chunks are only packed into
+                                              // super-window records, one count at the end (k <= 64); runs = one sorted run
+                                              // per chunk, merged on the GPU (the reference's shape; keepRuns, runBudget)
+    int64_t expectedReads = 0;                // expectedReads=: plan the accumulator for this many reads (0 = from file sizes)
     std::string parser = "gpu";               // parser=gpu|host: where FASTQ text is parsed (gpu falls back to host
                                               // for input that is not plain 4-line fixed-length FASTQ)
 

@@ -56,6 +56,30 @@ def test_cli_counts_a_fastq_directory(tmp_path, k, method):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,gpus,parser", [(31, 1, "gpu"), (31, 1, "host"), (63, 1, "gpu"), (31, 2, "gpu"), (31, 4, "host"), (63, 3, "gpu")])
+def test_cli_accumulates_and_counts_once(tmp_path, k, gpus, parser):
+    """Default mode: chunks are only packed into super-window records, one count at the end; with
+    gpus=N the chunks are dealt to N contexts and the exchanges run inside the counting kernels
+    (here all contexts share device 0: KC_CLI_SAME_DEVICE). The file is the oracle's artefact."""
+    d = tmp_path / "in"
+    d.mkdir()
+    L, per = 100, 2500
+    for i in range(3):
+        (d / ("part%d.fastq" % i)).write_bytes(oracle.gen_fastq(per, L, 60000, 0.01, 0.002, seed=18, first_read=i * per))
+    out = tmp_path / "out.bin"
+    out.write_bytes(b"stale")
+    env = dict(os.environ, KC_CLI_SAME_DEVICE="1")
+    r = subprocess.run([CLI, "kmerLength=%d" % k, "inputFileLocation=%s" % d, "outputFile=%s" % out,
+                        "gpuMemoryLimit=1500000", "gpus=%d" % gpus, "parser=%s" % parser], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert "mode=accumulate gpus=%d parser=%s" % (gpus, parser) in r.stderr
+    stats = dict(t.split("=") for t in r.stderr.split() if "=" in t and t.split("=")[1].isdigit())
+    assert int(stats["chunks"]) >= 4 and int(stats["reads"]) == 3 * per
+    reads = oracle.gen_reads(3 * per, L, 60000, 0.01, 0.002, seed=18)
+    assert out.read_bytes() == oracle.count(reads, L, k)
+
+
+@pytest.mark.gpu
 def test_cli_gpu_parser_host_parser_and_fallback(tmp_path):
     L, k, R = 100, 31, 4000
     fq = oracle.gen_fastq(R, L, 50000, 0.01, 0.002, seed=12)
