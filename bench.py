@@ -311,7 +311,11 @@ class Job:
         self.e2e = not a.no_e2e and self.runs == 1 and windows <= (1 << 30) - 1
         per_run = (self.R + self.runs - 1) // self.runs
         # distinct keys a flush may see: the genome's k-mers + ~k per sequencing error (bounded by the windows)
-        est_u = min(per_run * self.nk, c["genome"] + int(per_run * self.L * c["sub_rate"] * self.k * 1.2) + (1 << 20)) if c["genome"] else 0
+        # (with several GPUs a rank counts 1/N of the bins of the whole job: its share of the job's distinct keys)
+        est_u = 0
+        if c["genome"]:
+            est_u = (c["genome"] + int(per_run * world * self.L * c["sub_rate"] * self.k * 1.2)) // world + (1 << 20)
+            est_u = min(per_run * self.nk, est_u)
         self.counter = kc.Counter(self.k, self.L, device=local_rank, method=a.method, n_slots=E2E_SLOTS,
                                   max_chunk_bytes=self.n_bytes if self.e2e else 0, table_slots=a.occ,
                                   stream=self.stream.cuda_stream,

@@ -26,6 +26,9 @@ GPUStream **PrepareGPU(uint32_t streamCount, uint64_t inputSize, uint64_t lineLe
     for (uint32_t i = 0; i < streamCount; i++) {
         GPUStream *s = new GPUStream();
         s->_id = i + 1;
+        s->_kmer_db_line_length = 250ull * 1024 * 1024;
+        s->_kmer_db.push_front(new char[s->_kmer_db_line_length]);       // untouched until the caller writes keys into it
+        s->_kmer_db_line_index = 0;
         s->_ctx = ctx;
         s->_slot = i;
         s->_h_output_capacity = cap;

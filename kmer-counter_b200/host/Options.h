@@ -12,7 +12,8 @@ struct Options {
     int64_t gpuMemoryLimit = 100000000;       // gpuMemoryLimit=     (main.cpp:28)
     int64_t kmerLength = 32;                  // kmerLength=         (Options.cpp default)
     uint32_t noOfMergersAtOnce = 2;           // noOfMergersAtOnce=
-    uint32_t noOfMergeThreads = 2;            // noOfMergeThreads=   (accepted; merging runs on the GPU)
+    uint32_t noOfMergeThreads = 2;            // noOfMergeThreads=   (0: merge inside the producer loop; >= 1: merges run on a
+                                              // background thread while chunks are counted -- the GPU serialises them)
     // additions
     std::string method = "auto";              // method=auto|sort|hash
     std::string compat = "ref";               // compat=ref|strict

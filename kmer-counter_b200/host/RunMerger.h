@@ -2,9 +2,15 @@
 //
 // Replaces KMerFileMergeHandler (KMerFileMergeHandler.cpp:23-123), whose polling thread
 // hangs when InputComplete() arrives late or when there is a single run.
-// Same shape -- AddRun / InputComplete / result -- but synchronous and terminating for
-// 0, 1 or N runs: whenever noOfMergersAtOnce runs are pending they are merged on the GPU
-// (kc_merge_runs, the merge-path kernel), and InputComplete() merges whatever is left.
+// Same shape -- AddRun / InputComplete / result -- and, like the reference's, the merges run
+// on their own thread while the producer keeps counting chunks (noOfMergeThreads >= 1; the GPU
+// serialises the merge kernels on the context's stream, the chunk kernels run on the slot
+// streams). It terminates for 0, 1 or N runs.
+//
+// Schedule: runs are kept in levels, level i holding runs that are the merge of about
+// fanIn^i chunk runs. Whenever a level holds noOfMergersAtOnce runs they are merged on the GPU
+// (kc_merge_runs, the merge-path kernel) into one run of the next level, so every record takes
+// part in O(log_fanIn(chunks)) merges instead of one per chunk.
 //
 // Spill (the reference spills every chunk's run to tempFileLocation and merges files,
 // FileDump.cpp:51-58 + KMerFileMerger.cpp:49-135): with a run budget, a merged run that
@@ -19,44 +25,56 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/kc_api.h"
 
 class RunMerger {
 public:
-    // runBudgetBytes = packed-record bytes a merged run may hold on the device (0 = no limit, never spill)
-    RunMerger(kc_ctx *ctx, uint32_t noOfMergersAtOnce, uint32_t k = 0, uint64_t runBudgetBytes = 0)
+    // runBudgetBytes = packed-record bytes a merged run may hold on the device (0 = no limit, never spill);
+    // mergeThreads = 0: merges run inside AddRun; >= 1: on a background thread
+    RunMerger(kc_ctx *ctx, uint32_t noOfMergersAtOnce, uint32_t k = 0, uint64_t runBudgetBytes = 0, uint32_t mergeThreads = 1)
         : _ctx(ctx), _fanIn(noOfMergersAtOnce < 2 ? 2 : noOfMergersAtOnce), _budget(runBudgetBytes),
-          _W(k ? kc_key_words(k) : 1), _S(k ? kc_record_size(k) : 12) {}
+          _W(k ? kc_key_words(k) : 1), _S(k ? kc_record_size(k) : 12) {
+        if (mergeThreads >= 1) _worker = std::thread([this]() { workerLoop(); });
+    }
     ~RunMerger() {
-        for (kc_run *r : _pending) kc_run_free(_ctx, r);
+        stopWorker();
+        for (kc_run *r : _queue) kc_run_free(_ctx, r);
+        for (auto &lv : _levels)
+            for (kc_run *r : lv) kc_run_free(_ctx, r);
         for (HostRun &h : _spilled) kc_host_free(_ctx, h.data);
     }
     int AddRun(kc_run *run) {                       // takes ownership
-        _pending.push_back(run);
-        if (_pending.size() < _fanIn) return KC_OK;
-        int rc = mergePending();
-        if (rc != KC_OK) return rc;
-        if (_budget && !_pending.empty() && kc_run_records(_pending[0]) * _S > _budget) rc = spill();
-        return rc;
+        if (!_worker.joinable()) return place(run);
+        std::lock_guard<std::mutex> g(_mu);
+        if (_rc != KC_OK) { kc_run_free(_ctx, run); return _rc; }
+        _queue.push_back(run);
+        _cv.notify_all();
+        return KC_OK;
     }
     // Merges everything that is left; *out is the final run (an empty run for no input).
     // Only valid when nothing was spilled (spills() == 0); use Finish() otherwise.
     int InputComplete(kc_run **out) {
-        int rc = mergePending();
+        int rc = drain();
         if (rc != KC_OK) return rc;
+        if ((rc = mergeAll()) != KC_OK) return rc;
         if (!_spilled.empty()) return KC_ERR_STATE;
-        if (_pending.empty()) return kc_merge_runs(_ctx, nullptr, 0, out);
-        *out = _pending[0];
-        _pending.clear();
+        kc_run *last = takeOnly();
+        if (!last) return kc_merge_runs(_ctx, nullptr, 0, out);
+        *out = last;
         return KC_OK;
     }
     // Merges everything that is left and writes the artefact to `path` (truncating; the reference
     // appends to whatever is there, KMerFileMerger.cpp:129). *n_records = records written.
     int Finish(const char *path, uint64_t *n_records) {
-        int rc = mergePending();
+        int rc = drain();
         if (rc != KC_OK) return rc;
+        if ((rc = mergeAll()) != KC_OK) return rc;
         if (_spilled.empty()) {
             kc_run *out = nullptr;
             if ((rc = InputComplete(&out)) != KC_OK) return rc;
@@ -65,7 +83,8 @@ public:
             kc_run_free(_ctx, out);
             return rc;
         }
-        if (!_pending.empty() && (rc = spill()) != KC_OK) return rc;
+        kc_run *last = takeOnly();
+        if (last && (rc = spill(last)) != KC_OK) return rc;
         return mergeOutOfCore(path, n_records);
     }
     uint64_t merges() const { return _merges; }
@@ -81,29 +100,97 @@ private:
         uint64_t w[4];
     };
 
-    int mergePending() {
-        if (_pending.size() < 2) return KC_OK;
-        kc_run *merged = nullptr;
-        int rc = kc_merge_runs(_ctx, _pending.data(), (uint32_t)_pending.size(), &merged);
+    // ---- background merging
+    void workerLoop() {
+        for (;;) {
+            kc_run *run = nullptr;
+            {
+                std::unique_lock<std::mutex> g(_mu);
+                _cv.wait(g, [this]() { return _stop || !_queue.empty(); });
+                if (_queue.empty()) return;          // _stop and nothing left
+                run = _queue.front();
+                _queue.pop_front();
+                _busy = true;
+            }
+            const int rc = place(run);
+            {
+                std::lock_guard<std::mutex> g(_mu);
+                _busy = false;
+                if (rc != KC_OK && _rc == KC_OK) _rc = rc;
+                _cv.notify_all();
+            }
+        }
+    }
+    int drain() {                                   // everything queued has been placed
+        if (!_worker.joinable()) return _rc;
+        std::unique_lock<std::mutex> g(_mu);
+        _cv.wait(g, [this]() { return _queue.empty() && !_busy; });
+        return _rc;
+    }
+    void stopWorker() {
+        if (!_worker.joinable()) return;
+        {
+            std::lock_guard<std::mutex> g(_mu);
+            _stop = true;
+            _cv.notify_all();
+        }
+        _worker.join();
+    }
+    // ---- the level schedule (one thread at a time: the worker, or the caller after drain())
+    int place(kc_run *run) {
+        size_t lv = 0;
+        for (;;) {
+            if (_levels.size() <= lv) _levels.resize(lv + 1);
+            _levels[lv].push_back(run);
+            if (_levels[lv].size() < _fanIn) return KC_OK;
+            kc_run *merged = nullptr;
+            int rc = mergeList(_levels[lv], &merged);
+            if (rc != KC_OK) return rc;
+            if (_budget && kc_run_records(merged) * _S > _budget) return spill(merged);
+            run = merged;
+            lv++;
+        }
+    }
+    int mergeList(std::vector<kc_run *> &runs, kc_run **out) {      // frees the inputs
+        int rc = kc_merge_runs(_ctx, runs.data(), (uint32_t)runs.size(), out);
         if (rc != KC_OK) return rc;
-        for (kc_run *r : _pending) kc_run_free(_ctx, r);
-        _pending.assign(1, merged);
+        for (kc_run *r : runs) kc_run_free(_ctx, r);
+        runs.clear();
         _merges++;
         return KC_OK;
     }
-    // the (single) pending run goes to pinned host memory as packed records
-    int spill() {
-        kc_run *r = _pending[0];
+    int mergeAll() {                                // what is left in the levels -> at most one run (smallest first)
+        std::vector<kc_run *> rest;
+        for (auto &lv : _levels) {
+            for (kc_run *r : lv) rest.push_back(r);
+            lv.clear();
+        }
+        if (rest.size() < 2) { if (!rest.empty()) { _levels.resize(1); _levels[0].push_back(rest[0]); } return KC_OK; }
+        kc_run *merged = nullptr;
+        int rc = kc_merge_runs(_ctx, rest.data(), (uint32_t)rest.size(), &merged);
+        if (rc != KC_OK) { _levels.resize(1); _levels[0] = rest; return rc; }
+        for (kc_run *r : rest) kc_run_free(_ctx, r);
+        _merges++;
+        _levels.resize(1);
+        _levels[0].push_back(merged);
+        return KC_OK;
+    }
+    kc_run *takeOnly() {
+        for (auto &lv : _levels)
+            if (!lv.empty()) { kc_run *r = lv[0]; lv.clear(); return r; }
+        return nullptr;
+    }
+    // a run goes to pinned host memory as packed records
+    int spill(kc_run *r) {
         const uint64_t n = kc_run_records(r), nb = n * _S;
         void *buf = nullptr;
         int rc = kc_host_alloc(_ctx, nb ? nb : 1, &buf);
-        if (rc != KC_OK) return rc;
+        if (rc != KC_OK) { kc_run_free(_ctx, r); return rc; }
         uint64_t got = 0;
         rc = kc_run_copy_records(_ctx, r, buf, nb, &got);
+        kc_run_free(_ctx, r);
         if (rc != KC_OK) { kc_host_free(_ctx, buf); return rc; }
         _spilled.push_back(HostRun{buf, n});
-        kc_run_free(_ctx, r);
-        _pending.clear();
         _spills++;
         return KC_OK;
     }
@@ -183,7 +270,14 @@ private:
     size_t _fanIn;
     uint64_t _budget;
     uint32_t _W, _S;
-    std::vector<kc_run *> _pending;
+    std::vector<std::vector<kc_run *>> _levels;
     std::vector<HostRun> _spilled;
     uint64_t _merges = 0, _spills = 0, _ranges = 0;
+    // background worker
+    std::thread _worker;
+    std::mutex _mu;
+    std::condition_variable _cv;
+    std::deque<kc_run *> _queue;
+    bool _stop = false, _busy = false;
+    int _rc = KC_OK;
 };

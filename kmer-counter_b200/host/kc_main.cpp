@@ -183,6 +183,7 @@ static int run_accumulate(const Options &opt, FastqChunker &reader, int64_t L, i
     } else {
         kc_stats st;
         kc_stats_get(ctx[0], &st);
+        for (int g = 1; g < G; g++) { kc_stats sg; kc_stats_get(ctx[g], &sg); st.reads += sg.reads; }
         fprintf(stderr, "mode=accumulate gpus=%d parser=%s reads=%llu skipped=%llu chunks=%llu records=%llu\n", G,
                 opt.parser != "host" ? "gpu" : "host", (unsigned long long)(opt.parser != "host" ? st.reads : reader.totalReads()),
                 (unsigned long long)reader.skippedReads(), (unsigned long long)n_chunks, (unsigned long long)n_records);
@@ -247,7 +248,8 @@ int main(int argc, char **argv) {
     // attempt 0: FASTQ text goes to the GPU as it is and is parsed there (kc_submit_fastq);
     // attempt 1: the host chunker, for input the device parser refuses (or parser=host)
     for (int attempt = opt.parser == "host" ? 1 : 0; attempt < 2; attempt++) {
-        RunMerger merger(ctx, opt.noOfMergersAtOnce, (uint32_t)opt.kmerLength, opt.runBudget > 0 ? (uint64_t)opt.runBudget : 0);
+        RunMerger merger(ctx, opt.noOfMergersAtOnce, (uint32_t)opt.kmerLength, opt.runBudget > 0 ? (uint64_t)opt.runBudget : 0,
+                         opt.noOfMergeThreads);
         bool busy[2] = {false, false};
         bool refused = false;
         chunk_id = 0;

@@ -41,7 +41,10 @@ int main(int argc, char **argv) {
     }
     for (auto &t : th) t.join();
     FreeGPU(streams, n_streams);
-    for (uint32_t s = 0; s < n_streams; s++) delete streams[s];
+    for (uint32_t s = 0; s < n_streams; s++) {            // as KMerCounter.cpp:153-161 does
+        for (char *line : streams[s]->_kmer_db) delete[] line;
+        delete streams[s];
+    }
     delete[] streams;
     FILE *o = fopen(argv[5], "wb");
     if (!o) return 1;
