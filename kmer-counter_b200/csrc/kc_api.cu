@@ -138,19 +138,63 @@ namespace {
         if (_rc != KC_OK) return _rc;        \
     } while (0)
 
+// Device memory of runs and short-lived scratch: the stream-ordered pool. If the pool cannot grow
+// (the device is nearly full of plain allocations) its cached blocks are released and the request
+// is retried, then made with plain cudaMalloc; dev_free knows those by address.
+std::mutex g_plain_mu;
+std::vector<void *> g_plain;
+
 int dev_alloc(kc_ctx *c, cudaStream_t s, uint64_t bytes, void **out) {
     *out = nullptr;
     if (bytes == 0) bytes = 16;
+    const bool dbg = getenv("KC_DEBUG_PLAN") != nullptr;
+    if (dbg && bytes > (1ull << 30)) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        fprintf(stderr, "kc dev_alloc %llu bytes (%llu of %llu free)\n", (unsigned long long)bytes, (unsigned long long)fr, (unsigned long long)tot);
+    }
     cudaError_t e = cudaMallocAsync(out, bytes, s);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes failed: %s", (unsigned long long)bytes,
-                            cudaGetErrorString(e));
+        cudaStreamSynchronize(s);
+        cudaMemPool_t pool = nullptr;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocAsync(out, bytes, s);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(out, bytes);
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> g(g_plain_mu);
+            g_plain.push_back(*out);
+        }
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        *out = nullptr;
+        return c->set_error(KC_ERR_NOMEM, "device allocation of %llu bytes failed: %s (%llu of %llu bytes free on the device, "
+                            "accumulator workspace %llu bytes)", (unsigned long long)bytes, cudaGetErrorString(e),
+                            (unsigned long long)fr, (unsigned long long)tot, (unsigned long long)c->acc.ws_bytes);
     }
     return KC_OK;
 }
 void dev_free(cudaStream_t s, void *p) {
-    if (p) cudaFreeAsync(p, s);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_plain_mu);
+        auto it = std::find(g_plain.begin(), g_plain.end(), p);
+        if (it != g_plain.end()) {
+            g_plain.erase(it);
+            cudaStreamSynchronize(s);
+            cudaFree(p);
+            return;
+        }
+    }
+    cudaFreeAsync(p, s);
 }
 
 int pending_init(kc_ctx *c, Pending &p) {
@@ -201,6 +245,12 @@ void pending_release(cudaStream_t, Pending &p) {
     p.ws_sort = p.ws_rle = p.ws_part = p.ws_super = nullptr;
     p.table = HashTable{nullptr, 0, nullptr};
     p.active = false;
+}
+
+// KC_SW_FORCE_DUP=1 (test knob, read at every count): the super-window path always takes its folding variant
+bool env_force_dup() {
+    const char *v = getenv("KC_SW_FORCE_DUP");
+    return v && v[0] == '1';
 }
 
 uint64_t pow2_ceil(uint64_t x) {
@@ -365,6 +415,42 @@ int make_run(kc_ctx *c, cudaStream_t s, uint64_t n, kc_run **out) {
     return KC_OK;
 }
 
+// Super-window path: sub-buckets S3c left out because they exceed its shared memory (skewed input:
+// many distinct keys share a long prefix). Their records are gathered in sub-bucket order, sorted by
+// the radix sorter and put in place (folded first if records may repeat). n_big_records comes from
+// the scalars the caller has just read back; the scratch is stream-ordered.
+int super_finish_big(kc_ctx *c, const SuperPlan &pl, void *ws, unsigned long long *d_sc, bool dup, uint64_t n_big_records,
+                     uint64_t *out_keys, uint32_t *out_counts, cudaStream_t s) {
+    if (n_big_records == 0) return KC_OK;
+    if (n_big_records > kMaxSortKeys) return c->set_error(KC_ERR_CAPACITY, "%llu records in oversized key ranges", (unsigned long long)n_big_records);
+    const int W = c->W;
+    const uint64_t kb = n_big_records * W * 8, cb = n_big_records * 4, wsb = sort_workspace_bytes(n_big_records, W);
+    void *ka = nullptr, *kb2 = nullptr, *ca = nullptr, *cb2 = nullptr, *sw = nullptr;
+    int rc = dev_alloc(c, s, kb, &ka);
+    if (rc == KC_OK) rc = dev_alloc(c, s, kb, &kb2);
+    if (rc == KC_OK) rc = dev_alloc(c, s, cb, &ca);
+    if (rc == KC_OK) rc = dev_alloc(c, s, cb, &cb2);
+    if (rc == KC_OK) rc = dev_alloc(c, s, wsb, &sw);
+    cudaError_t e = cudaSuccess;
+    int launches = 0;
+    if (rc == KC_OK) {
+        uint64_t *sk = nullptr;
+        uint32_t *sv = nullptr;
+        e = super_big_gather(pl, ws, static_cast<uint64_t *>(ka), static_cast<uint32_t *>(ca), c->n_sms, s);
+        if (e == cudaSuccess)
+            e = radix_sort(static_cast<uint64_t *>(ka), static_cast<uint64_t *>(kb2), static_cast<uint32_t *>(ca),
+                           static_cast<uint32_t *>(cb2), n_big_records, W, static_zero_bits(c), SortWorkspace{sw, wsb}, s, &sk,
+                           &sv, &launches, nullptr, nullptr);
+        if (e == cudaSuccess) e = super_big_place(pl, dup, ws, d_sc, sk, sv, out_keys, out_counts, c->n_sms, s);
+    }
+    dev_free(s, ka); dev_free(s, kb2); dev_free(s, ca); dev_free(s, cb2); dev_free(s, sw);
+    if (rc != KC_OK) return rc;
+    if (e != cudaSuccess) return c->set_error(KC_ERR_CUDA, "oversized key ranges: %s", cudaGetErrorString(e));
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stats.launches += launches + 3;
+    return KC_OK;
+}
+
 int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_hash_global(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
@@ -482,9 +568,7 @@ int count_finish_super(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool
     const SuperPlan &pl = p.splan;
     if (p.h_scal[SW_FAIL]) { *failed = true; return KC_OK; }
     const uint64_t n_d = p.h_scal[SW_D];
-    static int force_dup = -1;                  // KC_SW_FORCE_DUP=1 (test knob): always take the folding path
-    if (force_dup < 0) { const char *v = getenv("KC_SW_FORCE_DUP"); force_dup = (v && v[0] == '1') ? 1 : 0; }
-    const bool dup = p.h_scal[SW_OVF] != 0 || force_dup;
+    const bool dup = p.h_scal[SW_OVF] != 0 || env_force_dup();
     kc_run *r = nullptr;
     if (!dup) {
         KC_TRY(make_run(c, s, n_d, &r));
@@ -492,12 +576,20 @@ int count_finish_super(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool
             KC_CUDA_TRY(c, super_finish(pl, false, p.ws_super, p.d_scal, r->d_keys, r->d_counts, c->n_sms, s));
             KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
             KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+            if (!p.h_scal[SW_FAIL] && p.h_scal[SW_BIG]) {
+                const int rc = super_finish_big(c, pl, p.ws_super, p.d_scal, false, p.h_scal[SW_BIG_RECORDS], r->d_keys, r->d_counts, s);
+                if (rc != KC_OK) { kc_run_free(c, r); return rc; }
+            }
         }
     } else {
         uint64_t *tk = nullptr;
         uint32_t *tc = nullptr;
         super_tmp_buffers(pl, p.ws_super, &tk, &tc);
         KC_CUDA_TRY(c, super_finish(pl, true, p.ws_super, p.d_scal, tk, tc, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (!p.h_scal[SW_FAIL] && p.h_scal[SW_BIG])
+            KC_TRY(super_finish_big(c, pl, p.ws_super, p.d_scal, true, p.h_scal[SW_BIG_RECORDS], tk, tc, s));
         KC_CUDA_TRY(c, super_fold_offsets(pl, p.ws_super, p.d_scal, s));
         KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
@@ -773,7 +865,17 @@ void accum_free(kc_ctx *c) {
 
 // Counts what the bins hold into one run (S2 .. S3c) and empties them. All slot streams are
 // drained first. An empty accumulator gives an empty run.
-int accum_finish(kc_ctx *c, bool force_dup, kc_run **out);
+int accum_finish(kc_ctx *c, bool force_dup, kc_run **out, kc_run *pre_run = nullptr, bool dup_known = false);
+
+// non-exchange accumulators keep the second record buffer (E) outside the workspace: this undoes
+// what accum_count attached for one flush
+void accum_detach_e(kc_ctx *c, cudaStream_t s, kc_run *pre_run) {
+    kc_ctx::Accum &a = c->acc;
+    if (!a.pl.ext_e) return;
+    if (!pre_run) { dev_free(s, a.pl.ext_ek); dev_free(s, a.pl.ext_ec); }
+    a.pl.ext_ek = nullptr;
+    a.pl.ext_ec = nullptr;
+}
 
 int accum_count(kc_ctx *c, kc_run **out) {
     kc_ctx::Accum &a = c->acc;
@@ -783,13 +885,51 @@ int accum_count(kc_ctx *c, kc_run **out) {
         if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
     if (a.fresh) return make_run(c, s, 0, out);
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[0], s));
-    KC_CUDA_TRY(c, super_count(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s, &a.ev[1]));
-    return accum_finish(c, false, out);
+    if (!a.pl.ext_e) {
+        KC_CUDA_TRY(c, super_count(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s, &a.ev[1]));
+        return accum_finish(c, false, out);
+    }
+    // S2 first: once the number of distinct records is known the run is allocated with exactly that
+    // size and serves as the second record buffer of S3a/S3b before S3c sorts the records into it
+    KC_CUDA_TRY(c, super_count_bins(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s));
+    KC_CUDA_TRY(c, cudaEventRecord(a.ev[1], s));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (a.h_sc[SW_FAIL])
+        return c->set_error(KC_ERR_CAPACITY, "accumulated input does not fit the plan (fail bits %llu): flush more often or "
+                            "raise the expected read count", (unsigned long long)a.h_sc[SW_FAIL]);
+    const uint64_t n_d = a.h_sc[SW_D];
+    const bool env_dup = env_force_dup();
+    const bool dup = env_dup || a.h_sc[SW_OVF] != 0;
+    kc_run *pre = nullptr;
+    if (!dup) {
+        KC_TRY(make_run(c, s, n_d, &pre));
+        a.pl.ext_ek = pre->d_keys;
+        a.pl.ext_ec = pre->d_counts;
+    } else {
+        void *m = nullptr;
+        KC_TRY(dev_alloc(c, s, n_d * c->W * 8 + 64, &m));
+        a.pl.ext_ek = static_cast<uint64_t *>(m);
+        const int rc = dev_alloc(c, s, n_d * 4 + 64, &m);
+        if (rc != KC_OK) { dev_free(s, a.pl.ext_ek); a.pl.ext_ek = nullptr; return rc; }
+        a.pl.ext_ec = static_cast<uint32_t *>(m);
+    }
+    cudaError_t e = super_place(a.pl, a.ws, a.d_sc, c->n_sms, s, &a.ev[2]);
+    if (e != cudaSuccess) {
+        accum_detach_e(c, s, pre);
+        if (pre) kc_run_free(c, pre);
+        return c->set_error(KC_ERR_CUDA, "super_place: %s", cudaGetErrorString(e));
+    }
+    const int rc = accum_finish(c, dup, out, pre, true);
+    accum_detach_e(c, s, pre);
+    if (rc != KC_OK && pre) kc_run_free(c, pre);
+    return rc;
 }
 
 // The sub-buckets are in place (S3b done or queued on the context's stream): sort them into a run
-// (folding equal keys if records may repeat), account, empty the bins.
-int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
+// (folding equal keys if records may repeat), account, empty the bins. pre_run: the run, already
+// allocated (its arrays were the second record buffer); dup_known: force_dup is the decision.
+int accum_finish(kc_ctx *c, bool force_dup, kc_run **out, kc_run *pre_run, bool dup_known) {
     kc_ctx::Accum &a = c->acc;
     cudaStream_t s = c->stream;
     *out = nullptr;
@@ -801,14 +941,19 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
     // exchange: this rank's records are the sub-buckets it pulled (n_recv), and they can only repeat if
     // some rank used its overflow list (those records are counted where they are, not by the bin's owner)
     const uint64_t n_d = a.xchg ? a.x_info.n_recv : a.h_sc[SW_D];
-    static int env_dup = -1;
-    if (env_dup < 0) { const char *v = getenv("KC_SW_FORCE_DUP"); env_dup = (v && v[0] == '1') ? 1 : 0; }
-    const bool dup = env_dup || (a.xchg ? (force_dup && a.x_info.any_ovf != 0) : (force_dup || a.h_sc[SW_OVF] != 0));
-    kc_run *r = nullptr;
+    const bool env_dup = env_force_dup();
+    const bool dup = dup_known ? force_dup
+                               : (env_dup || (a.xchg ? (force_dup && a.x_info.any_ovf != 0) : (force_dup || a.h_sc[SW_OVF] != 0)));
+    kc_run *r = pre_run;
     if (!dup) {
-        KC_TRY(make_run(c, s, n_d, &r));
+        if (!r) KC_TRY(make_run(c, s, n_d, &r));
         if (n_d) KC_CUDA_TRY(c, super_finish(a.pl, false, a.ws, a.d_sc, r->d_keys, r->d_counts, c->n_sms, s));
         KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (!a.h_sc[SW_FAIL] && a.h_sc[SW_BIG]) {
+            const int rc = super_finish_big(c, a.pl, a.ws, a.d_sc, false, a.h_sc[SW_BIG_RECORDS], r->d_keys, r->d_counts, s);
+            if (rc != KC_OK) { if (!pre_run) kc_run_free(c, r); return rc; }
+        }
         KC_CUDA_TRY(c, cudaEventRecord(a.ev[5], s));
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
     } else {
@@ -816,18 +961,37 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out) {
         uint32_t *tc = nullptr;
         super_tmp_buffers(a.pl, a.ws, &tk, &tc);
         KC_CUDA_TRY(c, super_finish(a.pl, true, a.ws, a.d_sc, tk, tc, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (!a.h_sc[SW_FAIL] && a.h_sc[SW_BIG])
+            KC_TRY(super_finish_big(c, a.pl, a.ws, a.d_sc, true, a.h_sc[SW_BIG_RECORDS], tk, tc, s));
         KC_CUDA_TRY(c, super_fold_offsets(a.pl, a.ws, a.d_sc, s));
         KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
         if (!a.h_sc[SW_FAIL]) {
-            KC_TRY(make_run(c, s, a.h_sc[SW_OUT], &r));
-            if (r->n) KC_CUDA_TRY(c, super_gather(a.pl, a.ws, tk, tc, r->d_keys, r->d_counts, c->n_sms, s));
+            const uint64_t n_out = a.h_sc[SW_OUT];
+            if (a.pl.ext_e) {
+                // the temporary is this flush's own allocation: close the gaps into D (dead by now), give the
+                // temporary back, then allocate the run -- the flush never holds both next to the workspace
+                uint64_t *dk = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(a.ws) + a.pl.off_dk);
+                uint32_t *dc = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(a.ws) + a.pl.off_dc);
+                if (n_out) KC_CUDA_TRY(c, super_gather(a.pl, a.ws, tk, tc, dk, dc, c->n_sms, s));
+                accum_detach_e(c, s, nullptr);
+                KC_TRY(make_run(c, s, n_out, &r));
+                if (n_out) {
+                    KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_keys, dk, n_out * c->W * 8, cudaMemcpyDeviceToDevice, s));
+                    KC_CUDA_TRY(c, cudaMemcpyAsync(r->d_counts, dc, n_out * 4, cudaMemcpyDeviceToDevice, s));
+                }
+            } else {
+                KC_TRY(make_run(c, s, n_out, &r));
+                if (r->n) KC_CUDA_TRY(c, super_gather(a.pl, a.ws, tk, tc, r->d_keys, r->d_counts, c->n_sms, s));
+            }
         }
         KC_CUDA_TRY(c, cudaEventRecord(a.ev[5], s));
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
     }
     if (a.h_sc[SW_FAIL]) {
-        if (r) kc_run_free(c, r);
+        if (r && r != pre_run) kc_run_free(c, r);
         return c->set_error(KC_ERR_CAPACITY, "a key range of the accumulated input does not fit shared memory (fail bits %llu)",
                             (unsigned long long)a.h_sc[SW_FAIL]);
     }
@@ -948,11 +1112,16 @@ static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange, u
     // exchange: a bin collects what ALL ranks put into it, so each rank plans bins 1/n_ranks the size
     uint32_t occ = (uint32_t)c->cfg.table_slots;
     if (exchange && n_ranks > 1) occ = (occ ? occ : 8192u) / n_ranks;
-    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, occ, &pl, exchange ? 0.25 : 0.0, c->cfg.distinct_hint))
+    if (!super_plan(c->cfg.k, c->cfg.read_len, c->strict, windows, occ, &pl, exchange ? 0.25 : 0.0, c->cfg.distinct_hint, !exchange))
         return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", c->cfg.k, c->cfg.read_len);
     if (!a.h_sc) {
         KC_CUDA_TRY(c, cudaMallocHost((void **)&a.h_sc, SC_COUNT * 8));
         for (auto &e : a.ev) KC_CUDA_TRY(c, cudaEventCreate(&e));
+    }
+    if (getenv("KC_DEBUG_PLAN")) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        fprintf(stderr, "kc accumulator: before the workspace %llu of %llu bytes free\n", (unsigned long long)fr, (unsigned long long)tot);
     }
     if (pl.ws_bytes > a.ws_bytes) {
         KC_CUDA_TRY(c, cudaDeviceSynchronize());
@@ -965,6 +1134,10 @@ static int accum_begin_impl(kc_ctx *c, uint64_t expected_reads, bool exchange, u
         }
         a.ws_bytes = pl.ws_bytes;
     }
+    if (getenv("KC_DEBUG_PLAN"))
+        fprintf(stderr, "kc accumulator plan: windows %llu, bins %u x %u records, overflow %llu, D %llu records, ext_e %d, workspace %llu bytes\n",
+                (unsigned long long)windows, pl.n_bins, pl.bin_cap, (unsigned long long)pl.ovf_cap, (unsigned long long)pl.d_cap,
+                (int)pl.ext_e, (unsigned long long)pl.ws_bytes);
     a.pl = pl;
     a.d_sc = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(a.ws) + pl.off_sc);   // (peers read the scalars too)
     a.max_windows = windows;

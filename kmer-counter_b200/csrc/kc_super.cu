@@ -1320,6 +1320,7 @@ struct FinishParams {
     uint64_t *out_keys;             // records of sub-bucket j at out[base2[j] ...)
     uint32_t *out_counts;
     uint32_t *m_out;                // DUP: records sub-bucket j kept
+    uint32_t *big;                  // records of sub-bucket j if it is too large for this kernel, else 0
     unsigned long long *sc;
 };
 
@@ -1359,15 +1360,21 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
         if (j >= n_sub) break;
         const uint32_t b = p.base2[j], n = p.base2[j + 1] - b;
         if (n == 0) {
-            if (DUP && tid == 0) p.m_out[j] = 0;
+            if (tid == 0) { p.big[j] = 0; if (DUP) p.m_out[j] = 0; }
             __syncthreads();
             continue;
         }
-        if (n > (uint32_t)CAP) {                     // does not fit: the caller re-counts this chunk another way
-            if (tid == 0) { atomicOr(&p.sc[SW_FAIL], 8ull); if (DUP) p.m_out[j] = 0; }
+        if (n > (uint32_t)CAP) {                     // does not fit: left to the radix sorter (super_big_*)
+            if (tid == 0) {
+                p.big[j] = n;
+                atomicAdd(&p.sc[SW_BIG], 1ull);
+                atomicAdd(&p.sc[SW_BIG_RECORDS], (unsigned long long)n);
+                if (DUP) p.m_out[j] = 0;
+            }
             __syncthreads();
             continue;
         }
+        if (tid == 0) p.big[j] = 0;
         // the loads are issued first; their latency overlaps the clearing of the bins
         Key<W> rk[kPer];
         uint32_t rc[kPer], rr[kPer];
@@ -1548,6 +1555,100 @@ __global__ void __launch_bounds__(256) sw_gather_kernel(const uint64_t *__restri
     }
 }
 
+// ---- sub-buckets too large for S3c (see kc_super.cuh): records of sub-bucket j are
+// D[base2[j] .. base2[j] + big[j]); in the gathered / sorted array they sit at bigoff[j].
+template <int W>
+__global__ void __launch_bounds__(256) big_gather_kernel(const uint64_t *__restrict__ in_keys,
+                                                         const uint32_t *__restrict__ in_counts,
+                                                         const uint32_t *__restrict__ base2,
+                                                         const uint32_t *__restrict__ big,
+                                                         const uint32_t *__restrict__ bigoff,
+                                                         const SuperPlanDev *__restrict__ plan,
+                                                         uint64_t *__restrict__ tk, uint32_t *__restrict__ tc) {
+    const uint32_t n_sub = plan->n_sub;
+    for (uint32_t j = blockIdx.x; j < n_sub; j += gridDim.x) {
+        const uint32_t n = big[j];
+        if (n == 0) continue;
+        const uint32_t b = base2[j], o = bigoff[j];
+        for (uint32_t i = threadIdx.x; i < n; i += 256) {
+            st_key<W>(tk, o + i, ld_key<W>(in_keys, b + i));
+            tc[o + i] = in_counts[b + i];
+        }
+    }
+}
+
+// Sorted records of every large sub-bucket -> its place in S3c's output. DUP: equal keys are
+// adjacent; the first of a group keeps the key, the counts are added up (uint32 wrap), the heads are
+// compacted and m_out[j] says how many there are.
+template <int W, bool DUP>
+__global__ void __launch_bounds__(256) big_place_kernel(const uint64_t *__restrict__ sk, const uint32_t *__restrict__ sc_counts,
+                                                        const uint32_t *__restrict__ base2,
+                                                        const uint32_t *__restrict__ big,
+                                                        const uint32_t *__restrict__ bigoff,
+                                                        const SuperPlanDev *__restrict__ plan,
+                                                        uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_counts,
+                                                        uint32_t *__restrict__ m_out, unsigned long long *__restrict__ sc) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_run;
+    const uint32_t n_sub = plan->n_sub;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t j = blockIdx.x; j < n_sub; j += gridDim.x) {
+        const uint32_t n = big[j];
+        if (n == 0) continue;
+        const uint32_t b = base2[j], o = bigoff[j];
+        if constexpr (!DUP) {
+            for (uint32_t i = tid; i < n; i += 256) {
+                st_key<W>(out_keys, b + i, ld_key<W>(sk, o + i));
+                out_counts[b + i] = sc_counts[o + i];
+            }
+        } else {
+        // two sweeps over the segment: heads take their place (key + own count), then the others add
+        // their counts to the head of their group; a record's group index = heads up to and including it - 1
+        for (int sweep = 0; sweep < 2; sweep++) {
+            if (tid == 0) s_run = 0;
+            __syncthreads();
+            for (uint32_t i0 = 0; i0 < n; i0 += 256) {
+                const uint32_t i = i0 + tid;
+                bool head = false;
+                Key<W> k;
+                if (i < n) {
+                    k = ld_key<W>(sk, o + i);
+                    head = i == 0 || !key_eq<W>(k, ld_key<W>(sk, o + i - 1));
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, head);
+                if (lane == 0) s_warp[warp] = __popc(bal);
+                __syncthreads();
+                uint32_t before = s_run;
+                for (uint32_t w = 0; w < warp; w++) before += s_warp[w];
+                const uint32_t incl = before + __popc(bal & (lanemask_lt() | (1u << lane)));   // heads in [0, i]
+                if (i < n) {
+                    if (sweep == 0 && head) {
+                        st_key<W>(out_keys, b + incl - 1, k);
+                        out_counts[b + incl - 1] = sc_counts[o + i];
+                    } else if (sweep == 1 && !head) {
+                        atomicAdd(&out_counts[b + incl - 1], sc_counts[o + i]);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t t = 0;
+                    for (int w = 0; w < 8; w++) t += s_warp[w];
+                    s_run += t;
+                }
+                __syncthreads();
+            }
+            __threadfence();
+            __syncthreads();
+        }
+        if (tid == 0) {
+            m_out[j] = s_run;
+            if (n > s_run) atomicAdd(&sc[SW_FOLDED], (unsigned long long)(n - s_run));
+        }
+        __syncthreads();
+        }
+    }
+}
+
 inline uint64_t round512(uint64_t b) { return (b + 511) & ~511ull; }
 
 constexpr int kFinCapSmall = 2048, kFinCapLarge = 4096;     // records a sub-bucket may hold (S3c variants)
@@ -1556,7 +1657,7 @@ constexpr int kFinCapSmall = 2048, kFinCapLarge = 4096;     // records a sub-buc
 
 // ------------------------------------------------------------------------ host
 bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
-                double record_headroom, uint64_t distinct_hint) {
+                double record_headroom, uint64_t distinct_hint, bool ext_e) {
     if (k == 0 || k > 64 || L < k || L > 4096) return false;
     SuperPlan pl{};
     pl.W = (int)((k + 31) / 32);
@@ -1567,14 +1668,7 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.span = masked ? k : 32u * pl.W;
     pl.last_mask = masked ? (~0ull << (64 - 2 * mm)) : ~0ull;
     if (pl.span < 22) return false;
-    pl.m = 12;
-    pl.w = pl.span - pl.m + 1;
     pl.nk = L - k + 1;
-    pl.nh = pl.nk + pl.w - 1;
-    pl.nh_stride = (pl.nh + 8) | 1u;                                   // odd stride: rows start in different banks
-    pl.seg_len = pl.w - 1 < (uint32_t)kSwMaxSeg - 1 ? pl.w - 1 : (uint32_t)kSwMaxSeg - 1;   // + the look-behind window
-    pl.segs_per_read = (pl.nk + pl.seg_len - 1) / pl.seg_len;
-    pl.seg_len = (pl.nk + pl.segs_per_read - 1) / pl.segs_per_read;    // even the segments out
     pl.cmax = 32u * pl.W - 3;
     if (max_windows == 0) max_windows = 1;
     if (occ_per_bin == 0) occ_per_bin = 8192;
@@ -1582,6 +1676,20 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     if (nb < 8) nb = 8;
     if (nb > (1ull << 24)) nb = 1ull << 24;
     pl.n_bins = (uint32_t)nb;
+    // Minimizer length: a bin's load is the sum of the weights of the m-mers hashed into it, and those
+    // weights are very uneven (an m-mer with a small hash is the minimizer of many windows). With
+    // ~190 m-mers per bin the load's sd is ~20% of the mean; with 16 it is 70% and half the bins
+    // overflow (seen at 1e6 bins with m = 12). So m grows with the bin count: 12 up to 87k bins
+    // (config 2), 13 up to 350k, 14 up to 1.4M, ... -- longer minimizers change more often
+    // (2 / (w + 1) records per window), which costs a few percent more records.
+    pl.m = 12;
+    while (pl.m < 16 && pl.m + 8 < pl.span && (1ull << (2 * pl.m)) < 192ull * pl.n_bins) pl.m++;
+    pl.w = pl.span - pl.m + 1;
+    pl.nh = pl.nk + pl.w - 1;
+    pl.nh_stride = (pl.nh + 8) | 1u;                                   // odd stride: rows start in different banks
+    pl.seg_len = pl.w - 1 < (uint32_t)kSwMaxSeg - 1 ? pl.w - 1 : (uint32_t)kSwMaxSeg - 1;   // + the look-behind window
+    pl.segs_per_read = (pl.nk + pl.seg_len - 1) / pl.seg_len;
+    pl.seg_len = (pl.nk + pl.segs_per_read - 1) / pl.segs_per_read;    // even the segments out
     // records per window: a new record whenever the minimizer changes (2 / (w + 1) of the windows for a
     // random order), at every read start, and every cmax windows
     const double rho = 2.0 / (pl.w + 1) + 1.2 / pl.nk + 1.0 / pl.cmax * 0.25;
@@ -1623,12 +1731,20 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.off_x = take(sizeof(XDev));
     pl.off_sc = take(SW_COUNT * 8);
     pl.off_h2m = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_big = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_bigoff = take((uint64_t)(kSuperMaxSub + 8) * 4);
     pl.off_bins = take((uint64_t)pl.n_bins * pl.bin_cap * rec_bytes);
     pl.off_ovf = take(pl.ovf_cap * rec_bytes);
     pl.off_dk = take(pl.d_cap * 8 * pl.W + 64);
     pl.off_dc = take(pl.d_cap * 4 + 64);
-    pl.off_ek = take(pl.d_cap * 8 * pl.W + 64);
-    pl.off_ec = take(pl.d_cap * 4 + 64);
+    pl.ext_e = ext_e;
+    pl.ext_ek = nullptr;
+    pl.ext_ec = nullptr;
+    pl.off_ek = pl.off_ec = o;
+    if (!ext_e) {
+        pl.off_ek = take(pl.d_cap * 8 * pl.W + 64);
+        pl.off_ec = take(pl.d_cap * 4 + 64);
+    }
     pl.ws_bytes = o;
     *out = pl;
     return true;
@@ -1636,6 +1752,9 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
 
 namespace {
 template <class T> T *at(void *ws, uint64_t off) { return reinterpret_cast<T *>(static_cast<uint8_t *>(ws) + off); }
+// the second record buffer: inside the workspace, or the caller's (SuperPlan::ext_e)
+uint64_t *ek_of(const SuperPlan &pl, void *ws) { return pl.ext_e ? pl.ext_ek : at<uint64_t>(ws, pl.off_ek); }
+uint32_t *ec_of(const SuperPlan &pl, void *ws) { return pl.ext_e ? pl.ext_ec : at<uint32_t>(ws, pl.off_ec); }
 }  // namespace
 
 cudaError_t super_reset(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s) {
@@ -1769,57 +1888,60 @@ cudaError_t super_count_bins(const SuperPlan &pl, bool add_phantom, void *ws, un
 }
 
 template <int W>
-static cudaError_t super_count_w(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
-                                 cudaStream_t s, cudaEvent_t *evs) {
+static cudaError_t super_place_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, int n_sms, cudaStream_t s,
+                                 cudaEvent_t *evs) {
     cudaError_t e;
-    uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
-    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
+    uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = ek_of(pl, ws);
+    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = ec_of(pl, ws);
+    if (!ek || !ec) return cudaErrorInvalidValue;
     uint32_t *hist1 = at<uint32_t>(ws, pl.off_hist1), *base1 = at<uint32_t>(ws, pl.off_base1),
              *cur1 = at<uint32_t>(ws, pl.off_cur1), *hist2 = at<uint32_t>(ws, pl.off_hist2),
              *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
     SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
-    // ---- S2
-    if ((e = super_count_bins_w<W>(pl, add_phantom, ws, d_sc, n_sms, s)) != cudaSuccess) return e;
-    if (evs) cudaEventRecord(evs[0], s);
     // ---- S3a: level-1 bases + device plan, scatter D -> E
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
     sw_plan_kernel<<<1, 1024, 0, s>>>(hist1, pl.b1, pl.d_cap, pl.sub_target, sig, base1, cur1, plan, d_sc);
     const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
-    {
-        auto k1 = rec_scatter_kernel<W, 1>;
-        auto k2 = rec_scatter_kernel<W, 2>;
-        if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kRsThreads, rs_smem);
-        if (per_sm < 1) per_sm = 1;
-        const uint32_t grid = (uint32_t)n_sms * per_sm;
-        k1<<<grid, kRsThreads, rs_smem, s>>>(dk, dc, ek, ec, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur1, nullptr);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (evs) cudaEventRecord(evs[1], s);
-        // ---- level-2 histogram + scan (b2 == 0: one counter per level-1 bucket)
-        rec_hist2_kernel<W><<<(uint32_t)n_sms * 8, 256, 0, s>>>(ek, plan, hist2);
-        sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(hist2, &plan->n_sub, 0, base2, cur2, nullptr);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (evs) cudaEventRecord(evs[2], s);
-        // ---- S3b: scatter E -> D by the level-2 digit
-        k2<<<grid, kRsThreads, rs_smem, s>>>(ek, ec, dk, dc, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur2, nullptr);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (evs) cudaEventRecord(evs[3], s);
-    }
+    auto k1 = rec_scatter_kernel<W, 1>;
+    auto k2 = rec_scatter_kernel<W, 2>;
+    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kRsThreads, rs_smem);
+    if (per_sm < 1) per_sm = 1;
+    const uint32_t grid = (uint32_t)n_sms * per_sm;
+    k1<<<grid, kRsThreads, rs_smem, s>>>(dk, dc, ek, ec, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur1, nullptr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (evs) cudaEventRecord(evs[0], s);
+    // ---- level-2 histogram + scan (b2 == 0: one counter per level-1 bucket)
+    rec_hist2_kernel<W><<<(uint32_t)n_sms * 8, 256, 0, s>>>(ek, plan, hist2);
+    sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(hist2, &plan->n_sub, 0, base2, cur2, nullptr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (evs) cudaEventRecord(evs[1], s);
+    // ---- S3b: scatter E -> D by the level-2 digit
+    k2<<<grid, kRsThreads, rs_smem, s>>>(ek, ec, dk, dc, plan, pl.b1, &d_sc[SW_D], pl.d_cap, cur2, nullptr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (evs) cudaEventRecord(evs[2], s);
     return cudaSuccess;
+}
+
+cudaError_t super_place(const SuperPlan &pl, void *ws, unsigned long long *d_sc, int n_sms, cudaStream_t s, cudaEvent_t *evs) {
+    if (pl.W == 1) return super_place_w<1>(pl, ws, d_sc, n_sms, s, evs);
+    if (pl.W == 2) return super_place_w<2>(pl, ws, d_sc, n_sms, s, evs);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t super_count(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
                         cudaStream_t s, cudaEvent_t *evs) {
-    if (pl.W == 1) return super_count_w<1>(pl, add_phantom, ws, d_sc, n_sms, s, evs);
-    if (pl.W == 2) return super_count_w<2>(pl, add_phantom, ws, d_sc, n_sms, s, evs);
-    return cudaErrorInvalidValue;
+    cudaError_t e = super_count_bins(pl, add_phantom, ws, d_sc, n_sms, s);
+    if (e != cudaSuccess) return e;
+    if (evs) cudaEventRecord(evs[0], s);
+    return super_place(pl, ws, d_sc, n_sms, s, evs ? evs + 1 : nullptr);
 }
 
 void super_tmp_buffers(const SuperPlan &pl, void *ws, uint64_t **tmp_keys, uint32_t **tmp_counts) {
-    *tmp_keys = at<uint64_t>(ws, pl.off_ek);
-    *tmp_counts = at<uint32_t>(ws, pl.off_ec);
+    *tmp_keys = ek_of(pl, ws);
+    *tmp_counts = ec_of(pl, ws);
 }
 
 template <int W, bool DUP, int THREADS, int CAP>
@@ -1833,6 +1955,7 @@ static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long l
     fp.out_keys = out_keys;
     fp.out_counts = out_counts;
     fp.m_out = at<uint32_t>(ws, pl.off_mout);
+    fp.big = at<uint32_t>(ws, pl.off_big);
     fp.sc = d_sc;
     const uint32_t smem = (DUP ? 2 : 1) * CAP * (8 * W + 4) + 2 * CAP * 4;
     auto kern = rec_finish_kernel<W, THREADS, CAP, DUP>;
@@ -1862,6 +1985,33 @@ cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long 
     return cudaErrorInvalidValue;
 }
 
+cudaError_t super_big_gather(const SuperPlan &pl, void *ws, uint64_t *tk, uint32_t *tc, int n_sms, cudaStream_t s) {
+    SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    uint32_t *big = at<uint32_t>(ws, pl.off_big), *bigoff = at<uint32_t>(ws, pl.off_bigoff), *base2 = at<uint32_t>(ws, pl.off_base2);
+    sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(big, &plan->n_sub, 0, bigoff, nullptr, nullptr);
+    const uint64_t *dk = at<uint64_t>(ws, pl.off_dk);
+    const uint32_t *dc = at<uint32_t>(ws, pl.off_dc);
+    if (pl.W == 1) big_gather_kernel<1><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
+    else big_gather_kernel<2><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
+    return cudaGetLastError();
+}
+
+cudaError_t super_big_place(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, const uint64_t *sk,
+                            const uint32_t *sc_counts, uint64_t *out_keys, uint32_t *out_counts, int n_sms, cudaStream_t s) {
+    const SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
+    const uint32_t *big = at<uint32_t>(ws, pl.off_big), *bigoff = at<uint32_t>(ws, pl.off_bigoff), *base2 = at<uint32_t>(ws, pl.off_base2);
+    uint32_t *m_out = at<uint32_t>(ws, pl.off_mout);
+    const uint32_t grid = (uint32_t)n_sms * 8;
+    if (pl.W == 1) {
+        if (dup) big_place_kernel<1, true><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+        else big_place_kernel<1, false><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+    } else {
+        if (dup) big_place_kernel<2, true><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+        else big_place_kernel<2, false><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t super_fold_offsets(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s) {
     SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
     sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(
@@ -1887,6 +2037,7 @@ static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long 
                                    uint32_t rank, uint32_t n_ranks, bool keep_ranges, void *const *peer_ws, int n_sms,
                                    cudaStream_t s) {
     cudaError_t e;
+    if (pl.ext_e) return cudaErrorInvalidValue;      // the peers find E through the workspace mapping
     uint64_t *dk = at<uint64_t>(ws, pl.off_dk), *ek = at<uint64_t>(ws, pl.off_ek);
     uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *ec = at<uint32_t>(ws, pl.off_ec);
     SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);

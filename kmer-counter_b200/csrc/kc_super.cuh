@@ -39,6 +39,8 @@ enum {
     SW_OUT = 9,         // records in the run (DUP mode: after folding)
     SW_RECORDS = 10,    // records S1 wrote (bins + overflow)
     SW_TICKET2 = 11,    // S3c work ticket
+    SW_BIG = 12,        // sub-buckets too large for S3c's shared memory (sorted by the radix sorter instead)
+    SW_BIG_RECORDS = 13,// records in them
     SW_COUNT = 16
 };
 
@@ -76,7 +78,13 @@ struct SuperPlan {
     uint64_t last_mask;
     // workspace layout (bytes from the workspace base)
     uint64_t off_cursor, off_bins, off_ovf, off_hist1, off_base1, off_cur1, off_hist2, off_base2, off_cur2,
-        off_mout, off_off, off_plan, off_x, off_sc, off_h2m, off_dk, off_dc, off_ek, off_ec, ws_bytes;
+        off_mout, off_off, off_plan, off_x, off_sc, off_h2m, off_big, off_bigoff, off_dk, off_dc, off_ek, off_ec, ws_bytes;
+    // The second record buffer (E: level-1 grouped records, later S3c's output) may live outside
+    // the workspace (ext_e): the accumulating mode makes it the run itself, sized once |D| is
+    // known, so a flush holds D and the run and nothing else of that size.
+    bool ext_e;
+    uint64_t *ext_ek;
+    uint32_t *ext_ec;
 };
 
 constexpr uint32_t kSuperMaxSub = 1u << 20;
@@ -85,7 +93,7 @@ constexpr uint32_t kSuperMaxSub = 1u << 20;
 // accumulated before the count). occ_per_bin = 0 -> default. Returns false for shapes the path
 // does not take (W > 2, span < 22, reads too long for the shared-memory tile).
 bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
-                double record_headroom = 0.0, uint64_t distinct_hint = 0);
+                double record_headroom = 0.0, uint64_t distinct_hint = 0, bool ext_e = false);
 
 // zero cursors, histograms and scalars: once before the first super_scatter of a pipeline
 cudaError_t super_reset(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s);
@@ -96,11 +104,22 @@ cudaError_t super_scatter(const SuperPlan &pl, const void *d_reads, uint64_t n_r
 // events recorded after S2, S3a, H2, S3b.
 cudaError_t super_count(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
                         cudaStream_t s, cudaEvent_t *evs);
+// S3a .. S3b alone (after super_count_bins): evs (may be NULL) recorded after S3a, H2, S3b
+cudaError_t super_place(const SuperPlan &pl, void *ws, unsigned long long *d_sc, int n_sms, cudaStream_t s, cudaEvent_t *evs);
 // S3c once the host knows |D| (= *d_sc[SW_D]) : sort every sub-bucket into (out_keys, out_counts).
 // dup == false: the records are distinct, the output is dense and final (n_d records).
 // dup == true : equal keys are folded; the output has gaps, m_out/off describe it; finish with super_gather.
 cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, uint64_t *out_keys,
                          uint32_t *out_counts, int n_sms, cudaStream_t s);
+// Sub-buckets S3c could not take (more than fin_cap records share a (b1+b2)-bit prefix: skewed
+// input) are left out by super_finish and counted in d_sc[SW_BIG] / [SW_BIG_RECORDS]. The caller
+// then (1) super_big_gather: their records, in sub-bucket order, into (tk, tc) -- room for
+// SW_BIG_RECORDS records; (2) sorts that array by key (any sorter: the sub-buckets are key
+// ranges, so the sorted array is the concatenation of the sorted sub-buckets); (3) super_big_place:
+// the sorted records go to their sub-buckets' places in S3c's output (dup: folded, m_out set).
+cudaError_t super_big_gather(const SuperPlan &pl, void *ws, uint64_t *tk, uint32_t *tc, int n_sms, cudaStream_t s);
+cudaError_t super_big_place(const SuperPlan &pl, bool dup, void *ws, unsigned long long *d_sc, const uint64_t *sk,
+                            const uint32_t *sc_counts, uint64_t *out_keys, uint32_t *out_counts, int n_sms, cudaStream_t s);
 // DUP mode: after super_finish, offsets of the survivors (d_sc[SW_OUT] = records) ...
 cudaError_t super_fold_offsets(const SuperPlan &pl, void *ws, unsigned long long *d_sc, cudaStream_t s);
 // ... and the gather that closes the gaps

@@ -16,7 +16,7 @@ STAGE_NAMES = {
 }
 
 SW_SCALARS = ["invalid", "overflow_records", "d_records", "fail", "ticket", "windows", "occurrences", "aborts", "folded",
-              "out_records", "records", "ticket2"]
+              "out_records", "records", "ticket2", "big_ranges", "big_records"]
 
 
 def xchg_run_all(counters):

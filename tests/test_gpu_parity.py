@@ -124,6 +124,43 @@ def test_super_heavy_hitters_overflow_list(kc):
             assert sc["overflow_records"] > 0 and sc["folded"] > 0, (reps, kk, sc)
 
 
+def test_super_oversized_key_ranges(kc):
+    """Skew in key space: thousands of distinct k-mers share their leading bases (reads that start
+    with the same 45 bases and then differ), so some sub-buckets of the placement exceed what the
+    shared-memory sort takes. They go through the radix sorter instead -- in chunk mode, in the
+    accumulating mode, and with the folding variant forced."""
+    import torch
+    L = 100
+    rng = np.random.default_rng(11)
+    head = rng.integers(0, 4, size=45)
+    n_skew = 9000
+    body = rng.integers(0, 4, size=(n_skew, L))
+    body[:, :45] = head
+    skew = np.frombuffer(b"ACGT", dtype=np.uint8)[body].reshape(-1)
+    reads = np.concatenate([skew, oracle.gen_reads(3000, L, 40000, 0.01, 0.001, seed=12)])
+    for k in (31, 63):
+        want = oracle.process_chunk(reads, L, k)
+        for force_dup in ("0", "1"):
+            os.environ["KC_SW_FORCE_DUP"] = force_dup
+            try:
+                with _counter(kc, k, L, method="super", cap=1 << 26) as c:
+                    got = c.process_chunk(reads)
+                    st, sc = c.stats(), c.debug_scalars()
+                assert got == want, (k, force_dup, sc)
+                assert st["method_used"] == "super" and sc["big_ranges"] > 0, (k, force_dup, sc)
+                with kc.Counter(k, L, method="super") as c:
+                    c.accum_begin(len(reads) // L)
+                    d = torch.from_numpy(reads.copy()).cuda()
+                    c.accum_add_device(d.data_ptr(), len(reads))
+                    run = c.accum_flush()
+                    sc = c.debug_scalars()
+                    assert run.to_bytes() == want, (k, force_dup, "accumulate", sc)
+                    assert sc["big_ranges"] > 0
+                    run.free()
+            finally:
+                os.environ["KC_SW_FORCE_DUP"] = "0"
+
+
 def test_super_accumulate_many_chunks_one_count(kc):
     """kc_accum_*: chunks are only packed into super-window records; one count at the end gives the
     artefact of counting the chunks separately and merging (KMerFileMerger). Also with a plan that
