@@ -75,6 +75,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--occ", type=int, default=0, help="k-mer occurrences per minimizer bin (0 = library default)")
+    ap.add_argument("--bench", default="count", choices=["count", "merge"],
+                    help="merge: time kc_merge_runs (GPU KMerFileMerger) over --runs runs of --reads reads each")
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config or "c2"])
     for key in ("reads", "k", "genome", "sub_rate", "n_rate", "seed", "zipf_loci", "runs"):
@@ -674,8 +676,85 @@ def run_e2e(job, a, distinct, kmers_step, barrier, numa):
     return out
 
 
+def run_merge_bench(a):
+    """kc_merge_runs (merge path, KMerFileMerger.cpp:49-135) over `runs` sorted unique runs, each the count of
+    `reads` reads of the workload (consecutive read ranges, so the runs overlap like chunks of one input do).
+    Algorithmic bytes per pairwise merge: S*(nA + nB) in, S*U out; a tree of log2(runs) levels."""
+    import torch
+    import kmer_counter_b200 as kc
+    from kmer_counter_b200 import synth
+    import oracle
+    c, L = a.cfg, a.read_len
+    k, R, runs = c["k"], c["reads"], max(2, c["runs"])
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev, priority=-1)
+    torch.cuda.set_stream(stream)
+    counter = kc.Counter(k, L, device=0, method=a.method, stream=stream.cuda_stream)
+    S = counter.record_size
+    parts = []
+    d = torch.empty(R * L + 256, dtype=torch.uint8, device=dev)
+    for i in range(runs):
+        synth.synth_reads_device(d.data_ptr(), R, L, c["genome"], c["sub_rate"], c["n_rate"], c["seed"], first_read=i * R,
+                                 zipf_loci=c["zipf_loci"], stream=stream.cuda_stream)
+        parts.append(counter.count_device(d.data_ptr(), R * L))
+    del d
+    n_in = sum(len(p) for p in parts)
+    # parity on a small instance of the same shape: merge of the runs of 4 x 20k reads against the oracle's merger
+    small = [oracle.gen_reads(20000, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], first_read=i * 20000) for i in range(4)]
+    sruns = [counter.upload_run(oracle.process_chunk(x, L, k)) for x in small]
+    mg = counter.merge(sruns)
+    import numpy as np
+    want = oracle.count(np.concatenate(small), L, k, chunk_reads=20000)
+    ok = mg.to_bytes() == want
+    mg.free()
+    for r in sruns:
+        r.free()
+    if not ok:
+        sys.stderr.write("bench.py: merge PARITY FAILED\n")
+        sys.exit(3)
+    for _ in range(a.warmup):
+        counter.merge(parts).free()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clk:
+        ev0.record(stream)
+        for _ in range(a.steps):
+            m = counter.merge(parts)
+            U = len(m)
+            m.free()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / a.steps
+    peak, peak_src = measured_peak_gbs()
+    # bytes of the tree: every level reads its inputs and writes its outputs once
+    sizes, tree_bytes = [len(p) for p in parts], 0
+    # (upper bound on the intermediate sizes: what the final level reads is at least U; use measured sizes of the first level
+    #  and U for the last when runs == 2)
+    if runs == 2:
+        tree_bytes = S * (n_in + U)
+    line = {"bench": "merge", "metric": "records merged/s (kc_merge_runs: merge path summing counts)", "unit": "records/s",
+            "value": n_in / (ms * 1e-3), "ms_per_merge": ms, "runs": runs, "records_in": n_in, "records_out": U,
+            "record_bytes": S, "steps": a.steps, "warmup": a.warmup, "parity": {"checked": True, "ok": True,
+            "what": "4 runs of 20k reads merged on the GPU == oracle.count of the 80k reads"},
+            "config": workload(a, 1, "merge"), "clocks": clk.summary()}
+    if runs == 2:
+        ach = tree_bytes / (ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "merge_tile_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "bytes_per_launch": tree_bytes, "definition": "S*(nA+nB) read + S*U written over the "
+                            "device time of kc_merge_runs (partition + tile kernels, allocation and the count read-back included)",
+                            "peak_source": peak_src + " HBM copy bandwidth (MEASURED_PEAKS.json)"}
+    print(json.dumps(line), flush=True)
+    for p in parts:
+        p.free()
+    counter.close()
+
+
 def main():
     a = parse_args()
+    if a.bench == "merge" and a.impl == "ours":
+        run_merge_bench(a)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

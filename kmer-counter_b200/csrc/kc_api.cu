@@ -1979,40 +1979,67 @@ int kc_merge_runs(kc_ctx *c, kc_run *const *runs, uint32_t n, kc_run **out) {
             // a range too large for a shared-memory table (or too many records): the tree handles anything
         }
     }
+    // Pairwise tree. The pairs of a level are queued back to back (each with its own output, sized for
+    // the no-overlap case, and its own record counter); the host reads the counters once per group of
+    // pairs instead of once per pair. A group closes early when its outputs would take more than a
+    // third of the free device memory.
+    const uint32_t max_pairs = (uint32_t)(level.size() / 2 + 1);
     unsigned long long *d_num = nullptr;
-    KC_TRY(dev_alloc(c, s, 8, (void **)&d_num));
+    KC_TRY(dev_alloc(c, s, 8ull * max_pairs, (void **)&d_num));
+    std::vector<unsigned long long> h_num(max_pairs, 0);
     int rc = KC_OK;
     int launches = 0;
+    const bool trace = getenv("KC_TRACE") != nullptr;
     while (level.size() > 1 && rc == KC_OK) {
         std::vector<kc_run *> next;
         std::vector<bool> next_owned;
-        for (size_t i = 0; i + 1 < level.size() && rc == KC_OK; i += 2) {
-            kc_run *a = level[i], *b = level[i + 1];
-            const uint64_t na = a->n - a->skip, nb = b->n - b->skip;
-            kc_run *m = nullptr;
-            rc = make_run(c, s, na + nb, &m);
-            if (rc != KC_OK) break;
-            void *ws = nullptr;
-            rc = dev_alloc(c, s, merge_workspace_bytes(na, nb), &ws);
-            if (rc != KC_OK) { kc_run_free(c, m); break; }
-            cudaError_t e = merge_pair(a->d_keys + a->skip * a->W, a->d_counts + a->skip, na,
-                                       b->d_keys + b->skip * b->W, b->d_counts + b->skip, nb, c->W, m->d_keys,
-                                       m->d_counts, d_num, ws, s, &launches);
-            unsigned long long U = 0;
-            if (e == cudaSuccess) e = cudaMemcpyAsync(&U, d_num, 8, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            dev_free(s, ws);
-            if (e != cudaSuccess) {
-                kc_run_free(c, m);
-                rc = c->set_error(KC_ERR_CUDA, "merge failed: %s", cudaGetErrorString(e));
-                break;
+        struct timespec t0;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        uint64_t level_records = 0;
+        size_t i = 0;
+        while (i + 1 < level.size() && rc == KC_OK) {
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            const uint64_t budget = fr / 3;
+            uint64_t group_bytes = 0;
+            std::vector<void *> group_ws;
+            const size_t g0 = i, n0 = next.size();
+            while (i + 1 < level.size()) {
+                kc_run *a = level[i], *b = level[i + 1];
+                const uint64_t na = a->n - a->skip, nb = b->n - b->skip;
+                const uint64_t bytes = (na + nb) * (8ull * c->W + 4);
+                if (i > g0 && group_bytes + bytes > budget) break;
+                kc_run *m = nullptr;
+                rc = make_run(c, s, na + nb, &m);
+                if (rc != KC_OK) break;
+                void *ws = nullptr;
+                rc = dev_alloc(c, s, merge_workspace_bytes(na, nb), &ws);
+                if (rc != KC_OK) { kc_run_free(c, m); break; }
+                group_ws.push_back(ws);
+                next.push_back(m);
+                next_owned.push_back(true);
+                cudaError_t e = merge_pair(a->d_keys + a->skip * a->W, a->d_counts + a->skip, na,
+                                           b->d_keys + b->skip * b->W, b->d_counts + b->skip, nb, c->W, m->d_keys,
+                                           m->d_counts, d_num + (next.size() - 1 - n0), ws, s, &launches);
+                if (e != cudaSuccess) { rc = c->set_error(KC_ERR_CUDA, "merge failed: %s", cudaGetErrorString(e)); break; }
+                group_bytes += bytes;
+                level_records += na + nb;
+                i += 2;
             }
-            m->n = U;
-            if (owned[i]) kc_run_free(c, a);
-            if (owned[i + 1]) kc_run_free(c, b);
-            owned[i] = owned[i + 1] = false;
-            next.push_back(m);
-            next_owned.push_back(true);
+            const size_t n_pairs = next.size() - n0;
+            cudaError_t e = cudaSuccess;
+            if (rc == KC_OK && n_pairs) e = cudaMemcpyAsync(h_num.data(), d_num, 8 * n_pairs, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            for (void *w : group_ws) dev_free(s, w);
+            if (rc == KC_OK && e != cudaSuccess) rc = c->set_error(KC_ERR_CUDA, "merge failed: %s", cudaGetErrorString(e));
+            if (rc != KC_OK) break;
+            for (size_t q = 0; q < n_pairs; q++) {
+                next[n0 + q]->n = h_num[q];
+                const size_t ia = g0 + 2 * q;
+                if (owned[ia]) kc_run_free(c, level[ia]);
+                if (owned[ia + 1]) kc_run_free(c, level[ia + 1]);
+                owned[ia] = owned[ia + 1] = false;
+            }
         }
         if (rc == KC_OK && (level.size() & 1)) {
             next.push_back(level.back());
@@ -2020,11 +2047,18 @@ int kc_merge_runs(kc_ctx *c, kc_run *const *runs, uint32_t n, kc_run **out) {
             owned.back() = false;
         }
         if (rc != KC_OK) {
-            for (size_t i = 0; i < next.size(); i++)
-                if (next_owned[i]) kc_run_free(c, next[i]);
-            for (size_t i = 0; i < level.size(); i++)
-                if (owned[i]) kc_run_free(c, level[i]);
+            cudaStreamSynchronize(s);
+            for (size_t q = 0; q < next.size(); q++)
+                if (next_owned[q]) kc_run_free(c, next[q]);
+            for (size_t q = 0; q < level.size(); q++)
+                if (owned[q]) kc_run_free(c, level[q]);
             break;
+        }
+        if (trace) {
+            struct timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "kc_merge_runs: level of %zu runs, %llu records in: %.2f ms\n", level.size(), (unsigned long long)level_records,
+                    (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
         }
         level.swap(next);
         owned.swap(next_owned);

@@ -145,10 +145,19 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *status, uint32_
     st_release_u64(&status[tile], kLbAggregate | aggregate);
     uint64_t excl = 0;
     int64_t t = (int64_t)tile - 1;
+#ifdef KC_LB_WATCHDOG
+    uint32_t spins = 0;
+#endif
     while (true) {
         uint64_t s = ld_acquire_u64(&status[t]);
         uint64_t st = s & ~kLbValueMask;
-        if (st == kLbEmpty) { __nanosleep(20); continue; }
+        if (st == kLbEmpty) {
+#ifdef KC_LB_WATCHDOG
+            if (++spins > (1u << 22)) { printf("look-back: tile %u waits for tile %lld forever\n", tile, (long long)t); __trap(); }
+#endif
+            __nanosleep(20);
+            continue;
+        }
         excl += s & kLbValueMask;
         if (st == kLbInclusive) break;
         t--;
