@@ -324,9 +324,9 @@ class Job:
                                   distinct_hint=est_u if self.mode != "chunk" and per_run * self.nk > (1 << 31) else 0)
         self.exchange = None
         if self.mode == "exchange":
-            self.exchange = multigpu.Exchange(self.counter, self.dev, per_run)
+            self.exchange = multigpu.Exchange(self.counter, self.dev, per_run + 4096)
         elif self.mode == "accumulate":
-            self.counter.accum_begin(per_run)
+            self.counter.accum_begin(per_run + 4096)          # (pieces are whole multiples of 16 reads: the last one is a little longer)
         self.per_run = per_run
         self.d_reads = None
 
@@ -345,24 +345,33 @@ class Job:
             return c.count_device(ptr, n_reads * L)
         # `runs` pieces of about equal size (whole multiples of 16 reads: device pieces stay 16-byte aligned),
         # each counted into its own run; the runs are then merged on the GPU (merge path = KMerFileMerger)
+        # Merge schedule = the tiered one of host/RunMerger.h (KMerFileMergeHandler's fan-in 2): two runs of the
+        # same level are merged as soon as both exist, so at most log2(runs) runs wait at any time.
         runs = self.runs if n_reads >= 16 * self.runs else 1
         per = (n_reads // runs) // 16 * 16 if runs > 1 else n_reads
-        parts = []
+        stack = []                                   # (level, run)
         for i in range(runs):
             r0 = i * per
             nr = per if i + 1 < runs else n_reads - r0
             c.accum_add_device(ptr + r0 * L, nr * L)
-            parts.append(self.exchange.finish() if self.exchange is not None else c.accum_flush())
+            stack.append((0, self.exchange.finish() if self.exchange is not None else c.accum_flush()))
             if self.exchange is not None and runs > 1 and i == 0:
                 c.xchg_fix_ranges(True)              # every run of this count is cut at the first run's key ranges
+            while len(stack) >= 2 and stack[-1][0] == stack[-2][0]:
+                (lv, b), (_, a2) = stack.pop(), stack.pop()
+                m = c.merge([a2, b])
+                a2.free()
+                b.free()
+                stack.append((lv + 1, m))
         if self.exchange is not None and runs > 1:
             c.xchg_fix_ranges(False)
-        if len(parts) == 1:
-            return parts[0]
-        merged = c.merge(parts)
-        for p in parts:
-            p.free()
-        return merged
+        while len(stack) >= 2:                       # a run count that is not a power of two
+            (lv, b), (_, a2) = stack.pop(), stack.pop()
+            m = c.merge([a2, b])
+            a2.free()
+            b.free()
+            stack.append((lv + 1, m))
+        return stack[0][1]
 
     def step(self):
         run = self.count(self.d_reads.data_ptr(), self.R)

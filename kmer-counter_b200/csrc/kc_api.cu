@@ -247,6 +247,20 @@ void pending_release(cudaStream_t, Pending &p) {
     p.active = false;
 }
 
+// KC_TRACE=1: wall-clock milestones of the accumulating flush on stderr (development aid)
+struct Trace {
+    bool on;
+    struct timespec t0;
+    Trace() : on(getenv("KC_TRACE") != nullptr) { if (on) clock_gettime(CLOCK_MONOTONIC, &t0); }
+    void mark(const char *what) {
+        if (!on) return;
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "kc trace: %-28s %9.3f ms\n", what, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+        t0 = t1;
+    }
+};
+
 // KC_SW_FORCE_DUP=1 (test knob, read at every count): the super-window path always takes its folding variant
 bool env_force_dup() {
     const char *v = getenv("KC_SW_FORCE_DUP");
@@ -884,7 +898,9 @@ int accum_count(kc_ctx *c, kc_run **out) {
     for (auto &sl : c->slots)
         if (sl.stream) KC_CUDA_TRY(c, cudaStreamSynchronize(sl.stream));
     if (a.fresh) return make_run(c, s, 0, out);
+    Trace tr;
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[0], s));
+    if (tr.on) { cudaStreamSynchronize(s); tr.mark("flush: S1 drained"); }
     if (!a.pl.ext_e) {
         KC_CUDA_TRY(c, super_count(a.pl, !c->strict, a.ws, a.d_sc, c->n_sms, s, &a.ev[1]));
         return accum_finish(c, false, out);
@@ -895,6 +911,7 @@ int accum_count(kc_ctx *c, kc_run **out) {
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[1], s));
     KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
     KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    tr.mark("flush: S2 count");
     if (a.h_sc[SW_FAIL])
         return c->set_error(KC_ERR_CAPACITY, "accumulated input does not fit the plan (fail bits %llu): flush more often or "
                             "raise the expected read count", (unsigned long long)a.h_sc[SW_FAIL]);
@@ -920,7 +937,12 @@ int accum_count(kc_ctx *c, kc_run **out) {
         if (pre) kc_run_free(c, pre);
         return c->set_error(KC_ERR_CUDA, "super_place: %s", cudaGetErrorString(e));
     }
+    if (tr.on) { cudaStreamSynchronize(s); tr.mark("flush: alloc + S3a/H2/S3b"); }
     const int rc = accum_finish(c, dup, out, pre, true);
+    tr.mark("flush: S3c + emit + reset");
+    if (tr.on) fprintf(stderr, "kc trace: records D %llu, overflow %llu, big ranges %llu (%llu records), aborts %llu, dup %d\n",
+                       (unsigned long long)c->last_scal[SW_D], (unsigned long long)c->last_scal[SW_OVF], (unsigned long long)c->last_scal[SW_BIG],
+                       (unsigned long long)c->last_scal[SW_BIG_RECORDS], (unsigned long long)c->last_scal[SW_ABORTS], (int)dup);
     accum_detach_e(c, s, pre);
     if (rc != KC_OK && pre) kc_run_free(c, pre);
     return rc;
@@ -1034,6 +1056,44 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out, kc_run *pre_run, bool 
         st.ms_extract = st.ms_stage[0];
         st.ms_emit = st.ms_stage[5];
         st.ms_count = st.ms_total - st.ms_extract - st.ms_emit;
+    }
+    // Bins sized for the wrong redundancy cost S2 a second and third pass over most bins (too many
+    // distinct keys for the table) or many nearly empty units. Now that the bins are empty and the
+    // ratio is known, later flushes of this accumulator get bins of the right size (same workspace
+    // if it fits, a larger one otherwise). Not with an explicit table_slots, not in exchange mode
+    // (the ranks must plan alike).
+    if (!a.xchg && c->cfg.table_slots == 0 && a.windows > (1u << 20) && r && r->n) {
+        const double per_key = (double)a.windows / (double)r->n;
+        double occ = 2200.0 * per_key;
+        occ = occ > 8192.0 ? 8192.0 : (occ < 1024.0 ? 1024.0 : occ);
+        const uint32_t want = ((uint32_t)occ + 255u) & ~255u;
+        const uint32_t have = (uint32_t)((a.max_windows + a.pl.n_bins - 1) / a.pl.n_bins);
+        if (want < have * 0.75 || want > have * 1.5) {
+            SuperPlan np;
+            if (super_plan(c->cfg.k, c->cfg.read_len, c->strict, a.max_windows, want, &np, 0.0, c->cfg.distinct_hint, true)) {
+                bool ok = true;
+                if (np.ws_bytes > a.ws_bytes) {
+                    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+                    void *nw = nullptr;
+                    cudaFree(a.ws);
+                    a.ws = nullptr;
+                    a.ws_bytes = 0;
+                    if (cudaMalloc(&nw, np.ws_bytes) != cudaSuccess) {
+                        cudaGetLastError();
+                        ok = cudaMalloc(&nw, a.pl.ws_bytes) == cudaSuccess;      // back to the old plan
+                        if (!ok) { kc_run_free(c, r); return c->set_error(KC_ERR_NOMEM, "accumulator workspace of %llu bytes", (unsigned long long)a.pl.ws_bytes); }
+                        a.ws = nw;
+                        a.ws_bytes = a.pl.ws_bytes;
+                        ok = false;
+                    } else {
+                        a.ws = nw;
+                        a.ws_bytes = np.ws_bytes;
+                    }
+                }
+                if (ok) a.pl = np;
+                a.d_sc = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(a.ws) + a.pl.off_sc);
+            }
+        }
     }
     // empty bins for whatever comes next
     KC_CUDA_TRY(c, super_reset(a.pl, a.ws, a.d_sc, s));

@@ -1671,7 +1671,17 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     pl.nk = L - k + 1;
     pl.cmax = 32u * pl.W - 3;
     if (max_windows == 0) max_windows = 1;
-    if (occ_per_bin == 0) occ_per_bin = 8192;
+    if (occ_per_bin == 0) {
+        // a bin's distinct keys should fit S2's table in one pass (3072 of its 4096 slots, bins vary by
+        // ~20%): 8192 occurrences at the 5x redundancy of config 2, fewer when the caller expects
+        // fewer repeats
+        occ_per_bin = 8192;
+        if (distinct_hint && distinct_hint < max_windows) {
+            const double per_key = (double)max_windows / (double)distinct_hint;
+            const double occ = 2200.0 * per_key;
+            if (occ < 8192.0) occ_per_bin = occ < 1024.0 ? 1024u : ((uint32_t)occ + 255u) & ~255u;
+        }
+    }
     uint64_t nb = (max_windows + occ_per_bin - 1) / occ_per_bin;
     if (nb < 8) nb = 8;
     if (nb > (1ull << 24)) nb = 1ull << 24;
