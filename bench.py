@@ -502,7 +502,17 @@ def run_ours(a, rank, world, local_rank):
         pulled_d = remote * (8 * counter.words + 4)
         x = torch.tensor([float(pulled_rec + pulled_d)], dtype=torch.float64, device=dev)
         dist.all_reduce(x, op=dist.ReduceOp.MAX)
-        nvlink = {"bytes_in_per_step_per_gpu": int(x.item()), "super_window_records_bytes": int(pulled_rec),
+        # per-stage device times of the last step over the ranks (a stage ends when its kernels end on that
+        # rank: a rank that waits for a slower peer shows the wait in the stage that follows the barrier)
+        stg = torch.tensor(list(st1["ms_stage"])[:6] + [float(sc["overflow_records"] != 0), float(sc["big_ranges"])],
+                           dtype=torch.float64, device=dev)
+        smax, smin = stg.clone(), stg.clone()
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(smin, op=dist.ReduceOp.MIN)
+        nvlink = {"bytes_in_per_step_per_gpu": int(x.item()),
+                  "stage_ms_max_over_ranks": [round(v, 3) for v in smax.tolist()[:6]],
+                  "stage_ms_min_over_ranks": [round(v, 3) for v in smin.tolist()[:6]],
+                  "ranks_with_overflow_records": bool(smax.tolist()[6]), "max_oversized_ranges": int(smax.tolist()[7]), "super_window_records_bytes": int(pulled_rec),
                   "distinct_records_bytes": int(pulled_d),
                   "achieved_gbs_over_step": x.item() / (ms_per_step * 1e-3) / 1e9, "peak": 900, "measured_peer_copy": 770,
                   "note": "both exchanges are the load side of the consuming kernels (peer loads over NVLink/NVSwitch), "
