@@ -236,10 +236,40 @@ def cpu_rows(a, budget_reads=None):
     return rows, cores
 
 
+def reference_gpu_seam(a):
+    """SURVEY F10 / 8(d) "reference-on-B200": the reference's own GPUHandler.cu, compiled unmodified for
+    sm_100a (oracle/_ref/ref_gpu, built by oracle/build_ref.sh), driven like KMerCounter::dispatchWork drives
+    it: PrepareGPU once, processKMers per default-sized chunk. The host hash accumulate that follows
+    at HEAD (KMerCounter.cpp:61-82) is not in it. None when the binary is not there."""
+    import subprocess
+    import oracle
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
+    if not os.path.isfile(exe):
+        return None
+    c, L = a.cfg, a.read_len
+    n = min(c["reads"], 16 * REF_CHUNK)
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    try:
+        reads = oracle.gen_reads(n, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], zipf_loci=c["zipf_loci"])
+        with tempfile.TemporaryDirectory(dir=tmp_root) as d:
+            path = os.path.join(d, "reads.bin")
+            with open(path, "wb") as f:
+                f.write(bytes(reads))
+            r = subprocess.run([exe, path, str(L), str(c["k"]), str(REF_CHUNK)], capture_output=True, timeout=300)
+        row = json.loads(r.stderr.decode().strip().splitlines()[-1])
+    except Exception as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    return {"value": row["kmers_per_s"], "unit": UNIT, "kind": "reference GPUHandler.cu (unmodified) built for sm_100a",
+            "seconds": row["seconds"], "reads": row["reads"], "chunks": row["chunks"], "chunk_reads": REF_CHUNK,
+            "what": "PrepareGPU + processKMers per chunk (GPUHandler.cu:397-508): H2D, bitEncode, extractKMers, D2H of the "
+                    "record block, host reduceKMers; one GPUStream; the TBB accumulate of KMerCounter.cpp:61-82 is not included"}
+
+
 def cpu_baseline(a):
     rows, cores = cpu_rows(a)
     best = max(rows, key=lambda r: r["value"])
     return {"value": best["value"], "unit": UNIT, "cores": best["threads"], "host_cores": cores, "kind": best["kind"],
+            "reference_gpu_seam": reference_gpu_seam(a),
             "sample": "first %d reads (%d k-mers) of the workload in chunks of %d reads (the reference's default), %d chunk-worker "
                       "threads busy, KMerFileMerger with fan-in %d on %d merger threads; rows: 1 thread and 8+2 threads"
                       % (best["reads"], best["kmers"], REF_CHUNK, best.get("threads_busy") or best["threads"],

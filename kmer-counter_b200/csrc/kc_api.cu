@@ -967,9 +967,11 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out, kc_run *pre_run, bool 
     const bool dup = dup_known ? force_dup
                                : (env_dup || (a.xchg ? (force_dup && a.x_info.any_ovf != 0) : (force_dup || a.h_sc[SW_OVF] != 0)));
     kc_run *r = pre_run;
+    SuperPlan fpl = a.pl;                                   // exchange: the S3c variant is the device plan's choice
+    if (a.xchg && a.x_info.fin_large) super_use_large_finish(&fpl);
     if (!dup) {
         if (!r) KC_TRY(make_run(c, s, n_d, &r));
-        if (n_d) KC_CUDA_TRY(c, super_finish(a.pl, false, a.ws, a.d_sc, r->d_keys, r->d_counts, c->n_sms, s));
+        if (n_d) KC_CUDA_TRY(c, super_finish(fpl, false, a.ws, a.d_sc, r->d_keys, r->d_counts, c->n_sms, s));
         KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
         if (!a.h_sc[SW_FAIL] && a.h_sc[SW_BIG]) {
@@ -982,7 +984,7 @@ int accum_finish(kc_ctx *c, bool force_dup, kc_run **out, kc_run *pre_run, bool 
         uint64_t *tk = nullptr;
         uint32_t *tc = nullptr;
         super_tmp_buffers(a.pl, a.ws, &tk, &tc);
-        KC_CUDA_TRY(c, super_finish(a.pl, true, a.ws, a.d_sc, tk, tc, c->n_sms, s));
+        KC_CUDA_TRY(c, super_finish(fpl, true, a.ws, a.d_sc, tk, tc, c->n_sms, s));
         KC_CUDA_TRY(c, cudaMemcpyAsync(a.h_sc, a.d_sc, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
         if (!a.h_sc[SW_FAIL] && a.h_sc[SW_BIG])
@@ -1407,7 +1409,7 @@ int kc_xchg_pull(kc_ctx *c) {
     for (uint32_t i = 0; i < a.n_ranks; i++)
         if (!a.peer_ws[i]) return c->set_error(KC_ERR_STATE, "kc_xchg_pull: rank %u's workspace is not mapped (kc_xchg_import / kc_xchg_set_peer)", i);
     cudaSetDevice(c->cfg.device);
-    KC_CUDA_TRY(c, super_x_pull(a.pl, a.ws, a.d_sc, a.peer_ws, a.n_ranks, c->n_sms, c->stream));
+    KC_CUDA_TRY(c, super_x_pull(a.pl, a.ws, a.d_sc, a.peer_ws, a.rank, a.n_ranks, c->n_sms, c->stream));
     KC_CUDA_TRY(c, cudaEventRecord(a.ev[4], c->stream));
     return KC_OK;
 }

@@ -974,11 +974,12 @@ __global__ void __launch_bounds__(1024) sw_plan_kernel(const uint32_t *__restric
 // level-1 bases (the local scatter), where its key range starts and ends inside every source's
 // grouped array, and the plan of its part of the key space.
 constexpr int kXB1 = 10;                // bits of the histogram the ranks exchange
+constexpr int kXB2Max = 11;             // most level-2 bits of an exchange (2^21 sub-buckets over all ranks)
 typedef SuperXInfo XDev;
 struct XScalars { const unsigned long long *sc[8]; };
 
 __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict__ all_hist, uint32_t rank, uint32_t P,
-                                                      int keep_ranges, uint64_t d_cap, uint32_t sub_target, int sig_bits,
+                                                      int keep_ranges, uint64_t d_cap, uint32_t sub_target, int large_plan, int sig_bits,
                                                       uint32_t *__restrict__ base1, uint32_t *__restrict__ cursor1,
                                                       SuperPlanDev *__restrict__ plan, XDev *__restrict__ x,
                                                       unsigned long long *__restrict__ sc, XScalars peers) {
@@ -986,7 +987,7 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
     __shared__ unsigned long long s_scan[32];
     __shared__ uint32_t s_lo[17];
     __shared__ unsigned long long s_total, s_b, s_e;
-    __shared__ int s_b1, s_b2;
+    __shared__ int s_b1, s_b2, s_large;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // block-wide inclusive scan of 64-bit values (1024 threads)
     auto block_incl = [&](unsigned long long v) -> unsigned long long {
@@ -1014,8 +1015,11 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         // digit widths from the job's record total: B bits so that a sub-bucket holds about sub_target
         // records, level 1 as narrow as level 2's limit of 10 bits allows but not below 8 (the key
         // ranges of up to 8 ranks are cut at level-1 buckets)
+        // A job too large for 2^20 sub-buckets of sub_target records takes an 11th level-2 bit (a rank
+        // holds 1/P of the sub-buckets, so its own arrays stay within kSuperMaxSub) and, if the
+        // sub-buckets are still too large for the small S3c variant, the large one (x->fin_large).
         int B = 8;
-        while (B < kXB1 + 10 && B < sig_bits && (total >> B) > sub_target) B++;
+        while (B < kXB1 + kXB2Max && B < sig_bits && (total >> B) > sub_target) B++;
         int b1 = B - 10 > 8 ? B - 10 : 8;
         if (b1 > kXB1 || keep_ranges) b1 = kXB1;     // kept ranges may have been cut at any histogram bin
         if (b1 > sig_bits) b1 = sig_bits;
@@ -1023,7 +1027,7 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         s_b2 = B - b1 > 0 ? B - b1 : 0;
     }
     __syncthreads();
-    const int b1 = s_b1, b2 = s_b2, fold = kXB1 - b1;          // 2^fold histogram bins per level-1 bucket
+    const int b1 = s_b1, fold = kXB1 - b1;                     // 2^fold histogram bins per level-1 bucket
     // owner of histogram bin tid = owner of its level-1 bucket: where the middle of the BUCKET falls in
     // P equal shares of the total (all bins of a bucket get the same owner)
     const uint32_t bk0 = ((uint32_t)tid >> fold) << fold;      // first bin of this bin's bucket
@@ -1045,6 +1049,15 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         if (keep_ranges)                              // the ranges of the previous exchange (runs that will be merged)
             for (uint32_t o = 0; o <= P; o++) s_lo[o] = x->lo[o];
         for (uint32_t o = 0; o <= P; o++) x->lo[o] = s_lo[o];
+        // no rank may end up with more than kSuperMaxSub sub-buckets (its arrays): the widest key range decides
+        uint32_t widest = 1;
+        for (uint32_t o = 0; o < P; o++) {
+            const uint32_t wd = ((s_lo[o + 1] + (1u << fold) - 1) >> fold) - (s_lo[o] >> fold);
+            widest = wd > widest ? wd : widest;
+        }
+        while (s_b2 > 0 && ((unsigned long long)widest << s_b2) > kSuperMaxSub) s_b2--;
+        // sub-buckets beyond the small S3c variant's reach: every rank sorts with the large one
+        s_large = (large_plan || (total >> (b1 + s_b2)) > sub_target) ? 1 : 0;
     }
     __syncthreads();
     const uint32_t my_lo = s_lo[rank], my_hi = s_lo[rank + 1];      // in histogram bins (multiples of 2^fold unless kept)
@@ -1075,6 +1088,7 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         }
     }
     if (tid == 0) {
+        const int b2 = s_b2;                                   // (as settled above)
         unsigned long long nd = sc[SW_D];
         if (nd > d_cap) nd = d_cap;
         uint32_t any_ovf = 0;
@@ -1090,6 +1104,7 @@ __global__ void __launch_bounds__(1024) x_plan_kernel(const uint32_t *__restrict
         plan->prefix_bits = b1 + b2;
         x->n_recv = (uint32_t)(n_recv > 0xffffffffull ? 0xffffffffull : n_recv);
         x->any_ovf = any_ovf;
+        x->fin_large = (uint32_t)s_large;
         if (n_recv > d_cap) atomicOr(&sc[SW_FAIL], 16ull);       // this rank's share does not fit its buffers
     }
 }
@@ -1165,7 +1180,8 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
         } else {
             p0 = ((uint32_t)(in_keys[(size_t)begin * W] >> shift) >> b2) << b2;       // first sub-bucket of the first key's bucket
             const uint32_t pl = (uint32_t)(in_keys[(size_t)(end - 1) * W] >> shift);
-            nb = (pl >> b2) == (p0 >> b2) ? nb2 : 2 * nb2;                            // 2 * nb2 <= kRsBins
+            // (b2 = 11: the counters hold one bucket; the keys of a tile's second bucket are placed one by one)
+            nb = (pl >> b2) == (p0 >> b2) || 2 * nb2 > (uint32_t)kRsBins ? nb2 : 2 * nb2;
         }
         for (uint32_t i = threadIdx.x; i < nb; i += kRsThreads) cnt[i] = 0;
         __syncthreads();
@@ -1227,7 +1243,7 @@ template <int W>
 __global__ void __launch_bounds__(256) rec_hist2_kernel(const uint64_t *__restrict__ keys,
                                                         const SuperPlanDev *__restrict__ plan,
                                                         uint32_t *__restrict__ g_hist2) {
-    __shared__ uint32_t sh[kNb1Max];
+    __shared__ uint32_t sh[kRsBins];             // nb2 <= 2048 (b2 <= kXB2Max)
     const uint32_t n = plan->n_d;
     const int b2 = (int)plan->b2, shift2 = (int)plan->shift2;
     const uint32_t nb2 = 1u << b2, m2 = nb2 - 1;
@@ -1722,6 +1738,10 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     // sub-buckets of 2048 records unless the 2^20 sub-buckets two levels can cut would be too few
     pl.fin_cap = pl.d_cap > (uint64_t)kSuperMaxSub * (kFinCapSmall * 7 / 10) ? kFinCapLarge : kFinCapSmall;
     pl.sub_target = pl.fin_cap * 7 / 10;
+    if (const char *v = getenv("KC_SW_SUB_TARGET")) {       // development / test knob: forces deep level-2 plans on small inputs
+        const int t = atoi(v);
+        if (t > 0) pl.sub_target = (uint32_t)t;
+    }
     const int sig = pl.W == 1 ? (masked ? (int)(2 * mm) : 64) : 64;
     pl.b1 = sig < 10 ? sig : 10;
     // workspace
@@ -1730,7 +1750,7 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     const uint64_t rec_bytes = 16ull * pl.W;
     pl.off_cursor = take((uint64_t)pl.n_bins * 4);
     pl.off_hist1 = take((kNb1Max + 8) * 4);
-    pl.off_hist2 = take((uint64_t)(kSuperMaxSub + 8) * 4);
+    pl.off_hist2 = take((uint64_t)(2 * kSuperMaxSub + 8) * 4);          // exchange: sub-buckets of ALL ranks (up to 2^21)
     pl.off_base1 = take((kNb1Max + 8) * 4);
     pl.off_cur1 = take((kNb1Max + 8) * 4);
     pl.off_base2 = take((uint64_t)(kSuperMaxSub + 8) * 4);
@@ -2040,6 +2060,8 @@ cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys
 
 bool super_supported(const SuperPlan &pl) { return super_scatter_fits(pl); }
 
+void super_use_large_finish(SuperPlan *pl) { pl->fin_cap = kFinCapLarge; }
+
 // ---- multi-GPU exchange (see x_plan_kernel). Every rank's workspace has the same layout, so a
 // peer's buffers are found from its workspace base.
 template <int W>
@@ -2054,7 +2076,8 @@ static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long 
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
     XScalars xs{};
     for (uint32_t i = 0; i < n_ranks; i++) xs.sc[i] = peer_ws ? at<unsigned long long>(peer_ws[i], pl.off_sc) : d_sc;
-    x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, keep_ranges ? 1 : 0, pl.d_cap, pl.sub_target, sig, at<uint32_t>(ws, pl.off_base1),
+    x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, keep_ranges ? 1 : 0, pl.d_cap, pl.sub_target,
+                                     pl.fin_cap == kFinCapLarge ? 1 : 0, sig, at<uint32_t>(ws, pl.off_base1),
                                      at<uint32_t>(ws, pl.off_cur1), plan, at<XDev>(ws, pl.off_x), d_sc, xs);
     const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
     auto k1 = rec_scatter_kernel<W, 1>;
@@ -2078,7 +2101,7 @@ cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_s
 
 template <int W>
 static cudaError_t super_x_pull_w(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws,
-                                  uint32_t n_ranks, int n_sms, cudaStream_t s) {
+                                  uint32_t rank, uint32_t n_ranks, int n_sms, cudaStream_t s) {
     cudaError_t e;
     SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
     XDev *x = at<XDev>(ws, pl.off_x);
@@ -2098,19 +2121,24 @@ static cudaError_t super_x_pull_w(const SuperPlan &pl, void *ws, unsigned long l
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, kRsThreads, rs_smem);
     if (per_sm < 1) per_sm = 1;
     // the level-2 scatter reads this rank's key range straight out of every source's grouped array:
-    // the exchange happens inside the kernel's loads (NVLink / NVSwitch for the peers)
-    for (uint32_t i = 0; i < n_ranks; i++)
+    // the exchange happens inside the kernel's loads (NVLink / NVSwitch for the peers). Rank r starts
+    // with source r + 1 and ends with its own records: at any time every source is read by one peer,
+    // not by all of them (the ranks enter this step together), so no GPU's outgoing links are the
+    // bottleneck of a round while the others idle.
+    for (uint32_t j = 1; j <= n_ranks; j++) {
+        const uint32_t i = (rank + j) % n_ranks;
         k2<<<(uint32_t)n_sms * per_sm, kRsThreads, rs_smem, s>>>(peers.keys[i], peers.counts[i], at<uint64_t>(ws, pl.off_dk),
                                                                 at<uint32_t>(ws, pl.off_dc), plan, pl.b1, &d_sc[SW_D],
                                                                 pl.d_cap, cur2, &x->src_range[i][0]);
+    }
     return cudaGetLastError();
 }
 
-cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t n_ranks,
-                         int n_sms, cudaStream_t s) {
-    if (n_ranks == 0 || n_ranks > 8) return cudaErrorInvalidValue;
-    if (pl.W == 1) return super_x_pull_w<1>(pl, ws, d_sc, peer_ws, n_ranks, n_sms, s);
-    if (pl.W == 2) return super_x_pull_w<2>(pl, ws, d_sc, peer_ws, n_ranks, n_sms, s);
+cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t rank,
+                         uint32_t n_ranks, int n_sms, cudaStream_t s) {
+    if (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks) return cudaErrorInvalidValue;
+    if (pl.W == 1) return super_x_pull_w<1>(pl, ws, d_sc, peer_ws, rank, n_ranks, n_sms, s);
+    if (pl.W == 2) return super_x_pull_w<2>(pl, ws, d_sc, peer_ws, rank, n_ranks, n_sms, s);
     return cudaErrorInvalidValue;
 }
 

@@ -58,7 +58,8 @@ struct SuperXInfo {             // multi-GPU exchange: what the device plan deci
     uint32_t src_range[8][2];   // records of this rank's key range inside rank s's grouped array
     uint32_t n_recv;            // records this rank pulls (its own included)
     uint32_t any_ovf;           // some rank's overflow list is in use: records may repeat across ranks
-    uint32_t pad[2];
+    uint32_t fin_large;         // the job's sub-buckets need S3c's large variant (more than 2^21 x sub_target records)
+    uint32_t pad[1];
 };
 
 struct SuperPlan {
@@ -141,8 +142,11 @@ cudaError_t super_x_local(const SuperPlan &pl, void *ws, unsigned long long *d_s
                           uint32_t rank, uint32_t n_ranks, bool keep_ranges, void *const *peer_ws, int n_sms, cudaStream_t s);
 // ... and, once every rank has done that, pulls its key range out of every rank's grouped array
 // (peer_ws[i] = rank i's workspace as mapped here) into sub-buckets. Then super_finish(dup = true).
-cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t n_ranks,
-                         int n_sms, cudaStream_t s);
+cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc, void *const *peer_ws, uint32_t rank,
+                         uint32_t n_ranks, int n_sms, cudaStream_t s);
+// exchange: the device plan found the job's sub-buckets too large for the small S3c variant
+// (SuperXInfo::fin_large); super_finish of a plan changed by this sorts with the large one
+void super_use_large_finish(SuperPlan *pl);
 // false when S1's shared-memory tile cannot hold 16 reads of this length
 bool super_supported(const SuperPlan &pl);
 // where S3c's temporary output may live in DUP mode (the level-1 buffer is dead by then)

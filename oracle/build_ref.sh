@@ -31,3 +31,9 @@ CXXFLAGS="-O2 -std=c++11 -w -fPIC -I$REF -I$TMP"
 g++ $CXXFLAGS -shared -o "$OUT/libkc_ref.so" $SRCS -lpthread
 g++ $CXXFLAGS -DREF_MAIN -o "$OUT/ref_count" $SRCS -lpthread
 echo "build_ref: built $OUT/libkc_ref.so and $OUT/ref_count from $REF"
+# The reference's GPU seam, unmodified, for sm_100a: GPUHandler.cu + FileDump.cpp + FASTQData.cpp + our driver.
+if command -v nvcc >/dev/null 2>&1; then
+    nvcc -gencode arch=compute_100a,code=sm_100a -O2 -w -I"$REF" -o "$OUT/ref_gpu" \
+        "$HERE/ref_gpu_driver.cpp" "$REF/GPUHandler.cu" "$REF/FileDump.cpp" "$REF/FASTQData.cpp"
+    echo "build_ref: built $OUT/ref_gpu (reference GPUHandler.cu for sm_100a)"
+fi

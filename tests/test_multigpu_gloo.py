@@ -160,16 +160,19 @@ def test_multi_gpu_count_matches_oracle(k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("P,R,L,k,G,e,n", [
-    (2, 20000, 100, 31, 100000, 0.01, 0.002),
-    (4, 30000, 100, 31, 50000, 0.01, 0.001),
-    (8, 40000, 100, 31, 0, 0.0, 0.0),          # iid reads: every record distinct, nothing to fold
-    (3, 9000, 100, 63, 40000, 0.001, 0.001),   # 128-bit keys, a rank count that is no power of two
-    (8, 800, 100, 31, 3000, 0.0, 0.01),        # tiny shards: ranks with few or no buckets
-    (4, 12000, 70, 28, 30000, 0.01, 0.001),    # masked tail
-    (5, 7, 100, 31, 0, 0.0, 0.0),              # fewer reads than ranks
+@pytest.mark.parametrize("P,R,L,k,G,e,n,sub_target", [
+    (2, 20000, 100, 31, 100000, 0.01, 0.002, 0),
+    (4, 30000, 100, 31, 50000, 0.01, 0.001, 0),
+    (8, 40000, 100, 31, 0, 0.0, 0.0, 0),          # iid reads: every record distinct, nothing to fold
+    (3, 9000, 100, 63, 40000, 0.001, 0.001, 0),   # 128-bit keys, a rank count that is no power of two
+    (8, 800, 100, 31, 3000, 0.0, 0.01, 0),        # tiny shards: ranks with few or no buckets
+    (4, 12000, 70, 28, 30000, 0.01, 0.001, 0),    # masked tail
+    (5, 7, 100, 31, 0, 0.0, 0.0, 0),              # fewer reads than ranks
+    (2, 40000, 100, 31, 0, 0.0, 0.0, 1),       # 11-bit level 2 (a job of > 2^20 x 1433 records): 2^20 sub-buckets per rank
+    (4, 80000, 100, 31, 0, 0.0, 0.0, 1),       # ... whose sub-buckets exceed the target: S3c's large variant, chosen on the device
+    (3, 30000, 100, 63, 0, 0.0, 0.001, 1),     # ... 128-bit keys
 ])
-def test_exchange_all_ranks_on_one_device(P, R, L, k, G, e, n):
+def test_exchange_all_ranks_on_one_device(monkeypatch, P, R, L, k, G, e, n, sub_target):
     """The multi-GPU exchange with all P ranks as contexts of this process on device 0
     (kc_xchg_run_all: nothing waits inside a kernel, ordering is by events). Rank r must end with
     the r-th key range, the concatenation must be the oracle's artefact."""
@@ -180,6 +183,8 @@ def test_exchange_all_ranks_on_one_device(P, R, L, k, G, e, n):
     reads = oracle.gen_reads(R, L, G, e, n, seed=P * 1000 + k)
     want = oracle.count(reads, L, k)
     per = (R + P - 1) // P
+    if sub_target:
+        monkeypatch.setenv("KC_SW_SUB_TARGET", str(sub_target))
     cs = [kc.Counter(k, L, method="super") for _ in range(P)]
     try:
         bufs = []
