@@ -359,6 +359,18 @@ class Job:
             self.counter.accum_begin(per_run + 4096)          # (pieces are whole multiples of 16 reads: the last one is a little longer)
         self.per_run = per_run
         self.d_reads = None
+        self.acc = self.new_acc()
+
+    @staticmethod
+    def new_acc():
+        return {"dom_ms": 0.0, "dom_bytes": 0, "dom_launch": 0, "tot_ms": 0.0, "counts": 0}
+
+    def note_count(self):
+        """Stage timers of the count / flush that just finished (libkc_b200 keeps the last one's)."""
+        s, acc = self.counter.stats(), self.acc
+        acc["dom_ms"] += s["ms_dominant"]; acc["dom_bytes"] += s["dominant_bytes"]; acc["dom_launch"] += s["dominant_launches"]
+        acc["tot_ms"] += s["ms_total"]
+        acc["counts"] += 1
 
     def make_reads(self):
         from kmer_counter_b200 import synth
@@ -372,7 +384,9 @@ class Job:
         """n_reads device-resident reads at ptr through the timed path -> Run of this rank's records."""
         c, L = self.counter, self.L
         if self.mode == "chunk":
-            return c.count_device(ptr, n_reads * L)
+            run = c.count_device(ptr, n_reads * L)
+            self.note_count()
+            return run
         # `runs` pieces of about equal size (whole multiples of 16 reads: device pieces stay 16-byte aligned),
         # each counted into its own run; the runs are then merged on the GPU (merge path = KMerFileMerger)
         # Merge schedule = the tiered one of host/RunMerger.h (KMerFileMergeHandler's fan-in 2): two runs of the
@@ -385,6 +399,7 @@ class Job:
             nr = per if i + 1 < runs else n_reads - r0
             c.accum_add_device(ptr + r0 * L, nr * L)
             stack.append((0, self.exchange.finish() if self.exchange is not None else c.accum_flush()))
+            self.note_count()
             if self.exchange is not None and runs > 1 and i == 0:
                 c.xchg_fix_ranges(True)              # every run of this count is cut at the first run's key ranges
             while len(stack) >= 2 and stack[-1][0] == stack[-2][0]:
@@ -495,7 +510,7 @@ def run_ours(a, rank, world, local_rank):
         job.step()
     barrier()
     st0 = counter.stats()
-    acc = {"dom_ms": 0.0, "dom_bytes": 0, "dom_launch": 0, "tot_ms": 0.0, "stage_ms": None}
+    acc = job.acc = job.new_acc()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         ev0.record(stream)
@@ -503,9 +518,6 @@ def run_ours(a, rank, world, local_rank):
         distinct = 0
         for _ in range(a.steps):
             distinct = job.step()
-            s = counter.stats()
-            acc["dom_ms"] += s["ms_dominant"]; acc["dom_bytes"] += s["dominant_bytes"]; acc["dom_launch"] += s["dominant_launches"]
-            acc["tot_ms"] += s["ms_total"]
         ev1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -578,12 +590,13 @@ def run_ours(a, rank, world, local_rank):
         except Exception:
             pass
         b_alg = R * L + N * (Kb + 8) + U * S
-        path_ms = ms_per_step if world > 1 else (tot_ms / a.steps if tot_ms > 0 else ms_per_step)
+        # (several runs per GPU: the step also merges them -- the whole step counts)
+        path_ms = ms_per_step if world > 1 or job.runs > 1 else (tot_ms / a.steps if tot_ms > 0 else ms_per_step)
         path_ach = b_alg / (path_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64" if k <= 32 else "u128", "data": "synthetic",
+            "dtype": "u%d" % (64 * counter.words), "data": "synthetic",
             "config": dict(workload(a, world, job.mode), method=method_used,
                            exchange=None if world == 1 else
                            "fused into the consuming kernels: the per-bin count loads every rank's super-window records of its bins, "
@@ -601,12 +614,14 @@ def run_ours(a, rank, world, local_rank):
                          "peak_source": peak_src + " HBM copy bandwidth (MEASURED_PEAKS.json)",
                          "bytes_per_launch": survey_bytes / max(dom_launch, 1), "launches_per_step": dom_launch / a.steps,
                          "ms_per_launch": dom_ms / max(dom_launch, 1),
-                         "share_of_step": dom_ms / tot_ms if tot_ms else None, "traffic": traffic,
+                         "share_of_step": dom_ms / (path_ms * a.steps) if path_ms else None, "traffic": traffic,
                          "traffic_source": traffic_src},
             "path_roofline": {"bound": "hbm", "b_alg_bytes": b_alg, "achieved": path_ach, "peak": peak, "unit": "GB/s",
                               "frac": path_ach / peak if peak else None, "ms": path_ms,
                               "definition": "SURVEY 8(d): B_in + N*(Kb+8) + U*S per GPU over the step time (device time of the "
                                             "counting path on one GPU; the whole step, exchange included, for N > 1)"},
+            "counts_per_step": acc["counts"] / a.steps,
+            "merge_ms_per_step": (ms_per_step - tot_ms / a.steps) if job.runs > 1 and world == 1 else None,
             "stages_last_step": {n: round(m, 4) for n, m in zip(names, st1["ms_stage"])},
             "stage_hbm_io_bytes_last_step": {n: int(b) for n, b in zip(names, st1["stage_bytes"])},
             "nvlink": nvlink,
@@ -671,25 +686,25 @@ def run_e2e(job, a, distinct, kmers_step, barrier, numa):
     barrier()
     single_ms = (time.perf_counter() - t0) / a.steps * 1e3
     parts_ms = {kx: v / a.steps * 1e3 for kx, v in parts.items()}
-    e2e_dt = single_ms * 1e-3
-    timing = "wall clock around K steps, one at a time (kc_accum_submit -> exchange -> kc_run_copy_records), sync on both sides, max over ranks"
+    # (2) the reported number: the same K steps pipelined, which is how the API is meant to be driven: the
+    # records are read back by a consumer thread (kc_run_copy_records on its own stream) while the producer
+    # is already submitting the next step.
+    todo, res = queue.Queue(maxsize=1), {"nb": 0, "err": None}
+
+    def reader():
+        while True:
+            run = todo.get()
+            if run is None:
+                return
+            try:
+                res["nb"] = run.copy_into(pinned_out.ctypes.data, out_cap)
+                run.free()
+            except Exception as e:
+                res["err"] = e
+
     if world == 1:
-        # (2) the reported number: the same K steps pipelined over the pinned slots, which is how the API is
-        # meant to be driven (kc_submit / kc_wait from the producer, the records read back by a consumer
-        # thread): H2D of step i, the kernels of step i-1 and the records D2H of step i-2 overlap.
-        todo, res = queue.Queue(maxsize=1), {"nb": 0, "err": None}
-
-        def reader():
-            while True:
-                run = todo.get()
-                if run is None:
-                    return
-                try:
-                    res["nb"] = run.copy_into(pinned_out.ctypes.data, out_cap)
-                    run.free()
-                except Exception as e:
-                    res["err"] = e
-
+        # kc_submit / kc_wait over the pinned slots: H2D of step i, the kernels of step i-1 and the records
+        # D2H of step i-2 overlap
         def pipelined(n_steps):
             th = threading.Thread(target=reader, daemon=True)
             th.start()
@@ -703,15 +718,33 @@ def run_e2e(job, a, distinct, kmers_step, barrier, numa):
             if res["err"] is not None:
                 raise res["err"]
 
-        pipelined(max(a.warmup, 2 * E2E_SLOTS))
-        barrier()
-        t0 = time.perf_counter()
-        pipelined(a.steps)
-        d2h = res["nb"]
-        barrier()
-        e2e_dt = (time.perf_counter() - t0) / a.steps
         timing = ("wall clock around K steps pipelined over %d pinned slots (kc_submit/kc_wait, records read back by a consumer "
                   "thread), sync on both sides; every step copies its reads H2D and its records D2H" % E2E_SLOTS)
+    else:
+        # exchange: the bins are shared by the ranks, so step i+1's reads are submitted once step i's exchange
+        # has returned (every peer has read this rank's bins by then); the records D2H of step i overlaps the
+        # H2D and the kernels of step i+1
+        def pipelined(n_steps):
+            th = threading.Thread(target=reader, daemon=True)
+            th.start()
+            for i in range(n_steps):
+                counter.accum_submit(i % E2E_SLOTS, n_bytes)
+                todo.put(job.exchange.finish())
+            todo.put(None)
+            th.join()
+            if res["err"] is not None:
+                raise res["err"]
+
+        timing = ("wall clock around K steps (kc_accum_submit -> exchange over NVLink -> kc_run_copy_records by a consumer thread: "
+                  "the records D2H of step i overlaps step i+1), sync on both sides, max over ranks; every step copies its reads "
+                  "H2D and its records D2H")
+    pipelined(max(a.warmup, 2 * E2E_SLOTS))
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(a.steps)
+    d2h = res["nb"]
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / a.steps
     t = torch.tensor([e2e_dt, single_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1688,6 +1688,7 @@ uint64_t kc_run_records(const kc_run *r) { return r ? r->n - r->skip : 0; }
 int kc_run_free(kc_ctx *c, kc_run *r) {
     KC_TRY(check_ctx(c));
     if (!r) return KC_OK;
+    cudaSetDevice(c->cfg.device);              // (may be called from a consumer thread that never touched the device)
     if (!r->placed) {
         dev_free(c->stream, r->d_keys);
         dev_free(c->stream, r->d_counts);
