@@ -166,6 +166,38 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *status, uint32_
     return excl;
 }
 
+// The same, called by ALL 32 lanes of one warp: a window of 32 predecessors is read per round
+// instead of one status word (a tile whose predecessors have only published their aggregates
+// walks back 32 at a time, not one L2 round trip each). Every lane returns the exclusive prefix.
+__device__ __forceinline__ uint64_t lookback_exclusive_warp(uint64_t *status, uint32_t tile, uint64_t aggregate) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st_release_u64(&status[0], kLbInclusive | aggregate);
+        return 0;
+    }
+    if (lane == 0) st_release_u64(&status[tile], kLbAggregate | aggregate);
+    uint64_t excl = 0;
+    int64_t base = (int64_t)tile - 1;
+    while (true) {
+        const int64_t t = base - (int64_t)lane;
+        const uint64_t s = t >= 0 ? ld_acquire_u64(&status[t]) : kLbInclusive;      // before tile 0: inclusive, 0
+        const uint64_t st = s & ~kLbValueMask;
+        const uint32_t inc = __ballot_sync(0xffffffffu, st == kLbInclusive);
+        const uint32_t emp = __ballot_sync(0xffffffffu, st == kLbEmpty);
+        const uint32_t fi = inc ? (uint32_t)__ffs(inc) - 1 : 32u;                    // nearest predecessor with an inclusive value
+        const uint32_t need = fi < 31 ? (2u << fi) - 1u : 0xffffffffu;               // lanes 0 .. fi
+        if (emp & need) { __nanosleep(20); continue; }
+        uint64_t v = lane <= fi ? (s & kLbValueMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (fi < 32) break;
+        base -= 32;
+    }
+    if (lane == 0) st_release_u64(&status[tile], kLbInclusive | (excl + aggregate));
+    return excl;
+}
+
 // ------------------------------------------------------- TMA bulk copy + mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

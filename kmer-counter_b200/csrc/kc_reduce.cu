@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kRleThreads) rle_kernel(const uint64_t *__rest
             if (c0 + lane < kRleItems * WARPS) s_cnt[c0 + lane] = total + incl - v;
             total += __shfl_sync(0xffffffffu, incl, 31);
         }
+        const uint64_t excl = lookback_exclusive_warp(status, tile, total);      // (32 predecessors per round)
         if (lane == 0) {
-            uint64_t excl = lookback_exclusive(status, tile, total);
             s_base = excl;
             if (base + kRleTile >= n) {          // the tile holding the last key closes the run list
                 const uint64_t u = excl + total;
