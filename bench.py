@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "k-mers counted/s at k=31"
+METRIC = "k-mers counted/s at k=31"          # BASELINE.json's metric; a line run with another k says so (metric_for)
 UNIT = "kmers/s"
 REF_CHUNK = 89364           # reads per chunk at the reference's defaults (KMerCounter.cpp:193-212)
 
@@ -79,10 +79,14 @@ def parse_args():
                     help="merge: time kc_merge_runs (GPU KMerFileMerger) over --runs runs of --reads reads each")
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config or "c2"])
+    changed = []
     for key in ("reads", "k", "genome", "sub_rate", "n_rate", "seed", "zipf_loci", "runs"):
         v = getattr(a, key)
-        if v is not None:
+        if v is not None and v != cfg[key]:
             cfg[key] = v
+            changed.append("%s=%s" % (key, v))
+    if changed:                                     # not a BASELINE configuration any more: say so in the workload name
+        cfg["name"] = "%s-shaped synthetic reads with %s (k=%d)" % ((a.config or "c2"), ", ".join(changed), cfg["k"])
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg["scaled_out"] = False
     if a.config is None and world > 1 and a.genome is None:
@@ -97,6 +101,10 @@ def parse_args():
 
 
 E2E_SLOTS = 2           # pinned input slots of the end-to-end pipeline (chunks whose H2D / kernels are in flight)
+
+
+def metric_for(k):
+    return METRIC if k == 31 else "k-mers counted/s at k=%d" % k
 
 
 def workload(a, world, mode=None):
@@ -300,7 +308,7 @@ def run_reference(a, rank):
     dt = sum(r["seconds"] for r in rows) / len(rows)
     kmers = sample * (L - c["k"] + 1)
     val = kmers / dt
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+    line = {"metric": metric_for(c["k"]), "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64" if c["k"] <= 32 else "u128", "data": "synthetic", "impl": "reference",
             "config": workload(a, max(a.gpus, 1), "reference CPU path"),
@@ -594,7 +602,7 @@ def run_ours(a, rank, world, local_rank):
         path_ms = ms_per_step if world > 1 or job.runs > 1 else (tot_ms / a.steps if tot_ms > 0 else ms_per_step)
         path_ach = b_alg / (path_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "metric": metric_for(k), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u%d" % (64 * counter.words), "data": "synthetic",
             "config": dict(workload(a, world, job.mode), method=method_used,

@@ -61,6 +61,12 @@ extern "C" {
                                      shared-memory tables, distinct records then placed in key order;
                                      k <= 64 with windows of >= 22 bases. What KC_COUNT_AUTO picks there. */
 
+#define KC_COUNT_PLACE      5u    /* one key per k-mer slot, placed by two most-significant-digit passes
+                                     into sub-buckets that are sorted and folded in shared memory:
+                                     three passes over the occurrences whatever the key width. What
+                                     KC_COUNT_AUTO picks for k > 64 (192/256-bit keys, KMerSizes.h:20-28),
+                                     where KC_COUNT_SORT needs 24..32 radix passes.            */
+
 typedef struct kc_ctx kc_ctx;
 typedef struct kc_run kc_run;
 
@@ -104,6 +110,8 @@ typedef struct kc_stats {
      *   KC_COUNT_HASH : 0 level-1 histogram, 1 extract+scatter1, 2 level-2 histogram, 3 scatter2,
      *                   4 shared-memory count+sort+write, 5 emit
      *   KC_COUNT_HASH_GLOBAL : 0 table clear, 1 extract+insert, 2 compact+sort, 3 emit
+     *   KC_COUNT_PLACE : 0 extract, 1 counts + level-1 histogram, 2 record scatter 1, 3 level-2
+     *                    histogram, 4 record scatter 2, 5 shared-memory sort + fold + write
      *   KC_COUNT_SUPER : 0 encode+minimizer+record scatter, 1 shared-memory count per bin,
      *                    2 record scatter level 1, 3 level-2 histogram, 4 record scatter level 2,
      *                    5 shared-memory sort + write                                             */

@@ -293,7 +293,8 @@ uint32_t pick_method(const kc_ctx *c) {
     uint32_t m = c->cfg.method;
     if (m == KC_COUNT_SUPER) return super_ok(c) ? KC_COUNT_SUPER : (c->W > 2 ? KC_COUNT_SORT : KC_COUNT_HASH);
     if (m == KC_COUNT_AUTO && super_ok(c)) return KC_COUNT_SUPER;
-    if (c->W > 2) return KC_COUNT_SORT;            // 192/256-bit keys: sort + run-length
+    if (m == KC_COUNT_PLACE) return KC_COUNT_PLACE;
+    if (c->W > 2) return m == KC_COUNT_AUTO ? KC_COUNT_PLACE : KC_COUNT_SORT;   // 192/256-bit keys: MSD placement + fold (auto), or sort + run-length
     if (c->W == 2) return (m == KC_COUNT_AUTO || m == KC_COUNT_HASH) ? KC_COUNT_HASH : KC_COUNT_SORT;
     // 64-bit keys: partitioned shared-memory hashing unless the key has too few significant
     // bits to partition on (tiny k); see DESIGN.md "method selection"
@@ -343,6 +344,20 @@ int count_enqueue_impl(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_by
         KC_CUDA_TRY(c, super_scatter(p.splan, d_reads, p.n_reads, c->strict, p.ws_super, p.d_scal, c->n_sms, s));
         KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));
         KC_CUDA_TRY(c, super_count(p.splan, !c->strict, p.ws_super, p.d_scal, c->n_sms, s, &p.ev[2]));
+        p.n_ev = 6;
+        p.n_passes = 1;
+        launches += 8;
+    } else if (method == KC_COUNT_PLACE) {
+        // key-placement path (kc_super.cuh): keys straight into D, then S3a..S3b; S3c folds in count_finish
+        if (!place_plan(k, c->strict, p.n_slots, &p.splan))
+            return c->set_error(KC_ERR_ARG, "unsupported shape k=%u read_len=%u", k, L);
+        KC_TRY(arena_reserve(c, p, arena_round(p.splan.ws_bytes), s));
+        p.ws_super = arena_take(p, p.splan.ws_bytes);
+        KC_CUDA_TRY(c, launch_extract_store(ep, W, place_keys(p.splan, p.ws_super), c->n_sms, s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[1], s));
+        KC_CUDA_TRY(c, place_init(p.splan, p.ws_super, p.d_scal, p.n_slots, c->n_sms, s));
+        KC_CUDA_TRY(c, cudaEventRecord(p.ev[2], s));
+        KC_CUDA_TRY(c, super_place(p.splan, p.ws_super, p.d_scal, c->n_sms, s, &p.ev[3]));
         p.n_ev = 6;
         p.n_passes = 1;
         launches += 8;
@@ -469,6 +484,8 @@ int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_hash_global(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out);
 int count_finish_super(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool *failed);
+int count_finish_place(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool *failed);
+int strict_hide_zero(kc_ctx *c, Pending &p, kc_run *r, cudaStream_t s);
 
 // Wait for the queued kernels, build the run, record stage timings.
 int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, cudaStream_t s, kc_run **out) {
@@ -492,6 +509,19 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
             KC_CUDA_TRY(c, cudaStreamSynchronize(s));
         }
     }
+    if (p.n_slots && p.method == KC_COUNT_PLACE) {
+        // a sub-bucket arrangement the path cannot take: the chunk is re-counted by sort + run-length
+        bool failed = false;
+        rc = count_finish_place(c, p, s, out, &failed);
+        if (rc != KC_OK) { pending_release(s, p); return rc; }
+        if (failed) {
+            if (*out) { kc_run_free(c, *out); *out = nullptr; }
+            pending_release(s, p);
+            used = KC_COUNT_SORT;
+            KC_TRY(count_enqueue(c, p, d_reads, n_bytes, s, used));
+            KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
+    }
     const bool overflow = p.n_slots && (used == KC_COUNT_HASH || used == KC_COUNT_HASH_GLOBAL) &&
                           p.h_scal[SC_SIDE + 1];
     if (overflow) {                               // table(s) full: redo this chunk with sort + run-length
@@ -500,7 +530,7 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
         KC_CUDA_TRY(c, cudaStreamSynchronize(s));
         used = KC_COUNT_SORT;
     }
-    if (used == KC_COUNT_SUPER && p.n_slots) rc = KC_OK;     // the run was built above
+    if ((used == KC_COUNT_SUPER || used == KC_COUNT_PLACE) && p.n_slots) rc = KC_OK;     // the run was built above
     else if (p.n_slots == 0) rc = make_run(c, s, 0, out);
     else if (used == KC_COUNT_HASH) rc = count_finish_partition(c, p, s, out);
     else if (used == KC_COUNT_HASH_GLOBAL) rc = count_finish_hash_global(c, p, s, out);
@@ -548,13 +578,21 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
             st.stage_bytes[3] = U * Kb;                                    st.stage_launches[3] = 1;   // level-2 histogram (+ scan)
             st.stage_bytes[4] = 2 * ub;                                    st.stage_launches[4] = 1;   // S3b
             st.stage_bytes[5] = 2 * ub;                                    st.stage_launches[5] = 1;   // S3c
+        } else if (used == KC_COUNT_PLACE && p.n_slots) {
+            const uint64_t N = p.n_slots, nb = N * (Kb + 4), ub = U * (Kb + 4);
+            st.stage_bytes[0] = in_bytes + Kb * N;                         st.stage_launches[0] = 1;   // extract: a key per slot
+            st.stage_bytes[1] = 8 * N + 4 * N;                             st.stage_launches[1] = 1;   // leading word in, count out
+            st.stage_bytes[2] = 2 * nb;                                    st.stage_launches[2] = 1;   // S3a (+ plan)
+            st.stage_bytes[3] = 8 * N;                                     st.stage_launches[3] = 1;   // level-2 histogram (+ scan)
+            st.stage_bytes[4] = 2 * nb;                                    st.stage_launches[4] = 1;   // S3b
+            st.stage_bytes[5] = nb + 3 * ub;                               st.stage_launches[5] = 3;   // S3c fold, offsets, gather
         } else if (used == KC_COUNT_HASH_GLOBAL && p.n_slots) {
             st.stage_bytes[0] = p.table.capacity * 16;                     st.stage_launches[0] = 1;
             st.stage_bytes[1] = in_bytes + nv * 16;                        st.stage_launches[1] = 1;   // SURVEY 8(d) terms
             st.stage_bytes[2] = p.table.capacity * 16 + U * 12 * 17;       st.stage_launches[2] = 10;
         }
         int dom = 0;
-        if (used == KC_COUNT_SUPER) {             // every stage is a kernel of the path
+        if (used == KC_COUNT_SUPER || used == KC_COUNT_PLACE) {             // every stage is a kernel of the path
             for (int i = 1; i < n_stages; i++)
                 if (st.ms_stage[i] > st.ms_stage[dom]) dom = i;
         } else {
@@ -622,6 +660,58 @@ int count_finish_super(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool
     return KC_OK;
 }
 
+// Key-placement path, after the extraction and S3a..S3b have drained: S3c sorts and folds every
+// sub-bucket into the level-1 buffer (dead by now), a scan gives the survivors' offsets, a gather
+// writes the run. Empty slots were placed as key 0 and are taken off that record's count.
+int count_finish_place(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out, bool *failed) {
+    *failed = false;
+    *out = nullptr;
+    const SuperPlan &pl = p.splan;
+    if (p.h_scal[SW_FAIL]) { *failed = true; return KC_OK; }
+    uint64_t *tk = nullptr;
+    uint32_t *tc = nullptr;
+    super_tmp_buffers(pl, p.ws_super, &tk, &tc);
+    KC_CUDA_TRY(c, super_finish(pl, true, p.ws_super, p.d_scal, tk, tc, c->n_sms, s));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (!p.h_scal[SW_FAIL] && p.h_scal[SW_BIG])
+        KC_TRY(super_finish_big(c, pl, p.ws_super, p.d_scal, true, p.h_scal[SW_BIG_RECORDS], tk, tc, s));
+    KC_CUDA_TRY(c, super_fold_offsets(pl, p.ws_super, p.d_scal, s));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(p.h_scal, p.d_scal, SC_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    memcpy(c->last_scal, p.h_scal, sizeof c->last_scal);
+    if (p.h_scal[SW_FAIL]) { *failed = true; return KC_OK; }
+    kc_run *r = nullptr;
+    KC_TRY(make_run(c, s, p.h_scal[SW_OUT], &r));
+    if (r->n) {
+        KC_CUDA_TRY(c, super_gather(pl, p.ws_super, tk, tc, r->d_keys, r->d_counts, c->n_sms, s));
+        if (p.h_scal[SC_INVALID])
+            KC_CUDA_TRY(c, place_fix_zero(c->W, r->d_keys, r->d_counts, &p.d_scal[SC_INVALID], s));
+    }
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stats.launches += 4;
+    }
+    const int rc = strict_hide_zero(c, p, r, s);
+    if (rc != KC_OK) { kc_run_free(c, r); return rc; }
+    *out = r;
+    return KC_OK;
+}
+
+// strict mode: empty slots were counted as key 0; if nothing real is left there, hide that record
+int strict_hide_zero(kc_ctx *c, Pending &p, kc_run *r, cudaStream_t s) {
+    if (!(c->strict && r->n && p.h_scal[SC_INVALID])) return KC_OK;
+    uint64_t k0[kMaxWords] = {0};
+    uint32_t c0 = 0;
+    KC_CUDA_TRY(c, cudaMemcpyAsync(k0, r->d_keys, c->W * 8, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaMemcpyAsync(&c0, r->d_counts, 4, cudaMemcpyDeviceToHost, s));
+    KC_CUDA_TRY(c, cudaStreamSynchronize(s));
+    bool zero = true;
+    for (int w = 0; w < c->W; w++) zero = zero && k0[w] == 0;
+    if (zero && c0 == 0) r->skip = 1;
+    return KC_OK;
+}
+
 int count_finish_partition(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
     const uint64_t U = p.h_scal[SC_UNIQUE];
     const int sig = c->W == 1 ? 64 - static_zero_bits(c) : 64;
@@ -680,16 +770,8 @@ int count_finish_sort(kc_ctx *c, Pending &p, cudaStream_t s, kc_run **out) {
         c->stats.launches += 1;
     }
     // strict mode: empty slots were sorted in as key 0; if nothing real is left there, hide that record
-    if (c->strict && U && p.h_scal[SC_INVALID]) {
-        uint64_t k0[kMaxWords] = {0};
-        uint32_t c0 = 0;
-        KC_CUDA_TRY(c, cudaMemcpyAsync(k0, r->d_keys, c->W * 8, cudaMemcpyDeviceToHost, s));
-        KC_CUDA_TRY(c, cudaMemcpyAsync(&c0, r->d_counts, 4, cudaMemcpyDeviceToHost, s));
-        KC_CUDA_TRY(c, cudaStreamSynchronize(s));
-        bool zero = true;
-        for (int w = 0; w < c->W; w++) zero = zero && k0[w] == 0;
-        if (zero && c0 == 0) r->skip = 1;
-    }
+    const int rc = strict_hide_zero(c, p, r, s);
+    if (rc != KC_OK) { kc_run_free(c, r); return rc; }
     *out = r;
     return KC_OK;
 }
@@ -747,7 +829,7 @@ int kc_create(const kc_config *cfg, kc_ctx **out) {
     memcpy(&c0, cfg, cfg->struct_size && cfg->struct_size < sizeof(kc_config) ? cfg->struct_size : sizeof(kc_config));
     if (c0.k < 1 || c0.k > 128) { g_create_error = "kc_create: k must be in 1..128 (KMerSizes.h holds 4 words)"; return KC_ERR_ARG; }
     if (c0.read_len < c0.k || c0.read_len > 4096) { g_create_error = "kc_create: read_len must be in k..4096"; return KC_ERR_ARG; }
-    if (c0.method > KC_COUNT_SUPER) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
+    if (c0.method > KC_COUNT_PLACE) { g_create_error = "kc_create: unknown method"; return KC_ERR_ARG; }
     if (c0.method == KC_COUNT_HASH && c0.k > 64) { g_create_error = "kc_create: hash counting needs k <= 64"; return KC_ERR_ARG; }
     if (c0.method == KC_COUNT_HASH_GLOBAL && c0.k > 32) { g_create_error = "kc_create: the HBM-resident table needs k <= 32"; return KC_ERR_ARG; }
     cudaError_t e = cudaSetDevice(c0.device);

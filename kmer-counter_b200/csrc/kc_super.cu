@@ -1236,6 +1236,38 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
     }
 }
 
+// Key-placement path: D's keys were written by the extraction (one per k-mer slot, key 0 where a
+// slot holds no k-mer). Every record gets count 1; the histogram of the leading b1 bits that S2
+// would have kept is built here; sc[SW_D] = n.
+template <int W>
+__global__ void __launch_bounds__(256) place_init_kernel(const uint64_t *__restrict__ keys, uint32_t *__restrict__ counts,
+                                                         uint64_t n, int shift1, uint32_t *__restrict__ hist1,
+                                                         unsigned long long *__restrict__ sc) {
+    __shared__ uint32_t sh[kNb1Max];
+    for (uint32_t i = threadIdx.x; i < kNb1Max; i += 256) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+        counts[i] = 1u;
+        atomicAdd(&sh[(uint32_t)(keys[i * W] >> shift1)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kNb1Max; i += 256) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&hist1[i], c);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc[SW_D] = n;
+}
+
+// the run's first record loses the empty slots that were counted as key 0 (the record
+// itself stays, with whatever real occurrences key 0 has)
+template <int W>
+__global__ void place_fix_zero_kernel(const uint64_t *__restrict__ keys, uint32_t *__restrict__ counts,
+                                      const unsigned long long *__restrict__ n_invalid) {
+    bool zero = true;
+    for (int w = 0; w < W; w++) zero = zero && keys[w] == 0;
+    if (zero) counts[0] -= (uint32_t)*n_invalid;
+}
+
 // Level-2 histogram of the level-1-grouped keys (flat chunks; counters of the chunk's first
 // bucket in shared memory, stragglers straight to the global counter).
 constexpr uint32_t kH2Chunk = 16384;
@@ -1672,6 +1704,8 @@ constexpr int kFinCapSmall = 2048, kFinCapLarge = 4096;     // records a sub-buc
 }  // namespace
 
 // ------------------------------------------------------------------------ host
+static void plan_layout(SuperPlan &pl, bool ext_e);
+
 bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint32_t occ_per_bin, SuperPlan *out,
                 double record_headroom, uint64_t distinct_hint, bool ext_e) {
     if (k == 0 || k > 64 || L < k || L > 4096) return false;
@@ -1744,7 +1778,13 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
     }
     const int sig = pl.W == 1 ? (masked ? (int)(2 * mm) : 64) : 64;
     pl.b1 = sig < 10 ? sig : 10;
-    // workspace
+    plan_layout(pl, ext_e);
+    *out = pl;
+    return true;
+}
+
+// workspace layout of a plan whose sizes are set
+static void plan_layout(SuperPlan &pl, bool ext_e) {
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) { uint64_t r = o; o += round512(bytes); return r; };
     const uint64_t rec_bytes = 16ull * pl.W;
@@ -1776,6 +1816,32 @@ bool super_plan(uint32_t k, uint32_t L, bool strict, uint64_t max_windows, uint3
         pl.off_ec = take(pl.d_cap * 4 + 64);
     }
     pl.ws_bytes = o;
+}
+
+// Plan of the key-placement path (see kc_super.cuh): no bins, no S1/S2 -- D is filled with one
+// (key, 1) record per k-mer slot by the caller, S3a..S3c place, sort and FOLD them. Any key width.
+bool place_plan(uint32_t k, bool strict, uint64_t n_records, SuperPlan *out) {
+    if (k == 0 || k > 128 || n_records == 0 || n_records > (1ull << 32) - 2) return false;
+    SuperPlan pl{};
+    pl.W = (int)((k + 31) / 32);
+    pl.k = k;
+    const uint32_t mm = k % 32;
+    const bool masked = strict ? (mm != 0) : (mm >= 1 && mm <= 28);
+    pl.span = masked ? k : 32u * pl.W;
+    pl.last_mask = masked ? (~0ull << (64 - 2 * mm)) : ~0ull;
+    pl.n_bins = 8;                                  // (unused: the arrays just exist)
+    pl.d_cap = n_records < 1024 ? 1024 : n_records;
+    // occurrences, not distinct keys, fill the sub-buckets; the folding S3c holds two copies of a
+    // sub-bucket, so only its 2048-record variant fits shared memory for every key width
+    pl.fin_cap = kFinCapSmall;
+    pl.sub_target = pl.fin_cap * 7 / 10;
+    if (const char *v = getenv("KC_SW_SUB_TARGET")) {
+        const int t = atoi(v);
+        if (t > 0) pl.sub_target = (uint32_t)t;
+    }
+    const int sig = pl.W == 1 ? (masked ? (int)(2 * mm) : 64) : 64;
+    pl.b1 = sig < 10 ? sig : 10;
+    plan_layout(pl, false);
     *out = pl;
     return true;
 }
@@ -1958,7 +2024,43 @@ static cudaError_t super_place_w(const SuperPlan &pl, void *ws, unsigned long lo
 cudaError_t super_place(const SuperPlan &pl, void *ws, unsigned long long *d_sc, int n_sms, cudaStream_t s, cudaEvent_t *evs) {
     if (pl.W == 1) return super_place_w<1>(pl, ws, d_sc, n_sms, s, evs);
     if (pl.W == 2) return super_place_w<2>(pl, ws, d_sc, n_sms, s, evs);
+    if (pl.W == 3) return super_place_w<3>(pl, ws, d_sc, n_sms, s, evs);
+    if (pl.W == 4) return super_place_w<4>(pl, ws, d_sc, n_sms, s, evs);
     return cudaErrorInvalidValue;
+}
+
+// ---- key-placement path
+cudaError_t place_init(const SuperPlan &pl, void *ws, unsigned long long *d_sc, uint64_t n, int n_sms, cudaStream_t s) {
+    cudaError_t e;
+    if (n > pl.d_cap) return cudaErrorInvalidValue;
+    // cursor, hist1, hist2 are contiguous at the start of the workspace
+    if ((e = cudaMemsetAsync(ws, 0, pl.off_base1, s)) != cudaSuccess) return e;
+    const uint64_t *dk = at<uint64_t>(ws, pl.off_dk);
+    uint32_t *dc = at<uint32_t>(ws, pl.off_dc), *hist1 = at<uint32_t>(ws, pl.off_hist1);
+    const uint32_t grid = (uint32_t)n_sms * 8;
+    const int shift1 = 64 - pl.b1;
+    switch (pl.W) {
+        case 1: place_init_kernel<1><<<grid, 256, 0, s>>>(dk, dc, n, shift1, hist1, d_sc); break;
+        case 2: place_init_kernel<2><<<grid, 256, 0, s>>>(dk, dc, n, shift1, hist1, d_sc); break;
+        case 3: place_init_kernel<3><<<grid, 256, 0, s>>>(dk, dc, n, shift1, hist1, d_sc); break;
+        case 4: place_init_kernel<4><<<grid, 256, 0, s>>>(dk, dc, n, shift1, hist1, d_sc); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+uint64_t *place_keys(const SuperPlan &pl, void *ws) { return at<uint64_t>(ws, pl.off_dk); }
+
+cudaError_t place_fix_zero(int W, const uint64_t *run_keys, uint32_t *run_counts, const unsigned long long *d_n_invalid,
+                           cudaStream_t s) {
+    switch (W) {
+        case 1: place_fix_zero_kernel<1><<<1, 1, 0, s>>>(run_keys, run_counts, d_n_invalid); break;
+        case 2: place_fix_zero_kernel<2><<<1, 1, 0, s>>>(run_keys, run_counts, d_n_invalid); break;
+        case 3: place_fix_zero_kernel<3><<<1, 1, 0, s>>>(run_keys, run_counts, d_n_invalid); break;
+        case 4: place_fix_zero_kernel<4><<<1, 1, 0, s>>>(run_keys, run_counts, d_n_invalid); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t super_count(const SuperPlan &pl, bool add_phantom, void *ws, unsigned long long *d_sc, int n_sms,
@@ -2012,6 +2114,10 @@ cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long 
                          uint32_t *out_counts, int n_sms, cudaStream_t s) {
     if (pl.W == 1) return super_finish_d<1>(pl, dup, ws, d_sc, out_keys, out_counts, n_sms, s);
     if (pl.W == 2) return super_finish_d<2>(pl, dup, ws, d_sc, out_keys, out_counts, n_sms, s);
+    // 192/256-bit keys (key-placement path): the folding variant over 2048-record sub-buckets only
+    if (!dup || pl.fin_cap != kFinCapSmall) return cudaErrorInvalidValue;
+    if (pl.W == 3) return super_finish_w<3, true, 512, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    if (pl.W == 4) return super_finish_w<4, true, 512, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
     return cudaErrorInvalidValue;
 }
 
@@ -2022,7 +2128,9 @@ cudaError_t super_big_gather(const SuperPlan &pl, void *ws, uint64_t *tk, uint32
     const uint64_t *dk = at<uint64_t>(ws, pl.off_dk);
     const uint32_t *dc = at<uint32_t>(ws, pl.off_dc);
     if (pl.W == 1) big_gather_kernel<1><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
-    else big_gather_kernel<2><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
+    else if (pl.W == 2) big_gather_kernel<2><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
+    else if (pl.W == 3) big_gather_kernel<3><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
+    else big_gather_kernel<4><<<(uint32_t)n_sms * 8, 256, 0, s>>>(dk, dc, base2, big, bigoff, plan, tk, tc);
     return cudaGetLastError();
 }
 
@@ -2035,9 +2143,15 @@ cudaError_t super_big_place(const SuperPlan &pl, bool dup, void *ws, unsigned lo
     if (pl.W == 1) {
         if (dup) big_place_kernel<1, true><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
         else big_place_kernel<1, false><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
-    } else {
+    } else if (pl.W == 2) {
         if (dup) big_place_kernel<2, true><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
         else big_place_kernel<2, false><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+    } else if (pl.W == 3 && dup) {
+        big_place_kernel<3, true><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+    } else if (pl.W == 4 && dup) {
+        big_place_kernel<4, true><<<grid, 256, 0, s>>>(sk, sc_counts, base2, big, bigoff, plan, out_keys, out_counts, m_out, d_sc);
+    } else {
+        return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
@@ -2054,7 +2168,9 @@ cudaError_t super_gather(const SuperPlan &pl, void *ws, const uint64_t *tmp_keys
     const SuperPlanDev *plan = at<SuperPlanDev>(ws, pl.off_plan);
     const uint32_t *src = at<uint32_t>(ws, pl.off_base2), *off = at<uint32_t>(ws, pl.off_off);
     if (pl.W == 1) sw_gather_kernel<1><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
-    else sw_gather_kernel<2><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
+    else if (pl.W == 2) sw_gather_kernel<2><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
+    else if (pl.W == 3) sw_gather_kernel<3><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
+    else sw_gather_kernel<4><<<(uint32_t)n_sms * 8, 256, 0, s>>>(tmp_keys, tmp_counts, src, off, plan, out_keys, out_counts);
     return cudaGetLastError();
 }
 

@@ -147,6 +147,19 @@ cudaError_t super_x_pull(const SuperPlan &pl, void *ws, unsigned long long *d_sc
 // exchange: the device plan found the job's sub-buckets too large for the small S3c variant
 // (SuperXInfo::fin_large); super_finish of a plan changed by this sorts with the large one
 void super_use_large_finish(SuperPlan *pl);
+// ---- key-placement path (KC_COUNT_PLACE): for keys the bins do not take (k > 64: 192/256-bit keys).
+// The extraction writes one key per k-mer slot straight into D (place_keys), place_init gives every
+// record count 1 and builds the level-1 histogram, and S3a..S3c do the rest: two MSD placement
+// passes and a shared-memory sort per sub-bucket that FOLDS equal keys (super_place, then
+// super_finish(dup = true), super_fold_offsets, super_gather) -- three passes over the occurrences
+// instead of one LSD radix pass per key byte (24..32 for these keys). Sub-buckets crowded by one
+// repeated key go through the radix sorter like any oversized sub-bucket (super_big_*).
+bool place_plan(uint32_t k, bool strict, uint64_t n_records, SuperPlan *out);
+uint64_t *place_keys(const SuperPlan &pl, void *ws);
+cudaError_t place_init(const SuperPlan &pl, void *ws, unsigned long long *d_sc, uint64_t n, int n_sms, cudaStream_t s);
+// empty slots were placed as key 0: the run's key-0 record (always first) loses *d_n_invalid occurrences
+cudaError_t place_fix_zero(int W, const uint64_t *run_keys, uint32_t *run_counts, const unsigned long long *d_n_invalid,
+                           cudaStream_t s);
 // false when S1's shared-memory tile cannot hold 16 reads of this length
 bool super_supported(const SuperPlan &pl);
 // where S3c's temporary output may live in DUP mode (the level-1 buffer is dead by then)

@@ -13,6 +13,8 @@ STAGE_NAMES = {
     "hash_global": ["table_clear", "extract_insert", "compact_sort", "emit"],
     "super": ["encode_minimizer_scatter", "smem_count_per_bin", "record_scatter1", "record_hist2", "record_scatter2",
               "smem_sort_write"],
+    "place": ["extract_keys", "count_init_hist1", "record_scatter1", "record_hist2", "record_scatter2",
+              "smem_sort_fold_write"],
 }
 
 SW_SCALARS = ["invalid", "overflow_records", "d_records", "fail", "ticket", "windows", "occurrences", "aborts", "folded",

@@ -65,6 +65,43 @@ def test_chunk_matches_oracle_hash(kc, R, L, k, G, e, n, method):
     assert got == want
 
 
+@pytest.mark.parametrize("R,L,k,G,e,n", [c for c in CASES if c[2] >= 5])
+def test_chunk_matches_oracle_place(kc, R, L, k, G, e, n):
+    """The key-placement path (what auto picks for k > 64): a key per slot, two MSD placement passes,
+    shared-memory sort + fold per sub-bucket. Every key width, with and without the phantom."""
+    reads = oracle.gen_reads(R, L, G, e, n, seed=R + k)
+    want = oracle.process_chunk(reads, L, k)
+    with _counter(kc, k, L, method="place") as c:
+        got = c.process_chunk(reads)
+        assert c.stats()["method_used"] == "place"
+        sc = c.debug_scalars()
+    assert got == want, sc
+
+
+@pytest.mark.parametrize("k", [96, 128, 100, 65])
+def test_place_path_heavy_hitters_deep_plans_and_strict(kc, monkeypatch, k):
+    """192/256-bit keys: many copies of one read (a sub-bucket crowded by one key goes through the
+    radix sorter), all-T and all-A reads (all-ones and zero keys), a forced deep level-2 plan, and
+    strict masking against the window model."""
+    L = 150
+    reads = np.concatenate([oracle.gen_reads(1500, L, 20000, 0.005, 0.002, seed=k),
+                            np.tile(oracle.gen_reads(1, L, 0, 0, 0, seed=k + 1), 4000),      # 4000 copies of every k-mer of one read
+                            np.frombuffer((b"T" * L) * 9 + (b"A" * L) * 6, dtype=np.uint8)])
+    want = oracle.process_chunk(reads, L, k)
+    for sub_target in (None, "3"):
+        if sub_target:
+            monkeypatch.setenv("KC_SW_SUB_TARGET", sub_target)
+        with _counter(kc, k, L, method="auto") as c:
+            got = c.process_chunk(reads)
+            assert c.stats()["method_used"] == "place"
+            sc = c.debug_scalars()
+        assert got == want, (sub_target, sc)
+    monkeypatch.delenv("KC_SW_SUB_TARGET")
+    want = oracle.naive_count(reads, L, k, strict=True)
+    with _counter(kc, k, L, compat="strict", method="place") as c:
+        assert c.process_chunk(reads) == want
+
+
 SUPER_CASES = [c for c in CASES if 22 <= c[2] <= 64]
 
 
@@ -89,7 +126,7 @@ def test_chunk_matches_oracle_super(kc, R, L, k, G, e, n):
 
 def test_auto_picks_super_where_it_applies(kc):
     reads = oracle.gen_reads(500, 100, 9000, 0.01, 0.002, seed=3)
-    for k, want_method in ((31, "super"), (63, "super"), (22, "super"), (21, "hash"), (5, "sort"), (96, "sort")):
+    for k, want_method in ((31, "super"), (63, "super"), (22, "super"), (21, "hash"), (5, "sort"), (96, "place"), (100, "place")):
         with _counter(kc, k, 100, method="auto") as c:
             assert c.process_chunk(reads) == oracle.process_chunk(reads, 100, k)
             assert c.stats()["method_used"] == want_method, k
@@ -291,7 +328,7 @@ def test_random_shapes_and_hostile_alphabet(kc):
             reads = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=R * L)].copy()
             reads[rng.integers(0, R * L, size=max(1, R * L // 40))] = rng.choice(alphabet, size=max(1, R * L // 40))
         want = oracle.process_chunk(reads, L, k)
-        for method in (("sort", "hash", "super") if k <= 64 else ("sort",)):       # super falls back where it does not apply
+        for method in (("sort", "hash", "super") if k <= 64 else ("sort", "place")):       # super falls back where it does not apply
             with _counter(kc, k, L, method=method) as c:
                 assert c.process_chunk(reads) == want, (L, k, R, method)
         done += 1
@@ -301,7 +338,7 @@ def test_strict_mode_matches_naive_model(kc):
     for (R, L, k) in [(800, 100, 31), (500, 80, 63), (500, 60, 28)]:
         reads = oracle.gen_reads(R, L, 9000, 0.005, 0.003, seed=k)
         want = oracle.naive_count(reads, L, k, strict=True)
-        for method in (("sort", "hash", "hash_global", "super") if k <= 32 else ("sort", "hash", "super")):
+        for method in (("sort", "hash", "hash_global", "super", "place") if k <= 32 else ("sort", "hash", "super", "place")):
             with _counter(kc, k, L, compat="strict", method=method) as c:
                 assert c.process_chunk(reads) == want, (k, method)
 
