@@ -1700,6 +1700,7 @@ __global__ void __launch_bounds__(256) big_place_kernel(const uint64_t *__restri
 inline uint64_t round512(uint64_t b) { return (b + 511) & ~511ull; }
 
 constexpr int kFinCapSmall = 2048, kFinCapLarge = 4096;     // records a sub-bucket may hold (S3c variants)
+constexpr int kFinCapWide = 1024;                           // ... of 192/256-bit keys (folding variant, 2-3 CTAs per SM)
 
 }  // namespace
 
@@ -1833,7 +1834,8 @@ bool place_plan(uint32_t k, bool strict, uint64_t n_records, SuperPlan *out) {
     pl.d_cap = n_records < 1024 ? 1024 : n_records;
     // occurrences, not distinct keys, fill the sub-buckets; the folding S3c holds two copies of a
     // sub-bucket, so only its 2048-record variant fits shared memory for every key width
-    pl.fin_cap = kFinCapSmall;
+    // (192/256-bit keys: 1024-record sub-buckets keep two or three CTAs on an SM, as long as 2^20 of them are enough)
+    pl.fin_cap = pl.W >= 3 && n_records <= (uint64_t)kSuperMaxSub * (kFinCapWide * 7 / 10) ? kFinCapWide : kFinCapSmall;
     pl.sub_target = pl.fin_cap * 7 / 10;
     if (const char *v = getenv("KC_SW_SUB_TARGET")) {
         const int t = atoi(v);
@@ -2115,9 +2117,14 @@ cudaError_t super_finish(const SuperPlan &pl, bool dup, void *ws, unsigned long 
     if (pl.W == 1) return super_finish_d<1>(pl, dup, ws, d_sc, out_keys, out_counts, n_sms, s);
     if (pl.W == 2) return super_finish_d<2>(pl, dup, ws, d_sc, out_keys, out_counts, n_sms, s);
     // 192/256-bit keys (key-placement path): the folding variant over 2048-record sub-buckets only
-    if (!dup || pl.fin_cap != kFinCapSmall) return cudaErrorInvalidValue;
-    if (pl.W == 3) return super_finish_w<3, true, 512, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
-    if (pl.W == 4) return super_finish_w<4, true, 512, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    if (!dup || (pl.fin_cap != kFinCapSmall && pl.fin_cap != kFinCapWide)) return cudaErrorInvalidValue;
+    if (pl.fin_cap == kFinCapWide) {
+        if (pl.W == 3) return super_finish_w<3, true, 256, kFinCapWide>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+        if (pl.W == 4) return super_finish_w<4, true, 256, kFinCapWide>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    } else {
+        if (pl.W == 3) return super_finish_w<3, true, 512, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+        if (pl.W == 4) return super_finish_w<4, true, 512, kFinCapSmall>(pl, ws, d_sc, out_keys, out_counts, n_sms, s);
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -199,6 +199,7 @@ static uint32_t method_of(const std::string &m) {
     if (m == "hash") return KC_COUNT_HASH;
     if (m == "hash_global") return KC_COUNT_HASH_GLOBAL;
     if (m == "super") return KC_COUNT_SUPER;
+    if (m == "place") return KC_COUNT_PLACE;
     return KC_COUNT_AUTO;
 }
 
