@@ -536,6 +536,10 @@ int count_finish(kc_ctx *c, Pending &p, const void *d_reads, uint64_t n_bytes, c
     else if (used == KC_COUNT_HASH_GLOBAL) rc = count_finish_hash_global(c, p, s, out);
     else rc = count_finish_sort(c, p, s, out);
     if (rc != KC_OK) { pending_release(s, p); return rc; }
+    if (used != KC_COUNT_HASH) {                  // kc_place_next_run is one-shot: a chunk that took another path disarms it too
+        std::lock_guard<std::mutex> g(c->mu);
+        c->place.set = false;
+    }
     const int n_stages = p.n_ev;                  // the last stage (emit) ends at the event recorded now
     KC_CUDA_TRY(c, cudaEventRecord(p.ev[p.n_ev], s));
     KC_CUDA_TRY(c, cudaEventSynchronize(p.ev[p.n_ev]));
