@@ -187,6 +187,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+class StdoutToStderr:
+    """The reference's own code prints progress on stdout (e.g. FASTQFileReader.cpp:40); while it runs, file
+    descriptor 1 points at stderr so that this program's stdout stays ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # --------------------------------------------------------- the reference's CPU path
 def _ref_row(oracle, reads, L, k, threads, fan_in, merge_threads, tmp_root):
     """One timed run of the reference's Pipeline B (oracle/_ref) -> row with per-stage seconds."""
@@ -274,10 +290,12 @@ def reference_gpu_seam(a):
 
 
 def cpu_baseline(a):
-    rows, cores = cpu_rows(a)
+    with StdoutToStderr():
+        rows, cores = cpu_rows(a)
+        gpu_seam = reference_gpu_seam(a)
     best = max(rows, key=lambda r: r["value"])
     return {"value": best["value"], "unit": UNIT, "cores": best["threads"], "host_cores": cores, "kind": best["kind"],
-            "reference_gpu_seam": reference_gpu_seam(a),
+            "reference_gpu_seam": gpu_seam,
             "sample": "first %d reads (%d k-mers) of the workload in chunks of %d reads (the reference's default), %d chunk-worker "
                       "threads busy, KMerFileMerger with fan-in %d on %d merger threads; rows: 1 thread and 8+2 threads"
                       % (best["reads"], best["kmers"], REF_CHUNK, best.get("threads_busy") or best["threads"],
@@ -301,10 +319,11 @@ def run_reference(a, rank):
     reads = oracle.gen_reads(sample, L, c["genome"], c["sub_rate"], c["n_rate"], seed=c["seed"], zipf_loci=c["zipf_loci"])
     threads = min(8, cores)
     rows = []
-    for _ in range(min(a.warmup, 1)):
-        _ref_row(oracle, reads, L, c["k"], threads, 2, 2, tmp_root)
-    for _ in range(max(a.steps, 1)):
-        rows.append(_ref_row(oracle, reads, L, c["k"], threads, 2, 2, tmp_root))
+    with StdoutToStderr():
+        for _ in range(min(a.warmup, 1)):
+            _ref_row(oracle, reads, L, c["k"], threads, 2, 2, tmp_root)
+        for _ in range(max(a.steps, 1)):
+            rows.append(_ref_row(oracle, reads, L, c["k"], threads, 2, 2, tmp_root))
     dt = sum(r["seconds"] for r in rows) / len(rows)
     kmers = sample * (L - c["k"] + 1)
     val = kmers / dt
