@@ -33,7 +33,7 @@ def test_printer_mode_matches_kmerprinter_format(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,method", [(31, "auto"), (31, "sort"), (63, "auto"), (28, "hash")])
+@pytest.mark.parametrize("k,method", [(31, "auto"), (31, "sort"), (63, "auto"), (28, "hash"), (96, "auto"), (100, "place")])
 def test_cli_counts_a_fastq_directory(tmp_path, k, method):
     d = tmp_path / "in"
     d.mkdir()
