@@ -878,6 +878,11 @@ __global__ void __launch_bounds__(THREADS) sw_count_kernel(SwCountParams p) {
 }
 
 // ============================================================ S3: ordering the records
+// Per-bin counters that one thread walks in runs of consecutive bins (the block scans below) live at
+// index i + i / 32: the stride of 8 or 16 words between neighbouring threads' runs then falls on
+// different banks (unpadded it was an 8- to 16-way bank conflict: 67 % of S3c's shared wavefronts).
+__device__ __forceinline__ uint32_t pad32(uint32_t i) { return i + (i >> 5); }
+constexpr int kRsBinsPadded = kRsBins + kRsBins / 32;
 // exclusive scan of nb (<= 1024) shared counters by THREADS threads; every thread returns the total
 template <int THREADS>
 __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_t *start, int nb, uint32_t *s_warp) {
@@ -888,7 +893,7 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         const int b = tid * PER + i;
-        v[i] = b < nb ? cnt[b] : 0;
+        v[i] = b < nb ? cnt[pad32((uint32_t)b)] : 0;
         sum += v[i];
     }
     uint32_t incl = sum;
@@ -910,7 +915,7 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t *cnt, uint32_
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         const int b = tid * PER + i;
-        if (b < nb) start[b] = run;
+        if (b < nb) start[pad32((uint32_t)b)] = run;
         run += v[i];
     }
     __syncthreads();
@@ -1146,7 +1151,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
     extern __shared__ __align__(16) uint8_t rs_smem[];
     Key<W> *stg_k = reinterpret_cast<Key<W> *>(rs_smem);                    // [TILE]
     uint32_t *stg_c = reinterpret_cast<uint32_t *>(stg_k + TILE);           // [TILE]
-    uint32_t *cnt = stg_c + TILE, *start = cnt + kRsBins, *gbase = start + kRsBins;
+    uint32_t *cnt = stg_c + TILE, *start = cnt + kRsBinsPadded, *gbase = start + kRsBinsPadded;   // indexed through pad32
     __shared__ uint32_t s_warp[kRsThreads / 32];
     uint32_t n, first = 0;
     if (LEVEL == 1) {
@@ -1183,7 +1188,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
             // (b2 = 11: the counters hold one bucket; the keys of a tile's second bucket are placed one by one)
             nb = (pl >> b2) == (p0 >> b2) || 2 * nb2 > (uint32_t)kRsBins ? nb2 : 2 * nb2;
         }
-        for (uint32_t i = threadIdx.x; i < nb; i += kRsThreads) cnt[i] = 0;
+        for (uint32_t i = threadIdx.x; i < nb; i += kRsThreads) cnt[pad32(i)] = 0;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
@@ -1192,7 +1197,7 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
             if (idx < end) {
                 const uint32_t pfx = (uint32_t)(key[i].w[0] >> shift);
                 const uint32_t rel = pfx - p0;
-                if (rel < nb) rank[i] = (uint16_t)atomicAdd(&cnt[rel], 1u);
+                if (rel < nb) rank[i] = (uint16_t)atomicAdd(&cnt[pad32(rel)], 1u);
                 else {
                     const uint32_t o = atomicAdd(&g_cursor[pfx - sub0], 1u);
                     st_key<W>(out_keys, o, key[i]);
@@ -1209,26 +1214,26 @@ __global__ void __launch_bounds__(kRsThreads) rec_scatter_kernel(const uint64_t 
             const uint32_t b = u * kRsThreads + threadIdx.x;
             reserved[u] = 0;
             if (b < nb) {
-                const uint32_t c = cnt[b];
+                const uint32_t c = cnt[pad32(b)];
                 if (c) reserved[u] = atomicAdd(&g_cursor[p0 - sub0 + b], c);
             }
         }
 #pragma unroll
         for (int i = 0; i < ITEMS; i++)
             if (rank[i] != 0xffffu) {
-                const uint32_t o = start[(uint32_t)(key[i].w[0] >> shift) - p0] + rank[i];
+                const uint32_t o = start[pad32((uint32_t)(key[i].w[0] >> shift) - p0)] + rank[i];
                 stg_k[o] = key[i];
                 stg_c[o] = val[i];
             }
 #pragma unroll
         for (int u = 0; u < kRsBins / kRsThreads; u++) {
             const uint32_t b = u * kRsThreads + threadIdx.x;
-            if (b < nb) gbase[b] = reserved[u] - start[b];
+            if (b < nb) gbase[pad32(b)] = reserved[u] - start[pad32(b)];
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < total; i += kRsThreads) {
             const Key<W> k = stg_k[i];
-            const uint32_t o = gbase[(uint32_t)(k.w[0] >> shift) - p0] + i;
+            const uint32_t o = gbase[pad32((uint32_t)(k.w[0] >> shift) - p0)] + i;
             st_key<W>(out_keys, o, k);
             out_counts[o] = stg_c[i];
         }
@@ -1387,8 +1392,8 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
     Key<W> *fk = sk + (DUP ? CAP : 0);                                 // DUP: in final order [CAP]
     uint32_t *scn = reinterpret_cast<uint32_t *>(fk + CAP);            // [CAP]
     uint32_t *fc = scn + (DUP ? CAP : 0);                              // DUP [CAP]
-    uint32_t *c3 = fc + CAP;                                           // counting-sort bins [CAP]
-    uint32_t *s3 = c3 + CAP;                                           // their starts       [CAP]
+    uint32_t *c3 = fc + CAP;                                           // counting-sort bins [CAP], indexed through pad32
+    uint32_t *s3 = c3 + CAP + CAP / 32;                                // their starts       [CAP], likewise
     __shared__ uint32_t s_maxbin, s_cnt, s_j;
     __shared__ uint32_t s_warp[THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1436,14 +1441,14 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
         nb3 = nb3 < 64 ? 64 : (nb3 > (uint32_t)CAP ? (uint32_t)CAP : nb3);
         int shift3 = 64 - prefix_bits - (31 - __clz(nb3));
         if (shift3 < 0) shift3 = 0;
-        for (uint32_t i = tid; i < nb3; i += THREADS) c3[i] = 0;
+        for (uint32_t i = tid; i < nb3; i += THREADS) c3[pad32(i)] = 0;
         if (tid == 0) { s_maxbin = 0; s_cnt = 0; }
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < kPer; u++) {
             const uint32_t i = u * THREADS + tid;
             if (u * THREADS >= n) break;
-            if (i < n) rr[u] = atomicAdd(&c3[(uint32_t)(rk[u].w[0] >> shift3) & (nb3 - 1)], 1u);
+            if (i < n) rr[u] = atomicAdd(&c3[pad32((uint32_t)(rk[u].w[0] >> shift3) & (nb3 - 1))], 1u);
         }
         __syncthreads();
         // exclusive scan of the nb3 bins: thread t owns bins [t * per3, (t + 1) * per3)
@@ -1452,7 +1457,7 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             const uint32_t b0 = tid * per3;
             uint32_t sum = 0, mx = 0;
             if (b0 < nb3)
-                for (uint32_t q = 0; q < per3; q++) { const uint32_t v = c3[b0 + q]; sum += v; mx = max(mx, v); }
+                for (uint32_t q = 0; q < per3; q++) { const uint32_t v = c3[pad32(b0 + q)]; sum += v; mx = max(mx, v); }
             if (mx > 2) atomicMax(&s_maxbin, mx);
             uint32_t incl = sum;
 #pragma unroll
@@ -1467,7 +1472,7 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             for (int w = 0; w < THREADS / 32; w++) if ((uint32_t)w < warp) off += s_warp[w];
             uint32_t run = off + incl - sum;
             if (b0 < nb3)
-                for (uint32_t q = 0; q < per3; q++) { s3[b0 + q] = run; run += c3[b0 + q]; }
+                for (uint32_t q = 0; q < per3; q++) { s3[pad32(b0 + q)] = run; run += c3[pad32(b0 + q)]; }
             __syncthreads();
         }
         const uint32_t maxbin = s_maxbin;
@@ -1476,7 +1481,7 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             const uint32_t i = u * THREADS + tid;
             if (u * THREADS >= n) break;
             if (i < n) {
-                const uint32_t o = s3[(uint32_t)(rk[u].w[0] >> shift3) & (nb3 - 1)] + rr[u];
+                const uint32_t o = s3[pad32((uint32_t)(rk[u].w[0] >> shift3) & (nb3 - 1))] + rr[u];
                 sk[o] = rk[u];
                 scn[o] = rc[u];
             }
@@ -1489,7 +1494,7 @@ __global__ void __launch_bounds__(THREADS) rec_finish_kernel(FinishParams p) {
             for (uint32_t i = tid; i < n; i += THREADS) {
                 const Key<W> k = sk[i];
                 const uint32_t d = (uint32_t)(k.w[0] >> shift3) & (nb3 - 1);
-                const uint32_t s0 = s3[d], cn = c3[d];
+                const uint32_t s0 = s3[pad32(d)], cn = c3[pad32(d)];
                 uint32_t less = 0;
                 for (uint32_t q = 0; q < cn; q++) {
                     const Key<W> o = sk[s0 + q];
@@ -1999,7 +2004,7 @@ static cudaError_t super_place_w(const SuperPlan &pl, void *ws, unsigned long lo
     // ---- S3a: level-1 bases + device plan, scatter D -> E
     const int sig = pl.W == 1 ? 64 - (int)__builtin_ctzll(pl.last_mask ? pl.last_mask : 1) : 64;
     sw_plan_kernel<<<1, 1024, 0, s>>>(hist1, pl.b1, pl.d_cap, pl.sub_target, sig, base1, cur1, plan, d_sc);
-    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBinsPadded * 4;
     auto k1 = rec_scatter_kernel<W, 1>;
     auto k2 = rec_scatter_kernel<W, 2>;
     if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
@@ -2091,7 +2096,7 @@ static cudaError_t super_finish_w(const SuperPlan &pl, void *ws, unsigned long l
     fp.m_out = at<uint32_t>(ws, pl.off_mout);
     fp.big = at<uint32_t>(ws, pl.off_big);
     fp.sc = d_sc;
-    const uint32_t smem = (DUP ? 2 : 1) * CAP * (8 * W + 4) + 2 * CAP * 4;
+    const uint32_t smem = (DUP ? 2 : 1) * CAP * (8 * W + 4) + 2 * (CAP + CAP / 32) * 4;
     auto kern = rec_finish_kernel<W, THREADS, CAP, DUP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -2202,7 +2207,7 @@ static cudaError_t super_x_local_w(const SuperPlan &pl, void *ws, unsigned long 
     x_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, rank, n_ranks, keep_ranges ? 1 : 0, pl.d_cap, pl.sub_target,
                                      pl.fin_cap == kFinCapLarge ? 1 : 0, sig, at<uint32_t>(ws, pl.off_base1),
                                      at<uint32_t>(ws, pl.off_cur1), plan, at<XDev>(ws, pl.off_x), d_sc, xs);
-    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBinsPadded * 4;
     auto k1 = rec_scatter_kernel<W, 1>;
     if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
     int per_sm = 1;
@@ -2237,7 +2242,7 @@ static cudaError_t super_x_pull_w(const SuperPlan &pl, void *ws, unsigned long l
     uint32_t *h2m = at<uint32_t>(ws, pl.off_h2m), *base2 = at<uint32_t>(ws, pl.off_base2), *cur2 = at<uint32_t>(ws, pl.off_cur2);
     x_merge_hist_kernel<<<(uint32_t)n_sms * 4, 256, 0, s>>>(peers, n_ranks, plan, h2m);
     sw_scan_kernel<<<(kSuperMaxSub + kScanTile - 1) / kScanTile, 1024, 0, s>>>(h2m, &plan->n_sub, 0, base2, cur2, nullptr);
-    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBins * 4;
+    const uint32_t rs_smem = RsCfg<W>::TILE * (8 * W + 4) + 3 * kRsBinsPadded * 4;
     auto k2 = rec_scatter_kernel<W, 2>;
     if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)) != cudaSuccess) return e;
     int per_sm = 1;
