@@ -245,6 +245,11 @@ int  kc_run_free(kc_ctx *ctx, kc_run *run);
  * submits and waits for later chunks (calls are serialised among themselves; returns when the bytes
  * are in dst). */
 int  kc_run_copy_records(kc_ctx *ctx, const kc_run *run, void *dst, uint64_t cap, uint64_t *out_bytes);
+/* The run as text, formatted on the device: replaces KMerPrinter::print (KMerPrinter.cpp:35-91). One
+ * line per record -- the 32 letters of every key word (A, C, G, T; most significant base first), a
+ * blank, the count in decimal, '\n' -- written to dst (host memory). *out_bytes = the text's size;
+ * KC_ERR_CAPACITY (with *out_bytes set) if cap is too small: at most 32 W + 12 bytes per record. */
+int  kc_run_print(kc_ctx *ctx, const kc_run *run, char *dst, uint64_t cap, uint64_t *out_bytes);
 /* packed records in: a run file's bytes (must be sorted; adjacent equal keys are
  * folded like SortedKMerFile::ReadKmer does, SortedKMerFile.cpp:57-82) */
 int  kc_run_upload(kc_ctx *ctx, const void *records, uint64_t n_bytes, kc_run **run);

@@ -85,6 +85,7 @@ SYMBOLS = {
     "kc_run_records": (_u64, [_vp]),
     "kc_run_free": (_i, [_vp, _vp]),
     "kc_run_copy_records": (_i, [_vp, _vp, _vp, _u64, _pu64]),
+    "kc_run_print": (_i, [_vp, _vp, _vp, _u64, _pu64]),
     "kc_run_upload": (_i, [_vp, _vp, _u64, _pp]),
     "kc_run_device": (_i, [_vp, _pp, _pp, _pu64]),
     "kc_run_from_device": (_i, [_vp, _vp, _vp, _u64, _pp]),

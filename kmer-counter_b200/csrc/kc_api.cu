@@ -1954,6 +1954,44 @@ int kc_run_copy_records(kc_ctx *c, const kc_run *r, void *dst, uint64_t cap, uin
     return KC_OK;
 }
 
+int kc_run_print(kc_ctx *c, const kc_run *r, char *dst, uint64_t cap, uint64_t *out_bytes) {
+    KC_TRY(check_ctx(c));
+    if (!r) return c->set_error(KC_ERR_ARG, "null run");
+    std::lock_guard<std::recursive_mutex> dg(c->direct_mu);
+    cudaSetDevice(c->cfg.device);
+    cudaStream_t s = c->stream;
+    const uint64_t n = r->n - r->skip;
+    if (out_bytes) *out_bytes = 0;
+    if (n == 0) return KC_OK;
+    void *text = nullptr, *ws = nullptr, *d_bytes = nullptr;
+    int rc = dev_alloc(c, s, print_max_bytes(n, r->W), &text);
+    if (rc == KC_OK) rc = dev_alloc(c, s, print_workspace_bytes(n), &ws);
+    if (rc == KC_OK) rc = dev_alloc(c, s, 8, &d_bytes);
+    unsigned long long total = 0;
+    cudaError_t e = cudaSuccess;
+    if (rc == KC_OK) {
+        e = print_records_text(r->d_keys + r->skip * r->W, r->d_counts + r->skip, n, r->W, static_cast<char *>(text),
+                               static_cast<unsigned long long *>(d_bytes), ws, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_bytes, 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) {
+            if (out_bytes) *out_bytes = total;
+            if (total > cap || !dst) rc = c->set_error(KC_ERR_CAPACITY, "the text needs %llu bytes, buffer holds %llu", total, (unsigned long long)cap);
+            else {
+                e = cudaMemcpyAsync(dst, text, total, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            }
+        }
+    }
+    dev_free(s, text); dev_free(s, ws); dev_free(s, d_bytes);
+    if (rc != KC_OK) return rc;
+    if (e != cudaSuccess) return c->set_error(KC_ERR_CUDA, "kc_run_print: %s", cudaGetErrorString(e));
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stats.launches += 1;
+    c->stats.d2h_bytes += total;
+    return KC_OK;
+}
+
 int kc_run_from_device(kc_ctx *c, const void *d_keys, const void *d_counts, uint64_t n, kc_run **out) {
     KC_TRY(check_ctx(c));
     std::lock_guard<std::recursive_mutex> dg(c->direct_mu);

@@ -45,6 +45,12 @@ cudaError_t pack_records(const uint64_t *keys, const uint32_t *counts, uint64_t 
                          cudaStream_t s);
 cudaError_t unpack_records(const void *records, uint64_t n, int W, uint64_t *keys, uint32_t *counts,
                            cudaStream_t s);
+// (keys, counts) -> KMerPrinter's text (KMerPrinter.cpp:35-91): 32 W letters, ' ', count, '\n' per record.
+// d_text holds print_max_bytes(n, W); *d_bytes = bytes written; ws: print_workspace_bytes(n).
+uint64_t print_workspace_bytes(uint64_t n);
+uint64_t print_max_bytes(uint64_t n, int W);
+cudaError_t print_records_text(const uint64_t *keys, const uint32_t *counts, uint64_t n, int W, char *d_text,
+                               unsigned long long *d_bytes, void *ws, cudaStream_t s);
 // fold adjacent equal keys of a sorted (keys, counts) sequence, summing counts
 cudaError_t fold_sorted_pairs(const uint64_t *keys, const uint32_t *counts, uint64_t n, int W, uint64_t *out_keys,
                               uint32_t *out_counts, unsigned long long *d_num_unique, void *ws, cudaStream_t s,

@@ -174,6 +174,114 @@ inline uint32_t grid_for(uint64_t n, int threads, uint32_t cap = 0) {
 
 }  // namespace
 
+// ---- text dump of a run: replaces KMerPrinter::print / printKmer (KMerPrinter.cpp:35-91)
+// One line per record: the 32 W letters of the key words (A, C, G, T for codes 0..3, most
+// significant pair first), a blank, the count in decimal, a newline. Lines differ in length by the
+// count's digits, so a tile of records ranks its bytes with a block scan and a decoupled look-back.
+constexpr int kPrintThreads = 256;
+constexpr int kPrintItems = 4;                      // consecutive records per thread
+constexpr int kPrintTile = kPrintThreads * kPrintItems;
+
+__device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
+    uint32_t d = 1;
+    while (v >= 10u) { v /= 10u; d++; }
+    return d;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kPrintThreads) print_kernel(const uint64_t *__restrict__ keys,
+                                                              const uint32_t *__restrict__ counts, uint64_t n,
+                                                              char *__restrict__ out, unsigned long long *d_bytes,
+                                                              unsigned long long *ticket, uint64_t *status) {
+    constexpr int WARPS = kPrintThreads / 32;
+    constexpr uint32_t kFixed = 32u * W + 2u;       // letters + blank + newline
+    __shared__ uint32_t s_warp[WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (uint32_t)atomicAdd(ticket, 1ull);     // tiles in the order CTAs start: a look-back never
+    __syncthreads();                                              // waits for a tile that has not been scheduled
+    const uint32_t tile = s_tile;
+    const uint64_t first = (uint64_t)tile * kPrintTile + (uint64_t)tid * kPrintItems;
+    uint32_t cnt[kPrintItems], len[kPrintItems], mine = 0;
+#pragma unroll
+    for (int j = 0; j < kPrintItems; j++) {
+        cnt[j] = 0;
+        len[j] = 0;
+        if (first + j < n) {
+            cnt[j] = counts[first + j];
+            len[j] = kFixed + dec_digits(cnt[j]);
+        }
+        mine += len[j];
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) {
+        if (w < (int)warp) woff += s_warp[w];
+        total += s_warp[w];
+    }
+    if (warp == 0) {
+        const uint64_t excl = lookback_exclusive_warp(status, tile, total);
+        if (lane == 0) {
+            s_base = excl;
+            if (tile + 1 == gridDim.x) *d_bytes = excl + total;     // the last tile closes the text
+        }
+    }
+    __syncthreads();
+    uint64_t o = s_base + woff + incl - mine;
+#pragma unroll
+    for (int j = 0; j < kPrintItems; j++) {
+        if (first + j >= n) break;
+        const Key<W> k = ld_key<W>(keys, first + j);
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const uint64_t v = k.w[w];
+#pragma unroll
+            for (int b = 0; b < 32; b++) out[o + 32 * w + b] = "ACGT"[(v >> (62 - 2 * b)) & 3ull];
+        }
+        out[o + 32 * W] = ' ';
+        const uint32_t nd = len[j] - kFixed;
+        uint32_t v = cnt[j];
+        for (uint32_t d = 0; d < nd; d++) {
+            out[o + 32 * W + nd - d] = (char)('0' + v % 10u);
+            v /= 10u;
+        }
+        out[o + len[j] - 1] = '\n';
+        o += len[j];
+    }
+}
+
+uint64_t print_workspace_bytes(uint64_t n) { return 256 + div_up(n ? n : 1, (uint64_t)kPrintTile) * 8 + 256; }
+uint64_t print_max_bytes(uint64_t n, int W) { return n * (32ull * W + 12ull); }
+
+cudaError_t print_records_text(const uint64_t *keys, const uint32_t *counts, uint64_t n, int W, char *d_text,
+                               unsigned long long *d_bytes, void *ws, cudaStream_t s) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(d_bytes, 0, 8, s)) != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    const uint64_t tiles = div_up(n, (uint64_t)kPrintTile);
+    if (tiles >= (1ull << 31)) return cudaErrorInvalidValue;
+    if ((e = cudaMemsetAsync(ws, 0, 256 + tiles * 8, s)) != cudaSuccess) return e;
+    unsigned long long *ticket = static_cast<unsigned long long *>(ws);
+    uint64_t *status = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(ws) + 256);
+    switch (W) {
+        case 1: print_kernel<1><<<(uint32_t)tiles, kPrintThreads, 0, s>>>(keys, counts, n, d_text, d_bytes, ticket, status); break;
+        case 2: print_kernel<2><<<(uint32_t)tiles, kPrintThreads, 0, s>>>(keys, counts, n, d_text, d_bytes, ticket, status); break;
+        case 3: print_kernel<3><<<(uint32_t)tiles, kPrintThreads, 0, s>>>(keys, counts, n, d_text, d_bytes, ticket, status); break;
+        case 4: print_kernel<4><<<(uint32_t)tiles, kPrintThreads, 0, s>>>(keys, counts, n, d_text, d_bytes, ticket, status); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 uint64_t rle_workspace_bytes(uint64_t n) {
     return 256 + div_up(n ? n : 1, (uint64_t)kRleTile) * 8 + 256;
 }

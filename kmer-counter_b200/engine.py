@@ -69,6 +69,17 @@ class Run:
         self._c._check(self._c._lib.kc_run_copy_records(self._c._ctx, self._h, buf.ctypes.data, buf.size, C.byref(n)))
         return buf[: n.value].tobytes()
 
+    def print_text(self) -> bytes:
+        """The run in KMerPrinter's text format (KMerPrinter.cpp:35-91), formatted on the device."""
+        n = len(self)
+        if n == 0:
+            return b""
+        cap = n * (32 * self._c.words + 12)
+        buf = np.empty(cap, dtype=np.uint8)
+        nb = C.c_uint64()
+        self._c._check(self._c._lib.kc_run_print(self._c._ctx, self._h, buf.ctypes.data, cap, C.byref(nb)))
+        return buf[: nb.value].tobytes()
+
     def copy_into(self, host_ptr, cap) -> int:
         n = C.c_uint64()
         self._c._check(self._c._lib.kc_run_copy_records(self._c._ctx, self._h, host_ptr, cap, C.byref(n)))

@@ -102,6 +102,28 @@ def test_place_path_heavy_hitters_deep_plans_and_strict(kc, monkeypatch, k):
         assert c.process_chunk(reads) == want
 
 
+@pytest.mark.parametrize("k", [31, 63, 96, 128])
+def test_run_print_matches_kmerprinter_format(kc, k):
+    """kc_run_print (the run as text, formatted on the device) against KMerPrinter's format applied to the
+    same records on the host (KMerPrinter.cpp:35-91: 32 letters per key word, a blank, the count): a hundred
+    tiles of records, counts of one to five digits and the zero-count phantom record."""
+    L = 150
+    reads = np.concatenate([oracle.gen_reads(900, L, 9000, 0.01, 0.003, seed=k),              # N bases: phantom (0, 0)
+                            np.tile(oracle.gen_reads(1, L, 0, 0, 0, seed=k + 1), 12345)])     # counts of 12345
+    with _counter(kc, k, L, method="auto", cap=1 << 26) as c:
+        run = c.count_reads(reads, chunk_reads=len(reads) // L)
+        rec, text = run.to_bytes(), run.print_text()
+        run.free()
+    assert rec == oracle.process_chunk(reads, L, k)
+    W = (k + 31) // 32
+    rows = np.frombuffer(rec, dtype=np.uint8).reshape(-1, 8 * W + 4)
+    words = np.ascontiguousarray(rows[:, :8 * W]).view("<u8")
+    counts = np.ascontiguousarray(rows[:, 8 * W:]).view("<u4")[:, 0]
+    assert counts.min() == 0 and counts.max() >= 12345
+    want = "".join("".join(oracle.print_word(int(w)) for w in ws) + " %d\n" % int(cn) for ws, cn in zip(words, counts))
+    assert text == want.encode()
+
+
 SUPER_CASES = [c for c in CASES if 22 <= c[2] <= 64]
 
 
